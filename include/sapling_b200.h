@@ -1,0 +1,155 @@
+/*
+ * sapling_b200.h -- C ABI of libsapling_b200.so: the B200 (sm_100a) implementation of SAPLING's
+ * suffix-array query hot path.
+ *
+ * This is the drop-in boundary.  Plain pointers and sizes only; every entry point cites the
+ * reference interface it replaces (file:line into mkirsche/sapling src/).  The C++ shim
+ * include/sapling_api.h wraps these into a `struct Sapling` with the reference's surface.
+ *
+ * Conventions: functions returning int give 0 on success, <0 on error (message in
+ * sapling_b200_last_error()).  A handle owns all host and device memory of one index on ONE GPU
+ * (the current CUDA device at creation).  Query calls do not mutate the index and may be issued
+ * concurrently from several host threads on distinct streams.  There is no CPU fallback: every
+ * call fails if no sm_100-class device is usable.
+ */
+#ifndef SAPLING_B200_H
+#define SAPLING_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sapling_b200_index sapling_b200_index;
+
+/* flags for the constructors */
+#define SAPLING_B200_QUIET 1u        /* do not print the reference's progress lines to stdout */
+#define SAPLING_B200_NO_COMPAT 2u    /* 64-bit-safe window arithmetic instead of the reference's
+                                        (int)predicted casts (sapling_api.h:209,225).
+                                        Identical results for genomes < 2^31 bp. */
+#define SAPLING_B200_KEEP_BUILD 4u   /* keep ISA / k-prefix runs on the device after construction
+                                        (needed by count_hits / sa_rank) */
+
+/* ---- construction -------------------------------------------------------------------------- */
+
+/* Sapling::Sapling(refFn, saFn, sapFn, numBuckets, maxMem, k, errorFn)   sapling_api.h:492-676.
+ * Reads the FASTA (same cleaning rule, :512-548), loads <saFn> if it exists, else builds the
+ * suffix array on the GPU and writes <saFn> in the reference format (:565-577,:593-599); loads
+ * <sapFn> if it exists, else builds the piecewise-linear model on the GPU (:384-487) and writes
+ * it (:656-674).  nb / maxMem / k = -1 select the reference defaults (:500-510,:387-391).
+ * err_fn may be NULL/"" (:396-400,:467).  Returns NULL on error. */
+sapling_b200_index *sapling_b200_open(const char *ref_fn, const char *sa_fn, const char *sap_fn, int nb,
+                                      int maxMem, int k, const char *err_fn, unsigned flags);
+
+/* Same index from memory: genome = n cleaned bases (ASCII A/C/G/T); sa = rank -> position
+ * (uint32, may be NULL: built on the GPU).  The model is built on the GPU. */
+sapling_b200_index *sapling_b200_create(const char *genome, uint64_t n, const uint32_t *sa, int nb,
+                                        int maxMem, int k, unsigned flags);
+
+/* Same, with the model supplied (contents of a .sap file: xlist/ylist of (1<<nb)+1 entries and
+ * the five error bounds maxOver,maxUnder,meanError,mostOver,mostUnder; sapling_api.h:639-645). */
+sapling_b200_index *sapling_b200_create_with_model(const char *genome, uint64_t n, const uint32_t *sa,
+                                                   int k, int nb, const int64_t *xlist,
+                                                   const int64_t *ylist, const int *five, unsigned flags);
+
+/* Synthetic genome generated on the device: base[i] = "ACGT"[splitmix64(seed+i)>>62]; suffix
+ * array and model built on the GPU.  keep_host_genome != 0 also materialises the ASCII genome
+ * on the host (needed for sapling_b200_genome()). */
+sapling_b200_index *sapling_b200_create_synthetic(uint64_t seed, uint64_t n, int nb, int maxMem, int k,
+                                                  int keep_host_genome, unsigned flags);
+
+void sapling_b200_close(sapling_b200_index *ix);
+
+/* ---- introspection ------------------------------------------------------------------------- */
+
+/* Public members of struct Sapling (sapling_api.h:26,29,44,50): any out pointer may be NULL. */
+int sapling_b200_info(const sapling_b200_index *ix, uint64_t *n, int *k, int *nb, int *maxOver,
+                      int *maxUnder, int *meanError, int *mostOver, int *mostUnder);
+/* Sapling::reference (sapling_api.h:20): NUL-terminated cleaned genome, or NULL if not kept. */
+const char *sapling_b200_genome(const sapling_b200_index *ix);
+/* Sapling::chrEnds (sapling_api.h:59): number of entries / i-th (end position, name). */
+size_t sapling_b200_num_chr(const sapling_b200_index *ix);
+uint64_t sapling_b200_chr(const sapling_b200_index *ix, size_t i, const char **name);
+/* Sapling::perfectPredictions and the over/under counts of the last model build (:47,:53). */
+int sapling_b200_build_stats(const sapling_b200_index *ix, uint64_t *perfect, uint64_t *n_over,
+                             uint64_t *n_under);
+/* Model checkpoints as the reference holds them (sapling_api.h:65): copies (1<<nb)+1 entries. */
+int sapling_b200_model(const sapling_b200_index *ix, int64_t *xlist, int64_t *ylist);
+/* Sapling::rev (sapling_api.h:41): copies count entries starting at rank `first` to the host. */
+int sapling_b200_rev(const sapling_b200_index *ix, uint64_t first, uint64_t count, uint32_t *out);
+/* Sapling::sa / lsa.inv (sapling_api.h:38; used by align.cpp:287): rank of text position pos.
+ * Needs SAPLING_B200_KEEP_BUILD.  Copies count entries starting at position `first`. */
+int sapling_b200_sa_rank(const sapling_b200_index *ix, uint64_t first, uint64_t count, uint32_t *out);
+/* Writes the index in the reference's on-disk formats. */
+int sapling_b200_write_sap(const sapling_b200_index *ix, const char *path);
+int sapling_b200_write_sa(const sapling_b200_index *ix, const char *path);
+/* sufcheck-style validation of the resident suffix array (the role of libdivsufsort's sufcheck,
+ * suffixarray/libdivsufsort/lib/utils.c:161): adjacent suffixes out of order, pairs undecided
+ * within max_chars characters, and (with SAPLING_B200_KEEP_BUILD) positions with isa[sa[r]] != r. */
+int sapling_b200_check_sa(const sapling_b200_index *ix, uint32_t max_chars, uint64_t *bad_order,
+                          uint64_t *undecided, uint64_t *bad_perm);
+/* Device memory held by the index, in bytes. */
+uint64_t sapling_b200_device_bytes(const sapling_b200_index *ix);
+
+/* ---- hashing (host, no GPU) ---------------------------------------------------------------- */
+
+/* Sapling::kmerize (sapling_api.h:73-78) and kmerizeAdjusted (:83-90). */
+int64_t sapling_b200_kmerize(int k, const char *s);
+int64_t sapling_b200_kmerize_adjusted(int k, int length, const char *s);
+
+/* ---- queries ------------------------------------------------------------------------------- */
+
+/* queryBatch: out[i] = plQuery(unpack(kmers[i], k), kmers[i], k)   (sapling_api.h:159-248 with the
+ * call shape of sapling_example.cpp:137 / align.cpp:279): genome position, or -1.
+ * Host pointers; the library streams chunks through the GPU (pinned buffers are copied directly). */
+int sapling_b200_query_batch(sapling_b200_index *ix, const uint64_t *kmers, size_t nq, int64_t *out);
+
+/* Same on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream),
+ * no copies, no synchronisation. */
+int sapling_b200_query_batch_dev(sapling_b200_index *ix, const uint64_t *d_kmers, size_t nq,
+                                 int64_t *d_out, void *stream);
+
+/* long long plQuery(string s, long kmer, size_t length)   sapling_api.h:159.  s holds slen bases
+ * (A/C/G/T), length <= slen is the reference's third argument. */
+int64_t sapling_b200_query_str(sapling_b200_index *ix, const char *s, size_t slen, int64_t kmer,
+                               size_t length);
+/* Batch of strings: query i is s[offsets[i] .. offsets[i]+slens[i]) with kmers[i] and lengths[i]
+ * (lengths == NULL means lengths[i] = slens[i]). */
+int sapling_b200_query_str_batch(sapling_b200_index *ix, const char *s, const uint64_t *offsets,
+                                 const uint32_t *slens, const uint32_t *lengths, const int64_t *kmers,
+                                 size_t nq, int64_t *out);
+
+/* queryPiecewiseLinear (sapling_api.h:98-109) for a batch of k-mers (host pointers). */
+int sapling_b200_predict_batch(sapling_b200_index *ix, const uint64_t *kmers, size_t nq, uint64_t *out);
+
+/* countHitsLeft / countHitsRight (sapling_api.h:254-263,:283-289) for a batch of ranks.
+ * Needs SAPLING_B200_KEEP_BUILD. */
+int sapling_b200_count_hits(sapling_b200_index *ix, const uint32_t *sa_pos, size_t count,
+                            uint32_t maxHits, uint32_t *left, uint32_t *right);
+
+/* Number of queries so far whose predicted rank was >= n (reference: out-of-bounds read). */
+uint64_t sapling_b200_oob_count(sapling_b200_index *ix);
+
+/* ---- measurement helpers ------------------------------------------------------------------- */
+
+/* Present queries sampled on the device: kmer j = genome[pos_j, pos_j+k), pos_j =
+ * splitmix64(seed + first + j) mod (n-k); if mut_seed != 0, odd (first+j) get 1-2 substitutions. */
+int sapling_b200_sample_queries_dev(sapling_b200_index *ix, uint64_t seed, uint64_t mut_seed,
+                                    uint64_t first, size_t nq, uint64_t *d_kmers, void *stream);
+/* Counts d_out[i] whose k bases equal the query (the self-check of sapling_example.cpp:144-154)
+ * and the number of -1 answers. */
+int sapling_b200_verify_dev(sapling_b200_index *ix, const uint64_t *d_kmers, const int64_t *d_out,
+                            size_t nq, uint64_t *n_match, uint64_t *n_minus1, void *stream);
+/* Random 32-byte-sector gather over `bytes` of scratch HBM: returns achieved GB/s (the
+ * "HBM random-sector roofline" denominator). */
+int sapling_b200_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double *gbps);
+
+const char *sapling_b200_last_error(void);
+const char *sapling_b200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

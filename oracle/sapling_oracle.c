@@ -531,6 +531,29 @@ so_index *so_from_memory(const char *genome, uint64_t n, const uint32_t *sa, int
   return ix;
 }
 
+/* Query-only index from parts already in memory (no LCP, no build): used to count probes and to
+   answer queries at sizes where rebuilding the model on the CPU would take too long. */
+so_index *so_from_parts(const char *genome, uint64_t n, const uint32_t *sa, int k, int nb,
+                        const int64_t *xlist, const int64_t *ylist, const int *five) {
+  so_index *ix = so_alloc();
+  ix->n = n;
+  ix->k = k;
+  ix->nb = nb;
+  ix->ref = (char *)malloc(n + 1);
+  memcpy(ix->ref, genome, n);
+  ix->ref[n] = 0;
+  ix->rev = (uint32_t *)malloc(n * 4);
+  memcpy(ix->rev, sa, n * 4);
+  uint64_t cnt = ((uint64_t)1 << nb) + 1;
+  ix->xlist = (int64_t *)malloc(cnt * 8);
+  ix->ylist = (int64_t *)malloc(cnt * 8);
+  memcpy(ix->xlist, xlist, cnt * 8);
+  memcpy(ix->ylist, ylist, cnt * 8);
+  ix->maxOver = five[0]; ix->maxUnder = five[1]; ix->meanError = five[2];
+  ix->mostOver = five[3]; ix->mostUnder = five[4];
+  return ix;
+}
+
 void so_close(so_index *ix) {
   if (!ix) return;
   free(ix->ref); free(ix->rev); free(ix->inv); free(ix->lcp); free(ix->krmqb);
@@ -604,6 +627,8 @@ int64_t so_plquery(const so_index *ix, const char *s, size_t slen, int64_t kmer,
       if (oLcp == length) return (int64_t)hiIdx;          /* :183 */
       if (slen > (uint64_t)ix->k) {                       /* :184-196 */
         while (oLcp + hiIdx != n && s[oLcp] > ix->ref[hiIdx + oLcp]) {
+          /* the reference spins forever once hi is pinned at n-1; defined here as: stop, flag */
+          if (hi == n - 1) { if (flags) *flags |= SO_FLAG_GALLOP_UB; break; }
           lo = hi;
           loLcp = oLcp;
           hi += (uint64_t)(int64_t)ix->maxOver;
@@ -640,9 +665,16 @@ int64_t so_plquery(const so_index *ix, const char *s, size_t slen, int64_t kmer,
       if (oLcp == slen) return (int64_t)loIdx;            /* :228 */
       if (slen > (uint64_t)ix->k) {                       /* :229-241 */
         while (oLcp + loIdx != n && s[oLcp] < ix->ref[loIdx + oLcp]) {
+          /* the reference does size_t arithmetic here (max((size_t)0,lo) is a no-op), so it reads
+             rev[] far out of bounds once lo < maxUnder; defined here as: clamp at 0, stop at 0, flag */
+          if (lo == 0) { if (flags) *flags |= SO_FLAG_GALLOP_UB; break; }
           hi = lo;
           hiLcp = oLcp;
-          lo -= (uint64_t)(int64_t)ix->maxUnder; /* size_t arithmetic; max((size_t)0,lo) is a no-op */
+          if (lo < (uint64_t)(int64_t)ix->maxUnder) {
+            if (flags) *flags |= SO_FLAG_GALLOP_UB;
+            lo = 0;
+          } else
+            lo -= (uint64_t)(int64_t)ix->maxUnder;
           loIdx = ix->rev[lo];
           oLcp = get_lcp(ix, loIdx, s, 0, length, probes);
           if (oLcp == slen) return (int64_t)loIdx;

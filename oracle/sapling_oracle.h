@@ -78,6 +78,9 @@ so_index *so_open(const char *ref_fn, const char *sa_fn, const char *sap_fn, int
 /* From memory: cleaned genome (ASCII), optional SA (rank->pos, may be NULL => built here). */
 so_index *so_from_memory(const char *genome, uint64_t n, const uint32_t *sa, int nb, int maxMem,
                          int k);
+/* Query-only index from parts (no LCP / build arrays). */
+so_index *so_from_parts(const char *genome, uint64_t n, const uint32_t *sa, int k, int nb,
+                        const int64_t *xlist, const int64_t *ylist, const int *five);
 void so_close(so_index *ix);
 
 /* ---- the hot path ---- */
@@ -86,7 +89,9 @@ uint64_t so_predict(const so_index *ix, int64_t x);
 /* plQuery (sapling_api.h:159-248).  s has slen chars; length is the third argument of the
    reference call.  probes (optional) is incremented once per getLcp call; flags (optional)
    gets SO_FLAG_* bits for inputs on which the reference has undefined behaviour. */
-#define SO_FLAG_PRED_OOB 1u /* predicted >= n: rev[predicted] out of bounds */
+#define SO_FLAG_PRED_OOB 1u  /* predicted >= n: rev[predicted] out of bounds */
+#define SO_FLAG_GALLOP_UB 2u /* s.length() > k gallop ran off either end of the suffix array: the
+                                reference hangs (:186-195) or reads out of bounds (:231-240) */
 int64_t so_plquery(const so_index *ix, const char *s, size_t slen, int64_t kmer, size_t length,
                    uint32_t *probes, uint32_t *flags);
 /* Batch of k-mers: out[i] = plQuery(unpack(kmers[i],k), kmers[i], k).  OpenMP over nthreads.

@@ -1,0 +1,874 @@
+// capi.cu -- host side of libsapling_b200.so: the index object, the loaders for the reference's
+// on-disk formats, and the extern "C" surface declared in include/sapling_b200.h.
+//
+// Mirrors Sapling::Sapling (reference sapling_api.h:492-676): FASTA cleaning, load-or-build of the
+// .sa and .sap files, same defaults, same progress lines on stdout (unless SAPLING_B200_QUIET).
+// There is no CPU query path in this library: if CUDA is unusable every constructor fails.
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/sapling_b200.h"
+#include "build.cuh"
+#include "common.cuh"
+
+namespace sb {
+
+// launchers in query.cu
+int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st);
+int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint64_t* d_word_off,
+                        const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
+                        long long* d_out, cudaStream_t st);
+int launch_predict(const IndexView& ix, const uint64_t* d_kmers, size_t nq, uint64_t* d_out, cudaStream_t st);
+int launch_sample(const IndexView& ix, uint64_t seed, uint64_t mut_seed, uint64_t first, size_t nq,
+                  uint64_t* d_kmers, cudaStream_t st);
+int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long* d_out, size_t nq,
+                  unsigned long long* d_counters, cudaStream_t st);
+int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps);
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+}  // namespace sb
+
+using namespace sb;
+
+struct sapling_b200_index {
+  int device = 0;
+  unsigned flags = 0;
+  uint64_t n = 0;
+  int k = 21, nb = 18, maxMem = 10;  // sapling_api.h:26,29,32
+  ModelStats stats{};
+  std::string genome;  // Sapling::reference (may be empty for synthetic indexes)
+  std::vector<std::pair<uint64_t, std::string>> chr_ends;  // Sapling::chrEnds, ascending
+
+  uint64_t* d_genome = nullptr;
+  uint32_t* d_sa = nullptr;
+  uint32_t* d_isa = nullptr;   // only with KEEP_BUILD
+  uint8_t* d_kflag = nullptr;  // only with KEEP_BUILD
+  ModelEntry* d_model = nullptr;
+  unsigned long long* d_oob = nullptr;
+  uint64_t device_bytes = 0;
+  int sa_rounds = 0;
+
+  // staging for the host-pointer batch API
+  std::mutex mu;
+  static constexpr size_t kChunk = 1u << 22;  // queries per chunk
+  cudaStream_t streams[2] = {nullptr, nullptr};
+  uint64_t* d_in[2] = {nullptr, nullptr};
+  long long* d_out[2] = {nullptr, nullptr};
+  uint64_t* h_in[2] = {nullptr, nullptr};
+  long long* h_out[2] = {nullptr, nullptr};
+
+  IndexView view() const {
+    IndexView v;
+    v.genome = d_genome;
+    v.sa = d_sa;
+    v.model = d_model;
+    v.n = n;
+    v.k = k;
+    v.nb = nb;
+    v.shift = 2 * k - nb;
+    v.maxOver = stats.maxOver;
+    v.maxUnder = stats.maxUnder;
+    v.mostOver = stats.mostOver;
+    v.mostUnder = stats.mostUnder;
+    v.oob_counter = d_oob;
+    v.compat = (flags & SAPLING_B200_NO_COMPAT) ? 0 : 1;
+    return v;
+  }
+
+  ~sapling_b200_index() {
+    cudaSetDevice(device);
+    for (int i = 0; i < 2; i++) {
+      if (streams[i]) cudaStreamDestroy(streams[i]);
+      cudaFree(d_in[i]);
+      cudaFree(d_out[i]);
+      if (h_in[i]) cudaFreeHost(h_in[i]);
+      if (h_out[i]) cudaFreeHost(h_out[i]);
+    }
+    cudaFree(d_genome);
+    cudaFree(d_sa);
+    cudaFree(d_isa);
+    cudaFree(d_kflag);
+    cudaFree(d_model);
+    cudaFree(d_oob);
+  }
+};
+
+namespace {
+
+struct Say {
+  bool on;
+  explicit Say(unsigned flags) : on(!(flags & SAPLING_B200_QUIET)) {}
+  void operator()(const char* fmt, ...) const {
+    if (!on) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vprintf(fmt, ap);
+    va_end(ap);
+    fflush(stdout);
+  }
+};
+
+int require_device(int* dev_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no usable CUDA device: %s (libsapling_b200 has no CPU fallback)", cudaGetErrorString(e));
+    return -1;
+  }
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, dev);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    return -1;
+  }
+  if (prop.major < 10) {
+    set_error("device %d (%s, sm_%d%d) is not a Blackwell sm_100-class GPU; this library is built for sm_100a only",
+              dev, prop.name, prop.major, prop.minor);
+    return -1;
+  }
+  *dev_out = dev;
+  return 0;
+}
+
+template <typename T>
+int dev_alloc(sapling_b200_index* ix, T** p, uint64_t count) {
+  const uint64_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(reinterpret_cast<void**>(p), bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%llu bytes) failed: %s", (unsigned long long)bytes, cudaGetErrorString(e));
+    return -1;
+  }
+  ix->device_bytes += bytes;
+  return 0;
+}
+
+// FASTA cleaning rule of sapling_api.h:520-548 / util.h:17-20
+void clean_fasta(const char* text, size_t len, std::string* out,
+                 std::vector<std::pair<uint64_t, std::string>>* ends) {
+  out->clear();
+  out->reserve(len);
+  std::string cur_name;
+  auto set_end = [&](uint64_t pos, const std::string& name) {
+    for (auto& e : *ends)
+      if (e.first == pos) { e.second = name; return; }  // std::map assignment semantics
+    ends->push_back({pos, name});
+  };
+  size_t p = 0;
+  while (p < len) {
+    const char* nl = static_cast<const char*>(memchr(text + p, '\n', len - p));
+    const size_t e = nl ? (size_t)(nl - text) : len;
+    if (e > p && text[p] == '>') {
+      if (!cur_name.empty()) set_end(out->size(), cur_name);
+      size_t t = p + 1;
+      while (t < e && text[t] != ' ') t++;
+      cur_name.assign(text + p + 1, t - (p + 1));
+    } else {
+      for (size_t i = p; i < e; i++) {
+        char c = text[i];
+        if (c >= 'a' && c <= 'z') c = (char)(c + 'A' - 'a');
+        if (c == 'A' || c == 'C' || c == 'G' || c == 'T') out->push_back(c);
+      }
+    }
+    p = e + 1;
+  }
+  if (!cur_name.empty()) set_end(out->size(), cur_name);
+}
+
+bool file_exists(const char* p) {
+  if (!p || !p[0]) return false;
+  FILE* f = fopen(p, "rb");
+  if (!f) return false;
+  fclose(f);
+  return true;
+}
+
+// upload ASCII genome and pack it on the device
+int upload_genome(sapling_b200_index* ix, const char* genome, uint64_t n) {
+  char* d_ascii = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&d_ascii, n + 64));
+  cudaError_t e = cudaMemcpy(d_ascii, genome, n, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(d_ascii); SB_CUDA_CHECK(e); }
+  if (dev_alloc(ix, &ix->d_genome, packed_words(n))) { cudaFree(d_ascii); return -1; }
+  int rc = pack_genome(d_ascii, n, ix->d_genome, 0);
+  e = cudaDeviceSynchronize();
+  cudaFree(d_ascii);
+  if (rc) return rc;
+  SB_CUDA_CHECK(e);
+  return 0;
+}
+
+// [u64 n][u64 inv[n]][u64 m][u64 lcp[m]]   (sapling_api.h:565-577): only inv is needed
+int read_sa_file(sapling_b200_index* ix, const char* path) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return -1; }
+  uint64_t sz = 0;
+  if (fread(&sz, 8, 1, f) != 1 || sz != ix->n) {
+    fclose(f);
+    set_error("%s: suffix array size %llu does not match genome length %llu", path, (unsigned long long)sz,
+              (unsigned long long)ix->n);
+    return -1;
+  }
+  if (dev_alloc(ix, &ix->d_isa, sz)) { fclose(f); return -1; }
+  const size_t CH = 1u << 22;
+  std::vector<uint64_t> buf(CH);
+  std::vector<uint32_t> buf32(CH);
+  for (uint64_t o = 0; o < sz; o += CH) {
+    const size_t c = (size_t)std::min<uint64_t>(CH, sz - o);
+    if (fread(buf.data(), 8, c, f) != c) { fclose(f); set_error("Error reading suffix array from file"); return -1; }
+    for (size_t i = 0; i < c; i++) buf32[i] = (uint32_t)buf[i];
+    cudaError_t e = cudaMemcpy(ix->d_isa + o, buf32.data(), c * 4, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { fclose(f); SB_CUDA_CHECK(e); }
+  }
+  fclose(f);
+  if (dev_alloc(ix, &ix->d_sa, sz)) return -1;
+  // rev[inv[i]] = i  (sapling_api.h:609-611)
+  if (invert_permutation(ix->d_isa, sz, ix->d_sa, 0)) return -1;
+  SB_CUDA_CHECK(cudaDeviceSynchronize());
+  return 0;
+}
+
+int write_sa_file(const sapling_b200_index* ix, const char* path) {
+  if (!ix->d_isa) { set_error("write_sa: ISA not resident (open with SAPLING_B200_KEEP_BUILD)"); return -1; }
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot write %s", path); return -1; }
+  const uint64_t n = ix->n;
+  uint32_t* d_lcp = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&d_lcp, (n ? n : 1) * 4));
+  if (compute_lcp(ix->d_genome, n, ix->d_sa, d_lcp, 0)) { cudaFree(d_lcp); fclose(f); return -1; }
+  const size_t CH = 1u << 22;
+  std::vector<uint64_t> buf(CH);
+  std::vector<uint32_t> buf32(CH);
+  auto dump = [&](const uint32_t* d, uint64_t count) -> int {
+    fwrite(&count, 8, 1, f);
+    for (uint64_t o = 0; o < count; o += CH) {
+      const size_t c = (size_t)std::min<uint64_t>(CH, count - o);
+      if (cudaMemcpy(buf32.data(), d + o, c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+      for (size_t i = 0; i < c; i++) buf[i] = buf32[i];
+      if (fwrite(buf.data(), 8, c, f) != c) return -1;
+    }
+    return 0;
+  };
+  int rc = dump(ix->d_isa, n);
+  if (!rc) rc = dump(d_lcp, n - 1);
+  cudaFree(d_lcp);
+  fclose(f);
+  if (rc) set_error("error writing %s", path);
+  return rc;
+}
+
+// [int nb][int|size_t count][i64 xlist][i64 ylist][5 x int]   (sapling_api.h:616-645)
+int read_sap_file(sapling_b200_index* ix, const char* path, std::vector<int64_t>* xs, std::vector<int64_t>* ys) {
+  FILE* f = fopen(path, "rb");
+  if (!f) { set_error("cannot open %s", path); return -1; }
+  int nb = 0;
+  uint64_t count = 0;
+  bool ok = fread(&nb, sizeof(int), 1, f) == 1;
+  if (ok && nb <= 30) {
+    int c32 = 0;
+    ok = fread(&c32, sizeof(int), 1, f) == 1;
+    count = (uint64_t)(int64_t)c32;
+  } else if (ok) {
+    ok = fread(&count, 8, 1, f) == 1;
+  }
+  if (!ok || nb < 1 || nb > 31 || count != (1ull << nb) + 1) {
+    fclose(f);
+    set_error("Error reading sapling data structure from file %s", path);
+    return -1;
+  }
+  xs->resize(count);
+  ys->resize(count);
+  int five[5];
+  ok = fread(xs->data(), 8, count, f) == count && fread(ys->data(), 8, count, f) == count &&
+       fread(five, sizeof(int), 5, f) == 5;
+  fclose(f);
+  if (!ok) { set_error("Error reading sapling data structure from file %s", path); return -1; }
+  ix->nb = nb;  // buckets is overwritten from the file (:618)
+  ix->stats.maxOver = five[0]; ix->stats.maxUnder = five[1]; ix->stats.meanError = five[2];
+  ix->stats.mostOver = five[3]; ix->stats.mostUnder = five[4];
+  return 0;
+}
+
+int upload_model(sapling_b200_index* ix, const int64_t* xs, const int64_t* ys) {
+  const uint64_t count = (1ull << ix->nb) + 1;
+  std::vector<ModelEntry> m(count);
+  for (uint64_t i = 0; i < count; i++) { m[i].x = xs[i]; m[i].y = ys[i]; }
+  if (dev_alloc(ix, &ix->d_model, count)) return -1;
+  SB_CUDA_CHECK(cudaMemcpy(ix->d_model, m.data(), count * sizeof(ModelEntry), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int validate_params(sapling_b200_index* ix) {
+  if (ix->k < 1 || ix->k > 32) { set_error("k=%d out of range (1..32)", ix->k); return -1; }
+  if (ix->n < (uint64_t)ix->k + 1) { set_error("genome (%llu bp) shorter than k+1", (unsigned long long)ix->n); return -1; }
+  if (ix->n >= 0xFFFFFF00ull) { set_error("genome of %llu bp needs a suffix array wider than 32 bits", (unsigned long long)ix->n); return -1; }
+  return 0;
+}
+
+int finish_model_checks(sapling_b200_index* ix) {
+  if (ix->nb < 1 || ix->nb > 31 || ix->nb > 2 * ix->k) {
+    set_error("nb=%d out of range for k=%d (need 1 <= nb <= min(2k,31))", ix->nb, ix->k);
+    return -1;
+  }
+  const ModelStats& s = ix->stats;
+  if (s.maxOver < 0 || s.maxUnder < 0 || s.mostOver < 0 || s.mostUnder < 0) {
+    set_error("negative error bounds in model");
+    return -1;
+  }
+  if (!ix->d_oob) {
+    if (dev_alloc(ix, &ix->d_oob, 1)) return -1;
+    SB_CUDA_CHECK(cudaMemset(ix->d_oob, 0, 8));
+  }
+  return 0;
+}
+
+// builds whatever is missing: SA (+ISA), kflags, model.  model_given: d_model & stats already set.
+int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, const Say& say) {
+  const uint64_t n = ix->n;
+  const bool keep = (ix->flags & SAPLING_B200_KEEP_BUILD) != 0;
+  if (!ix->d_sa) {
+    say("Building suffix array\n");
+    if (dev_alloc(ix, &ix->d_sa, n) || dev_alloc(ix, &ix->d_isa, n)) return -1;
+    if (build_suffix_array(ix->d_genome, n, ix->d_sa, ix->d_isa, 0, &ix->sa_rounds)) return -1;
+    say("Built suffix array of size %llu\n", (unsigned long long)n);
+  }
+  const bool need_build_arrays = !model_given || keep;
+  if (need_build_arrays) {
+    if (!ix->d_isa) {
+      if (dev_alloc(ix, &ix->d_isa, n)) return -1;
+      if (invert_permutation(ix->d_sa, n, ix->d_isa, 0)) return -1;
+    }
+    if (dev_alloc(ix, &ix->d_kflag, n)) return -1;
+    if (compute_kflags(ix->d_genome, n, ix->d_sa, ix->k, ix->d_kflag, 0)) return -1;
+  }
+  if (!model_given) {
+    say("Building Sapling\n");
+    if (ix->nb == -1) {  // sapling_api.h:387-391
+      ix->nb = 1;
+      while ((uint64_t)(1ull << ix->nb) * (uint64_t)ix->maxMem * 2 <= n) ix->nb++;
+    }
+    say("Buckets (log): %d\n", ix->nb);
+    if (ix->nb < 1 || ix->nb > 31 || ix->nb > 2 * ix->k) {
+      set_error("nb=%d out of range for k=%d (need 1 <= nb <= min(2k,31))", ix->nb, ix->k);
+      return -1;
+    }
+    if (dev_alloc(ix, &ix->d_model, (1ull << ix->nb) + 1)) return -1;
+    std::vector<int64_t> dump;
+    const bool want_dump = err_fn && err_fn[0];
+    const uint64_t nk = n - (uint64_t)ix->k + 1;
+    if (want_dump) dump.resize(nk * 3);
+    if (build_model(ix->d_genome, n, ix->d_sa, ix->d_isa, ix->d_kflag, ix->k, ix->nb, ix->d_model, &ix->stats,
+                    want_dump ? dump.data() : nullptr, 0))
+      return -1;
+    say("Computing error stats\n");
+    say("All overestimates within: %d\n", ix->stats.maxOver);
+    say("All underestimates within: %d\n", ix->stats.maxUnder);
+    say("Prefect predictions: %llu\n", (unsigned long long)ix->stats.perfect);
+    say("Mean error: %d\n", ix->stats.meanError);
+    say("0.95 of overestimates within: %d\n", ix->stats.mostOver);
+    say("0.95 of underestimates within: %d\n", ix->stats.mostUnder);
+    if (want_dump) {  // :396-400,:467 -- "x y predict val" per k-mer, first line nb
+      FILE* ef = fopen(err_fn, "w");
+      if (ef) {
+        fprintf(ef, "%d\n", ix->nb);
+        if (!ix->genome.empty()) {
+          uint64_t hash = (uint64_t)sapling_b200_kmerize(ix->k, ix->genome.c_str());
+          const uint64_t keep_mask = ix->k >= 32 ? ~0ull >> 2 : ((1ull << (2 * (ix->k - 1))) - 1);
+          for (uint64_t i = 0; i < nk; i++) {
+            fprintf(ef, "%lld %zu %zu %d\n", (long long)hash, (size_t)dump[3 * i], (size_t)dump[3 * i + 1],
+                    (int)dump[3 * i + 2]);
+            hash = (hash & keep_mask) << 2;
+            if (i + ix->k < n) hash |= (uint64_t)sapling_b200_kmerize(1, ix->genome.c_str() + i + ix->k);
+          }
+        }
+        fclose(ef);
+      }
+    }
+  }
+  if (!keep) {
+    if (ix->d_isa) { cudaFree(ix->d_isa); ix->d_isa = nullptr; ix->device_bytes -= n * 4; }
+    if (ix->d_kflag) { cudaFree(ix->d_kflag); ix->d_kflag = nullptr; ix->device_bytes -= n; }
+  }
+  SB_CUDA_CHECK(cudaDeviceSynchronize());
+  return finish_model_checks(ix);
+}
+
+int ensure_staging(sapling_b200_index* ix) {
+  if (ix->streams[0]) return 0;
+  for (int i = 0; i < 2; i++) {
+    SB_CUDA_CHECK(cudaStreamCreateWithFlags(&ix->streams[i], cudaStreamNonBlocking));
+    SB_CUDA_CHECK(cudaMalloc(&ix->d_in[i], sapling_b200_index::kChunk * 8));
+    SB_CUDA_CHECK(cudaMalloc(&ix->d_out[i], sapling_b200_index::kChunk * 8));
+  }
+  return 0;
+}
+
+int ensure_pinned(sapling_b200_index* ix) {
+  if (ix->h_in[0]) return 0;
+  for (int i = 0; i < 2; i++) {
+    SB_CUDA_CHECK(cudaMallocHost(&ix->h_in[i], sapling_b200_index::kChunk * 8));
+    SB_CUDA_CHECK(cudaMallocHost(&ix->h_out[i], sapling_b200_index::kChunk * 8));
+  }
+  return 0;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+const char* sapling_b200_last_error(void) { return last_error(); }
+const char* sapling_b200_version(void) { return "sapling_b200 0.1 (sm_100a)"; }
+
+int64_t sapling_b200_kmerize(int k, const char* s) {
+  // sapling_api.h:73-78 with vals[] of :494-498 (non-ACGT bytes hash as 0)
+  uint64_t h = 0;
+  for (int i = 0; i < k; i++) {
+    const char c = s[i];
+    const uint64_t v = c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0;
+    h = (h << 2) | v;
+  }
+  return (int64_t)h;
+}
+
+int64_t sapling_b200_kmerize_adjusted(int k, int length, const char* s) {
+  // sapling_api.h:83-90
+  if (length >= k) return sapling_b200_kmerize(k, s);
+  uint64_t h = (uint64_t)sapling_b200_kmerize(length, s);
+  h = (h << 2) | 2u;
+  return (int64_t)(h << (2 * (k - length - 1)));
+}
+
+static sapling_b200_index* new_index(unsigned flags, int nb, int maxMem, int k) {
+  int dev = 0;
+  if (require_device(&dev)) return nullptr;
+  sapling_b200_index* ix = new sapling_b200_index();
+  ix->device = dev;
+  ix->flags = flags;
+  ix->nb = nb;                          // sapling_api.h:500
+  if (k != -1) ix->k = k;               // :503-506
+  if (maxMem != -1) ix->maxMem = maxMem;  // :507-510
+  return ix;
+}
+
+sapling_b200_index* sapling_b200_open(const char* ref_fn, const char* sa_fn, const char* sap_fn, int nb, int maxMem,
+                                      int k, const char* err_fn, unsigned flags) {
+  sapling_b200_index* ix = new_index(flags, nb, maxMem, k);
+  if (!ix) return nullptr;
+  Say say(flags);
+  auto fail = [&]() { delete ix; return (sapling_b200_index*)nullptr; };
+
+  say("Reading reference genome\n");
+  FILE* f = fopen(ref_fn, "rb");
+  if (!f) { set_error("cannot open genome file %s", ref_fn); return fail(); }
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  std::string text((size_t)sz, '\0');
+  const size_t got = fread(&text[0], 1, (size_t)sz, f);
+  fclose(f);
+  clean_fasta(text.data(), got, &ix->genome, &ix->chr_ends);
+  text.clear();
+  text.shrink_to_fit();
+  ix->n = ix->genome.size();
+  if (validate_params(ix)) return fail();
+  if (upload_genome(ix, ix->genome.data(), ix->n)) return fail();
+
+  const bool have_sa = file_exists(sa_fn);
+  const bool have_sap = file_exists(sap_fn);
+  const unsigned user_flags = ix->flags;
+  if (!have_sa) ix->flags |= SAPLING_B200_KEEP_BUILD;  // ISA needed to write the .sa file
+  if (have_sa) {
+    say("Reading suffix array from file\n");
+    if (read_sa_file(ix, sa_fn)) return fail();
+    say("Loaded suffix array of size %llu\n", (unsigned long long)ix->n);
+  }
+  bool model_given = false;
+  if (have_sap) {
+    say("Reading Sapling from file\n");
+    std::vector<int64_t> xs, ys;
+    if (read_sap_file(ix, sap_fn, &xs, &ys)) return fail();
+    if (upload_model(ix, xs.data(), ys.data())) return fail();
+    model_given = true;
+  }
+  if (build_missing(ix, model_given, err_fn, say)) return fail();
+  if (!have_sa && sa_fn && sa_fn[0]) {
+    say("Writing suffix array to file\n");
+    if (write_sa_file(ix, sa_fn)) return fail();
+  }
+  if (!model_given && sap_fn && sap_fn[0]) {
+    say("Writing Sapling to file\n");
+    if (sapling_b200_write_sap(ix, sap_fn)) return fail();
+  }
+  if (!(user_flags & SAPLING_B200_KEEP_BUILD)) {
+    ix->flags = user_flags;
+    if (ix->d_isa) { cudaFree(ix->d_isa); ix->d_isa = nullptr; ix->device_bytes -= ix->n * 4; }
+    if (ix->d_kflag) { cudaFree(ix->d_kflag); ix->d_kflag = nullptr; ix->device_bytes -= ix->n; }
+  }
+  return ix;
+}
+
+static sapling_b200_index* create_common(const char* genome, uint64_t n, const uint32_t* sa, int nb, int maxMem,
+                                         int k, const int64_t* xlist, const int64_t* ylist, const int* five,
+                                         unsigned flags) {
+  sapling_b200_index* ix = new_index(flags, nb, maxMem, k);
+  if (!ix) return nullptr;
+  Say say(flags | SAPLING_B200_QUIET);
+  auto fail = [&]() { delete ix; return (sapling_b200_index*)nullptr; };
+  ix->n = n;
+  ix->genome.assign(genome, n);
+  if (validate_params(ix)) return fail();
+  if (upload_genome(ix, genome, n)) return fail();
+  if (sa) {
+    if (dev_alloc(ix, &ix->d_sa, n)) return fail();
+    if (cudaMemcpy(ix->d_sa, sa, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+      set_error("suffix array upload failed");
+      return fail();
+    }
+  }
+  bool model_given = false;
+  if (xlist && ylist && five) {
+    ix->stats.maxOver = five[0]; ix->stats.maxUnder = five[1]; ix->stats.meanError = five[2];
+    ix->stats.mostOver = five[3]; ix->stats.mostUnder = five[4];
+    if (ix->nb < 1 || ix->nb > 31) { set_error("nb must be given with a model"); return fail(); }
+    if (upload_model(ix, xlist, ylist)) return fail();
+    model_given = true;
+  }
+  if (build_missing(ix, model_given, nullptr, say)) return fail();
+  return ix;
+}
+
+sapling_b200_index* sapling_b200_create(const char* genome, uint64_t n, const uint32_t* sa, int nb, int maxMem, int k,
+                                        unsigned flags) {
+  return create_common(genome, n, sa, nb, maxMem, k, nullptr, nullptr, nullptr, flags);
+}
+
+sapling_b200_index* sapling_b200_create_with_model(const char* genome, uint64_t n, const uint32_t* sa, int k, int nb,
+                                                   const int64_t* xlist, const int64_t* ylist, const int* five,
+                                                   unsigned flags) {
+  return create_common(genome, n, sa, nb, -1, k, xlist, ylist, five, flags);
+}
+
+sapling_b200_index* sapling_b200_create_synthetic(uint64_t seed, uint64_t n, int nb, int maxMem, int k,
+                                                  int keep_host_genome, unsigned flags) {
+  sapling_b200_index* ix = new_index(flags, nb, maxMem, k);
+  if (!ix) return nullptr;
+  Say say(flags);
+  auto fail = [&]() { delete ix; return (sapling_b200_index*)nullptr; };
+  ix->n = n;
+  if (validate_params(ix)) return fail();
+  if (dev_alloc(ix, &ix->d_genome, packed_words(n))) return fail();
+  if (synth_genome_packed(seed, n, ix->d_genome, 0)) return fail();
+  if (keep_host_genome) {
+    char* d_ascii = nullptr;
+    if (cudaMalloc(&d_ascii, n) != cudaSuccess) { set_error("cudaMalloc ascii genome failed"); return fail(); }
+    ix->genome.resize(n);
+    int rc = unpack_genome(ix->d_genome, n, d_ascii, 0);
+    cudaError_t e = cudaMemcpy(&ix->genome[0], d_ascii, n, cudaMemcpyDeviceToHost);
+    cudaFree(d_ascii);
+    if (rc || e != cudaSuccess) { set_error("genome download failed"); return fail(); }
+  }
+  ix->chr_ends.push_back({n, "chr1"});
+  if (build_missing(ix, false, nullptr, say)) return fail();
+  return ix;
+}
+
+void sapling_b200_close(sapling_b200_index* ix) { delete ix; }
+
+int sapling_b200_info(const sapling_b200_index* ix, uint64_t* n, int* k, int* nb, int* maxOver, int* maxUnder,
+                      int* meanError, int* mostOver, int* mostUnder) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (n) *n = ix->n;
+  if (k) *k = ix->k;
+  if (nb) *nb = ix->nb;
+  if (maxOver) *maxOver = ix->stats.maxOver;
+  if (maxUnder) *maxUnder = ix->stats.maxUnder;
+  if (meanError) *meanError = ix->stats.meanError;
+  if (mostOver) *mostOver = ix->stats.mostOver;
+  if (mostUnder) *mostUnder = ix->stats.mostUnder;
+  return 0;
+}
+
+const char* sapling_b200_genome(const sapling_b200_index* ix) {
+  return (ix && !ix->genome.empty()) ? ix->genome.c_str() : nullptr;
+}
+size_t sapling_b200_num_chr(const sapling_b200_index* ix) { return ix ? ix->chr_ends.size() : 0; }
+uint64_t sapling_b200_chr(const sapling_b200_index* ix, size_t i, const char** name) {
+  if (!ix || i >= ix->chr_ends.size()) return 0;
+  if (name) *name = ix->chr_ends[i].second.c_str();
+  return ix->chr_ends[i].first;
+}
+
+int sapling_b200_build_stats(const sapling_b200_index* ix, uint64_t* perfect, uint64_t* n_over, uint64_t* n_under) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (perfect) *perfect = ix->stats.perfect;
+  if (n_over) *n_over = ix->stats.nOver;
+  if (n_under) *n_under = ix->stats.nUnder;
+  return 0;
+}
+
+int sapling_b200_model(const sapling_b200_index* ix, int64_t* xlist, int64_t* ylist) {
+  if (!ix) { set_error("null index"); return -1; }
+  const uint64_t count = (1ull << ix->nb) + 1;
+  std::vector<ModelEntry> m(count);
+  cudaSetDevice(ix->device);
+  SB_CUDA_CHECK(cudaMemcpy(m.data(), ix->d_model, count * sizeof(ModelEntry), cudaMemcpyDeviceToHost));
+  for (uint64_t i = 0; i < count; i++) {
+    if (xlist) xlist[i] = m[i].x;
+    if (ylist) ylist[i] = m[i].y;
+  }
+  return 0;
+}
+
+int sapling_b200_rev(const sapling_b200_index* ix, uint64_t first, uint64_t count, uint32_t* out) {
+  if (!ix || first + count > ix->n) { set_error("rev: range out of bounds"); return -1; }
+  cudaSetDevice(ix->device);
+  SB_CUDA_CHECK(cudaMemcpy(out, ix->d_sa + first, count * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int sapling_b200_sa_rank(const sapling_b200_index* ix, uint64_t first, uint64_t count, uint32_t* out) {
+  if (!ix || first + count > ix->n) { set_error("sa_rank: range out of bounds"); return -1; }
+  if (!ix->d_isa) { set_error("sa_rank: ISA not resident (open with SAPLING_B200_KEEP_BUILD)"); return -1; }
+  cudaSetDevice(ix->device);
+  SB_CUDA_CHECK(cudaMemcpy(out, ix->d_isa + first, count * 4, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int sapling_b200_write_sap(const sapling_b200_index* ix, const char* path) {
+  if (!ix) { set_error("null index"); return -1; }
+  const uint64_t count = (1ull << ix->nb) + 1;
+  std::vector<int64_t> xs(count), ys(count);
+  if (sapling_b200_model(ix, xs.data(), ys.data())) return -1;
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot write %s", path); return -1; }
+  // sapling_api.h:656-674
+  fwrite(&ix->nb, sizeof(int), 1, f);
+  if (ix->nb <= 30) { const int c32 = (int)count; fwrite(&c32, sizeof(int), 1, f); }
+  else fwrite(&count, 8, 1, f);
+  fwrite(xs.data(), 8, count, f);
+  fwrite(ys.data(), 8, count, f);
+  const int five[5] = {ix->stats.maxOver, ix->stats.maxUnder, ix->stats.meanError, ix->stats.mostOver,
+                       ix->stats.mostUnder};
+  fwrite(five, sizeof(int), 5, f);
+  fclose(f);
+  return 0;
+}
+
+int sapling_b200_write_sa(const sapling_b200_index* ix, const char* path) {
+  if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
+  return write_sa_file(ix, path);
+}
+
+int sapling_b200_check_sa(const sapling_b200_index* ix, uint32_t max_chars, uint64_t* bad_order, uint64_t* undecided,
+                          uint64_t* bad_perm) {
+  if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
+  return check_suffix_array(ix->d_genome, ix->n, ix->d_sa, ix->d_isa, max_chars, bad_order, undecided, bad_perm, 0);
+}
+
+uint64_t sapling_b200_device_bytes(const sapling_b200_index* ix) { return ix ? ix->device_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------
+
+int sapling_b200_query_batch_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, int64_t* d_out,
+                                 void* stream) {
+  if (!ix) { set_error("null index"); return -1; }
+  return launch_kmer_query(ix->view(), d_kmers, nq, reinterpret_cast<long long*>(d_out),
+                           static_cast<cudaStream_t>(stream));
+}
+
+int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size_t nq, int64_t* out) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (nq == 0) return 0;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  cudaSetDevice(ix->device);
+  if (ensure_staging(ix)) return -1;
+  const bool pin_in = is_pinned(kmers), pin_out = is_pinned(out);
+  if ((!pin_in || !pin_out) && ensure_pinned(ix)) return -1;
+  const IndexView v = ix->view();
+  const size_t CH = sapling_b200_index::kChunk;
+  const size_t nchunks = (nq + CH - 1) / CH;
+  // two-deep pipeline: chunk c uses slot c&1; its H2D, kernel and D2H are ordered on that
+  // slot's stream, so chunk c+1's upload overlaps chunk c's kernel and download
+  for (size_t c = 0; c < nchunks + 2; c++) {
+    if (c >= 2) {  // retire chunk c-2
+      const size_t r = c - 2;
+      const int s = (int)(r & 1);
+      SB_CUDA_CHECK(cudaStreamSynchronize(ix->streams[s]));
+      if (!pin_out) {
+        const size_t o = r * CH, m = std::min(CH, nq - o);
+        memcpy(out + o, ix->h_out[s], m * 8);
+      }
+    }
+    if (c < nchunks) {
+      const int s = (int)(c & 1);
+      const size_t o = c * CH, m = std::min(CH, nq - o);
+      const uint64_t* src = kmers + o;
+      if (!pin_in) {
+        memcpy(ix->h_in[s], kmers + o, m * 8);
+        src = ix->h_in[s];
+      }
+      SB_CUDA_CHECK(cudaMemcpyAsync(ix->d_in[s], src, m * 8, cudaMemcpyHostToDevice, ix->streams[s]));
+      if (launch_kmer_query(v, ix->d_in[s], m, ix->d_out[s], ix->streams[s])) return -1;
+      void* dst = pin_out ? (void*)(out + o) : (void*)ix->h_out[s];
+      SB_CUDA_CHECK(cudaMemcpyAsync(dst, ix->d_out[s], m * 8, cudaMemcpyDeviceToHost, ix->streams[s]));
+    }
+  }
+  return 0;
+}
+
+int sapling_b200_query_str_batch(sapling_b200_index* ix, const char* s, const uint64_t* offsets, const uint32_t* slens,
+                                 const uint32_t* lengths, const int64_t* kmers, size_t nq, int64_t* out) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (nq == 0) return 0;
+  cudaSetDevice(ix->device);
+  // pack every string to 2 bits/base, 32 bases per word, each query starting on a word boundary
+  std::vector<uint64_t> word_off(nq);
+  uint64_t total = 0;
+  for (size_t i = 0; i < nq; i++) {
+    if (lengths && lengths[i] > slens[i]) { set_error("query %zu: length > s.length() reads past the string in the reference", i); return -1; }
+    word_off[i] = total;
+    total += (slens[i] + 31) / 32 + 1;
+  }
+  std::vector<uint64_t> words(total, 0);
+  for (size_t i = 0; i < nq; i++) {
+    const char* q = s + offsets[i];
+    uint64_t* w = words.data() + word_off[i];
+    for (uint32_t j = 0; j < slens[i]; j++) {
+      const char c = q[j];
+      const uint64_t v = c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0;
+      w[j >> 5] |= v << (62 - 2 * (j & 31));
+    }
+  }
+  uint64_t *d_words = nullptr, *d_off = nullptr;
+  uint32_t *d_slen = nullptr, *d_len = nullptr;
+  long long *d_km = nullptr, *d_o = nullptr;
+  int rc = -1;
+  do {
+    if (cudaMalloc(&d_words, total * 8) || cudaMalloc(&d_off, nq * 8) || cudaMalloc(&d_slen, nq * 4) ||
+        cudaMalloc(&d_km, nq * 8) || cudaMalloc(&d_o, nq * 8) || (lengths && cudaMalloc(&d_len, nq * 4))) {
+      set_error("query_str_batch: device allocation failed");
+      break;
+    }
+    cudaMemcpy(d_words, words.data(), total * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_off, word_off.data(), nq * 8, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_slen, slens, nq * 4, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_km, kmers, nq * 8, cudaMemcpyHostToDevice);
+    if (lengths) cudaMemcpy(d_len, lengths, nq * 4, cudaMemcpyHostToDevice);
+    if (launch_string_query(ix->view(), d_words, d_off, d_slen, d_len, d_km, nq, d_o, 0)) break;
+    cudaError_t e = cudaMemcpy(out, d_o, nq * 8, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("query_str_batch: %s", cudaGetErrorString(e)); break; }
+    rc = 0;
+  } while (0);
+  cudaFree(d_words); cudaFree(d_off); cudaFree(d_slen); cudaFree(d_len); cudaFree(d_km); cudaFree(d_o);
+  return rc;
+}
+
+int64_t sapling_b200_query_str(sapling_b200_index* ix, const char* s, size_t slen, int64_t kmer, size_t length) {
+  const uint64_t off = 0;
+  const uint32_t sl = (uint32_t)slen, ln = (uint32_t)length;
+  int64_t out = -1;
+  if (sapling_b200_query_str_batch(ix, s, &off, &sl, &ln, &kmer, 1, &out)) return -2;
+  return out;
+}
+
+int sapling_b200_predict_batch(sapling_b200_index* ix, const uint64_t* kmers, size_t nq, uint64_t* out) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (nq == 0) return 0;
+  cudaSetDevice(ix->device);
+  uint64_t *d_k = nullptr, *d_o = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&d_k, nq * 8));
+  if (cudaMalloc(&d_o, nq * 8) != cudaSuccess) { cudaFree(d_k); set_error("predict_batch: allocation failed"); return -1; }
+  cudaMemcpy(d_k, kmers, nq * 8, cudaMemcpyHostToDevice);
+  int rc = launch_predict(ix->view(), d_k, nq, d_o, 0);
+  cudaError_t e = cudaMemcpy(out, d_o, nq * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d_k);
+  cudaFree(d_o);
+  if (rc) return rc;
+  SB_CUDA_CHECK(e);
+  return 0;
+}
+
+int sapling_b200_count_hits(sapling_b200_index* ix, const uint32_t* sa_pos, size_t count, uint32_t maxHits,
+                            uint32_t* left, uint32_t* right) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (!ix->d_kflag) { set_error("count_hits: k-prefix flags not resident (open with SAPLING_B200_KEEP_BUILD)"); return -1; }
+  if (count == 0) return 0;
+  cudaSetDevice(ix->device);
+  uint32_t *d_p = nullptr, *d_l = nullptr, *d_r = nullptr;
+  if (cudaMalloc(&d_p, count * 4) || cudaMalloc(&d_l, count * 4) || cudaMalloc(&d_r, count * 4)) {
+    cudaFree(d_p); cudaFree(d_l); cudaFree(d_r);
+    set_error("count_hits: allocation failed");
+    return -1;
+  }
+  cudaMemcpy(d_p, sa_pos, count * 4, cudaMemcpyHostToDevice);
+  int rc = count_hits(ix->d_kflag, ix->n, ix->k, d_p, count, maxHits, d_l, d_r, 0);
+  cudaMemcpy(left, d_l, count * 4, cudaMemcpyDeviceToHost);
+  cudaError_t e = cudaMemcpy(right, d_r, count * 4, cudaMemcpyDeviceToHost);
+  cudaFree(d_p); cudaFree(d_l); cudaFree(d_r);
+  if (rc) return rc;
+  SB_CUDA_CHECK(e);
+  return 0;
+}
+
+uint64_t sapling_b200_oob_count(sapling_b200_index* ix) {
+  if (!ix || !ix->d_oob) return 0;
+  unsigned long long v = 0;
+  cudaSetDevice(ix->device);
+  cudaMemcpy(&v, ix->d_oob, 8, cudaMemcpyDeviceToHost);
+  return v;
+}
+
+int sapling_b200_sample_queries_dev(sapling_b200_index* ix, uint64_t seed, uint64_t mut_seed, uint64_t first,
+                                    size_t nq, uint64_t* d_kmers, void* stream) {
+  if (!ix) { set_error("null index"); return -1; }
+  return launch_sample(ix->view(), seed, mut_seed, first, nq, d_kmers, static_cast<cudaStream_t>(stream));
+}
+
+int sapling_b200_verify_dev(sapling_b200_index* ix, const uint64_t* d_kmers, const int64_t* d_out, size_t nq,
+                            uint64_t* n_match, uint64_t* n_minus1, void* stream) {
+  if (!ix) { set_error("null index"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* d_c = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&d_c, 16));
+  SB_CUDA_CHECK(cudaMemsetAsync(d_c, 0, 16, st));
+  int rc = launch_verify(ix->view(), d_kmers, reinterpret_cast<const long long*>(d_out), nq, d_c, st);
+  unsigned long long h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, d_c, 16, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_c);
+  if (rc) return rc;
+  SB_CUDA_CHECK(e);
+  if (n_match) *n_match = h[0];
+  if (n_minus1) *n_minus1 = h[1];
+  return 0;
+}
+
+int sapling_b200_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps) {
+  int dev = 0;
+  if (require_device(&dev)) return -1;
+  return run_gather_bench(bytes, n_loads, reps, gbps);
+}
+
+}  // extern "C"

@@ -1,0 +1,198 @@
+// query.cu -- query kernels and their launchers.
+//
+// Hot path: kmer_query_kernel.  One thread per query, grid-stride over the batch so that the
+// k-mer reads and result writes are coalesced; every dependent access (model checkpoint pair,
+// SA entry, packed-genome window) is a read-only 32-byte-sector gather (ld.global.nc).  The
+// kernel is bound by random-sector HBM/L2 throughput and by the length of the dependent chain, so
+// it runs at full occupancy (see DESIGN.md for the roofline and profiles/ for ncu evidence).
+#include "build.cuh"
+#include "common.cuh"
+#include "query.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int kQueryThreads = 256;
+
+__global__ void __launch_bounds__(kQueryThreads)
+kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = __ldg(kmers + i);
+    KmerQuery q;
+    q.q = x << lsh;
+    q.k = (uint32_t)ix.k;
+    out[i] = pl_query<false>(ix, q, x);
+  }
+}
+
+__global__ void __launch_bounds__(kQueryThreads)
+string_query_kernel(const IndexView ix, const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_off,
+                    const uint32_t* __restrict__ slens, const uint32_t* __restrict__ lengths,
+                    const long long* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    StringQuery q;
+    q.w = words + word_off[i];
+    q.slen_ = slens[i];
+    q.length_ = lengths ? lengths[i] : slens[i];
+    out[i] = pl_query<true>(ix, q, (uint64_t)kmers[i]);
+  }
+}
+
+__global__ void predict_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq,
+                               uint64_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride)
+    out[i] = predict_rank(ix, kmers[i]);
+}
+
+// pos_j = splitmix64(seed + j) mod (n-k); optional 1-2 substitutions on odd j
+__global__ void sample_kernel(const IndexView ix, uint64_t seed, uint64_t mut_seed, uint64_t first, size_t nq,
+                              uint64_t* __restrict__ kmers) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned k = (unsigned)ix.k;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t j = first + i;
+    const uint64_t pos = splitmix64(seed + j) % (ix.n - k);
+    uint64_t x = load_bases_upto(ix.genome, pos, k) >> (64u - 2u * k);
+    if (mut_seed && (j & 1ull)) {
+      const uint64_t h = splitmix64(mut_seed + j);
+      const unsigned nsub = 1u + (unsigned)(h & 1ull);
+      for (unsigned r = 0; r < nsub; r++) {
+        const uint64_t hi = splitmix64(h + r + 1);
+        const unsigned p = (unsigned)(hi % k);
+        const unsigned sh = 2u * (k - 1u - p);
+        const uint64_t old = (x >> sh) & 3ull;
+        const uint64_t nw = (old + 1ull + (hi >> 32) % 3ull) & 3ull;
+        x = (x & ~(3ull << sh)) | (nw << sh);
+      }
+    }
+    kmers[i] = x;
+  }
+}
+
+// the self-check of sapling_example.cpp:144-154 on the device
+__global__ void verify_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, const long long* __restrict__ out,
+                              size_t nq, unsigned long long* __restrict__ counters) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned k = (unsigned)ix.k;
+  unsigned long long ok = 0, m1 = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const long long a = out[i];
+    if (a == -1) { m1++; continue; }
+    if ((uint64_t)a + k <= ix.n) {
+      const uint64_t g = load_bases_upto(ix.genome, (uint64_t)a, k) >> (64u - 2u * k);
+      if (g == kmers[i]) ok++;
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    ok += __shfl_xor_sync(0xffffffffu, ok, o);
+    m1 += __shfl_xor_sync(0xffffffffu, m1, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (ok) atomicAdd(counters + 0, ok);
+    if (m1) atomicAdd(counters + 1, m1);
+  }
+}
+
+// random 32-byte-sector gather: each thread chases nothing, it just issues independent sector
+// reads at hashed addresses -- the "HBM random-sector roofline" denominator
+__global__ void __launch_bounds__(256)
+gather_kernel(const uint4* __restrict__ buf, uint64_t nsectors, uint64_t nloads, uint64_t salt,
+              unsigned long long* __restrict__ sink) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloads; i += stride) {
+    const uint64_t s = splitmix64(salt + i) % nsectors;
+    const uint4 v = __ldg(buf + 2 * s);  // first 16 bytes of the sector: one sector transaction
+    acc ^= v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
+inline int query_grid(size_t nq, int blocks_per_sm) {
+  size_t g = (nq + kQueryThreads - 1) / kQueryThreads;
+  const size_t cap = (size_t)148 * blocks_per_sm;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+
+int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st) {
+  if (nq == 0) return 0;
+  kmer_query_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint64_t* d_word_off,
+                        const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
+                        long long* d_out, cudaStream_t st) {
+  if (nq == 0) return 0;
+  string_query_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_words, d_word_off, d_slens, d_lengths,
+                                                                   d_kmers, nq, d_out);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_predict(const IndexView& ix, const uint64_t* d_kmers, size_t nq, uint64_t* d_out, cudaStream_t st) {
+  if (nq == 0) return 0;
+  predict_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_sample(const IndexView& ix, uint64_t seed, uint64_t mut_seed, uint64_t first, size_t nq,
+                  uint64_t* d_kmers, cudaStream_t st) {
+  if (nq == 0) return 0;
+  sample_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, seed, mut_seed, first, nq, d_kmers);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long* d_out, size_t nq,
+                  unsigned long long* d_counters, cudaStream_t st) {
+  if (nq == 0) return 0;
+  verify_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, d_out, nq, d_counters);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps) {
+  if (bytes < (1ull << 20)) bytes = 1ull << 20;
+  void* buf = nullptr;
+  unsigned long long* sink = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&buf, bytes));
+  SB_CUDA_CHECK(cudaMalloc(&sink, 8));
+  SB_CUDA_CHECK(cudaMemset(buf, 0x5A, bytes));
+  SB_CUDA_CHECK(cudaMemset(sink, 0, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const uint64_t nsect = bytes / 32;
+  double best = 0;
+  for (int r = 0; r < reps + 1; r++) {
+    cudaEventRecord(e0);
+    gather_kernel<<<148 * 8, 256>>>(reinterpret_cast<const uint4*>(buf), nsect, n_loads, 0x1234ull + (uint64_t)r * n_loads, sink);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(buf); cudaFree(sink); SB_CUDA_CHECK(e); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double g = (double)n_loads * 32.0 / (ms * 1e-3) / 1e9;
+    if (r > 0 && g > best) best = g;  // first rep is warm-up
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (gbps) *gbps = best;
+  return 0;
+}
+
+}  // namespace sb

@@ -1,0 +1,236 @@
+// query.cuh -- device-side replay of Sapling::plQuery (reference sapling_api.h:159-248) with
+// binarySearch (:133-153) and getLcp (:115-120) on the packed index.
+//
+// The reference's control flow is restated as a state machine whose every iteration performs
+// exactly one probe (one SA load followed by one packed-genome compare).  All lanes of a warp
+// therefore issue their dependent loads from the same instruction, whatever branch of plQuery
+// they are in; only the (cheap, register-only) transition code diverges.
+#pragma once
+
+#include "common.cuh"
+
+namespace sb {
+
+enum ProbeState : int {
+  ST_PRED = 0,  // probing rev[predicted]                      (:162-164)
+  ST_R1,        // probing hi = min(n-1, predicted+mostOver)    (:171-174)
+  ST_R2,        // probing hi = min(n-1, predicted+maxOver+1)   (:180-183)
+  ST_RG,        // galloping right by maxOver (s.length() > k)  (:186-195)
+  ST_L1,        // probing lo = max(0,(int)predicted-mostUnder) (:209-213)
+  ST_L2,        // probing lo = max(0,(int)predicted-maxUnder-1)(:225-228)
+  ST_LG,        // galloping left by maxUnder (s.length() > k)  (:231-240)
+  ST_BS,        // binarySearch probing mid                     (:138-141)
+  ST_FINAL      // hi == lo+2: return rev[lo+1] unverified      (:136,:247)
+};
+
+struct ProbeResult {
+  uint32_t lcp;   // getLcp result
+  bool at_end;    // lcp + idx == n
+  bool q_gt;      // s[lcp] > reference[idx+lcp]   (meaningful when !at_end)
+  bool q_lt;      // s[lcp] < reference[idx+lcp]   (meaningful when !at_end)
+};
+
+// ---- query flavours ---------------------------------------------------------------------------
+
+// A k-mer given as its kmerize() value: s = the k bases, s.length() == length == k <= 32.
+struct KmerQuery {
+  uint64_t q;  // bases left-aligned (base 0 in the top two bits)
+  uint32_t k;
+  __device__ __forceinline__ uint32_t slen() const { return k; }
+  __device__ __forceinline__ uint32_t length() const { return k; }
+  __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start) const {
+    const uint64_t g = load_bases_upto(ix.genome, idx, k);
+    uint64_t diff = q ^ g;
+    if (start) diff &= (~0ull) >> (2u * start);  // getLcp trusts the first `start` characters
+    const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
+    const uint64_t room = ix.n - idx;            // characters left in the text
+    const uint32_t leff = room < (uint64_t)k ? (uint32_t)room : k;
+    ProbeResult r;
+    r.lcp = m < leff ? m : leff;
+    r.at_end = (uint64_t)r.lcp == room;
+    const uint32_t sh = 62u - 2u * (r.lcp & 31u);
+    const uint32_t qb = (uint32_t)(q >> sh) & 3u, gb = (uint32_t)(g >> sh) & 3u;
+    r.q_gt = qb > gb;
+    r.q_lt = qb < gb;
+    return r;
+  }
+};
+
+// A string of slen bases (2-bit packed, 32 per word, left-aligned, zero padded) queried with the
+// reference's separate `length` argument (plQuery(s, kmer, length), length <= slen).
+struct StringQuery {
+  const uint64_t* __restrict__ w;
+  uint32_t slen_, length_;
+  __device__ __forceinline__ uint32_t slen() const { return slen_; }
+  __device__ __forceinline__ uint32_t length() const { return length_; }
+  __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start) const {
+    const uint64_t room = ix.n - idx;
+    const uint32_t leff = room < (uint64_t)length_ ? (uint32_t)room : length_;
+    uint32_t lcp = leff > start ? leff : start;
+    for (uint32_t pos = start & ~31u; pos < leff; pos += 32u) {
+      uint64_t diff = w[pos >> 5] ^ load_bases32(ix.genome, idx + pos);
+      if (pos < start) diff &= (~0ull) >> (2u * (start - pos));
+      if (diff) {
+        const uint32_t m = pos + ((uint32_t)__clzll((long long)diff) >> 1);
+        lcp = m < leff ? m : leff;
+        break;
+      }
+    }
+    ProbeResult r;
+    r.lcp = lcp;
+    r.at_end = (uint64_t)lcp == room;
+    r.q_gt = r.q_lt = false;
+    if (!r.at_end && lcp < slen_) {
+      const uint32_t qb = (uint32_t)(w[lcp >> 5] >> (62u - 2u * (lcp & 31u))) & 3u;
+      const uint64_t gi = idx + lcp;
+      const uint32_t gb = (uint32_t)(__ldg(ix.genome + (gi >> 5)) >> (62u - 2u * (uint32_t)(gi & 31u))) & 3u;
+      r.q_gt = qb > gb;
+      r.q_lt = qb < gb;
+    }
+    return r;
+  }
+};
+
+// ---- the replay --------------------------------------------------------------------------------
+
+template <bool kGallop, typename Query>
+__device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& qy, uint64_t kmer) {
+  const uint64_t n = ix.n;
+  const uint64_t nm1 = n - 1;
+  const uint32_t slen = qy.slen(), length = qy.length();
+
+  uint64_t pred = predict_rank(ix, kmer);  // :161
+  if (pred >= n) {                         // reference: rev[] out of bounds.  Defined here: clamp + count.
+    atomicAdd(ix.oob_counter, 1ull);
+    pred = nm1;
+  }
+  // (int)predicted of :209/:225 -- wraps negative for predicted >= 2^31
+  const int32_t p32 = (int32_t)(uint32_t)pred;
+
+  uint64_t lo = 0, hi = 0, r = pred;
+  uint32_t loLcp = 0, hiLcp = 0, lcp0 = 0, start = 0;
+  int state = ST_PRED;
+
+  for (;;) {
+    const uint64_t idx = __ldg(ix.sa + r);
+    if (state == ST_FINAL) return (long long)idx;
+    const ProbeResult pr = qy.probe(ix, idx, start);
+    const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
+    bool to_search = false;
+    switch (state) {
+      case ST_PRED:
+        if (pr.lcp == length) return (long long)idx;  // :164
+        lcp0 = pr.lcp;
+        if (small) {  // :167-172
+          lo = pred;
+          hi = pred + (uint64_t)(long long)ix.mostOver;
+          if (hi > nm1) hi = nm1;
+          r = hi;
+          state = ST_R1;
+        } else {  // :209-211
+          if (ix.compat) {
+            const int32_t v = (int32_t)((uint32_t)p32 - (uint32_t)ix.mostUnder);
+            lo = (uint64_t)(v > 0 ? v : 0);
+          } else {
+            const uint64_t d = (uint64_t)(long long)ix.mostUnder;
+            lo = pred > d ? pred - d : 0;
+          }
+          hi = pred;
+          r = lo;
+          state = ST_L1;
+        }
+        break;
+      case ST_R1:
+        if (pr.lcp == length) return (long long)idx;  // :174
+        if (small) {                                  // :175-181
+          lo = hi;
+          loLcp = pr.lcp;
+          hi = pred + (uint64_t)(long long)ix.maxOver + 1;
+          if (hi > nm1) hi = nm1;
+          r = hi;
+          state = ST_R2;
+        } else {  // :199-204
+          loLcp = lcp0;
+          hiLcp = pr.lcp;
+          to_search = true;
+        }
+        break;
+      case ST_R2:
+      case ST_RG:
+        if (pr.lcp == (state == ST_R2 ? length : slen)) return (long long)idx;  // :183 / :194
+        // :184-196 (reference loops forever once hi is pinned at n-1; we stop there)
+        if (kGallop && slen > (uint32_t)ix.k && !pr.at_end && pr.q_gt && hi != nm1) {
+          lo = hi;
+          loLcp = pr.lcp;
+          hi += (uint64_t)(long long)ix.maxOver;
+          if (hi > nm1) hi = nm1;
+          r = hi;
+          state = ST_RG;
+        } else {
+          hiLcp = pr.lcp;  // :197
+          to_search = true;
+        }
+        break;
+      case ST_L1:
+        if (pr.lcp == slen) return (long long)idx;  // :213
+        if (small) {                                // :214-219
+          hiLcp = lcp0;
+          loLcp = pr.lcp;
+          to_search = true;
+        } else {  // :220-226
+          hi = lo;
+          hiLcp = pr.lcp;
+          if (ix.compat) {
+            const int32_t v = (int32_t)((uint32_t)p32 - (uint32_t)ix.maxUnder - 1u);
+            lo = (uint64_t)(v > 0 ? v : 0);
+          } else {
+            const uint64_t d = (uint64_t)(long long)ix.maxUnder + 1;
+            lo = pred > d ? pred - d : 0;
+          }
+          r = lo;
+          state = ST_L2;
+        }
+        break;
+      case ST_L2:
+      case ST_LG:
+        if (pr.lcp == slen) return (long long)idx;  // :228 / :239
+        // :229-241 (reference underflows lo below rank 0; we stop at 0)
+        if (kGallop && slen > (uint32_t)ix.k && !pr.at_end && pr.q_lt && lo != 0) {
+          hi = lo;
+          hiLcp = pr.lcp;
+          const uint64_t step = (uint64_t)(long long)ix.maxUnder;
+          lo = lo > step ? lo - step : 0;
+          r = lo;
+          state = ST_LG;
+        } else {
+          loLcp = pr.lcp;  // :242
+          to_search = true;
+        }
+        break;
+      default:  // ST_BS, probed mid == r  (:139-152)
+        if (pr.lcp == slen) return (long long)idx;  // :141 then :247 (rev[mid] == idx)
+        if (lo + 1 >= hi) return -1;                // :142
+        if (small) {
+          lo = r;
+          loLcp = pr.lcp;
+        } else {
+          hi = r;
+          hiLcp = pr.lcp;
+        }
+        to_search = true;
+        break;
+    }
+    if (to_search) {  // top of binarySearch (:136-140)
+      if (hi == lo + 2) {
+        r = lo + 1;
+        state = ST_FINAL;
+      } else {
+        r = (lo + hi) >> 1;
+        start = loLcp < hiLcp ? loLcp : hiLcp;
+        state = ST_BS;
+      }
+    }
+  }
+}
+
+}  // namespace sb

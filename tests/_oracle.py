@@ -58,6 +58,9 @@ def port_lib():
         L.so_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p]
         L.so_from_memory.restype = P
         L.so_from_memory.argtypes = [C.c_char_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.so_from_parts.restype = P
+        L.so_from_parts.argtypes = [C.c_char_p, C.c_uint64, u32p, C.c_int, C.c_int, i64p, i64p,
+                                    np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")]
         L.so_close.argtypes = [P]
         L.so_predict.restype = C.c_uint64
         L.so_predict.argtypes = [P, C.c_int64]
@@ -110,6 +113,13 @@ class Port:
             sa = np.ascontiguousarray(sa, dtype=np.uint32)
             sap = sa.ctypes.data_as(C.c_void_p)
         return cls(port_lib().so_from_memory(genome, len(genome), sap, nb, maxMem, k))
+
+    @classmethod
+    def from_parts(cls, genome: bytes, sa, k, nb, xlist, ylist, five):
+        return cls(port_lib().so_from_parts(genome, len(genome), np.ascontiguousarray(sa, dtype=np.uint32), k, nb,
+                                            np.ascontiguousarray(xlist, dtype=np.int64),
+                                            np.ascontiguousarray(ylist, dtype=np.int64),
+                                            np.ascontiguousarray(five, dtype=np.int32)))
 
     def close(self):
         if self.h:

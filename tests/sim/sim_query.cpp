@@ -1,0 +1,56 @@
+// sim_query.cpp -- TEST INFRASTRUCTURE ONLY.
+// Compiles the *device* query code (sapling_b200/csrc/query.cuh, common.cuh) for the host with g++
+// by supplying host stand-ins for the handful of CUDA intrinsics it uses, so that the control-flow
+// replay can be differential-tested against the oracle on a machine without a GPU.  It is never
+// linked into libsapling_b200.so and never used by the product.
+#include <cstdint>
+#include <cstring>
+#include <cuda_runtime.h>
+
+template <typename T> static inline T __ldg(const T* p) { return *p; }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+static inline double __ll2double_rn(long long x) { return (double)x; }
+static inline double __ddiv_rn(double a, double b) { volatile double r = a / b; return r; }
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+static inline long long __double2ll_rz(double a) { return (long long)a; }
+static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  unsigned long long o = *p; *p += v; return o;
+}
+
+#include "../../sapling_b200/csrc/query.cuh"
+
+namespace sb { void set_error(const char*, ...) {} const char* last_error() { return ""; } }
+
+extern "C" {
+
+// genome: packed words (with pad), sa: n entries, model: interleaved {x,y} x ((1<<nb)+1)
+void sim_kmer_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
+                    const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
+                    unsigned long long* oob) {
+  sb::IndexView ix;
+  ix.genome = genome; ix.sa = sa; ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
+  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
+  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
+  ix.compat = compat; ix.oob_counter = oob;
+  for (size_t i = 0; i < nq; i++) {
+    sb::KmerQuery q; q.q = kmers[i] << (64 - 2 * k); q.k = (uint32_t)k;
+    out[i] = sb::pl_query<false>(ix, q, kmers[i]);
+  }
+}
+
+void sim_string_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
+                      const int* five, int compat, const uint64_t* words, const uint64_t* word_off,
+                      const uint32_t* slens, const uint32_t* lengths, const int64_t* kmers, size_t nq, int64_t* out,
+                      unsigned long long* oob) {
+  sb::IndexView ix;
+  ix.genome = genome; ix.sa = sa; ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
+  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
+  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
+  ix.compat = compat; ix.oob_counter = oob;
+  for (size_t i = 0; i < nq; i++) {
+    sb::StringQuery q; q.w = words + word_off[i]; q.slen_ = slens[i]; q.length_ = lengths[i];
+    out[i] = sb::pl_query<true>(ix, q, (uint64_t)kmers[i]);
+  }
+}
+}

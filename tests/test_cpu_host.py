@@ -1,0 +1,115 @@
+"""CPU-side tests (-m "not gpu"): the oracle against the golden vectors, the host logic of the
+library that needs no GPU, the C-ABI export list, and the device query code compiled for the host
+(tests/sim) against the oracle."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import _fixtures as F
+import _oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as G
+    G.build()
+    return True
+
+
+def test_capi_exports_every_declared_symbol(built):
+    import sapling_b200
+    hdr = open(os.path.join(ROOT, "include", "sapling_b200.h")).read()
+    declared = set(re.findall(r"\b(sapling_b200_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    L = C.CDLL(sapling_b200.lib_path())
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/sapling_b200.h but not exported"
+    # the Python binding covers the same list
+    from sapling_b200.api import SYMBOLS
+    assert declared == set(SYMBOLS), declared ^ set(SYMBOLS)
+
+
+def test_no_cpu_fallback(built):
+    """Without a GPU every constructor must fail loudly (never silently compute on the CPU)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sapling_b200 as S
+    with pytest.raises(S.SaplingError, match="no usable CUDA device|not a Blackwell"):
+        S.Sapling.from_memory(b"ACGT" * 100, k=11)
+    with pytest.raises(S.SaplingError):
+        S.Sapling.synthetic(1, 10000, k=11)
+
+
+def test_product_does_not_touch_oracle():
+    """Nothing under sapling_b200/ or include/ may reference oracle/ (the checker is not the product)."""
+    for base in ("sapling_b200", "include"):
+        for dp, _, fns in os.walk(os.path.join(ROOT, base)):
+            for fn in fns:
+                if fn.endswith((".so", ".o", ".pyc")):
+                    continue
+                txt = open(os.path.join(dp, fn), errors="replace").read()
+                assert "oracle/" not in txt and "sapling_oracle" not in txt and "_oracle" not in txt, (dp, fn)
+
+
+def test_kmerize_host(built, oracle_built):
+    import sapling_b200 as S
+    rng = np.random.default_rng(3)
+    for k in (1, 11, 16, 21, 31):
+        for _ in range(50):
+            L = int(rng.integers(1, 120))
+            s = bytes(rng.choice(np.frombuffer(b"ACGTN", dtype=np.uint8), size=max(L, k)))
+            assert S.kmerize(k, s) == O.kmerize(k, s)
+            assert S.kmerize_adjusted(k, L, s) == O.kmerize_adjusted(k, L, s)
+
+
+def _sim():
+    so = os.path.join(ROOT, "build", "libsim_query.so")
+    src = os.path.join(ROOT, "tests", "sim", "sim_query.cpp")
+    os.makedirs(os.path.dirname(so), exist_ok=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                    "-I/usr/local/cuda/include", "-o", so, src], check=True)
+    L = C.CDLL(so)
+    i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.sim_kmer_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
+                                 C.c_size_t, O.i64p, C.POINTER(C.c_uint64)]
+    L.sim_string_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
+                                   O.u64p, O.u32p, O.u32p, O.i64p, C.c_size_t, O.i64p, C.POINTER(C.c_uint64)]
+    return L
+
+
+@pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])
+def test_device_query_code_on_host_matches_oracle(oracle_built, name):
+    """query.cuh (the device replay of plQuery) compiled for the host == oracle, k-mers and strings."""
+    L = _sim()
+    g = F.small_genomes()[name]
+    n = len(g)
+    for k, nb in ((21, -1), (11, 4), (31, 10), (16, -1)):
+        if n < 4 * k:
+            continue
+        port = O.Port.from_memory(g, nb=nb, k=k)
+        packed, sa = F.pack_genome(g), port.sa
+        model = np.ascontiguousarray(np.stack([port.xlist, port.ylist], axis=1).reshape(-1))
+        five = np.array(port.five, dtype=np.int32)
+        kmers = F.query_mix(g, k, 3000)
+        exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
+        out = np.empty(len(kmers), dtype=np.int64)
+        c = C.c_uint64(0)
+        L.sim_kmer_batch(packed, sa, model, n, k, port.nb, five, 1, kmers, len(kmers), out, C.byref(c))
+        assert np.array_equal(out, exp) and c.value == oob
+        strs = F.var_len_strings(g, k, 25)
+        words, offs = F.pack_strings(strs)
+        slens = np.array([len(s) for s in strs], dtype=np.uint32)
+        km = np.array([O.kmerize_adjusted(k, len(s), s) for s in strs], dtype=np.int64)
+        exp2 = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
+        out2 = np.empty(len(strs), dtype=np.int64)
+        L.sim_string_batch(packed, sa, model, n, k, port.nb, five, 1, words, offs, slens, slens, km, len(strs), out2,
+                           C.byref(c))
+        assert np.array_equal(out2, exp2)
+        port.close()

@@ -1,0 +1,182 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsapling_b200.so) against the oracle
+(oracle/sapling_oracle.c, itself pinned to the unmodified reference) on the same seeded inputs.
+Bar: bit-exact (integer / index work)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import _fixtures as F
+import _oracle as O
+
+pytestmark = pytest.mark.gpu
+
+GENOMES = F.small_genomes()
+CASES = [(name, k, nb) for name in GENOMES for k in (11, 16, 21, 31) for nb in (-1, 4, 10)
+         if len(GENOMES[name]) >= 4 * k and nb <= 2 * k]
+
+
+@pytest.fixture(scope="module")
+def S():
+    import sapling_b200
+    return sapling_b200
+
+
+@pytest.mark.parametrize("name,k,nb", CASES)
+def test_query_parity_with_reference_model(S, oracle_built, name, k, nb):
+    """Index parts (SA, model) from the oracle -> isolates the query kernel."""
+    g = GENOMES[name]
+    port = O.Port.from_memory(g, nb=nb, k=k)
+    ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+    kmers = F.query_mix(g, k, 6000)
+    exp, probes, oob = port.query_batch(kmers, nthreads=4, stats=True)
+    got = ix.queryBatch(kmers)
+    assert np.array_equal(got, exp)
+    assert ix.oob_count() == oob
+    # predictions alone (queryPiecewiseLinear, IEEE double, no FMA)
+    pred = ix.queryPiecewiseLinear(kmers[:2000])
+    assert [int(p) for p in pred] == [port.predict(int(x)) for x in kmers[:2000]]
+    # variable-length strings through plQuery(s, kmerizeAdjusted, length)
+    strs = F.var_len_strings(g, k, 30)
+    km = [S.kmerize_adjusted(k, len(s), s) for s in strs]
+    assert km == [O.kmerize_adjusted(k, len(s), s) for s in strs]
+    exp_s = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
+    got_s = ix.plQueryBatch(strs, km)
+    assert np.array_equal(got_s, exp_s)
+    # single-call surface
+    for s, x, e in list(zip(strs, km, exp_s))[:5]:
+        assert ix.plQuery(s, x, len(s)) == e
+    ix.close()
+    port.close()
+
+
+@pytest.mark.parametrize("name", list(GENOMES))
+def test_gpu_built_index_matches_oracle(S, oracle_built, name):
+    """Suffix array, model checkpoints and error bounds built on the GPU == the oracle's; the .sa and
+    .sap files are byte-identical."""
+    g = GENOMES[name]
+    for k, nb in ((21, -1), (16, 8), (11, -1), (31, 12)):
+        if len(g) < 4 * k:
+            continue
+        port = O.Port.from_memory(g, nb=nb, k=k)
+        ix = S.Sapling.from_memory(g, None, numBuckets=nb, k=k, flags=S.QUIET | S.KEEP_BUILD)
+        assert np.array_equal(ix.rev(), port.sa), "suffix array"
+        assert np.array_equal(ix.sa(), port.isa), "inverse suffix array"
+        assert ix.check_sa() == (0, 0, 0)
+        assert ix.buckets == port.nb
+        x, y = ix.model()
+        assert np.array_equal(x, port.xlist), "xlist"
+        assert np.array_equal(y, port.ylist), "ylist"
+        assert ix.five == port.five
+        assert ix.perfectPredictions == port.perfect
+        with tempfile.TemporaryDirectory() as tmp:
+            a, b = os.path.join(tmp, "a.sap"), os.path.join(tmp, "b.sap")
+            ix.write_sap(a)
+            port.write_sap(b)
+            assert open(a, "rb").read() == open(b, "rb").read(), ".sap bytes"
+            a, b = os.path.join(tmp, "a.sa"), os.path.join(tmp, "b.sa")
+            ix.write_sa(a)
+            port.write_sa(b)
+            assert open(a, "rb").read() == open(b, "rb").read(), ".sa bytes"
+        # countHitsLeft/Right
+        ranks = np.arange(0, len(g), max(1, len(g) // 500), dtype=np.uint32)
+        left, right = ix.countHits(ranks, 32)
+        exp = [port.count_hits(int(r), 32) for r in ranks]
+        assert [(int(a), int(b)) for a, b in zip(left, right)] == exp
+        kmers = F.query_mix(g, k, 3000, seed=5)
+        assert np.array_equal(ix.queryBatch(kmers), port.query_batch(kmers, nthreads=4))
+        ix.close()
+        port.close()
+
+
+def test_constructor_from_files(S, oracle_built, tmp_path):
+    """Sapling(refFn, saFn, sapFn, ...) load-or-build semantics (sapling_api.h:492-676)."""
+    text = b">chrA some description\nacgtNNacgtTTGA\nCCGATRYK\n>chrB\n" + GENOMES["rand20k"][:5000] + \
+        b"\n\n>chrC x\n" + GENOMES["gc2332"][:3000] + b"\n"
+    fa = tmp_path / "g.fa"
+    fa.write_bytes(text)
+    g_exp, ends_exp = O.clean_fasta_text(text)
+    sa_fn, sap_fn = str(tmp_path / "g.fa.sa"), str(tmp_path / "g.fa.sap")
+    ix = S.Sapling(str(fa), sa_fn, sap_fn, -1, -1, 16, "")
+    assert ix.reference == g_exp
+    assert ix.chrEnds == sorted(ends_exp)
+    port = O.Port.open(str(fa), str(tmp_path / "p.sa"), str(tmp_path / "p.sap"), k=16)
+    assert open(sa_fn, "rb").read() == open(tmp_path / "p.sa", "rb").read()
+    assert open(sap_fn, "rb").read() == open(tmp_path / "p.sap", "rb").read()
+    kmers = F.query_mix(g_exp, 16, 2000)
+    exp = port.query_batch(kmers)
+    assert np.array_equal(ix.queryBatch(kmers), exp)
+    ix.close()
+    # second open: both files exist -> loaded, not rebuilt
+    ix2 = S.Sapling(str(fa), sa_fn, sap_fn, -1, -1, 16, "")
+    assert ix2.buckets == port.nb and ix2.five == port.five
+    assert np.array_equal(ix2.queryBatch(kmers), exp)
+    ix2.close()
+    port.close()
+
+
+def test_errors_file(S, oracle_built, tmp_path):
+    g = GENOMES["rand20k"]
+    fa = tmp_path / "g.fa"
+    O.write_fasta(str(fa), g)
+    e1, e2 = str(tmp_path / "gpu.err"), str(tmp_path / "cpu.err")
+    ix = S.Sapling(str(fa), str(tmp_path / "a.sa"), str(tmp_path / "a.sap"), 8, -1, 21, e1)
+    port = O.Port.open(str(fa), str(tmp_path / "b.sa"), str(tmp_path / "b.sap"), nb=8, k=21, err_fn=e2)
+    assert open(e1).read() == open(e2).read()
+    ix.close()
+    port.close()
+
+
+def test_empty_and_tiny_batches(S, oracle_built):
+    g = GENOMES["rand20k"]
+    port = O.Port.from_memory(g, k=21)
+    ix = S.Sapling.from_model(g, port.sa, 21, port.nb, port.xlist, port.ylist, port.five)
+    assert len(ix.queryBatch(np.empty(0, dtype=np.uint64))) == 0
+    one = F.query_mix(g, 21, 4)[:1]
+    assert np.array_equal(ix.queryBatch(one), port.query_batch(one))
+    ix.close()
+    port.close()
+
+
+def test_large_batch_properties_and_chunking(S, oracle_built):
+    """> 1 staging chunk (2^22 queries) through the host API; every present k-mer must come back as a
+    position that spells it (the self-check of sapling_example.cpp:144-154), and a 200k-query prefix
+    must equal the oracle."""
+    n = 3_000_000
+    g = O.synth_genome(O.SEED_G + 3, n)
+    ix = S.Sapling.from_memory(g, None, k=21)
+    nq = (1 << 22) + 12345
+    kmers, pos = O.present_queries(g, 21, nq)
+    got = ix.queryBatch(kmers)
+    assert (got >= 0).all()
+    assert np.array_equal(O.kmers_at(g, got, 21), kmers)
+    port = O.Port.from_memory(g, sa=ix.rev(), k=21)
+    assert ix.five == port.five
+    assert np.array_equal(got[:200000], port.query_batch(kmers[:200000], nthreads=8))
+    # device-side generator and verifier agree with the host ones
+    import torch
+    d_k = torch.empty(100000, dtype=torch.int64, device="cuda")
+    d_o = torch.empty(100000, dtype=torch.int64, device="cuda")
+    ix.sample_queries_device(O.SEED_Q, 0, 0, 100000, d_k.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_k.cpu().numpy().astype(np.uint64), kmers[:100000])
+    ix.queryBatchDevice(d_k.data_ptr(), 100000, d_o.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o.cpu().numpy(), got[:100000])
+    assert ix.verify_device(d_k.data_ptr(), d_o.data_ptr(), 100000) == (100000, 0)
+    ix.sample_queries_device(O.SEED_Q, O.SEED_M, 0, 100000, d_k.data_ptr())
+    torch.cuda.synchronize()
+    assert np.array_equal(d_k.cpu().numpy().astype(np.uint64), O.mutate_queries(kmers[:100000], 21))
+    ix.close()
+    port.close()
+
+
+def test_no_compat_equals_compat_below_2g(S, oracle_built):
+    g = GENOMES["rand200k"]
+    port = O.Port.from_memory(g, k=21)
+    a = S.Sapling.from_model(g, port.sa, 21, port.nb, port.xlist, port.ylist, port.five)
+    b = S.Sapling.from_model(g, port.sa, 21, port.nb, port.xlist, port.ylist, port.five, flags=S.QUIET | S.NO_COMPAT)
+    kmers = F.query_mix(g, 21, 20000)
+    assert np.array_equal(a.queryBatch(kmers), b.queryBatch(kmers))
+    a.close(); b.close(); port.close()
