@@ -71,6 +71,12 @@ struct sapling_b200_index {
   uint64_t* h_in[2] = {nullptr, nullptr};
   long long* h_out[2] = {nullptr, nullptr};
 
+  // single-query path (plQuery drop-in): one mapped pinned block, no per-call allocation
+  std::mutex mu1;
+  cudaStream_t s1 = nullptr;
+  uint64_t* m1 = nullptr;  // [0..65] packed words, [66] word offset (0), [67] kmer, [68] result, [69] slen|length
+  static constexpr uint32_t kSingleMaxBases = 64 * 32;
+
   IndexView view() const {
     IndexView v;
     v.genome = d_genome;
@@ -98,6 +104,8 @@ struct sapling_b200_index {
       if (h_in[i]) cudaFreeHost(h_in[i]);
       if (h_out[i]) cudaFreeHost(h_out[i]);
     }
+    if (s1) cudaStreamDestroy(s1);
+    if (m1) cudaFreeHost(m1);
     cudaFree(d_genome);
     cudaFree(d_sa);
     cudaFree(d_isa);
@@ -786,6 +794,39 @@ int sapling_b200_query_str_batch(sapling_b200_index* ix, const char* s, const ui
 }
 
 int64_t sapling_b200_query_str(sapling_b200_index* ix, const char* s, size_t slen, int64_t kmer, size_t length) {
+  if (!ix) { set_error("null index"); return -2; }
+  if (length > slen) { set_error("plQuery: length > s.length() reads past the string in the reference"); return -2; }
+  if (slen <= sapling_b200_index::kSingleMaxBases) {
+    std::lock_guard<std::mutex> lock(ix->mu1);
+    cudaSetDevice(ix->device);
+    if (!ix->m1) {
+      if (cudaStreamCreateWithFlags(&ix->s1, cudaStreamNonBlocking) != cudaSuccess ||
+          cudaHostAlloc(reinterpret_cast<void**>(&ix->m1), 72 * 8, cudaHostAllocMapped) != cudaSuccess) {
+        set_error("plQuery: cannot allocate the mapped staging block");
+        return -2;
+      }
+    }
+    uint64_t* m = ix->m1;
+    const size_t nw = (slen + 31) / 32 + 1;
+    for (size_t i = 0; i < nw; i++) m[i] = 0;
+    for (size_t j = 0; j < slen; j++) {
+      const char c = s[j];
+      const uint64_t v = c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0;
+      m[j >> 5] |= v << (62 - 2 * (j & 31));
+    }
+    m[66] = 0;
+    m[67] = (uint64_t)kmer;
+    m[68] = (uint64_t)(int64_t)-2;
+    uint32_t* sl = reinterpret_cast<uint32_t*>(m + 69);
+    sl[0] = (uint32_t)slen;
+    sl[1] = (uint32_t)length;
+    if (launch_string_query(ix->view(), m, m + 66, sl, sl + 1, reinterpret_cast<const long long*>(m + 67), 1,
+                            reinterpret_cast<long long*>(m + 68), ix->s1))
+      return -2;
+    cudaError_t e = cudaStreamSynchronize(ix->s1);
+    if (e != cudaSuccess) { set_error("plQuery: %s", cudaGetErrorString(e)); return -2; }
+    return (int64_t)m[68];
+  }
   const uint64_t off = 0;
   const uint32_t sl = (uint32_t)slen, ln = (uint32_t)length;
   int64_t out = -1;

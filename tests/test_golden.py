@@ -1,0 +1,64 @@
+"""Golden vectors produced by the unmodified reference (tests/golden/make_golden.py).
+
+CPU (-m "not gpu"): the oracle port reproduces every golden fixture (this is what pins the oracle on a
+box without /root/reference).  GPU (-m gpu): the CUDA path reproduces them through the C ABI."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+IDS = [os.path.basename(p)[:-4] for p in FIXTURES]
+
+
+def _load(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    d["genome"] = d["genome"].tobytes()
+    blob = d["strings"].tobytes()
+    offs = np.concatenate([[0], np.cumsum(d["string_lens"])]).astype(np.int64)
+    d["strs"] = [blob[offs[i]:offs[i + 1]] for i in range(len(d["string_lens"]))]
+    return d
+
+
+def test_fixtures_present():
+    assert len(FIXTURES) >= 10
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_oracle_port_reproduces_reference(oracle_built, path):
+    d = _load(path)
+    port = O.Port.from_memory(d["genome"], nb=int(d["nb_arg"]), k=int(d["k"]))
+    assert np.array_equal(port.sa, d["sa"])
+    assert port.nb == int(d["nb"])
+    assert np.array_equal(port.xlist, d["xlist"]) and np.array_equal(port.ylist, d["ylist"])
+    assert port.five == tuple(int(v) for v in d["five"])
+    assert port.perfect == int(d["perfect"])
+    assert np.array_equal(port.query_batch(d["kmers"]), d["answers"])
+    got = [port.query_str(s, int(x)) for s, x in zip(d["strs"], d["string_kmers"])]
+    assert got == [int(v) for v in d["string_answers"]]
+    port.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", FIXTURES, ids=IDS)
+def test_cuda_reproduces_reference(path):
+    import sapling_b200 as S
+    d = _load(path)
+    k = int(d["k"])
+    ix = S.Sapling.from_memory(d["genome"], None, numBuckets=int(d["nb_arg"]), k=k)
+    assert np.array_equal(ix.rev(), d["sa"])
+    assert ix.buckets == int(d["nb"])
+    x, y = ix.model()
+    assert np.array_equal(x, d["xlist"]) and np.array_equal(y, d["ylist"])
+    assert ix.five == tuple(int(v) for v in d["five"])
+    assert ix.perfectPredictions == int(d["perfect"])
+    assert np.array_equal(ix.queryBatch(d["kmers"]), d["answers"])
+    assert np.array_equal(ix.plQueryBatch(d["strs"], d["string_kmers"]), d["string_answers"])
+    for s, x, e in list(zip(d["strs"], d["string_kmers"], d["string_answers"]))[:8]:
+        assert ix.plQuery(s, int(x), len(s)) == int(e)
+    ix.close()
