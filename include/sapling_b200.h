@@ -146,6 +146,11 @@ int sapling_b200_verify_dev(sapling_b200_index *ix, const uint64_t *d_kmers, con
  * "HBM random-sector roofline" denominator). */
 int sapling_b200_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double *gbps);
 
+/* Generalised gather: n_access random accesses of `gran` (32/64/128) contiguous bytes; chain > 1 makes
+ * each thread follow a dependent chain of that many accesses.  Returns 1e9 accesses/s. */
+int sapling_b200_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm,
+                               int reps, double *gacc_per_s);
+
 const char *sapling_b200_last_error(void);
 const char *sapling_b200_version(void);
 

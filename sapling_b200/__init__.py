@@ -5,7 +5,8 @@ The product is the C-ABI shared library ``libsapling_b200.so`` (sources in ``csr
 thin ctypes binding the tests and ``bench.py`` use; it mirrors the reference's ``struct Sapling``
 surface (same member / method names and argument meaning).  There is no CPU fallback.
 """
-from .api import Sapling, SaplingError, kmerize, kmerize_adjusted, lib, lib_path, gather_bench  # noqa: F401
+from .api import (Sapling, SaplingError, kmerize, kmerize_adjusted, lib, lib_path, gather_bench,  # noqa: F401
+                  gather_bench2)
 
 QUIET = 1
 NO_COMPAT = 2

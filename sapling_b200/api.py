@@ -52,6 +52,7 @@ SYMBOLS = {
     "sapling_b200_verify_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]),
     "sapling_b200_check_sa": (C.c_int, [C.c_void_p, C.c_uint32] + [C.POINTER(C.c_uint64)] * 3),
     "sapling_b200_gather_bench": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
+    "sapling_b200_gather_bench2": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "sapling_b200_last_error": (C.c_char_p, []),
     "sapling_b200_version": (C.c_char_p, []),
 }
@@ -95,6 +96,14 @@ def kmerize_adjusted(k, length, s):
 def gather_bench(nbytes, n_loads, reps=3):
     g = C.c_double(0)
     if lib().sapling_b200_gather_bench(nbytes, n_loads, reps, C.byref(g)):
+        raise SaplingError(_err())
+    return g.value
+
+
+def gather_bench2(nbytes, n_access, gran=32, chain=1, blocks_per_sm=8, reps=2):
+    """1e9 random accesses/s of `gran` contiguous bytes over an nbytes buffer."""
+    g = C.c_double(0)
+    if lib().sapling_b200_gather_bench2(nbytes, n_access, gran, chain, blocks_per_sm, reps, C.byref(g)):
         raise SaplingError(_err())
     return g.value
 

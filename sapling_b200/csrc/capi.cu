@@ -29,6 +29,8 @@ int launch_sample(const IndexView& ix, uint64_t seed, uint64_t mut_seed, uint64_
 int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long* d_out, size_t nq,
                   unsigned long long* d_counters, cudaStream_t st);
 int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps);
+int run_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm, int reps,
+                      double* gacc_per_s);
 
 static thread_local char g_err[1024] = "";
 
@@ -910,6 +912,14 @@ int sapling_b200_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double
   int dev = 0;
   if (require_device(&dev)) return -1;
   return run_gather_bench(bytes, n_loads, reps, gbps);
+}
+
+int sapling_b200_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm, int reps,
+                               double* gacc_per_s) {
+  int dev = 0;
+  if (require_device(&dev)) return -1;
+  if (gran != 32 && gran != 64 && gran != 128) { set_error("gran must be 32, 64 or 128"); return -1; }
+  return run_gather_bench2(bytes, n_access, gran, chain, blocks_per_sm, reps, gacc_per_s);
 }
 
 }  // extern "C"

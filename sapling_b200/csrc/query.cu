@@ -15,7 +15,8 @@ namespace {
 
 constexpr int kQueryThreads = 256;
 
-__global__ void __launch_bounds__(kQueryThreads)
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
@@ -113,6 +114,33 @@ gather_kernel(const uint4* __restrict__ buf, uint64_t nsectors, uint64_t nloads,
   if (acc == 0x12345678u) atomicAdd(sink, 1ull);
 }
 
+// generalised: each access reads `gran` contiguous bytes (32/64/128) at a random gran-aligned address;
+// `chain` > 1 makes each thread follow a dependent chain of that many accesses (address of the next
+// access derived from the loaded value), the access pattern of one query
+template <int kGran>
+__global__ void __launch_bounds__(256)
+gather2_kernel(const uint4* __restrict__ buf, uint64_t nunits, uint64_t nthreads_work, int chain, uint64_t salt,
+               unsigned long long* __restrict__ sink) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  unsigned acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads_work; i += stride) {
+    uint64_t h = splitmix64(salt + i);
+    for (int c = 0; c < chain; c++) {
+      const uint64_t u = h % nunits;
+      const uint4* p = buf + u * (kGran / 16);
+      unsigned v = 0;
+#pragma unroll
+      for (int j = 0; j < kGran / 16; j++) {
+        const uint4 t = __ldg(p + j);
+        v ^= t.x ^ t.y ^ t.z ^ t.w;
+      }
+      acc ^= v;
+      h = splitmix64(h ^ v);  // next address depends on the data
+    }
+  }
+  if (acc == 0x12345678u) atomicAdd(sink, 1ull);
+}
+
 inline int query_grid(size_t nq, int blocks_per_sm) {
   size_t g = (nq + kQueryThreads - 1) / kQueryThreads;
   const size_t cap = (size_t)148 * blocks_per_sm;
@@ -123,9 +151,23 @@ inline int query_grid(size_t nq, int blocks_per_sm) {
 
 }  // namespace
 
+// Experiment knob (tools/gpu_experiments.py): SAPLING_B200_QV = resident blocks per SM the kernel is
+// compiled for (4: <=64 regs, 5, 6: <=40 regs, 8: <=32 regs).  Default chosen by measurement.
+static int query_variant() {
+  const char* e = getenv("SAPLING_B200_QV");  // read per launch so one process can sweep variants
+  int v = e ? atoi(e) : 5;
+  if (v != 4 && v != 5 && v != 6 && v != 8) v = 5;
+  return v;
+}
+
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st) {
   if (nq == 0) return 0;
-  kmer_query_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out);
+  switch (query_variant()) {
+    case 4: kmer_query_kernel<4><<<query_grid(nq, 4), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    case 6: kmer_query_kernel<6><<<query_grid(nq, 6), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    case 8: kmer_query_kernel<8><<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    default: kmer_query_kernel<5><<<query_grid(nq, 5), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+  }
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -192,6 +234,45 @@ int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps) {
   cudaFree(buf);
   cudaFree(sink);
   if (gbps) *gbps = best;
+  return 0;
+}
+
+int run_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm, int reps,
+                      double* gacc_per_s) {
+  if (bytes < (1ull << 20)) bytes = 1ull << 20;
+  if (chain < 1) chain = 1;
+  void* buf = nullptr;
+  unsigned long long* sink = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&buf, bytes));
+  SB_CUDA_CHECK(cudaMalloc(&sink, 8));
+  SB_CUDA_CHECK(cudaMemset(buf, 0x5A, bytes));
+  SB_CUDA_CHECK(cudaMemset(sink, 0, 8));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  const uint64_t nunits = bytes / (uint64_t)gran;
+  const uint64_t work = n_access / (uint64_t)chain;
+  const int grid = 148 * blocks_per_sm;
+  double best = 0;
+  for (int r = 0; r < reps + 1; r++) {
+    const uint64_t salt = 0x9999ull + (uint64_t)r * work;
+    cudaEventRecord(e0);
+    if (gran == 32) gather2_kernel<32><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink);
+    else if (gran == 64) gather2_kernel<64><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink);
+    else gather2_kernel<128><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink);
+    cudaEventRecord(e1);
+    cudaError_t e = cudaEventSynchronize(e1);
+    if (e != cudaSuccess) { cudaFree(buf); cudaFree(sink); SB_CUDA_CHECK(e); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double g = (double)(work * (uint64_t)chain) / (ms * 1e-3) / 1e9;
+    if (r > 0 && g > best) best = g;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (gacc_per_s) *gacc_per_s = best;
   return 0;
 }
 
