@@ -43,6 +43,9 @@ int build_model(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, cons
                 const uint8_t* d_kflag, int k, int nb, ModelEntry* d_model, ModelStats* stats,
                 int64_t* h_errdump, cudaStream_t st);
 
+// narrow device layout of the model (model.cu)
+int build_narrow_model(const ModelEntry* d_model, int nb, int shift, uint2* d_narrow, int* ok, cudaStream_t st);
+
 // countHitsLeft/Right (sapling_api.h:254-263, 283-289) over kflag
 int count_hits(const uint8_t* d_kflag, uint64_t n, int k, const uint32_t* d_sa_pos, size_t count,
                uint32_t maxHits, uint32_t* d_left, uint32_t* d_right, cudaStream_t st);

@@ -60,6 +60,9 @@ struct sapling_b200_index {
   uint32_t* d_isa = nullptr;   // only with KEEP_BUILD
   uint8_t* d_kflag = nullptr;  // only with KEEP_BUILD
   ModelEntry* d_model = nullptr;
+  uint2* d_narrow = nullptr;  // 8-byte-per-bucket layout used by the query kernels (model.cu)
+  long long last_x = 0, last_y = 0;
+  unsigned hints = 0;
   unsigned long long* d_oob = nullptr;
   uint64_t device_bytes = 0;
   int sa_rounds = 0;
@@ -94,6 +97,10 @@ struct sapling_b200_index {
     v.mostUnder = stats.mostUnder;
     v.oob_counter = d_oob;
     v.compat = (flags & SAPLING_B200_NO_COMPAT) ? 0 : 1;
+    v.narrow = d_narrow;
+    v.last_x = last_x;
+    v.last_y = last_y;
+    v.hints = hints;
     return v;
   }
 
@@ -113,6 +120,7 @@ struct sapling_b200_index {
     cudaFree(d_isa);
     cudaFree(d_kflag);
     cudaFree(d_model);
+    cudaFree(d_narrow);
     cudaFree(d_oob);
   }
 };
@@ -341,6 +349,33 @@ int finish_model_checks(sapling_b200_index* ix) {
   if (!ix->d_oob) {
     if (dev_alloc(ix, &ix->d_oob, 1)) return -1;
     SB_CUDA_CHECK(cudaMemset(ix->d_oob, 0, 8));
+  }
+  // query-side layout + L2 residency policy (experiment knobs: SAPLING_B200_NARROW=0, SAPLING_B200_HINTS=<bits>)
+  const char* e_narrow = getenv("SAPLING_B200_NARROW");
+  const char* e_hints = getenv("SAPLING_B200_HINTS");
+  ix->hints = e_hints ? (unsigned)atoi(e_hints) : (HINT_GENOME_KEEP | HINT_MODEL_KEEP | HINT_SA_STREAM | HINT_IO_STREAM);
+  if (const char* e_persist = getenv("SAPLING_B200_L2_PERSIST_MB")) {
+    // optional: widen the L2 set-aside that evict_last ("persisting") lines may occupy
+    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(e_persist) << 20);
+    cudaGetLastError();
+  }
+  const uint64_t B = 1ull << ix->nb;
+  ModelEntry last;
+  SB_CUDA_CHECK(cudaMemcpy(&last, ix->d_model + B, sizeof(last), cudaMemcpyDeviceToHost));
+  ix->last_x = last.x;
+  ix->last_y = last.y;
+  if (!ix->d_narrow && !(e_narrow && atoi(e_narrow) == 0)) {
+    const int shift = 2 * ix->k - ix->nb;
+    if (shift >= 0 && shift <= 31) {
+      if (dev_alloc(ix, &ix->d_narrow, B)) return -1;
+      int ok = 0;
+      if (build_narrow_model(ix->d_model, ix->nb, shift, ix->d_narrow, &ok, 0)) return -1;
+      if (!ok) {
+        cudaFree(ix->d_narrow);
+        ix->d_narrow = nullptr;
+        ix->device_bytes -= B * sizeof(uint2);
+      }
+    }
   }
   return 0;
 }

@@ -35,6 +35,18 @@ struct IndexView {
   int maxOver, maxUnder, mostOver, mostUnder;
   int compat;  // 1: the reference's (int)predicted window arithmetic (sapling_api.h:209,225)
   unsigned long long* oob_counter;  // incremented when predicted >= n (reference: UB)
+  // Narrow model (8 bytes per bucket, see model.cu); nullptr -> use the wide `model` table.
+  const uint2* narrow;
+  long long last_x, last_y;  // checkpoint (1<<nb): the largest k-mer of the genome
+  // L2 residency hints (HINT_* bits)
+  unsigned hints;
+};
+
+enum : unsigned {
+  HINT_GENOME_KEEP = 1u,   // packed genome loads: L2 evict_last
+  HINT_MODEL_KEEP = 2u,    // model loads: L2 evict_last
+  HINT_SA_STREAM = 4u,     // suffix-array loads: L2 evict_first
+  HINT_IO_STREAM = 8u      // k-mer reads / result writes: ld.cs / st.cs
 };
 
 #define SB_CUDA_CHECK(expr)                                                          \
@@ -54,7 +66,55 @@ const char* last_error();
 // device helpers
 // ---------------------------------------------------------------------------------------------
 
-__device__ __forceinline__ uint64_t ldg_u64(const uint64_t* p) { return __ldg(p); }
+// L2 eviction-priority policies for ld.global.nc.L2::cache_hint (PTX createpolicy).  The index is
+// far larger than L2 and is gathered at 32-byte granularity, so without hints the random SA / model
+// sectors flush the small, hot packed genome out of L2 (ncu: 27% L2 hit rate, profiles/).
+#ifdef SB_HOST_SIM
+// tests/sim: the same code compiled for the host (no PTX); policies are inert
+struct L2Policies {
+  uint64_t genome, model, sa;
+};
+inline L2Policies make_policies(unsigned) { return L2Policies{0, 0, 0}; }
+inline uint64_t ld_u64_pol(const uint64_t* p, uint64_t) { return *p; }
+inline uint32_t ld_u32_pol(const uint32_t* p, uint64_t) { return *p; }
+inline uint2 ld_u32x2_pol(const uint2* p, uint64_t) { return *p; }
+inline longlong2 ld_s64x2_pol(const longlong2* p, uint64_t) { return *p; }
+#else
+struct L2Policies {
+  uint64_t genome, model, sa;
+};
+__device__ __forceinline__ L2Policies make_policies(unsigned hints) {
+  uint64_t keep, first, normal;
+  asm("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep));
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(first));
+  asm("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(normal));
+  L2Policies p;
+  p.genome = (hints & HINT_GENOME_KEEP) ? keep : normal;
+  p.model = (hints & HINT_MODEL_KEEP) ? keep : normal;
+  p.sa = (hints & HINT_SA_STREAM) ? first : normal;
+  return p;
+}
+__device__ __forceinline__ uint64_t ld_u64_pol(const uint64_t* p, uint64_t pol) {
+  uint64_t v;
+  asm("ld.global.nc.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint32_t ld_u32_pol(const uint32_t* p, uint64_t pol) {
+  uint32_t v;
+  asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint2 ld_u32x2_pol(const uint2* p, uint64_t pol) {
+  uint2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.u32 {%0, %1}, [%2], %3;" : "=r"(v.x), "=r"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ longlong2 ld_s64x2_pol(const longlong2* p, uint64_t pol) {
+  longlong2 v;
+  asm("ld.global.nc.L2::cache_hint.v2.s64 {%0, %1}, [%2], %3;" : "=l"(v.x), "=l"(v.y) : "l"(p), "l"(pol));
+  return v;
+}
+#endif
 
 // 32 bases starting at text position idx, left-aligned in a 64-bit word (base idx in the top
 // two bits).  Reads genome words idx/32 and idx/32+1 (the pad makes the second read safe).
@@ -78,6 +138,24 @@ __device__ __forceinline__ uint64_t load_bases_upto(const uint64_t* __restrict__
   const uint64_t lo = __ldg(genome + w + 1);
   return (hi << o) | (lo >> (64u - o));
 }
+// same two loads with an L2 eviction policy
+__device__ __forceinline__ uint64_t load_bases_upto_pol(const uint64_t* __restrict__ genome, uint64_t idx,
+                                                        unsigned need, uint64_t pol) {
+  const uint64_t w = idx >> 5;
+  const unsigned o = (unsigned)(idx & 31u) * 2u;
+  const uint64_t hi = ld_u64_pol(genome + w, pol);
+  if (o + 2u * need <= 64u) return hi << o;
+  const uint64_t lo = ld_u64_pol(genome + w + 1, pol);
+  return (hi << o) | (lo >> (64u - o));
+}
+__device__ __forceinline__ uint64_t load_bases32_pol(const uint64_t* __restrict__ genome, uint64_t idx, uint64_t pol) {
+  const uint64_t w = idx >> 5;
+  const unsigned o = (unsigned)(idx & 31u) * 2u;
+  const uint64_t hi = ld_u64_pol(genome + w, pol);
+  if (o == 0) return hi;
+  const uint64_t lo = ld_u64_pol(genome + w + 1, pol);
+  return (hi << o) | (lo >> (64u - o));
+}
 
 // queryPiecewiseLinear (sapling_api.h:98-109).  IEEE double, one rounding per operation, no FMA
 // contraction, in the reference's evaluation order:
@@ -95,10 +173,37 @@ __device__ __forceinline__ uint64_t interpolate(long long x, long long xlo, long
   return (uint64_t)p;
 }
 
-__device__ __forceinline__ uint64_t predict_rank(const IndexView& ix, uint64_t x) {
+// Narrow model entry (model.cu): {xoff, y}.  xoff bit 31 clear: the bucket holds a k-mer, its checkpoint
+// is x = (b << shift) + xoff.  Bit 31 set: the bucket is empty and copies the checkpoint of bucket
+// b - (xoff & 0x7fffffff) (the reference's forward fill, sapling_api.h:437-449).
+constexpr uint32_t kNarrowFill = 0x80000000u;
+
+__device__ __forceinline__ uint64_t predict_rank(const IndexView& ix, uint64_t x, uint64_t pol) {
   const uint64_t b = x >> ix.shift;
-  const longlong2 lo = __ldg(reinterpret_cast<const longlong2*>(ix.model + b));
-  const longlong2 hi = __ldg(reinterpret_cast<const longlong2*>(ix.model + b + 1));
+  if (ix.narrow) {
+    const uint64_t B = 1ull << ix.nb;
+    const uint2 e0 = ld_u32x2_pol(ix.narrow + b, pol);
+    long long xhi, yhi;
+    if (b + 1 == B) {
+      xhi = ix.last_x;
+      yhi = ix.last_y;
+    } else {
+      const uint2 e1 = ld_u32x2_pol(ix.narrow + b + 1, pol);
+      if (e1.x & kNarrowFill) return (uint64_t)e0.y;  // next bucket is a copy of this one: xlo == xhi (:105)
+      xhi = (long long)(((b + 1) << ix.shift) + e1.x);
+      yhi = (long long)e1.y;
+    }
+    long long xlo;
+    if (e0.x & kNarrowFill) {
+      const uint64_t src = b - (e0.x & ~kNarrowFill);
+      xlo = (long long)((src << ix.shift) + ld_u32x2_pol(ix.narrow + src, pol).x);
+    } else {
+      xlo = (long long)((b << ix.shift) + e0.x);
+    }
+    return interpolate((long long)x, xlo, (long long)e0.y, xhi, yhi);
+  }
+  const longlong2 lo = ld_s64x2_pol(reinterpret_cast<const longlong2*>(ix.model + b), pol);
+  const longlong2 hi = ld_s64x2_pol(reinterpret_cast<const longlong2*>(ix.model + b + 1), pol);
   return interpolate((long long)x, lo.x, lo.y, hi.x, hi.y);
 }
 

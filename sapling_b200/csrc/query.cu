@@ -21,11 +21,13 @@ kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
-    const uint64_t x = __ldg(kmers + i);
+    const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
     KmerQuery q;
     q.q = x << lsh;
     q.k = (uint32_t)ix.k;
-    out[i] = pl_query<false>(ix, q, x);
+    const long long r = pl_query<false>(ix, q, x);
+    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
+    else out[i] = r;
   }
 }
 
@@ -47,7 +49,7 @@ __global__ void predict_kernel(const IndexView ix, const uint64_t* __restrict__ 
                                uint64_t* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride)
-    out[i] = predict_rank(ix, kmers[i]);
+    out[i] = predict_rank(ix, kmers[i], make_policies(0).model);
 }
 
 // pos_j = splitmix64(seed + j) mod (n-k); optional 1-2 substitutions on odd j
@@ -107,7 +109,7 @@ gather_kernel(const uint4* __restrict__ buf, uint64_t nsectors, uint64_t nloads,
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   unsigned acc = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nloads; i += stride) {
-    const uint64_t s = splitmix64(salt + i) % nsectors;
+    const uint64_t s = __umul64hi(splitmix64(salt + i), nsectors);  // uniform in [0, nsectors)
     const uint4 v = __ldg(buf + 2 * s);  // first 16 bytes of the sector: one sector transaction
     acc ^= v.x ^ v.y ^ v.z ^ v.w;
   }
@@ -126,7 +128,7 @@ gather2_kernel(const uint4* __restrict__ buf, uint64_t nunits, uint64_t nthreads
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads_work; i += stride) {
     uint64_t h = splitmix64(salt + i);
     for (int c = 0; c < chain; c++) {
-      const uint64_t u = h % nunits;
+      const uint64_t u = __umul64hi(h, nunits);  // uniform in [0, nunits)
       const uint4* p = buf + u * (kGran / 16);
       unsigned v = 0;
 #pragma unroll
@@ -162,11 +164,13 @@ static int query_variant() {
 
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st) {
   if (nq == 0) return 0;
+  const char* gm = getenv("SAPLING_B200_GRID_MULT");  // grid = 148 * blocks/SM * mult (experiment knob)
+  const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 1) : 1;
   switch (query_variant()) {
-    case 4: kmer_query_kernel<4><<<query_grid(nq, 4), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-    case 6: kmer_query_kernel<6><<<query_grid(nq, 6), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-    case 8: kmer_query_kernel<8><<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-    default: kmer_query_kernel<5><<<query_grid(nq, 5), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    case 4: kmer_query_kernel<4><<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    case 6: kmer_query_kernel<6><<<query_grid(nq, 6 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    case 8: kmer_query_kernel<8><<<query_grid(nq, 8 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    default: kmer_query_kernel<5><<<query_grid(nq, 5 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
   }
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;

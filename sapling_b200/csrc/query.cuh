@@ -38,8 +38,9 @@ struct KmerQuery {
   uint32_t k;
   __device__ __forceinline__ uint32_t slen() const { return k; }
   __device__ __forceinline__ uint32_t length() const { return k; }
-  __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start) const {
-    const uint64_t g = load_bases_upto(ix.genome, idx, k);
+  __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start,
+                                               uint64_t pol) const {
+    const uint64_t g = load_bases_upto_pol(ix.genome, idx, k, pol);
     uint64_t diff = q ^ g;
     if (start) diff &= (~0ull) >> (2u * start);  // getLcp trusts the first `start` characters
     const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
@@ -63,12 +64,13 @@ struct StringQuery {
   uint32_t slen_, length_;
   __device__ __forceinline__ uint32_t slen() const { return slen_; }
   __device__ __forceinline__ uint32_t length() const { return length_; }
-  __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start) const {
+  __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start,
+                                               uint64_t pol) const {
     const uint64_t room = ix.n - idx;
     const uint32_t leff = room < (uint64_t)length_ ? (uint32_t)room : length_;
     uint32_t lcp = leff > start ? leff : start;
     for (uint32_t pos = start & ~31u; pos < leff; pos += 32u) {
-      uint64_t diff = w[pos >> 5] ^ load_bases32(ix.genome, idx + pos);
+      uint64_t diff = w[pos >> 5] ^ load_bases32_pol(ix.genome, idx + pos, pol);
       if (pos < start) diff &= (~0ull) >> (2u * (start - pos));
       if (diff) {
         const uint32_t m = pos + ((uint32_t)__clzll((long long)diff) >> 1);
@@ -83,7 +85,7 @@ struct StringQuery {
     if (!r.at_end && lcp < slen_) {
       const uint32_t qb = (uint32_t)(w[lcp >> 5] >> (62u - 2u * (lcp & 31u))) & 3u;
       const uint64_t gi = idx + lcp;
-      const uint32_t gb = (uint32_t)(__ldg(ix.genome + (gi >> 5)) >> (62u - 2u * (uint32_t)(gi & 31u))) & 3u;
+      const uint32_t gb = (uint32_t)(ld_u64_pol(ix.genome + (gi >> 5), pol) >> (62u - 2u * (uint32_t)(gi & 31u))) & 3u;
       r.q_gt = qb > gb;
       r.q_lt = qb < gb;
     }
@@ -99,7 +101,8 @@ __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& 
   const uint64_t nm1 = n - 1;
   const uint32_t slen = qy.slen(), length = qy.length();
 
-  uint64_t pred = predict_rank(ix, kmer);  // :161
+  const L2Policies pol = make_policies(ix.hints);
+  uint64_t pred = predict_rank(ix, kmer, pol.model);  // :161
   if (pred >= n) {                         // reference: rev[] out of bounds.  Defined here: clamp + count.
     atomicAdd(ix.oob_counter, 1ull);
     pred = nm1;
@@ -112,9 +115,9 @@ __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& 
   int state = ST_PRED;
 
   for (;;) {
-    const uint64_t idx = __ldg(ix.sa + r);
+    const uint64_t idx = ld_u32_pol(ix.sa + r, pol.sa);
     if (state == ST_FINAL) return (long long)idx;
-    const ProbeResult pr = qy.probe(ix, idx, start);
+    const ProbeResult pr = qy.probe(ix, idx, start, pol.genome);
     const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
     bool to_search = false;
     switch (state) {

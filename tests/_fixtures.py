@@ -89,3 +89,21 @@ def var_len_strings(genome: bytes, k, count, seed=0):
                 s[j] = b"ACGT"[(b"ACGT".index(s[j]) + 1 + int(rng.integers(0, 3))) % 4]
             out.append(bytes(s))
     return out
+
+
+def narrow_model(xlist, ylist, k, nb):
+    """The 8-byte-per-bucket device layout of sapling_b200/csrc/model.cu, restated in numpy:
+    returns (uint32 array of shape (B, 2) = {xoff | fill flag, y}, ok)."""
+    shift = 2 * k - nb
+    B = 1 << nb
+    if shift < 0 or shift > 31:
+        return None, False
+    x = np.asarray(xlist[:B], dtype=np.int64)
+    y = np.asarray(ylist[:B], dtype=np.int64)
+    base = np.arange(B, dtype=np.int64) << shift
+    inside = (x >= base) & (x < base + (1 << shift))
+    src = np.where(inside, np.arange(B), x >> shift).astype(np.int64)
+    ok = bool(((x >= 0) & (y >= 0) & (y <= 0xFFFFFFFF)).all() and (x[src] == x).all() and (y[src] == y).all()
+              and (inside | (x < base)).all())
+    xoff = np.where(inside, x - base, 0x80000000 | (np.arange(B) - src)).astype(np.uint32)
+    return np.ascontiguousarray(np.stack([xoff, y.astype(np.uint32)], axis=1)), ok

@@ -3,6 +3,7 @@
 // by supplying host stand-ins for the handful of CUDA intrinsics it uses, so that the control-flow
 // replay can be differential-tested against the oracle on a machine without a GPU.  It is never
 // linked into libsapling_b200.so and never used by the product.
+#define SB_HOST_SIM 1
 #include <cstdint>
 #include <cstring>
 #include <cuda_runtime.h>
@@ -27,12 +28,13 @@ extern "C" {
 // genome: packed words (with pad), sa: n entries, model: interleaved {x,y} x ((1<<nb)+1)
 void sim_kmer_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                     const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
-                    unsigned long long* oob) {
+                    unsigned long long* oob, const uint2* narrow, const int64_t* last_xy) {
   sb::IndexView ix;
   ix.genome = genome; ix.sa = sa; ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
   ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
   ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
   ix.compat = compat; ix.oob_counter = oob;
+  ix.narrow = narrow; ix.last_x = last_xy[0]; ix.last_y = last_xy[1]; ix.hints = 0;
   for (size_t i = 0; i < nq; i++) {
     sb::KmerQuery q; q.q = kmers[i] << (64 - 2 * k); q.k = (uint32_t)k;
     out[i] = sb::pl_query<false>(ix, q, kmers[i]);
@@ -42,12 +44,13 @@ void sim_kmer_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* m
 void sim_string_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                       const int* five, int compat, const uint64_t* words, const uint64_t* word_off,
                       const uint32_t* slens, const uint32_t* lengths, const int64_t* kmers, size_t nq, int64_t* out,
-                      unsigned long long* oob) {
+                      unsigned long long* oob, const uint2* narrow, const int64_t* last_xy) {
   sb::IndexView ix;
   ix.genome = genome; ix.sa = sa; ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
   ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
   ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
   ix.compat = compat; ix.oob_counter = oob;
+  ix.narrow = narrow; ix.last_x = last_xy[0]; ix.last_y = last_xy[1]; ix.hints = 0;
   for (size_t i = 0; i < nq; i++) {
     sb::StringQuery q; q.w = words + word_off[i]; q.slen_ = slens[i]; q.length_ = lengths[i];
     out[i] = sb::pl_query<true>(ix, q, (uint64_t)kmers[i]);

@@ -78,9 +78,10 @@ def _sim():
     L = C.CDLL(so)
     i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
     L.sim_kmer_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
-                                 C.c_size_t, O.i64p, C.POINTER(C.c_uint64)]
+                                 C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_void_p, O.i64p]
     L.sim_string_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
-                                   O.u64p, O.u32p, O.u32p, O.i64p, C.c_size_t, O.i64p, C.POINTER(C.c_uint64)]
+                                   O.u64p, O.u32p, O.u32p, O.i64p, C.c_size_t, O.i64p, C.POINTER(C.c_uint64),
+                                   C.c_void_p, O.i64p]
     return L
 
 
@@ -99,10 +100,15 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
         five = np.array(port.five, dtype=np.int32)
         kmers = F.query_mix(g, k, 3000)
         exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
-        out = np.empty(len(kmers), dtype=np.int64)
-        c = C.c_uint64(0)
-        L.sim_kmer_batch(packed, sa, model, n, k, port.nb, five, 1, kmers, len(kmers), out, C.byref(c))
-        assert np.array_equal(out, exp) and c.value == oob
+        last = np.array([port.xlist[-1], port.ylist[-1]], dtype=np.int64)
+        narrow, nok = F.narrow_model(port.xlist, port.ylist, k, port.nb)
+        layouts = [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else [])
+        assert nok or 2 * k - port.nb > 31
+        for nptr in layouts:  # wide table, then the narrow 8-byte layout
+            out = np.empty(len(kmers), dtype=np.int64)
+            c = C.c_uint64(0)
+            L.sim_kmer_batch(packed, sa, model, n, k, port.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last)
+            assert np.array_equal(out, exp) and c.value == oob
         strs = F.var_len_strings(g, k, 25)
         words, offs = F.pack_strings(strs)
         slens = np.array([len(s) for s in strs], dtype=np.uint32)
@@ -110,6 +116,6 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
         exp2 = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
         out2 = np.empty(len(strs), dtype=np.int64)
         L.sim_string_batch(packed, sa, model, n, k, port.nb, five, 1, words, offs, slens, slens, km, len(strs), out2,
-                           C.byref(c))
+                           C.byref(c), layouts[-1], last)
         assert np.array_equal(out2, exp2)
         port.close()

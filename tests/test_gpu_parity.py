@@ -180,3 +180,24 @@ def test_no_compat_equals_compat_below_2g(S, oracle_built):
     kmers = F.query_mix(g, 21, 20000)
     assert np.array_equal(a.queryBatch(kmers), b.queryBatch(kmers))
     a.close(); b.close(); port.close()
+
+
+def test_layout_and_hint_variants_agree(S, oracle_built, monkeypatch):
+    """The narrow (8 B/bucket) model layout and every L2-hint combination return the oracle's answers; genomes with
+    many empty buckets exercise the forward-fill encoding."""
+    for name, k, nb in (("gc0110", 16, 10), ("gc1991", 21, -1), ("rand200k", 21, -1), ("tandem50", 21, 8)):
+        g = GENOMES[name]
+        port = O.Port.from_memory(g, nb=nb, k=k)
+        kmers = F.query_mix(g, k, 8000, seed=11)
+        exp = port.query_batch(kmers, nthreads=4)
+        for narrow, hints in ((0, 0), (1, 0), (1, 15), (0, 15), (1, 5)):
+            monkeypatch.setenv("SAPLING_B200_NARROW", str(narrow))
+            monkeypatch.setenv("SAPLING_B200_HINTS", str(hints))
+            ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+            for qv in ("4", "5", "6", "8"):
+                monkeypatch.setenv("SAPLING_B200_QV", qv)
+                assert np.array_equal(ix.queryBatch(kmers), exp), (name, narrow, hints, qv)
+            pred = ix.queryPiecewiseLinear(kmers[:500])
+            assert [int(p) for p in pred] == [port.predict(int(x)) for x in kmers[:500]]
+            ix.close()
+        port.close()
