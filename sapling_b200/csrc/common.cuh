@@ -178,30 +178,43 @@ __device__ __forceinline__ uint64_t interpolate(long long x, long long xlo, long
 // b - (xoff & 0x7fffffff) (the reference's forward fill, sapling_api.h:437-449).
 constexpr uint32_t kNarrowFill = 0x80000000u;
 
+// The two narrow entries of x's bucket (the second one is clamped at the table end and ignored there).
+struct NarrowPair {
+  uint2 e0, e1;
+};
+__device__ __forceinline__ NarrowPair narrow_load(const IndexView& ix, uint64_t x, uint64_t pol) {
+  const uint64_t b = x >> ix.shift;
+  const uint64_t B = 1ull << ix.nb;
+  NarrowPair p;
+  p.e0 = ld_u32x2_pol(ix.narrow + b, pol);
+  p.e1 = ld_u32x2_pol(ix.narrow + (b + 1 < B ? b + 1 : b), pol);
+  return p;
+}
+__device__ __forceinline__ uint64_t narrow_finish(const IndexView& ix, uint64_t x, const NarrowPair& p, uint64_t pol) {
+  const uint64_t b = x >> ix.shift;
+  const uint64_t B = 1ull << ix.nb;
+  long long xhi, yhi;
+  if (b + 1 == B) {
+    xhi = ix.last_x;
+    yhi = ix.last_y;
+  } else {
+    if (p.e1.x & kNarrowFill) return (uint64_t)p.e0.y;  // next bucket is a copy of this one: xlo == xhi (:105)
+    xhi = (long long)(((b + 1) << ix.shift) + p.e1.x);
+    yhi = (long long)p.e1.y;
+  }
+  long long xlo;
+  if (p.e0.x & kNarrowFill) {
+    const uint64_t src = b - (p.e0.x & ~kNarrowFill);
+    xlo = (long long)((src << ix.shift) + ld_u32x2_pol(ix.narrow + src, pol).x);
+  } else {
+    xlo = (long long)((b << ix.shift) + p.e0.x);
+  }
+  return interpolate((long long)x, xlo, (long long)p.e0.y, xhi, yhi);
+}
+
 __device__ __forceinline__ uint64_t predict_rank(const IndexView& ix, uint64_t x, uint64_t pol) {
   const uint64_t b = x >> ix.shift;
-  if (ix.narrow) {
-    const uint64_t B = 1ull << ix.nb;
-    const uint2 e0 = ld_u32x2_pol(ix.narrow + b, pol);
-    long long xhi, yhi;
-    if (b + 1 == B) {
-      xhi = ix.last_x;
-      yhi = ix.last_y;
-    } else {
-      const uint2 e1 = ld_u32x2_pol(ix.narrow + b + 1, pol);
-      if (e1.x & kNarrowFill) return (uint64_t)e0.y;  // next bucket is a copy of this one: xlo == xhi (:105)
-      xhi = (long long)(((b + 1) << ix.shift) + e1.x);
-      yhi = (long long)e1.y;
-    }
-    long long xlo;
-    if (e0.x & kNarrowFill) {
-      const uint64_t src = b - (e0.x & ~kNarrowFill);
-      xlo = (long long)((src << ix.shift) + ld_u32x2_pol(ix.narrow + src, pol).x);
-    } else {
-      xlo = (long long)((b << ix.shift) + e0.x);
-    }
-    return interpolate((long long)x, xlo, (long long)e0.y, xhi, yhi);
-  }
+  if (ix.narrow) return narrow_finish(ix, x, narrow_load(ix, x, pol), pol);
   const longlong2 lo = ld_s64x2_pol(reinterpret_cast<const longlong2*>(ix.model + b), pol);
   const longlong2 hi = ld_s64x2_pol(reinterpret_cast<const longlong2*>(ix.model + b + 1), pol);
   return interpolate((long long)x, lo.x, lo.y, hi.x, hi.y);

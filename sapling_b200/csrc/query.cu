@@ -31,6 +31,52 @@ kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t
   }
 }
 
+// Software-pipelined variant (narrow model layout only).  While a thread replays query t it already has in
+// flight: the first suffix-array entry of query t+1, the model checkpoints of query t+2 and the k-mer of
+// query t+3, so three of the dependent DRAM round trips of a query (k-mer -> model -> rev[predicted]) are
+// overlapped with the probe chain of the previous queries instead of heading it.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_pipelined_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq,
+                            long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= nq) return;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  const size_t last = nq - 1;
+  auto kmer_at = [&](size_t i) { return __ldcs(kmers + (i < last ? i : last)); };
+
+  // prologue: fill the pipeline
+  uint64_t x0 = kmer_at(i0);
+  uint64_t x1 = kmer_at(i0 + stride);
+  uint64_t x2 = kmer_at(i0 + 2 * stride);
+  uint64_t pred0 = clamp_prediction(ix, narrow_finish(ix, x0, narrow_load(ix, x0, pol.model), pol.model));
+  uint32_t idx0 = ld_u32_pol(ix.sa + pred0, pol.sa);
+  NarrowPair m1 = narrow_load(ix, x1, pol.model);
+
+  for (size_t i = i0; i < nq; i += stride) {
+    // stage C: k-mer of query t+3
+    const uint64_t x3 = kmer_at(i + 3 * stride);
+    // stage B: model checkpoints of query t+2 (x2 was loaded one iteration ago)
+    const NarrowPair m2 = narrow_load(ix, x2, pol.model);
+    // stage A: prediction of query t+1 (checkpoints loaded one iteration ago) and its first SA entry
+    const bool have1 = i + stride < nq;
+    uint64_t pred1 = narrow_finish(ix, x1, m1, pol.model);
+    if (have1) pred1 = clamp_prediction(ix, pred1);
+    else pred1 = pred0;
+    const uint32_t idx1 = ld_u32_pol(ix.sa + pred1, pol.sa);
+    // stage D: replay query t
+    KmerQuery q;
+    q.q = x0 << lsh;
+    q.k = (uint32_t)ix.k;
+    const long long r = pl_query_from<false, true>(ix, q, pred0, idx0, pol);
+    __stcs(out + i, r);
+    x0 = x1; x1 = x2; x2 = x3;
+    pred0 = pred1; idx0 = idx1; m1 = m2;
+  }
+}
+
 __global__ void __launch_bounds__(kQueryThreads)
 string_query_kernel(const IndexView ix, const uint64_t* __restrict__ words, const uint64_t* __restrict__ word_off,
                     const uint32_t* __restrict__ slens, const uint32_t* __restrict__ lengths,
@@ -157,8 +203,8 @@ inline int query_grid(size_t nq, int blocks_per_sm) {
 // compiled for (4: <=64 regs, 5, 6: <=40 regs, 8: <=32 regs).  Default chosen by measurement.
 static int query_variant() {
   const char* e = getenv("SAPLING_B200_QV");  // read per launch so one process can sweep variants
-  int v = e ? atoi(e) : 5;
-  if (v != 4 && v != 5 && v != 6 && v != 8) v = 5;
+  int v = e ? atoi(e) : 4;
+  if (v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
   return v;
 }
 
@@ -166,6 +212,18 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   if (nq == 0) return 0;
   const char* gm = getenv("SAPLING_B200_GRID_MULT");  // grid = 148 * blocks/SM * mult (experiment knob)
   const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 1) : 1;
+  const char* pe = getenv("SAPLING_B200_PIPELINE");  // 0 = plain kernel (experiment knob)
+  const bool pipelined = ix.narrow != nullptr && !(pe && atoi(pe) == 0);
+  if (pipelined) {
+    switch (query_variant()) {
+      case 3: kmer_query_pipelined_kernel<3><<<query_grid(nq, 3 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+      case 5: kmer_query_pipelined_kernel<5><<<query_grid(nq, 5 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+      case 6: kmer_query_pipelined_kernel<6><<<query_grid(nq, 6 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+      default: kmer_query_pipelined_kernel<4><<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+    }
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   switch (query_variant()) {
     case 4: kmer_query_kernel<4><<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
     case 6: kmer_query_kernel<6><<<query_grid(nq, 6 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;

@@ -95,18 +95,24 @@ struct StringQuery {
 
 // ---- the replay --------------------------------------------------------------------------------
 
-template <bool kGallop, typename Query>
-__device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& qy, uint64_t kmer) {
+// Clamp of an out-of-range prediction.  The reference reads rev[] out of bounds there;
+// defined here as: count it, use the last rank.
+__device__ __forceinline__ uint64_t clamp_prediction(const IndexView& ix, uint64_t pred) {
+  if (pred >= ix.n) {
+    atomicAdd(ix.oob_counter, 1ull);
+    pred = ix.n - 1;
+  }
+  return pred;
+}
+
+// The replay from a known prediction.  kHaveFirst: idx0 = rev[pred] was already loaded by the caller
+// (software-pipelined kernels issue that load one query ahead).
+template <bool kGallop, bool kHaveFirst, typename Query>
+__device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
+                                                   const uint64_t idx0, const L2Policies& pol) {
   const uint64_t n = ix.n;
   const uint64_t nm1 = n - 1;
   const uint32_t slen = qy.slen(), length = qy.length();
-
-  const L2Policies pol = make_policies(ix.hints);
-  uint64_t pred = predict_rank(ix, kmer, pol.model);  // :161
-  if (pred >= n) {                         // reference: rev[] out of bounds.  Defined here: clamp + count.
-    atomicAdd(ix.oob_counter, 1ull);
-    pred = nm1;
-  }
   // (int)predicted of :209/:225 -- wraps negative for predicted >= 2^31
   const int32_t p32 = (int32_t)(uint32_t)pred;
 
@@ -115,7 +121,7 @@ __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& 
   int state = ST_PRED;
 
   for (;;) {
-    const uint64_t idx = ld_u32_pol(ix.sa + r, pol.sa);
+    const uint64_t idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)ld_u32_pol(ix.sa + r, pol.sa);
     if (state == ST_FINAL) return (long long)idx;
     const ProbeResult pr = qy.probe(ix, idx, start, pol.genome);
     const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
@@ -234,6 +240,13 @@ __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& 
       }
     }
   }
+}
+
+template <bool kGallop, typename Query>
+__device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& qy, uint64_t kmer) {
+  const L2Policies pol = make_policies(ix.hints);
+  const uint64_t pred = clamp_prediction(ix, predict_rank(ix, kmer, pol.model));  // :161
+  return pl_query_from<kGallop, false>(ix, qy, pred, 0, pol);
 }
 
 }  // namespace sb

@@ -48,34 +48,31 @@ def _time_queries(ix, d_k, d_o, nq, st, reps=5):
 
 
 def variants(workload_n=100_000_000, nq=50_000_000):
-    """Layout / L2-hint / occupancy sweep of the query kernel on the c2 workload."""
+    """Layout / L2-hint / pipelining / occupancy sweep of the query kernel on the c2 workload."""
     import torch
     d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
     d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     rows, ref = [], None
-    configs = [  # (narrow, hints, persist_mb)
-        (0, 0, None), (0, 1, None), (0, 5, None), (0, 15, None),
-        (1, 0, None), (1, 1, None), (1, 5, None), (1, 7, None), (1, 13, None), (1, 15, None), (1, 15, 96), (1, 3, None),
-    ]
-    for narrow, hints, persist in configs:
+    index_cfgs = [(0, 0), (1, 0), (1, 15)]          # (narrow, hints): fixed at index creation
+    launch_cfgs = [(0, 4, 1), (0, 4, 2), (1, 3, 1), (1, 4, 1), (1, 4, 2), (1, 5, 1), (1, 3, 2), (1, 6, 1)]  # (pipeline, qv, mult)
+    for narrow, hints in index_cfgs:
         os.environ["SAPLING_B200_NARROW"] = str(narrow)
         os.environ["SAPLING_B200_HINTS"] = str(hints)
-        if persist is None:
-            os.environ.pop("SAPLING_B200_L2_PERSIST_MB", None)
-        else:
-            os.environ["SAPLING_B200_L2_PERSIST_MB"] = str(persist)
         ix = S.Sapling.synthetic(0x5A911C0DE5EED001, workload_n, k=21, maxMem=10)
         ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
         torch.cuda.synchronize()
-        for qv, mult in ((4, 1), (5, 1), (4, 2), (8, 1)):
+        for pipe, qv, mult in launch_cfgs:
+            if pipe and not narrow:
+                continue
+            os.environ["SAPLING_B200_PIPELINE"] = str(pipe)
             os.environ["SAPLING_B200_QV"] = str(qv)
             os.environ["SAPLING_B200_GRID_MULT"] = str(mult)
             ms = _time_queries(ix, d_k, d_o, nq, st)
             out = d_o.cpu()
             if ref is None:
                 ref = out
-            rows.append({"narrow": narrow, "hints": hints, "persist_mb": persist, "blocks_per_sm": qv, "grid_mult": mult,
+            rows.append({"narrow": narrow, "hints": hints, "pipeline": pipe, "blocks_per_sm": qv, "grid_mult": mult,
                          "ms": round(ms, 3), "Gq_per_s": round(nq / ms / 1e6, 2), "same_results": bool(torch.equal(out, ref))})
             print(rows[-1], flush=True)
         ix.close()
