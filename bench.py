@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[1], "c2"): synthetic 100 Mbp random-ACGT genome 
 generator), suffix array and .sap model built on the GPU with the reference's default
 parameters (k=21, maxMem=10 -> nb=23), 50 M 21-mers sampled from the genome per step.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|small]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3|small]
 
 One "step" = one pass of the query hot path over one batch (50 M queries at c2).
   value  : device-resident throughput (queries already in HBM), CUDA events on the launching stream
@@ -40,6 +40,10 @@ WORKLOADS = {
     # name: (genome bp, queries per step, cpu sample)
     "c2": (100_000_000, 50_000_000, 5_000_000),
     "c1": (10_000_000, 5_000_000, 5_000_000),
+    # BASELINE.json configs[2]: human-scale genome; 250 M queries per GPU per step (4 GPU-steps make the 1 B of the
+    # config).  The reference itself needs ~90 GB of host RAM and ~1 h to construct at this size, so the CPU baseline
+    # and the parity check use the oracle port built from the GPU index's parts.
+    "c3": (3_100_000_000, 250_000_000, 2_000_000),
     "small": (2_000_000, 1_000_000, 500_000),
 }
 K = 21
@@ -49,7 +53,7 @@ MAXMEM = 10
 def workload_name(w):
     n, nq, _ = WORKLOADS[w]
     return (f"{w}: synthetic {n // 1_000_000} Mbp random-ACGT genome, k={K}, maxMem={MAXMEM}, "
-            f"{nq // 1_000_000}M present 21-mers per step")
+            f"{nq // 1_000_000}M present 21-mers per GPU per step")
 
 
 def peaks():
@@ -241,6 +245,77 @@ def run_reference_arm(args):
     return 0
 
 
+def cpu_baseline_and_parity(ix, d_batch, n, sample, stream, log):
+    """Rank 0, N=1: (probes/query counted by the oracle, cpu_baseline dict, parity dict) on the first `sample` queries of
+    batch 0.  The oracle is only the checker / the reported CPU arm here; nothing of it is on the GPU path."""
+    import numpy as np
+    import torch
+    import _oracle as O
+    genome = ix.reference
+    samp = d_batch[:sample].cpu().numpy().astype(np.uint64)
+    gpu_ans = torch.empty(sample, dtype=torch.int64, device="cuda")
+    ix.queryBatchDevice(d_batch.data_ptr(), sample, gpu_ans.data_ptr(), stream)
+    torch.cuda.synchronize()
+    gpu_ans = gpu_ans.cpu().numpy()
+    threads = cpu_threads()
+    # P: probes/query of the reference algorithm, counted by the oracle port on this sample
+    xl, yl = ix.model()
+    port = O.Port.from_parts(genome, ix.rev(), K, ix.buckets, xl, yl, ix.five)
+    psamp = samp[:min(sample, 2_000_000)]
+    pans, ptot, _ = port.query_batch(psamp, nthreads=threads, stats=True)
+    probes_per_q = ptot / len(psamp)
+    port_equal = bool(np.array_equal(pans, gpu_ans[:len(psamp)]))
+    if n >= (1 << 31):
+        # c3: the oracle port is the CPU arm (the reference needs ~90 GB and ~1 h to construct at this size)
+        _, t = port.query_batch_timed(samp, nthreads=threads)
+        port.close()
+        cpu = {"value": sample / t, "unit": "queries/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} queries of batch 0 (present 21-mers), OpenMP over the oracle's plQuery "
+                         f"restatement on the GPU-built index parts, string construction untimed"}
+        parity = {"checked": int(len(psamp)), "mismatches_vs_port": int((pans != gpu_ans[:len(psamp)]).sum()),
+                  "oracle_port_equal": port_equal, "five": list(ix.five), "nb": ix.buckets}
+        return probes_per_q, cpu, parity
+    port.close()
+    # the reference itself, through its own constructor and files
+    tmp = scratch_dir()
+    fa, sa_fn, sap_fn = (os.path.join(tmp, "g.fa"), os.path.join(tmp, "g.fa.sa"), os.path.join(tmp, "g.fa.sap"))
+    gpu_sap = os.path.join(tmp, "gpu.sap")
+    try:
+        t0 = time.time()
+        open(fa, "wb").write(fasta_bytes(genome))
+        ix.write_sa(sa_fn)
+        kind = "reference" if O.ref_available() else "port"
+        if kind == "reference":
+            ref = O.Ref(fa, sa_fn, sap_fn, nb=-1, maxMem=MAXMEM, k=K)
+        else:
+            ref = O.Port.open(fa, sa_fn, sap_fn, nb=-1, maxMem=MAXMEM, k=K)
+        log(f"cpu_baseline: {kind} constructed from files in {time.time() - t0:.1f}s")
+        ix.write_sap(gpu_sap)
+        sap_identical = open(gpu_sap, "rb").read() == open(sap_fn, "rb").read()
+        if kind == "reference":
+            ref_ans, t = ref.query_batch(samp, nthreads=threads, timed=True)
+        else:
+            ref_ans, t = ref.query_batch_timed(samp, nthreads=threads)
+        ref.close()
+    finally:
+        for f in (fa, sa_fn, sap_fn, gpu_sap):
+            try:
+                os.remove(f)
+            except OSError:
+                pass
+        try:
+            os.rmdir(tmp)
+        except OSError:
+            pass
+    cpu = {"value": sample / t, "unit": "queries/s", "cores": threads, "kind": kind,
+           "sample": f"first {sample} queries of batch 0 (present 21-mers), OpenMP over Sapling::plQuery, "
+                     f"string construction untimed as in sapling_example.cpp:113-140"}
+    parity = {"checked": int(sample), "mismatches_vs_" + kind: int((ref_ans != gpu_ans).sum()),
+              "oracle_port_equal": port_equal, "sap_bytes_identical_to_" + kind: bool(sap_identical),
+              "five": list(ix.five), "nb": ix.buckets}
+    return probes_per_q, cpu, parity
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,8 +348,9 @@ def main():
     n, nq, sample = WORKLOADS[args.workload]
     t0 = time.time()
     want_cpu = (args.cpu_baseline == "auto" and rank == 0 and world == 1)
+    # KEEP_BUILD keeps the inverse suffix array on the device: needed to write the .sa file the reference arm reads
     ix = S.Sapling.synthetic(SEED_G, n, k=K, maxMem=MAXMEM, keep_host_genome=want_cpu,
-                             flags=S.QUIET | (S.KEEP_BUILD if want_cpu else 0))
+                             flags=S.QUIET | (S.KEEP_BUILD if want_cpu and n < (1 << 31) else 0))
     torch.cuda.synchronize()
     log(f"index built on GPU in {time.time() - t0:.1f}s: n={ix.n} k={ix.k} nb={ix.buckets} five={ix.five} "
         f"device_bytes={ix.device_bytes() / 1e6:.0f} MB")
@@ -352,63 +428,12 @@ def main():
     # ---- roofline + CPU baseline (rank 0) ----------------------------------------------------
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     peak, peak_src = peaks()
-    probes_per_q, cpu = None, None
-    parity = None
-    try:
-        import _oracle as O
-        if want_cpu:
-            genome = ix.reference
-            samp = d_kmers[0][:sample].cpu().numpy().astype(np.uint64)
-            gpu_ans = torch.empty(sample, dtype=torch.int64, device="cuda")
-            ix.queryBatchDevice(d_kmers[0].data_ptr(), sample, gpu_ans.data_ptr(), stream)
-            torch.cuda.synchronize()
-            gpu_ans = gpu_ans.cpu().numpy()
-            # P: probes/query of the reference algorithm, counted by the oracle port on this sample
-            xl, yl = ix.model()
-            port = O.Port.from_parts(genome, ix.rev(), K, ix.buckets, xl, yl, ix.five)
-            psamp = samp[:min(sample, 2_000_000)]
-            pans, ptot, _ = port.query_batch(psamp, nthreads=cpu_threads(), stats=True)
-            probes_per_q = ptot / len(psamp)
-            port_equal = bool(np.array_equal(pans, gpu_ans[:len(psamp)]))
-            port.close()
-            # the reference itself, through its own constructor and files
-            tmp = scratch_dir()
-            fa, sa_fn, sap_fn = (os.path.join(tmp, "g.fa"), os.path.join(tmp, "g.fa.sa"), os.path.join(tmp, "g.fa.sap"))
-            t0 = time.time()
-            open(fa, "wb").write(fasta_bytes(genome))
-            ix.write_sa(sa_fn)
-            kind = "reference" if O.ref_available() else "port"
-            if kind == "reference":
-                ref = O.Ref(fa, sa_fn, sap_fn, nb=-1, maxMem=MAXMEM, k=K)
-            else:
-                ref = O.Port.open(fa, sa_fn, sap_fn, nb=-1, maxMem=MAXMEM, k=K)
-            log(f"cpu_baseline: {kind} constructed from files in {time.time() - t0:.1f}s")
-            gpu_sap = os.path.join(tmp, "gpu.sap")
-            ix.write_sap(gpu_sap)
-            sap_identical = open(gpu_sap, "rb").read() == open(sap_fn, "rb").read()
-            threads = cpu_threads()
-            if kind == "reference":
-                ref_ans, t = ref.query_batch(samp, nthreads=threads, timed=True)
-            else:
-                ref_ans, t = ref.query_batch_timed(samp, nthreads=threads)
-            cpu = {"value": sample / t, "unit": "queries/s", "cores": threads, "kind": kind,
-                   "sample": f"first {sample} queries of batch 0 (present 21-mers), OpenMP over Sapling::plQuery, "
-                             f"string construction untimed as in sapling_example.cpp:113-140"}
-            parity = {"checked": int(sample), "mismatches_vs_" + kind: int((ref_ans != gpu_ans).sum()),
-                      "oracle_port_equal": port_equal, "sap_bytes_identical_to_" + kind: bool(sap_identical),
-                      "five": list(ix.five), "nb": ix.buckets}
-            ref.close()
-            for f in (fa, sa_fn, sap_fn, gpu_sap):
-                try:
-                    os.remove(f)
-                except OSError:
-                    pass
-            try:
-                os.rmdir(tmp)
-            except OSError:
-                pass
-    except Exception as e:  # the baseline is reported, never required for the GPU numbers
-        log(f"cpu_baseline failed: {type(e).__name__}: {e}")
+    probes_per_q, cpu, parity = None, None, None
+    if want_cpu:
+        try:
+            probes_per_q, cpu, parity = cpu_baseline_and_parity(ix, d_kmers[0], n, sample, stream, log)
+        except Exception as e:  # the baseline is reported, never required for the GPU numbers
+            log(f"cpu_baseline failed: {type(e).__name__}: {e}")
 
     if probes_per_q is None:
         probes_per_q = {"c2": 2.34, "c1": 2.47}.get(args.workload, 2.4)  # SURVEY 3.3 [probe]
@@ -435,12 +460,13 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload), "queries_per_step_per_gpu": nq, "index": "replicated per GPU",
-                   "nb": ix.buckets, "error_bounds": list(ix.five), "l2": "inputs larger than L2 (400 MB k-mers + 400 MB "
-                   "results streamed per step, 3 rotating batches; 400 MB SA + 134 MB model gathered)",
+                   "nb": ix.buckets, "error_bounds": list(ix.five), "l2": f"inputs larger than L2 ({nq * 8 // 1_000_000} MB k-mers + "
+                   f"{nq * 8 // 1_000_000} MB results streamed per step, 3 rotating batches; "
+                   f"{ix.device_bytes() // 1_000_000} MB index gathered)",
                    "seeds": {"genome": hex(SEED_G), "queries": hex(SEED_Q)}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_query": bytes_per_query,
-                     "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": "kmer_query_kernel",
+                     "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": "kmer_query_kernel<4>",
                      "kernel_ms": kernel_ms, "random_sector_gather_gbs": gather},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8,

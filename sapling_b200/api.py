@@ -179,7 +179,9 @@ class Sapling:
         p = self._L.sapling_b200_genome(self._h)
         if not p:
             raise SaplingError("host genome not kept for this index")
-        return C.string_at(p, self.n)
+        if self.n < (1 << 31):
+            return C.string_at(p, self.n)
+        return bytes((C.c_char * self.n).from_address(p))  # string_at takes an int-sized length
 
     @property
     def chrEnds(self):

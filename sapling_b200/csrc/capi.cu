@@ -174,6 +174,14 @@ int dev_alloc(sapling_b200_index* ix, T** p, uint64_t count) {
   return 0;
 }
 
+// suffix array: whole 64-byte lines, tail zeroed (the query kernel fetches the aligned line around a rank)
+int alloc_sa(sapling_b200_index* ix, uint64_t n) {
+  const uint64_t m = sa_alloc_entries(n);
+  if (dev_alloc(ix, &ix->d_sa, m)) return -1;
+  if (m > n) SB_CUDA_CHECK(cudaMemset(ix->d_sa + n, 0, (m - n) * 4));
+  return 0;
+}
+
 // FASTA cleaning rule of sapling_api.h:520-548 / util.h:17-20
 void clean_fasta(const char* text, size_t len, std::string* out,
                  std::vector<std::pair<uint64_t, std::string>>* ends) {
@@ -252,7 +260,7 @@ int read_sa_file(sapling_b200_index* ix, const char* path) {
     if (e != cudaSuccess) { fclose(f); SB_CUDA_CHECK(e); }
   }
   fclose(f);
-  if (dev_alloc(ix, &ix->d_sa, sz)) return -1;
+  if (alloc_sa(ix, sz)) return -1;
   // rev[inv[i]] = i  (sapling_api.h:609-611)
   if (invert_permutation(ix->d_isa, sz, ix->d_sa, 0)) return -1;
   SB_CUDA_CHECK(cudaDeviceSynchronize());
@@ -353,10 +361,15 @@ int finish_model_checks(sapling_b200_index* ix) {
   // query-side layout + L2 residency policy (experiment knobs: SAPLING_B200_NARROW=0, SAPLING_B200_HINTS=<bits>)
   const char* e_narrow = getenv("SAPLING_B200_NARROW");
   const char* e_hints = getenv("SAPLING_B200_HINTS");
-  ix->hints = e_hints ? (unsigned)atoi(e_hints) : (HINT_GENOME_KEEP | HINT_MODEL_KEEP | HINT_SA_STREAM | HINT_IO_STREAM);
+  ix->hints = e_hints ? (unsigned)atoi(e_hints) : (HINT_GENOME_KEEP | HINT_MODEL_KEEP);
   if (const char* e_persist = getenv("SAPLING_B200_L2_PERSIST_MB")) {
     // optional: widen the L2 set-aside that evict_last ("persisting") lines may occupy
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(e_persist) << 20);
+    cudaGetLastError();
+  }
+  if (const char* e_fetch = getenv("SAPLING_B200_L2_FETCH")) {
+    // optional: DRAM -> L2 fetch granularity hint (32/64/128 bytes)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e_fetch));
     cudaGetLastError();
   }
   const uint64_t B = 1ull << ix->nb;
@@ -386,7 +399,7 @@ int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, 
   const bool keep = (ix->flags & SAPLING_B200_KEEP_BUILD) != 0;
   if (!ix->d_sa) {
     say("Building suffix array\n");
-    if (dev_alloc(ix, &ix->d_sa, n) || dev_alloc(ix, &ix->d_isa, n)) return -1;
+    if (alloc_sa(ix, n) || dev_alloc(ix, &ix->d_isa, n)) return -1;
     if (build_suffix_array(ix->d_genome, n, ix->d_sa, ix->d_isa, 0, &ix->sa_rounds)) return -1;
     say("Built suffix array of size %llu\n", (unsigned long long)n);
   }
@@ -584,7 +597,7 @@ static sapling_b200_index* create_common(const char* genome, uint64_t n, const u
   if (validate_params(ix)) return fail();
   if (upload_genome(ix, genome, n)) return fail();
   if (sa) {
-    if (dev_alloc(ix, &ix->d_sa, n)) return fail();
+    if (alloc_sa(ix, n)) return fail();
     if (cudaMemcpy(ix->d_sa, sa, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("suffix array upload failed");
       return fail();
@@ -953,7 +966,7 @@ int sapling_b200_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int 
                                double* gacc_per_s) {
   int dev = 0;
   if (require_device(&dev)) return -1;
-  if (gran != 32 && gran != 64 && gran != 128) { set_error("gran must be 32, 64 or 128"); return -1; }
+  if (gran != 16 && gran != 32 && gran != 64 && gran != 128) { set_error("gran must be 16, 32, 64 or 128"); return -1; }
   return run_gather_bench2(bytes, n_access, gran, chain, blocks_per_sm, reps, gacc_per_s);
 }
 

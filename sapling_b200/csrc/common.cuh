@@ -16,6 +16,9 @@
 namespace sb {
 
 constexpr int GENOME_PAD_WORDS = 4;
+// The suffix array is allocated in whole 64-byte lines (16 ranks) so that the query kernel may fetch the
+// aligned line around any rank (query.cuh SaLine).
+inline uint64_t sa_alloc_entries(uint64_t n) { return (n + 15ull) & ~15ull; }
 
 struct __align__(16) ModelEntry {
   long long x;
@@ -102,6 +105,13 @@ __device__ __forceinline__ uint64_t ld_u64_pol(const uint64_t* p, uint64_t pol) 
 __device__ __forceinline__ uint32_t ld_u32_pol(const uint32_t* p, uint64_t pol) {
   uint32_t v;
   asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ uint4 ld_u32x4_pol(const uint4* p, uint64_t pol) {
+  uint4 v;
+  asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"
+      : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+      : "l"(p), "l"(pol));
   return v;
 }
 __device__ __forceinline__ uint2 ld_u32x2_pol(const uint2* p, uint64_t pol) {

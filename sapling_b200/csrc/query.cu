@@ -70,11 +70,80 @@ kmer_query_pipelined_kernel(const IndexView ix, const uint64_t* __restrict__ kme
     KmerQuery q;
     q.q = x0 << lsh;
     q.k = (uint32_t)ix.k;
-    const long long r = pl_query_from<false, true>(ix, q, pred0, idx0, pol);
+    const long long r = pl_query_from<false, true>(ix, q, pred0, idx0, pol, SaDirect());
     __stcs(out + i, r);
     x0 = x1; x1 = x2; x2 = x3;
     pred0 = pred1; idx0 = idx1; m1 = m2;
   }
+}
+
+// Line-cached variant: the aligned 64-byte suffix-array line around rev[predicted] is fetched once per query
+// into shared memory (query.cuh SaLine); works with either model layout.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_line_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+  __shared__ uint4 lines[4 * kQueryThreads];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  SaLine<kQueryThreads> sa;
+  sa.buf = lines + threadIdx.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = __ldcs(kmers + i);
+    KmerQuery q;
+    q.q = x << lsh;
+    q.k = (uint32_t)ix.k;
+    const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
+    sa.issue(ix, pred, pol.sa);
+    sa.template wait<0>();
+    __stcs(out + i, pl_query_from<false, false>(ix, q, pred, 0, pol, sa));
+  }
+}
+
+// Line-cached + software-pipelined (narrow model layout only).  While a thread replays query t out of line
+// buffer t&1, the cp.async of query t+1's suffix-array line into the other buffer, the model checkpoints of
+// query t+2 and the k-mer of query t+3 are in flight.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_line_pipelined_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq,
+                                 long long* __restrict__ out) {
+  __shared__ uint4 lines[2][4 * kQueryThreads];
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 >= nq) return;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  const size_t last = nq - 1;
+  auto kmer_at = [&](size_t i) { return __ldcs(kmers + (i < last ? i : last)); };
+
+  SaLine<kQueryThreads> sa0, sa1;
+  sa0.buf = lines[0] + threadIdx.x;
+  sa1.buf = lines[1] + threadIdx.x;
+  uint64_t x0 = kmer_at(i0);
+  uint64_t x1 = kmer_at(i0 + stride);
+  uint64_t x2 = kmer_at(i0 + 2 * stride);
+  uint64_t pred0 = clamp_prediction(ix, narrow_finish(ix, x0, narrow_load(ix, x0, pol.model), pol.model));
+  sa0.issue(ix, pred0, pol.sa);
+  NarrowPair m1 = narrow_load(ix, x1, pol.model);
+
+  for (size_t i = i0; i < nq; i += stride) {
+    const uint64_t x3 = kmer_at(i + 3 * stride);                 // k-mer of query t+3
+    const NarrowPair m2 = narrow_load(ix, x2, pol.model);        // checkpoints of query t+2
+    uint64_t pred1 = narrow_finish(ix, x1, m1, pol.model);       // prediction of query t+1 ...
+    if (i + stride < nq) pred1 = clamp_prediction(ix, pred1);
+    else pred1 = pred0;
+    sa1.issue(ix, pred1, pol.sa);                                // ... and its suffix-array line
+    sa0.template wait<1>();                                      // line of query t has landed
+    KmerQuery q;
+    q.q = x0 << lsh;
+    q.k = (uint32_t)ix.k;
+    __stcs(out + i, pl_query_from<false, false>(ix, q, pred0, 0, pol, sa0));
+    x0 = x1; x1 = x2; x2 = x3;
+    pred0 = pred1; m1 = m2;
+    uint4* t = sa0.buf; sa0.buf = sa1.buf; sa1.buf = t;
+    sa0.base = sa1.base;
+  }
+  sa0.template wait<0>();
 }
 
 __global__ void __launch_bounds__(kQueryThreads)
@@ -168,13 +237,16 @@ gather_kernel(const uint4* __restrict__ buf, uint64_t nsectors, uint64_t nloads,
 template <int kGran>
 __global__ void __launch_bounds__(256)
 gather2_kernel(const uint4* __restrict__ buf, uint64_t nunits, uint64_t nthreads_work, int chain, uint64_t salt,
-               unsigned long long* __restrict__ sink) {
+               unsigned long long* __restrict__ sink, unsigned nslices) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   unsigned acc = 0;
+  // nslices > 1: block b only touches slice (b mod nslices) of the buffer (TLB-friendly, still DRAM-random)
+  const uint64_t per_slice = nunits / nslices;
+  const uint64_t slice_base = (uint64_t)(blockIdx.x % nslices) * per_slice;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nthreads_work; i += stride) {
     uint64_t h = splitmix64(salt + i);
     for (int c = 0; c < chain; c++) {
-      const uint64_t u = __umul64hi(h, nunits);  // uniform in [0, nunits)
+      const uint64_t u = slice_base + __umul64hi(h, per_slice);  // uniform in the slice
       const uint4* p = buf + u * (kGran / 16);
       unsigned v = 0;
 #pragma unroll
@@ -211,25 +283,46 @@ static int query_variant() {
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st) {
   if (nq == 0) return 0;
   const char* gm = getenv("SAPLING_B200_GRID_MULT");  // grid = 148 * blocks/SM * mult (experiment knob)
-  const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 1) : 1;
-  const char* pe = getenv("SAPLING_B200_PIPELINE");  // 0 = plain kernel (experiment knob)
-  const bool pipelined = ix.narrow != nullptr && !(pe && atoi(pe) == 0);
-  if (pipelined) {
-    switch (query_variant()) {
-      case 3: kmer_query_pipelined_kernel<3><<<query_grid(nq, 3 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-      case 5: kmer_query_pipelined_kernel<5><<<query_grid(nq, 5 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-      case 6: kmer_query_pipelined_kernel<6><<<query_grid(nq, 6 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-      default: kmer_query_pipelined_kernel<4><<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
+  const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 2) : 2;
+  // Measured on the c2 workload (profiles/r1_experiments.md): the plain one-thread-per-query kernel at 4 blocks/SM
+  // and two waves is the fastest; the software-pipelined and line-cached variants stay selectable for experiments.
+  const char* pe = getenv("SAPLING_B200_PIPELINE");  // 1 = software-pipelined
+  const char* le = getenv("SAPLING_B200_LINE");      // 1 = suffix-array line cached in shared memory
+  const bool pipelined = ix.narrow != nullptr && pe && atoi(pe) == 1;
+  const bool line = le && atoi(le) == 1;
+  const int qv = query_variant();
+#define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
+  if (line && pipelined) {
+    switch (qv) {
+      case 3: SB_LAUNCH(kmer_query_line_pipelined_kernel, 3); break;
+      case 5: SB_LAUNCH(kmer_query_line_pipelined_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_line_pipelined_kernel, 6); break;
+      default: SB_LAUNCH(kmer_query_line_pipelined_kernel, 4); break;
     }
-    SB_CUDA_CHECK(cudaGetLastError());
-    return 0;
+  } else if (line) {
+    switch (qv) {
+      case 3: SB_LAUNCH(kmer_query_line_kernel, 3); break;
+      case 5: SB_LAUNCH(kmer_query_line_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_line_kernel, 6); break;
+      case 8: SB_LAUNCH(kmer_query_line_kernel, 8); break;
+      default: SB_LAUNCH(kmer_query_line_kernel, 4); break;
+    }
+  } else if (pipelined) {
+    switch (qv) {
+      case 3: SB_LAUNCH(kmer_query_pipelined_kernel, 3); break;
+      case 5: SB_LAUNCH(kmer_query_pipelined_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_pipelined_kernel, 6); break;
+      default: SB_LAUNCH(kmer_query_pipelined_kernel, 4); break;
+    }
+  } else {
+    switch (qv) {
+      case 5: SB_LAUNCH(kmer_query_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_kernel, 6); break;
+      case 8: SB_LAUNCH(kmer_query_kernel, 8); break;
+      default: SB_LAUNCH(kmer_query_kernel, 4); break;
+    }
   }
-  switch (query_variant()) {
-    case 4: kmer_query_kernel<4><<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-    case 6: kmer_query_kernel<6><<<query_grid(nq, 6 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-    case 8: kmer_query_kernel<8><<<query_grid(nq, 8 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-    default: kmer_query_kernel<5><<<query_grid(nq, 5 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out); break;
-  }
+#undef SB_LAUNCH
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
@@ -315,13 +408,16 @@ int run_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, in
   const uint64_t nunits = bytes / (uint64_t)gran;
   const uint64_t work = n_access / (uint64_t)chain;
   const int grid = 148 * blocks_per_sm;
+  const char* se = getenv("SAPLING_B200_GATHER_SLICES");  // experiment knob, see gather2_kernel
+  const unsigned nslices = se && atoi(se) > 0 ? (unsigned)atoi(se) : 1u;
   double best = 0;
   for (int r = 0; r < reps + 1; r++) {
     const uint64_t salt = 0x9999ull + (uint64_t)r * work;
     cudaEventRecord(e0);
-    if (gran == 32) gather2_kernel<32><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink);
-    else if (gran == 64) gather2_kernel<64><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink);
-    else gather2_kernel<128><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink);
+    if (gran == 16) gather2_kernel<16><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink, nslices);
+    else if (gran == 32) gather2_kernel<32><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink, nslices);
+    else if (gran == 64) gather2_kernel<64><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink, nslices);
+    else gather2_kernel<128><<<grid, 256>>>(reinterpret_cast<const uint4*>(buf), nunits, work, chain, salt, sink, nslices);
     cudaEventRecord(e1);
     cudaError_t e = cudaEventSynchronize(e1);
     if (e != cudaSuccess) { cudaFree(buf); cudaFree(sink); SB_CUDA_CHECK(e); }

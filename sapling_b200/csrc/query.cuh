@@ -105,11 +105,60 @@ __device__ __forceinline__ uint64_t clamp_prediction(const IndexView& ix, uint64
   return pred;
 }
 
+// ---- suffix-array readers -----------------------------------------------------------------------
+// Every rev[r] read of the replay goes through one of these.
+
+// plain gather: one 4-byte load per read
+struct SaDirect {
+  __device__ __forceinline__ uint32_t ld(const IndexView& ix, uint64_t r, uint64_t pol) const {
+    return ld_u32_pol(ix.sa + r, pol);
+  }
+};
+
+#ifndef SB_HOST_SIM
+// Line-cached reader.  Almost every rank a query touches (predicted, predicted +- mostOver/mostUnder, the
+// binary-search mids and the final lo+1) lies within a few entries of `predicted`, but the reads are
+// separated by dependent genome probes (~1 us), by which time neither L1 nor L2 still holds the line
+// (ncu, profiles/r1b: 3.3 SA sector fetches per query reach DRAM for 1.25 distinct lines).  So the thread
+// fetches the aligned 64-byte line (16 ranks: one DRAM burst) around `predicted` ONCE, with cp.async
+// (LDGSTS: global -> shared without staging registers, bypassing L1), and serves later reads from shared
+// memory; ranks outside the line fall back to a global load.
+// Shared-memory layout of one buffer: uint4 chunk c (0..3) of thread t at buf[c * kThreads + t].
+template <int kThreads>
+struct SaLine {
+  uint4* buf;     // this thread's column: buf[c * kThreads], c = 0..3
+  uint64_t base;  // first rank of the cached line (multiple of 16)
+  __device__ __forceinline__ void issue(const IndexView& ix, uint64_t pred, uint64_t pol) {
+    base = pred & ~15ull;
+    const uint4* p = reinterpret_cast<const uint4*>(ix.sa + base);  // the SA allocation is padded to 16 entries
+    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf);
+#pragma unroll
+    for (int c = 0; c < 4; c++)
+      asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst + c * kThreads * 16),
+                   "l"(p + c), "l"(pol)
+                   : "memory");
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  // wait until at most kPending later groups are still in flight
+  template <int kPending>
+  __device__ __forceinline__ void wait() const {
+    asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory");
+  }
+  __device__ __forceinline__ uint32_t ld(const IndexView& ix, uint64_t r, uint64_t pol) const {
+    if ((r & ~15ull) == base) {
+      const unsigned j = (unsigned)(r & 15u);
+      return reinterpret_cast<const uint32_t*>(buf + (j >> 2) * kThreads)[j & 3u];
+    }
+    return ld_u32_pol(ix.sa + r, pol);
+  }
+};
+#endif
+
 // The replay from a known prediction.  kHaveFirst: idx0 = rev[pred] was already loaded by the caller
 // (software-pipelined kernels issue that load one query ahead).
-template <bool kGallop, bool kHaveFirst, typename Query>
+template <bool kGallop, bool kHaveFirst, typename Query, typename Sa>
 __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
-                                                   const uint64_t idx0, const L2Policies& pol) {
+                                                   const uint64_t idx0, const L2Policies& pol, const Sa& sa) {
   const uint64_t n = ix.n;
   const uint64_t nm1 = n - 1;
   const uint32_t slen = qy.slen(), length = qy.length();
@@ -121,7 +170,7 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
   int state = ST_PRED;
 
   for (;;) {
-    const uint64_t idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)ld_u32_pol(ix.sa + r, pol.sa);
+    const uint64_t idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)sa.ld(ix, r, pol.sa);
     if (state == ST_FINAL) return (long long)idx;
     const ProbeResult pr = qy.probe(ix, idx, start, pol.genome);
     const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
@@ -246,7 +295,7 @@ template <bool kGallop, typename Query>
 __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& qy, uint64_t kmer) {
   const L2Policies pol = make_policies(ix.hints);
   const uint64_t pred = clamp_prediction(ix, predict_rank(ix, kmer, pol.model));  // :161
-  return pl_query_from<kGallop, false>(ix, qy, pred, 0, pol);
+  return pl_query_from<kGallop, false>(ix, qy, pred, 0, pol, SaDirect());
 }
 
 }  // namespace sb

@@ -33,6 +33,82 @@ def gather():
     return rows
 
 
+def footprint():
+    """Random-access throughput against footprint: locates the L2-capacity and TLB-reach knees."""
+    rows = []
+    for mb in (16, 48, 96, 192, 400, 800, 1600, 3200, 12800, 51200):
+        for gran in (16, 64):
+            g = S.gather_bench2(mb << 20, 1 << 28, gran, 1, 8, reps=2)
+            rows.append({"footprint_MB": mb, "gran_B": gran, "Gaccess_per_s": round(g, 2), "GB_per_s": round(g * gran, 1)})
+            print(rows[-1], flush=True)
+    return rows
+
+
+def tlb():
+    """Is DRAM-resident random access limited by address translation?  Same 12.8 GB / 51 GB buffers, but each block
+    confined to one of `slices` contiguous slices (a few pages per SM) -- DRAM rows and L2 stay just as cold."""
+    rows = []
+    for mb in (400, 12800, 51200):
+        for slices in (1, 8, 148, 1184, 148 * 64):
+            os.environ["SAPLING_B200_GATHER_SLICES"] = str(slices)
+            for gran in (16, 64):
+                g = S.gather_bench2(mb << 20, 1 << 28, gran, 1, 8, reps=2)
+                rows.append({"footprint_MB": mb, "slices": slices, "gran_B": gran, "Gaccess_per_s": round(g, 2),
+                             "GB_per_s": round(g * gran, 1)})
+                print(rows[-1], flush=True)
+    os.environ.pop("SAPLING_B200_GATHER_SLICES", None)
+    return rows
+
+
+def hints():
+    """Which arrays to pin in L2 (the effective capacity for data shared by all SMs is ~60 MB, see footprint())."""
+    import torch
+    nq = 50_000_000
+    d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
+    d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for n in (100_000_000,):
+        for h in (13, 5, 1, 9, 12, 4, 3, 15, 0, 7):
+            os.environ["SAPLING_B200_HINTS"] = str(h)
+            ix = S.Sapling.synthetic(0x5A911C0DE5EED001, n, k=21, maxMem=10)
+            ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
+            torch.cuda.synchronize()
+            for ln, pipe, qv, mult in ((0, 0, 4, 2), (0, 1, 3, 2), (1, 0, 4, 2), (1, 0, 5, 2)):
+                os.environ.update({"SAPLING_B200_LINE": str(ln), "SAPLING_B200_PIPELINE": str(pipe),
+                                   "SAPLING_B200_QV": str(qv), "SAPLING_B200_GRID_MULT": str(mult)})
+                ms = _time_queries(ix, d_k, d_o, nq, st)
+                rows.append({"n": n, "hints": h, "line": ln, "pipeline": pipe, "blocks_per_sm": qv, "grid_mult": mult,
+                             "ms": round(ms, 3), "Gq_per_s": round(nq / ms / 1e6, 2)})
+                print(rows[-1], flush=True)
+            ix.close()
+    return rows
+
+
+def sizes():
+    """Throughput against genome size (index footprint): where the L2-capacity and TLB-reach knees are."""
+    import torch
+    nq = 50_000_000
+    d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
+    d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    os.environ["SAPLING_B200_HINTS"] = "15"
+    for n in (5_000_000, 10_000_000, 25_000_000, 50_000_000, 100_000_000, 200_000_000, 400_000_000, 800_000_000):
+        ix = S.Sapling.synthetic(0x5A911C0DE5EED001, n, k=21, maxMem=10)
+        ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
+        torch.cuda.synchronize()
+        for ln, pipe, qv, mult in ((0, 0, 4, 2), (1, 0, 4, 2)):
+            os.environ.update({"SAPLING_B200_LINE": str(ln), "SAPLING_B200_PIPELINE": str(pipe),
+                               "SAPLING_B200_QV": str(qv), "SAPLING_B200_GRID_MULT": str(mult)})
+            ms = _time_queries(ix, d_k, d_o, nq, st)
+            rows.append({"n": n, "nb": ix.buckets, "five": list(ix.five), "device_MB": round(ix.device_bytes() / 1e6),
+                         "line": ln, "ms": round(ms, 3), "Gq_per_s": round(nq / ms / 1e6, 2)})
+            print(rows[-1], flush=True)
+        ix.close()
+    return rows
+
+
 def _time_queries(ix, d_k, d_o, nq, st, reps=5):
     import torch
     for _ in range(3):
@@ -48,23 +124,33 @@ def _time_queries(ix, d_k, d_o, nq, st, reps=5):
 
 
 def variants(workload_n=100_000_000, nq=50_000_000):
-    """Layout / L2-hint / pipelining / occupancy sweep of the query kernel on the c2 workload."""
+    """Layout / L2-hint / line-cache / pipelining / occupancy sweep of the query kernel on the c2 workload."""
     import torch
     d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
     d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    p = torch.cuda.get_device_properties(0)
+    print({"l2_bytes": p.L2_cache_size, "sms": p.multi_processor_count}, flush=True)
     rows, ref = [], None
-    index_cfgs = [(0, 0), (1, 0), (1, 15)]          # (narrow, hints): fixed at index creation
-    launch_cfgs = [(0, 4, 1), (0, 4, 2), (1, 3, 1), (1, 4, 1), (1, 4, 2), (1, 5, 1), (1, 3, 2), (1, 6, 1)]  # (pipeline, qv, mult)
-    for narrow, hints in index_cfgs:
+    # (narrow, hints, fetch granularity, persisting-L2 MB): fixed at index creation
+    index_cfgs = [(1, 15, None, None), (1, 0, None, None), (1, 3, None, None), (1, 11, None, None),
+                  (1, 15, 32, None), (1, 15, 128, None), (1, 15, 64, 64), (0, 15, 64, 0)]
+    launch_cfgs = [(ln, pipe, qv, mult) for ln in (1, 0) for pipe in (1, 0) for qv in (3, 4, 5) for mult in (1, 2)]
+    for narrow, hints, fetch, persist in index_cfgs:
         os.environ["SAPLING_B200_NARROW"] = str(narrow)
         os.environ["SAPLING_B200_HINTS"] = str(hints)
+        for name, v in (("SAPLING_B200_L2_FETCH", fetch), ("SAPLING_B200_L2_PERSIST_MB", persist)):
+            if v is None:
+                os.environ.pop(name, None)
+            else:
+                os.environ[name] = str(v)
         ix = S.Sapling.synthetic(0x5A911C0DE5EED001, workload_n, k=21, maxMem=10)
         ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
         torch.cuda.synchronize()
-        for pipe, qv, mult in launch_cfgs:
-            if pipe and not narrow:
+        for ln, pipe, qv, mult in launch_cfgs:
+            if (pipe and not narrow) or (narrow and (fetch or persist)) and not (ln and qv == 4 and mult == 1):
                 continue
+            os.environ["SAPLING_B200_LINE"] = str(ln)
             os.environ["SAPLING_B200_PIPELINE"] = str(pipe)
             os.environ["SAPLING_B200_QV"] = str(qv)
             os.environ["SAPLING_B200_GRID_MULT"] = str(mult)
@@ -72,17 +158,22 @@ def variants(workload_n=100_000_000, nq=50_000_000):
             out = d_o.cpu()
             if ref is None:
                 ref = out
-            rows.append({"narrow": narrow, "hints": hints, "pipeline": pipe, "blocks_per_sm": qv, "grid_mult": mult,
-                         "ms": round(ms, 3), "Gq_per_s": round(nq / ms / 1e6, 2), "same_results": bool(torch.equal(out, ref))})
+            rows.append({"narrow": narrow, "hints": hints, "fetch": fetch, "persist": persist, "line": ln,
+                         "pipeline": pipe, "blocks_per_sm": qv, "grid_mult": mult, "ms": round(ms, 3),
+                         "Gq_per_s": round(nq / ms / 1e6, 2), "same_results": bool(torch.equal(out, ref))})
             print(rows[-1], flush=True)
         ix.close()
+    # restore defaults for whatever runs next in this process
+    for name in ("SAPLING_B200_L2_FETCH", "SAPLING_B200_L2_PERSIST_MB", "SAPLING_B200_LINE", "SAPLING_B200_PIPELINE",
+                 "SAPLING_B200_QV", "SAPLING_B200_GRID_MULT", "SAPLING_B200_NARROW", "SAPLING_B200_HINTS"):
+        os.environ.pop(name, None)
     return rows
 
 
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gather"
     t0 = time.time()
-    res = {"gather": gather, "variants": variants}[what]()
+    res = {"gather": gather, "variants": variants, "footprint": footprint, "tlb": tlb, "hints": hints, "sizes": sizes}[what]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"exp_{what}.json"), "w"), indent=1)
     print(f"done in {time.time() - t0:.1f}s")
