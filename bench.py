@@ -466,7 +466,7 @@ def main():
                    "seeds": {"genome": hex(SEED_G), "queries": hex(SEED_Q)}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_query": bytes_per_query,
-                     "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": "kmer_query_kernel<4>",
+                     "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": "kmer_query_sector_kernel",
                      "kernel_ms": kernel_ms, "random_sector_gather_gbs": gather},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8,

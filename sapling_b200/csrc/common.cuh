@@ -107,6 +107,17 @@ __device__ __forceinline__ uint32_t ld_u32_pol(const uint32_t* p, uint64_t pol) 
   asm("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
   return v;
 }
+// one 256-bit load (LDG.E.256, sm_100+): a whole 32-byte sector in ONE request
+struct U32x8 {
+  uint32_t v[8];
+};
+__device__ __forceinline__ U32x8 ld_u32x8_pol(const uint32_t* p, uint64_t pol) {
+  U32x8 r;
+  asm("ld.global.nc.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+      : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+      : "l"(p), "l"(pol));
+  return r;
+}
 __device__ __forceinline__ uint4 ld_u32x4_pol(const uint4* p, uint64_t pol) {
   uint4 v;
   asm("ld.global.nc.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;"

@@ -77,6 +77,48 @@ kmer_query_pipelined_kernel(const IndexView ix, const uint64_t* __restrict__ kme
   }
 }
 
+// Sector-cached variant (default): the 8 suffix-array ranks around rev[predicted] come in one 256-bit load and stay
+// in registers (query.cuh SaSector); works with either model layout.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
+    KmerQuery q;
+    q.q = x << lsh;
+    q.k = (uint32_t)ix.k;
+    const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
+    SaSector sa;
+    sa.fill(ix, pred, pol.sa);
+    const long long r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
+    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
+    else out[i] = r;
+  }
+}
+
+// Traffic attribution (tools/ncu_hints.sh, SAPLING_B200_STAGES=1|2): the same kernel cut short after the model
+// lookup (1) or after the suffix-array sector fetch (2); never used to answer queries.
+__global__ void __launch_bounds__(kQueryThreads, 4)
+kmer_query_stages_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+                         int stages) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const L2Policies pol = make_policies(ix.hints);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = __ldg(kmers + i);
+    const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
+    long long r = (long long)pred;
+    if (stages >= 2) {
+      SaSector sa;
+      sa.fill(ix, pred, pol.sa);
+      r = (long long)sa.ld(ix, pred, pol.sa);
+    }
+    out[i] = r;
+  }
+}
+
 // Line-cached variant: the aligned 64-byte suffix-array line around rev[predicted] is fetched once per query
 // into shared memory (query.cuh SaLine); works with either model layout.
 template <int kMinBlocks>
@@ -273,9 +315,11 @@ inline int query_grid(size_t nq, int blocks_per_sm) {
 
 // Experiment knob (tools/gpu_experiments.py): SAPLING_B200_QV = resident blocks per SM the kernel is
 // compiled for (4: <=64 regs, 5, 6: <=40 regs, 8: <=32 regs).  Default chosen by measurement.
-static int query_variant() {
+static int query_variant(const IndexView& ix) {
   const char* e = getenv("SAPLING_B200_QV");  // read per launch so one process can sweep variants
-  int v = e ? atoi(e) : 4;
+  // Measured (profiles/r1_experiments.md): while the genome and model mostly hit L2 more resident warps help (5
+  // blocks/SM at c2: +8 %); once every access is a DRAM line and a TLB miss fewer do better (3 blocks/SM at c3: +9 %).
+  int v = e ? atoi(e) : (ix.n > 1000000000ull ? 3 : 5);
   if (v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
   return v;
 }
@@ -288,11 +332,27 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   // and two waves is the fastest; the software-pipelined and line-cached variants stay selectable for experiments.
   const char* pe = getenv("SAPLING_B200_PIPELINE");  // 1 = software-pipelined
   const char* le = getenv("SAPLING_B200_LINE");      // 1 = suffix-array line cached in shared memory
+  const char* se = getenv("SAPLING_B200_SECTOR");    // 0 = per-read suffix-array gathers (the round-1 baseline kernel)
   const bool pipelined = ix.narrow != nullptr && pe && atoi(pe) == 1;
   const bool line = le && atoi(le) == 1;
-  const int qv = query_variant();
+  const bool sector = !(se && atoi(se) == 0) && !pipelined && !line;
+  const int qv = query_variant(ix);
+  if (const char* sg = getenv("SAPLING_B200_STAGES")) {
+    if (atoi(sg) == 1 || atoi(sg) == 2) {
+      kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));
+      SB_CUDA_CHECK(cudaGetLastError());
+      return 0;
+    }
+  }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
-  if (line && pipelined) {
+  if (sector) {
+    switch (qv) {
+      case 3: SB_LAUNCH(kmer_query_sector_kernel, 3); break;
+      case 5: SB_LAUNCH(kmer_query_sector_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_sector_kernel, 6); break;
+      default: SB_LAUNCH(kmer_query_sector_kernel, 4); break;
+    }
+  } else if (line && pipelined) {
     switch (qv) {
       case 3: SB_LAUNCH(kmer_query_line_pipelined_kernel, 3); break;
       case 5: SB_LAUNCH(kmer_query_line_pipelined_kernel, 5); break;

@@ -20,7 +20,8 @@ enum ProbeState : int {
   ST_L2,        // probing lo = max(0,(int)predicted-maxUnder-1)(:225-228)
   ST_LG,        // galloping left by maxUnder (s.length() > k)  (:231-240)
   ST_BS,        // binarySearch probing mid                     (:138-141)
-  ST_FINAL      // hi == lo+2: return rev[lo+1] unverified      (:136,:247)
+  ST_FINAL,     // hi == lo+2: return rev[lo+1] unverified      (:136,:247)
+  ST_SKIP       // verifying a run of skipped binarySearch steps (see pl_query_from)
 };
 
 struct ProbeResult {
@@ -105,6 +106,14 @@ __device__ __forceinline__ uint64_t clamp_prediction(const IndexView& ix, uint64
   return pred;
 }
 
+#ifdef SB_HOST_SIM
+// tests/sim only: how often the long-window shortcut was tried / accepted
+static unsigned long long g_sim_skip_tried = 0, g_sim_skip_ok = 0;
+#define SB_SIM_COUNT(x) (++(x))
+#else
+#define SB_SIM_COUNT(x) ((void)0)
+#endif
+
 // ---- suffix-array readers -----------------------------------------------------------------------
 // Every rev[r] read of the replay goes through one of these.
 
@@ -154,9 +163,35 @@ struct SaLine {
 };
 #endif
 
+#ifndef SB_HOST_SIM
+// Sector-cached reader: the aligned 32-byte sector (8 ranks) around `predicted` is fetched with ONE 256-bit load
+// and kept in registers; the later reads of the replay (predicted +- mostOver/mostUnder, mids, final lo+1) that
+// fall into it cost no memory request at all.  Measured motivation (profiles/r1_experiments.md): the kernel is
+// bound by the number of L1-missing requests in flight per SM, and the plain reader spends 3.3 of its ~6.8
+// requests per query re-reading this one sector.
+struct SaSector {
+  U32x8 e;
+  uint64_t base;  // first rank of the cached sector (multiple of 8)
+  __device__ __forceinline__ void fill(const IndexView& ix, uint64_t pred, uint64_t pol) {
+    base = pred & ~7ull;
+    e = ld_u32x8_pol(ix.sa + base, pol);  // the SA allocation is padded to whole lines
+  }
+  __device__ __forceinline__ uint32_t ld(const IndexView& ix, uint64_t r, uint64_t pol) const {
+    if ((r & ~7ull) == base) {
+      const unsigned j = (unsigned)r & 7u;
+      const uint32_t a = (j & 1u) ? e.v[1] : e.v[0], b = (j & 1u) ? e.v[3] : e.v[2];
+      const uint32_t c = (j & 1u) ? e.v[5] : e.v[4], d = (j & 1u) ? e.v[7] : e.v[6];
+      const uint32_t ab = (j & 2u) ? b : a, cd = (j & 2u) ? d : c;
+      return (j & 4u) ? cd : ab;
+    }
+    return ld_u32_pol(ix.sa + r, pol);
+  }
+};
+#endif
+
 // The replay from a known prediction.  kHaveFirst: idx0 = rev[pred] was already loaded by the caller
 // (software-pipelined kernels issue that load one query ahead).
-template <bool kGallop, bool kHaveFirst, typename Query, typename Sa>
+template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true>
 __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
                                                    const uint64_t idx0, const L2Policies& pol, const Sa& sa) {
   const uint64_t n = ix.n;
@@ -235,6 +270,32 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
           hiLcp = lcp0;
           loLcp = pr.lcp;
           to_search = true;
+          // Long-window shortcut.  For ranks >= 2^31 the reference's (int)predicted arithmetic collapses lo to 0
+          //  and binarySearch(0, predicted) then walks ~31 mids m_1 = (lo+hi)>>1, m_{j+1} = (m_j+hi)>>1,
+          // nearly all of which "go right" because the query sits just left of `predicted`.  Those mids are a pure
+          // function of (lo, hi).  Take the last one still at least maxUnder+1 ranks left of hi and probe only it:
+          // if that suffix is strictly smaller than the query and not a match then, the suffix array being sorted,
+          // so was every earlier mid (none can have matched either), and because every carried LCP on this branch
+          // is a true LCP the reference arrives at exactly lo = that mid, loLcp = this probe's LCP.  Otherwise
+          // nothing is assumed and the literal chain is replayed from (lo, hi).
+          if (kSkip) {
+            const uint64_t guard = (uint64_t)(long long)ix.maxUnder + 1;
+            if (hi - lo > 4 * guard + 64) {
+              uint64_t cand = lo;
+              for (;;) {
+                const uint64_t m = (cand + hi) >> 1;
+                if (m + guard > hi) break;
+                cand = m;
+              }
+              if (cand != lo) {
+                SB_SIM_COUNT(g_sim_skip_tried);
+                r = cand;
+                start = 0;
+                state = ST_SKIP;
+                to_search = false;
+              }
+            }
+          }
         } else {  // :220-226
           hi = lo;
           hiLcp = pr.lcp;
@@ -264,6 +325,14 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
           loLcp = pr.lcp;  // :242
           to_search = true;
         }
+        break;
+      case ST_SKIP:
+        if (pr.lcp != slen && small) {  // verified: every skipped step went right
+          SB_SIM_COUNT(g_sim_skip_ok);
+          lo = r;
+          loLcp = pr.lcp;
+        }
+        to_search = true;
         break;
       default:  // ST_BS, probed mid == r  (:139-152)
         if (pr.lcp == slen) return (long long)idx;  // :141 then :247 (rev[mid] == idx)

@@ -25,6 +25,11 @@ namespace sb { void set_error(const char*, ...) {} const char* last_error() { re
 
 extern "C" {
 
+void sim_skip_counters(unsigned long long* tried, unsigned long long* ok) {
+  *tried = sb::g_sim_skip_tried;
+  *ok = sb::g_sim_skip_ok;
+}
+
 // genome: packed words (with pad), sa: n entries, model: interleaved {x,y} x ((1<<nb)+1)
 void sim_kmer_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                     const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,

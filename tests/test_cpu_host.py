@@ -94,28 +94,38 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
     for k, nb in ((21, -1), (11, 4), (31, 10), (16, -1)):
         if n < 4 * k:
             continue
-        port = O.Port.from_memory(g, nb=nb, k=k)
-        packed, sa = F.pack_genome(g), port.sa
-        model = np.ascontiguousarray(np.stack([port.xlist, port.ylist], axis=1).reshape(-1))
-        five = np.array(port.five, dtype=np.int32)
-        kmers = F.query_mix(g, k, 3000)
-        exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
-        last = np.array([port.xlist[-1], port.ylist[-1]], dtype=np.int64)
-        narrow, nok = F.narrow_model(port.xlist, port.ylist, k, port.nb)
+        base = O.Port.from_memory(g, nb=nb, k=k)
+        packed, sa = F.pack_genome(g), base.sa
+        model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
+        last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
+        narrow, nok = F.narrow_model(base.xlist, base.ylist, k, base.nb)
         layouts = [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else [])
-        assert nok or 2 * k - port.nb > 31
-        for nptr in layouts:  # wide table, then the narrow 8-byte layout
-            out = np.empty(len(kmers), dtype=np.int64)
-            c = C.c_uint64(0)
-            L.sim_kmer_batch(packed, sa, model, n, k, port.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last)
-            assert np.array_equal(out, exp) and c.value == oob
+        assert nok or 2 * k - base.nb > 31
+        kmers = F.query_mix(g, k, 3000)
         strs = F.var_len_strings(g, k, 25)
         words, offs = F.pack_strings(strs)
         slens = np.array([len(s) for s in strs], dtype=np.uint32)
         km = np.array([O.kmerize_adjusted(k, len(s), s) for s in strs], dtype=np.int64)
-        exp2 = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
-        out2 = np.empty(len(strs), dtype=np.int64)
-        L.sim_string_batch(packed, sa, model, n, k, port.nb, five, 1, words, offs, slens, slens, km, len(strs), out2,
-                           C.byref(c), layouts[-1], last)
-        assert np.array_equal(out2, exp2)
-        port.close()
+        # the model's own error bounds, then bounds that collapse the left window to rank 0 the way the reference's
+        # (int)predicted cast does beyond 2^31: exercises the long-window shortcut of pl_query_from
+        f0 = list(base.five)
+        for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30]):
+            port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
+            five = np.array(five_t, dtype=np.int32)
+            exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
+            for nptr in layouts:  # wide table, then the narrow 8-byte layout
+                out = np.empty(len(kmers), dtype=np.int64)
+                c = C.c_uint64(0)
+                L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last)
+                assert np.array_equal(out, exp) and c.value == oob, (name, k, nb, five_t)
+            exp2 = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
+            out2 = np.empty(len(strs), dtype=np.int64)
+            L.sim_string_batch(packed, sa, model, n, k, base.nb, five, 1, words, offs, slens, slens, km, len(strs), out2,
+                               C.byref(c), layouts[-1], last)
+            assert np.array_equal(out2, exp2), (name, k, nb, five_t)
+            port.close()
+        base.close()
+    tried, ok = C.c_uint64(0), C.c_uint64(0)
+    L.sim_skip_counters(C.byref(tried), C.byref(ok))
+    assert tried.value > 1000 and ok.value > 1000, (tried.value, ok.value)  # the shortcut was exercised (cumulative)
+    print(f"long-window shortcut: tried {tried.value}, accepted {ok.value}")

@@ -194,13 +194,16 @@ def test_layout_and_hint_variants_agree(S, oracle_built, monkeypatch):
             monkeypatch.setenv("SAPLING_B200_NARROW", str(narrow))
             monkeypatch.setenv("SAPLING_B200_HINTS", str(hints))
             ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
-            for line, pipe, qv in (("1", "1", "4"), ("1", "1", "3"), ("1", "1", "6"), ("1", "0", "4"), ("1", "0", "5"),
-                                   ("1", "0", "8"), ("0", "1", "4"), ("0", "1", "5"), ("0", "0", "4"), ("0", "0", "6"),
-                                   ("0", "0", "8")):
+            for sector, line, pipe, qv in (("1", "0", "0", "4"), ("1", "0", "0", "3"), ("1", "0", "0", "5"),
+                                           ("1", "0", "0", "6"), ("0", "1", "1", "4"), ("0", "1", "1", "3"),
+                                           ("0", "1", "0", "4"), ("0", "1", "0", "8"), ("0", "0", "1", "4"),
+                                           ("0", "0", "1", "5"), ("0", "0", "0", "4"), ("0", "0", "0", "6"),
+                                           ("0", "0", "0", "8")):
+                monkeypatch.setenv("SAPLING_B200_SECTOR", sector)
                 monkeypatch.setenv("SAPLING_B200_LINE", line)
                 monkeypatch.setenv("SAPLING_B200_PIPELINE", pipe)
                 monkeypatch.setenv("SAPLING_B200_QV", qv)
-                assert np.array_equal(ix.queryBatch(kmers), exp), (name, narrow, hints, line, pipe, qv)
+                assert np.array_equal(ix.queryBatch(kmers), exp), (name, narrow, hints, sector, line, pipe, qv)
             pred = ix.queryPiecewiseLinear(kmers[:500])
             assert [int(p) for p in pred] == [port.predict(int(x)) for x in kmers[:500]]
             ix.close()

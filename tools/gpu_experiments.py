@@ -109,6 +109,88 @@ def sizes():
     return rows
 
 
+def pin():
+    """L2 pinning for the default (sector) kernel on c2: eviction hints x persisting-L2 carve-out x occupancy."""
+    import torch
+    nq = 50_000_000
+    d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
+    d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for persist in (0, 40, 79):
+        for h in (3, 4, 5, 7, 13, 15):
+            os.environ["SAPLING_B200_HINTS"] = str(h)
+            os.environ["SAPLING_B200_L2_PERSIST_MB"] = str(persist)
+            ix = S.Sapling.synthetic(0x5A911C0DE5EED001, 100_000_000, k=21, maxMem=10)
+            ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
+            torch.cuda.synchronize()
+            for qv in (4, 5):
+                os.environ.update({"SAPLING_B200_QV": str(qv), "SAPLING_B200_GRID_MULT": "2"})
+                ms = _time_queries(ix, d_k, d_o, nq, st)
+                rows.append({"persist_MB": persist, "hints": h, "blocks_per_sm": qv, "ms": round(ms, 3),
+                             "Gq_per_s": round(nq / ms / 1e6, 2)})
+                print(rows[-1], flush=True)
+            ix.close()
+    os.environ["SAPLING_B200_L2_PERSIST_MB"] = "0"
+    return rows
+
+
+def nbsweep():
+    """c2 genome with other bucket counts: how much a smaller model table (L2 residency) buys, probes held ~constant."""
+    import torch
+    nq = 50_000_000
+    d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
+    d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rows = []
+    for persist, h in ((0, 3), (40, 1), (79, 3)):
+        os.environ["SAPLING_B200_HINTS"] = str(h)
+        os.environ["SAPLING_B200_L2_PERSIST_MB"] = str(persist)
+        for nb in (19, 20, 21, 22, 23, 24, 25):
+            ix = S.Sapling.synthetic(0x5A911C0DE5EED001, 100_000_000, numBuckets=nb, k=21, maxMem=10)
+            ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
+            torch.cuda.synchronize()
+            for qv in (4, 5):
+                os.environ.update({"SAPLING_B200_QV": str(qv), "SAPLING_B200_GRID_MULT": "2"})
+                ms = _time_queries(ix, d_k, d_o, nq, st)
+                rows.append({"persist_MB": persist, "hints": h, "nb": nb, "five": list(ix.five), "model_MB": (8 << nb) >> 20,
+                             "blocks_per_sm": qv, "ms": round(ms, 3), "Gq_per_s": round(nq / ms / 1e6, 2)})
+                print(rows[-1], flush=True)
+            ix.close()
+    os.environ["SAPLING_B200_L2_PERSIST_MB"] = "0"
+    return rows
+
+
+def kernels():
+    """Kernel variants on c2 and c3-like sizes with the default index configuration."""
+    import torch
+    rows = []
+    st = torch.cuda.current_stream().cuda_stream
+    for n, nq in ((100_000_000, 50_000_000), (10_000_000, 50_000_000), (3_100_000_000, 250_000_000)):
+        d_k = torch.empty(nq, dtype=torch.int64, device="cuda")
+        d_o = torch.empty(nq, dtype=torch.int64, device="cuda")
+        ix = S.Sapling.synthetic(0x5A911C0DE5EED001, n, k=21, maxMem=10)
+        ix.sample_queries_device(0x5A911C0DE5EED002, 0, 0, nq, d_k.data_ptr(), st)
+        torch.cuda.synchronize()
+        ref = None
+        for sector, line, pipe, qv, mult in ((0, 0, 0, 4, 2), (1, 0, 0, 4, 2), (1, 0, 0, 4, 1), (1, 0, 0, 3, 2), (1, 0, 0, 5, 2),
+                                             (1, 0, 0, 4, 4)):
+            os.environ.update({"SAPLING_B200_SECTOR": str(sector), "SAPLING_B200_LINE": str(line),
+                               "SAPLING_B200_PIPELINE": str(pipe), "SAPLING_B200_QV": str(qv),
+                               "SAPLING_B200_GRID_MULT": str(mult)})
+            ms = _time_queries(ix, d_k, d_o, nq, st, reps=3)
+            out = d_o.cpu()
+            if ref is None:
+                ref = out
+            rows.append({"n": n, "sector": sector, "line": line, "pipeline": pipe, "blocks_per_sm": qv, "grid_mult": mult,
+                         "ms": round(ms, 3), "Gq_per_s": round(nq / ms / 1e6, 2), "same_results": bool(torch.equal(out, ref))})
+            print(rows[-1], flush=True)
+        ix.close()
+        del d_k, d_o
+        torch.cuda.empty_cache()
+    return rows
+
+
 def _time_queries(ix, d_k, d_o, nq, st, reps=5):
     import torch
     for _ in range(3):
@@ -173,7 +255,7 @@ def variants(workload_n=100_000_000, nq=50_000_000):
 if __name__ == "__main__":
     what = sys.argv[1] if len(sys.argv) > 1 else "gather"
     t0 = time.time()
-    res = {"gather": gather, "variants": variants, "footprint": footprint, "tlb": tlb, "hints": hints, "sizes": sizes}[what]()
+    res = {"gather": gather, "variants": variants, "footprint": footprint, "tlb": tlb, "hints": hints, "sizes": sizes, "kernels": kernels, "pin": pin, "nbsweep": nbsweep}[what]()
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", f"exp_{what}.json"), "w"), indent=1)
     print(f"done in {time.time() - t0:.1f}s")

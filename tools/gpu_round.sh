@@ -14,7 +14,7 @@ for s in $STEPS; do
     variants) timeout 600 python tools/gpu_experiments.py variants > $OUT/${TAG}_variants.log 2>&1; echo "variants rc=$?";;
     footprint) timeout 600 python tools/gpu_experiments.py footprint > $OUT/${TAG}_footprint.log 2>&1; echo "footprint rc=$?";;
     tlb) timeout 600 python tools/gpu_experiments.py tlb > $OUT/${TAG}_tlb.log 2>&1; echo "tlb rc=$?";;
-    hints|sizes) timeout 900 python tools/gpu_experiments.py $s > $OUT/${TAG}_$s.log 2>&1; echo "$s rc=$?";;
+    hints|sizes|kernels|pin|nbsweep) timeout 900 python tools/gpu_experiments.py $s > $OUT/${TAG}_$s.log 2>&1; echo "$s rc=$?";;
     gather)  timeout 600 python tools/gpu_experiments.py gather > $OUT/${TAG}_gather.log 2>&1; echo "gather rc=$?";;
     bench)   timeout 900 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; echo "bench rc=$?";;
     benchref) timeout 900 python bench.py --impl reference --steps 3 > $OUT/${TAG}_bench_ref.json 2> $OUT/${TAG}_bench_ref.err; echo "benchref rc=$?";;
