@@ -334,6 +334,7 @@ def main():
     import numpy as np
     import torch
     import sapling_b200 as S
+    from sapling_b200.dist import max_over_ranks, my_shard
 
     rank, world, local = dist_env()
     log = (lambda m: print("[bench] " + m, file=sys.stderr, flush=True)) if rank == 0 else (lambda m: None)
@@ -360,8 +361,9 @@ def main():
     d_kmers = [torch.empty(nq, dtype=torch.int64, device="cuda") for _ in range(nbatch)]
     d_out = torch.empty(nq, dtype=torch.int64, device="cuda")
     for b in range(nbatch):
-        # distinct batches per rank and per slot
-        ix.sample_queries_device(SEED_Q, 0, (rank * nbatch + b) * nq, nq, d_kmers[b].data_ptr(), stream)
+        # batch b of the job is a stream of world*nq queries; this rank answers its contiguous slice of it
+        lo, hi = my_shard(world * nq, rank, world)
+        ix.sample_queries_device(SEED_Q, 0, b * world * nq + lo, hi - lo, d_kmers[b].data_ptr(), stream)
     torch.cuda.synchronize()
 
     def barrier():
@@ -386,10 +388,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     total_ms = ev[0].elapsed_time(ev[-1])
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    if dist is not None:
-        t = torch.tensor([total_ms], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms, dist, "cuda")
     value = world * nq * args.steps / (total_ms * 1e-3)
     kernel_ms = sum(step_ms) / len(step_ms)
 
@@ -411,10 +410,7 @@ def main():
         ix.queryBatch(h_kmers, out=h_out)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    if dist is not None:
-        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
+    e2e_s = max_over_ranks(e2e_s, dist, "cuda")
     e2e_value = world * nq * e2e_steps / e2e_s
     chunk = 1 << 22
     e2e_launches = e2e_steps * ((nq + chunk - 1) // chunk)

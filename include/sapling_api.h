@@ -106,6 +106,26 @@ struct Sapling
     return out;
   }
 
+  /* addition: the seed lookups of align.cpp:267-300 for a block of reads in one call; slot ((r*2+strand)*num_seeds+i) */
+  struct SeedHits
+  {
+    vector<long long> ref_pos;            /* verified hit position or -1 */
+    vector<uint32_t> sa_pos, left, right; /* sa[ref_pos], countHitsLeft/Right(sa_pos, maxHits) */
+  };
+  SeedHits seedBatch(const vector<string> &reads, size_t numSeeds, size_t maxHits)
+  {
+    string blob;
+    vector<uint64_t> off(reads.size() + 1, 0);
+    for (size_t i = 0; i < reads.size(); i++) { blob += reads[i]; off[i + 1] = blob.size(); }
+    SeedHits o;
+    size_t m = reads.size() * 2 * numSeeds;
+    o.ref_pos.resize(m); o.sa_pos.resize(m); o.left.resize(m); o.right.resize(m);
+    check(sapling_b200_seed_batch(h.get(), blob.data(), off.data(), reads.size(), (uint32_t)numSeeds, (uint32_t)maxHits,
+                                  reinterpret_cast<int64_t *>(o.ref_pos.data()), o.sa_pos.data(), o.left.data(),
+                                  o.right.data()));
+    return o;
+  }
+
   /* :254-263 */
   size_t countHitsRight(size_t sa_pos, size_t maxHits)
   {

@@ -129,6 +129,20 @@ int sapling_b200_predict_batch(sapling_b200_index *ix, const uint64_t *kmers, si
 int sapling_b200_count_hits(sapling_b200_index *ix, const uint32_t *sa_pos, size_t count,
                             uint32_t maxHits, uint32_t *left, uint32_t *right);
 
+/* The seed lookups of align.cpp seed_extend (align.cpp:259-300) for a block of reads, both strands, num_seeds seeds per
+ * strand at cur_pos = 0, last/(num_seeds-1)*i, ..., last (:271-275).  reads = concatenated ASCII, read r occupies
+ * [read_off[r], read_off[r+1]).  Output slot ((r*2 + strand)*num_seeds + i): ref_pos = the hit position that
+ * plQuery(query, kmerize(query), k) returned AND whose k bases equal the seed (:279-285), else -1; for hits
+ * sa_pos = Sapling::sa[ref_pos] (:287) and left/right = countHitsLeft/Right(sa_pos, max_hits) (:288-289), i.e. the
+ * tuple the reference pushes at :291-297 (its first element is left+right+1).  Seeds with a non-ACGT byte and reads
+ * shorter than k give -1.  Needs SAPLING_B200_KEEP_BUILD.  Host pointers / device pointers + stream. */
+int sapling_b200_seed_batch(sapling_b200_index *ix, const char *reads, const uint64_t *read_off, size_t n_reads,
+                            uint32_t num_seeds, uint32_t max_hits, int64_t *ref_pos, uint32_t *sa_pos,
+                            uint32_t *left, uint32_t *right);
+int sapling_b200_seed_batch_dev(sapling_b200_index *ix, const char *d_reads, const uint64_t *d_read_off,
+                                size_t n_reads, uint32_t num_seeds, uint32_t max_hits, int64_t *d_ref_pos,
+                                uint32_t *d_sa_pos, uint32_t *d_left, uint32_t *d_right, void *stream);
+
 /* Number of queries so far whose predicted rank was >= n (reference: out-of-bounds read). */
 uint64_t sapling_b200_oob_count(sapling_b200_index *ix);
 

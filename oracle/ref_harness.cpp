@@ -114,6 +114,61 @@ size_t ref_count_hits_right(void *h, size_t sa_pos, size_t maxHits) {
   return ((Sapling *)h)->countHitsRight(sa_pos, maxHits);
 }
 
+/* The seed lookups of align.cpp seed_extend (:267-300) for a block of reads, written against the reference's own
+   methods.  Output slot ((r*2+strand)*num_seeds + i): ref_pos = verified hit position or -1 (plQuery returned -1, or
+   the k bases at the returned position differ from the seed, :280-285); for hits sa_pos/left/right as pushed at
+   :287-297.  The reference reads `sapling->sa[ref_pos]` (:287), a member that is declared (sapling_api.h:38) but never
+   filled, so the shipped align crashes there; the intended array is the inverse suffix array lsa.inv (the one
+   countHitsLeft/Right index by rank), which is what is used here.  Reads shorter than k are skipped (the reference
+   underflows `last`, :261). */
+static char ref_complement(char c) { /* align.cpp:241-248 */
+  if (c == 'A') return 'T';
+  if (c == 'C') return 'G';
+  if (c == 'G') return 'C';
+  if (c == 'T') return 'A';
+  return c;
+}
+void ref_seed_batch(void *h, const char *reads, const uint64_t *off, size_t n_reads, size_t num_seeds, size_t maxHits,
+                    long long *ref_pos_out, uint32_t *sa_pos_out, uint32_t *left_out, uint32_t *right_out, int nthreads) {
+  Sapling *sapling = (Sapling *)h;
+  if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 64)
+  for (size_t r = 0; r < n_reads; r++) {
+    std::string readSeq(reads + off[r], (size_t)(off[r + 1] - off[r]));
+    for (int iter = 0; iter < 2; iter++) {
+      for (size_t i = 0; i < num_seeds; i++) {
+        size_t slot = (r * 2 + (size_t)iter) * num_seeds + i;
+        ref_pos_out[slot] = -1;
+        sa_pos_out[slot] = left_out[slot] = right_out[slot] = 0;
+      }
+      if (readSeq.length() < (size_t)sapling->k) continue;
+      size_t last = readSeq.length() - sapling->k; /* :261 */
+      std::string seq = readSeq;
+      if (iter) { /* revComp, :251-256 */
+        for (size_t j = 0; j < readSeq.length(); j++) seq[j] = ref_complement(readSeq[readSeq.length() - 1 - j]);
+      }
+      for (size_t i = 0; i < num_seeds; i++) {
+        size_t cur_pos = 0; /* :273-275 */
+        if (i == num_seeds - 1) cur_pos = last;
+        else if (i > 0) cur_pos = last / (num_seeds - 1) * i;
+        std::string query = seq.substr(cur_pos, sapling->k);
+        long long val = sapling->kmerize(query);
+        long long ref_pos_signed = sapling->plQuery(query, val, sapling->k);
+        if (ref_pos_signed == -1) continue;
+        size_t ref_pos = (size_t)ref_pos_signed;
+        std::string ref_seq = sapling->reference.substr(ref_pos, sapling->k);
+        if (query.compare(ref_seq)) continue;
+        size_t slot = (r * 2 + (size_t)iter) * num_seeds + i;
+        size_t sa_pos = sapling->lsa.inv[ref_pos];
+        ref_pos_out[slot] = ref_pos_signed;
+        sa_pos_out[slot] = (uint32_t)sa_pos;
+        left_out[slot] = (uint32_t)sapling->countHitsLeft(sa_pos, maxHits);
+        right_out[slot] = (uint32_t)sapling->countHitsRight(sa_pos, maxHits);
+      }
+    }
+  }
+}
+
 int ref_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -733,8 +733,62 @@ uint64_t so_count_hits_right(const so_index *ix, uint64_t sa_pos, uint64_t maxHi
 /* sapling_api.h:283-289 */
 uint64_t so_count_hits_left(const so_index *ix, uint64_t sa_pos, uint64_t maxHits) {
   for (uint64_t i = 0; i < maxHits; i++)
-    if (sa_pos < i || ix->lcp[sa_pos - i] < (uint32_t)ix->k) return i;
+    if (sa_pos < i || sa_pos - i >= ix->n - 1 /* lcp has n-1 entries; the reference reads one past for the last rank */ ||
+        ix->lcp[sa_pos - i] < (uint32_t)ix->k)
+      return i;
   return maxHits;
+}
+
+/* align.cpp:241-248 */
+static char seed_complement(char c) {
+  if (c == 'A') return 'T';
+  if (c == 'C') return 'G';
+  if (c == 'G') return 'C';
+  if (c == 'T') return 'A';
+  return c;
+}
+
+/* align.cpp:259-300, the seed part of seed_extend.  The comparisons run on the raw read bytes exactly as the
+   reference's do (kmerize hashes a non-ACGT byte as 'A', sapling_api.h:494-498, while getLcp and the verify compare see
+   the byte itself), so a seed holding an N can never verify. */
+void so_seed_batch(const so_index *ix, const char *reads, const uint64_t *off, size_t n_reads, size_t num_seeds,
+                   size_t maxHits, int64_t *ref_pos, uint32_t *sa_pos, uint32_t *left, uint32_t *right, int nthreads) {
+  const size_t k = (size_t)ix->k;
+  if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(dynamic, 64)
+  for (size_t r = 0; r < n_reads; r++) {
+    const char *read = reads + off[r];
+    const size_t len = (size_t)(off[r + 1] - off[r]);
+    char *seq = (char *)malloc(len + 1);
+    for (int iter = 0; iter < 2; iter++) { /* :267-269 */
+      for (size_t i = 0; i < num_seeds; i++) {
+        const size_t slot = (r * 2 + (size_t)iter) * num_seeds + i;
+        ref_pos[slot] = -1;
+        sa_pos[slot] = left[slot] = right[slot] = 0;
+      }
+      if (len < k) continue; /* the reference underflows `last` here (:261) */
+      const size_t last = len - k;
+      for (size_t j = 0; j < len; j++) seq[j] = iter ? seed_complement(read[len - 1 - j]) : read[j];
+      seq[len] = 0;
+      for (size_t i = 0; i < num_seeds; i++) {
+        size_t cur_pos = 0; /* :273-275 */
+        if (i == num_seeds - 1) cur_pos = last;
+        else if (i > 0) cur_pos = last / (num_seeds - 1) * i;
+        const char *query = seq + cur_pos;
+        const int64_t val = so_kmerize((int)k, query);                          /* :278 */
+        const int64_t p = so_plquery(ix, query, k, val, k, NULL, NULL);         /* :279 */
+        if (p == -1) continue;                                                  /* :281 */
+        if ((uint64_t)p + k > ix->n || memcmp(query, ix->ref + p, k) != 0) continue; /* :283-285 */
+        const size_t slot = (r * 2 + (size_t)iter) * num_seeds + i;
+        const uint64_t rank = ix->inv[p];                                       /* :287 */
+        ref_pos[slot] = p;
+        sa_pos[slot] = (uint32_t)rank;
+        left[slot] = (uint32_t)so_count_hits_left(ix, rank, maxHits);           /* :288 */
+        right[slot] = (uint32_t)so_count_hits_right(ix, rank, maxHits);         /* :289 */
+      }
+    }
+    free(seq);
+  }
 }
 
 /* ------------------------------------------------------------------------------------------ */

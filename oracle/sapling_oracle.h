@@ -107,6 +107,14 @@ double so_query_batch_timed(const so_index *ix, const uint64_t *kmers, size_t nq
 uint64_t so_count_hits_right(const so_index *ix, uint64_t sa_pos, uint64_t maxHits);
 uint64_t so_count_hits_left(const so_index *ix, uint64_t sa_pos, uint64_t maxHits);
 
+/* The seed lookups of align.cpp seed_extend (:259-300) for a block of reads (both strands, num_seeds seeds per strand
+   at cur_pos = 0, last/(num_seeds-1)*i, last; :271-275).  reads = concatenated ASCII, read r = [off[r], off[r+1]).
+   Output slot ((r*2+strand)*num_seeds + i): ref_pos = the verified hit position (:279-285) or -1; for hits
+   sa_pos = inv[ref_pos] (:287, see oracle/ref_harness.cpp on the unfilled `sa` member), left/right =
+   countHitsLeft/Right(sa_pos, maxHits) (:288-289).  Needs inv and lcp. */
+void so_seed_batch(const so_index *ix, const char *reads, const uint64_t *off, size_t n_reads, size_t num_seeds,
+                   size_t maxHits, int64_t *ref_pos, uint32_t *sa_pos, uint32_t *left, uint32_t *right, int nthreads);
+
 /* Independent range oracle: [*lb, *ub) = ranks whose suffix has s as a prefix (the contract of
    libdivsufsort sa_search, suffixarray/libdivsufsort/lib/utils.c:259-326). */
 void so_equal_range(const so_index *ix, const char *s, size_t slen, uint64_t *lb, uint64_t *ub);

@@ -47,6 +47,9 @@ SYMBOLS = {
     "sapling_b200_query_str_batch": (C.c_int, [C.c_void_p, C.c_char_p, _u64p, _u32p, C.c_void_p, _i64p, C.c_size_t, _i64p]),
     "sapling_b200_predict_batch": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p]),
     "sapling_b200_count_hits": (C.c_int, [C.c_void_p, _u32p, C.c_size_t, C.c_uint32, _u32p, _u32p]),
+    "sapling_b200_seed_batch": (C.c_int, [C.c_void_p, C.c_char_p, _u64p, C.c_size_t, C.c_uint32, C.c_uint32, _i64p, _u32p, _u32p, _u32p]),
+    "sapling_b200_seed_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sapling_b200_oob_count": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_sample_queries_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]),
     "sapling_b200_verify_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]),
@@ -281,6 +284,24 @@ class Sapling:
         right = np.empty(len(sa_pos), dtype=np.uint32)
         self._ck(self._L.sapling_b200_count_hits(self._h, sa_pos, len(sa_pos), maxHits, left, right))
         return left, right
+
+    def seedBatch(self, reads, num_seeds=7, max_hits=32):
+        """Seed lookups of align.cpp seed_extend (:259-300) for a list of reads (bytes): returns (ref_pos, sa_pos, left,
+        right), each of shape (n_reads, 2 strands, num_seeds); ref_pos is -1 where the seed has no verified hit."""
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(r) for r in reads])
+        blob = b"".join(reads)
+        m = len(reads) * 2 * num_seeds
+        rp, sp = np.empty(m, np.int64), np.empty(m, np.uint32)
+        lf, rt = np.empty(m, np.uint32), np.empty(m, np.uint32)
+        self._ck(self._L.sapling_b200_seed_batch(self._h, blob, off, len(reads), num_seeds, max_hits, rp, sp, lf, rt))
+        shp = (len(reads), 2, num_seeds)
+        return rp.reshape(shp), sp.reshape(shp), lf.reshape(shp), rt.reshape(shp)
+
+    def seedBatchDevice(self, d_reads_ptr, d_off_ptr, n_reads, num_seeds, max_hits, d_ref_pos, d_sa_pos, d_left, d_right,
+                        stream=0):
+        self._ck(self._L.sapling_b200_seed_batch_dev(self._h, d_reads_ptr, d_off_ptr, n_reads, num_seeds, max_hits,
+                                                     d_ref_pos, d_sa_pos, d_left, d_right, stream))
 
     def oob_count(self):
         return int(self._L.sapling_b200_oob_count(self._h))

@@ -24,6 +24,9 @@ int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint
                         const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
                         long long* d_out, cudaStream_t st);
 int launch_predict(const IndexView& ix, const uint64_t* d_kmers, size_t nq, uint64_t* d_out, cudaStream_t st);
+int launch_seeds(const IndexView& ix, const uint32_t* d_isa, const uint8_t* d_kflag, const char* d_reads,
+                 const uint64_t* d_off, size_t n_reads, uint32_t num_seeds, uint32_t maxHits, long long* d_ref_pos,
+                 uint32_t* d_sa_pos, uint32_t* d_left, uint32_t* d_right, cudaStream_t st);
 int launch_sample(const IndexView& ix, uint64_t seed, uint64_t mut_seed, uint64_t first, size_t nq,
                   uint64_t* d_kmers, cudaStream_t st);
 int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long* d_out, size_t nq,
@@ -939,6 +942,60 @@ int sapling_b200_count_hits(sapling_b200_index* ix, const uint32_t* sa_pos, size
   if (rc) return rc;
   SB_CUDA_CHECK(e);
   return 0;
+}
+
+int sapling_b200_seed_batch(sapling_b200_index* ix, const char* reads, const uint64_t* read_off, size_t n_reads,
+                            uint32_t num_seeds, uint32_t max_hits, int64_t* ref_pos, uint32_t* sa_pos, uint32_t* left,
+                            uint32_t* right) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (!ix->d_kflag || !ix->d_isa) {
+    set_error("seed_batch: inverse suffix array / k-prefix flags not resident (open with SAPLING_B200_KEEP_BUILD)");
+    return -1;
+  }
+  if (num_seeds == 0) { set_error("seed_batch: num_seeds must be >= 1"); return -1; }
+  if (n_reads == 0) return 0;
+  cudaSetDevice(ix->device);
+  const size_t total = n_reads * 2 * (size_t)num_seeds;
+  const uint64_t nbytes = read_off[n_reads];
+  char* d_reads = nullptr;
+  uint64_t* d_off = nullptr;
+  long long* d_rp = nullptr;
+  uint32_t *d_sp = nullptr, *d_l = nullptr, *d_r = nullptr;
+  int rc = -1;
+  do {
+    if (cudaMalloc(&d_reads, nbytes ? nbytes : 1) || cudaMalloc(&d_off, (n_reads + 1) * 8) || cudaMalloc(&d_rp, total * 8) ||
+        cudaMalloc(&d_sp, total * 4) || cudaMalloc(&d_l, total * 4) || cudaMalloc(&d_r, total * 4)) {
+      set_error("seed_batch: device allocation failed");
+      break;
+    }
+    cudaMemcpy(d_reads, reads, nbytes, cudaMemcpyHostToDevice);
+    cudaMemcpy(d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice);
+    if (launch_seeds(ix->view(), ix->d_isa, ix->d_kflag, d_reads, d_off, n_reads, num_seeds, max_hits, d_rp, d_sp, d_l,
+                     d_r, 0))
+      break;
+    cudaMemcpy(ref_pos, d_rp, total * 8, cudaMemcpyDeviceToHost);
+    cudaMemcpy(sa_pos, d_sp, total * 4, cudaMemcpyDeviceToHost);
+    cudaMemcpy(left, d_l, total * 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(right, d_r, total * 4, cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) { set_error("seed_batch: %s", cudaGetErrorString(e)); break; }
+    rc = 0;
+  } while (0);
+  cudaFree(d_reads); cudaFree(d_off); cudaFree(d_rp); cudaFree(d_sp); cudaFree(d_l); cudaFree(d_r);
+  return rc;
+}
+
+int sapling_b200_seed_batch_dev(sapling_b200_index* ix, const char* d_reads, const uint64_t* d_read_off, size_t n_reads,
+                                uint32_t num_seeds, uint32_t max_hits, int64_t* d_ref_pos, uint32_t* d_sa_pos,
+                                uint32_t* d_left, uint32_t* d_right, void* stream) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (!ix->d_kflag || !ix->d_isa) {
+    set_error("seed_batch: inverse suffix array / k-prefix flags not resident (open with SAPLING_B200_KEEP_BUILD)");
+    return -1;
+  }
+  if (num_seeds == 0) { set_error("seed_batch: num_seeds must be >= 1"); return -1; }
+  return launch_seeds(ix->view(), ix->d_isa, ix->d_kflag, d_reads, d_read_off, n_reads, num_seeds, max_hits,
+                      reinterpret_cast<long long*>(d_ref_pos), d_sa_pos, d_left, d_right,
+                      static_cast<cudaStream_t>(stream));
 }
 
 uint64_t sapling_b200_oob_count(sapling_b200_index* ix) {

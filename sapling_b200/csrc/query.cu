@@ -202,6 +202,71 @@ string_query_kernel(const IndexView ix, const uint64_t* __restrict__ words, cons
   }
 }
 
+// The seed lookups of align.cpp seed_extend (:259-300) for a block of reads: one thread per (read, strand, seed).
+// Seed position per :271-275, reverse complement per :241-256, kmerize + plQuery(query, val, k) :278-279, verification
+// against the genome :283-285, then sa_pos = inverse-SA[ref_pos] and countHitsLeft/Right (:287-289, sapling_api.h:254-289)
+// over the lcp>=k flags.  A seed holding a byte other than A/C/G/T can never verify in the reference (the compare at
+// :284 is on raw bytes against a pure-ACGT genome), so it is answered -1 without a query.
+__global__ void __launch_bounds__(kQueryThreads)
+seed_kernel(const IndexView ix, const uint32_t* __restrict__ isa, const uint8_t* __restrict__ kflag,
+            const char* __restrict__ reads, const uint64_t* __restrict__ off, size_t n_reads, uint32_t num_seeds,
+            uint32_t maxHits, long long* __restrict__ ref_pos, uint32_t* __restrict__ sa_pos,
+            uint32_t* __restrict__ left, uint32_t* __restrict__ right) {
+  const size_t total = n_reads * 2 * (size_t)num_seeds;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const uint32_t k = (uint32_t)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += stride) {
+    const size_t r = t / (2 * (size_t)num_seeds);
+    const uint32_t rem = (uint32_t)(t - r * 2 * (size_t)num_seeds);
+    const uint32_t strand = rem / num_seeds, i = rem - strand * num_seeds;
+    const uint64_t o = off[r], len = off[r + 1] - o;
+    long long hit = -1;
+    uint32_t rank = 0, lf = 0, rt = 0;
+    if (len >= k) {
+      const uint64_t last = len - k;
+      uint64_t cur = 0;
+      if (i == num_seeds - 1) cur = last;
+      else if (i > 0) cur = last / (num_seeds - 1) * i;
+      uint64_t x = 0;
+      bool valid = true;
+      for (uint32_t j = 0; j < k; j++) {
+        const char c = strand ? reads[o + (len - 1 - (cur + j))] : reads[o + cur + j];
+        uint32_t v;
+        if (c == 'A') v = 0; else if (c == 'C') v = 1; else if (c == 'G') v = 2; else if (c == 'T') v = 3;
+        else { v = 0; valid = false; }
+        x = (x << 2) | (uint64_t)(strand ? 3u - v : v);  // complement: A<->T, C<->G
+      }
+      if (valid) {
+        KmerQuery q;
+        q.q = x << (64u - 2u * k);
+        q.k = k;
+        const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
+        SaSector sa;
+        sa.fill(ix, pred, pol.sa);
+        const long long a = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
+        if (a >= 0 && (uint64_t)a + k <= ix.n &&
+            (load_bases_upto(ix.genome, (uint64_t)a, k) >> (64u - 2u * k)) == x) {
+          hit = a;
+          rank = isa[a];
+          const uint64_t p = rank;
+          uint32_t c = 0;
+          for (; c < maxHits; c++)  // countHitsRight, sapling_api.h:254-263
+            if ((uint64_t)c + p > ix.n - k || !kflag[c + p]) break;
+          rt = c;
+          for (c = 0; c < maxHits; c++)  // countHitsLeft, :283-289
+            if (p < c || !kflag[p - c]) break;
+          lf = c;
+        }
+      }
+    }
+    ref_pos[t] = hit;
+    sa_pos[t] = rank;
+    left[t] = lf;
+    right[t] = rt;
+  }
+}
+
 __global__ void predict_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq,
                                uint64_t* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -393,6 +458,17 @@ int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint
   if (nq == 0) return 0;
   string_query_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_words, d_word_off, d_slens, d_lengths,
                                                                    d_kmers, nq, d_out);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_seeds(const IndexView& ix, const uint32_t* d_isa, const uint8_t* d_kflag, const char* d_reads,
+                 const uint64_t* d_off, size_t n_reads, uint32_t num_seeds, uint32_t maxHits, long long* d_ref_pos,
+                 uint32_t* d_sa_pos, uint32_t* d_left, uint32_t* d_right, cudaStream_t st) {
+  const size_t total = n_reads * 2 * (size_t)num_seeds;
+  if (total == 0) return 0;
+  seed_kernel<<<query_grid(total, 8), kQueryThreads, 0, st>>>(ix, d_isa, d_kflag, d_reads, d_off, n_reads, num_seeds,
+                                                              maxHits, d_ref_pos, d_sa_pos, d_left, d_right);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

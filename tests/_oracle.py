@@ -75,6 +75,7 @@ def port_lib():
         L.so_count_hits_left.argtypes = [P, C.c_uint64, C.c_uint64]
         L.so_count_hits_right.restype = C.c_uint64
         L.so_count_hits_right.argtypes = [P, C.c_uint64, C.c_uint64]
+        L.so_seed_batch.argtypes = [P, C.c_char_p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, i64p, u32p, u32p, u32p, C.c_int]
         L.so_equal_range.argtypes = [P, C.c_char_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.so_read_sap_file.argtypes = [P, C.c_char_p]
         L.so_write_sap_file.argtypes = [P, C.c_char_p]
@@ -192,8 +193,24 @@ class Port:
         return (int(self.L.so_count_hits_left(self.h, sa_pos, max_hits)),
                 int(self.L.so_count_hits_right(self.h, sa_pos, max_hits)))
 
+    def seed_batch(self, reads, num_seeds=7, max_hits=32, nthreads=4):
+        """align.cpp:259-300 seed lookups: (ref_pos, sa_pos, left, right), each of shape (n_reads, 2, num_seeds)."""
+        blob, off = pack_reads(reads)
+        m = len(reads) * 2 * num_seeds
+        rp, sp, lf, rt = (np.empty(m, np.int64), np.empty(m, np.uint32), np.empty(m, np.uint32), np.empty(m, np.uint32))
+        self.L.so_seed_batch(self.h, blob, off, len(reads), num_seeds, max_hits, rp, sp, lf, rt, nthreads)
+        shp = (len(reads), 2, num_seeds)
+        return rp.reshape(shp), sp.reshape(shp), lf.reshape(shp), rt.reshape(shp)
+
     def write_sap(self, path): return self.L.so_write_sap_file(self.h, _b(path))
     def write_sa(self, path): return self.L.so_write_sa_file(self.h, _b(path))
+
+
+def pack_reads(reads):
+    """Concatenated ASCII + uint64 offsets (n_reads + 1)."""
+    off = np.zeros(len(reads) + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(r) for r in reads])
+    return b"".join(reads), off
 
 
 def kmerize(k, s): return int(port_lib().so_kmerize(k, _b(s)))
@@ -258,6 +275,8 @@ def ref_lib():
         L.ref_count_hits_left.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
         L.ref_count_hits_right.restype = C.c_size_t
         L.ref_count_hits_right.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t]
+        L.ref_seed_batch.argtypes = [C.c_void_p, C.c_char_p, u64p, C.c_size_t, C.c_size_t, C.c_size_t, i64p, u32p, u32p, u32p,
+                                     C.c_int]
         L.ref_max_threads.restype = C.c_int
         _ref = L
     return _ref
@@ -324,6 +343,14 @@ class Ref:
         t = self.L.ref_query_batch(self.h, kmers, len(kmers), out, nthreads)
         return (out, float(t)) if timed else out
 
+    def seed_batch(self, reads, num_seeds=7, max_hits=32, nthreads=4):
+        blob, off = pack_reads(reads)
+        m = len(reads) * 2 * num_seeds
+        rp, sp, lf, rt = (np.empty(m, np.int64), np.empty(m, np.uint32), np.empty(m, np.uint32), np.empty(m, np.uint32))
+        self.L.ref_seed_batch(self.h, blob, off, len(reads), num_seeds, max_hits, rp, sp, lf, rt, nthreads)
+        shp = (len(reads), 2, num_seeds)
+        return rp.reshape(shp), sp.reshape(shp), lf.reshape(shp), rt.reshape(shp)
+
     def count_hits(self, sa_pos, max_hits):
         return (int(self.L.ref_count_hits_left(self.h, sa_pos, max_hits)),
                 int(self.L.ref_count_hits_right(self.h, sa_pos, max_hits)))
@@ -384,6 +411,31 @@ def mutate_queries(kmers, k, seed=SEED_M, every=2):
             apply = sel & (nsub > np.uint64(r))
             x = np.where(apply, (x & ~(np.uint64(3) << sh)) | (new << sh), x)
     return x
+
+
+def simulate_reads(genome: bytes, n_reads, length=150, sub_rate=0.01, seed=SEED_Q, n_rate=0.0005, revcomp_every=3):
+    """Reads sampled from the genome: start = splitmix64(seed+j) mod (n-length), substitutions at
+    `sub_rate`, a few N, every `revcomp_every`-th read reverse-complemented.  Deterministic."""
+    n = len(genome)
+    g = np.frombuffer(genome, dtype=np.uint8)
+    rng = np.random.default_rng(seed & 0xFFFFFFFF)
+    with np.errstate(over="ignore"):
+        starts = (splitmix64_np(np.uint64(seed) + np.arange(n_reads, dtype=np.uint64)) % np.uint64(n - length)).astype(np.int64)
+    comp = np.zeros(256, dtype=np.uint8)
+    comp[:] = np.arange(256)
+    for a, b in (b"AT", b"CG", b"GC", b"TA"):
+        comp[a] = b
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    reads = []
+    for j, s0 in enumerate(starts):
+        r = g[s0:s0 + length].copy()
+        m = rng.random(length) < sub_rate
+        r[m] = acgt[rng.integers(0, 4, int(m.sum()))]
+        r[rng.random(length) < n_rate] = ord("N")
+        if revcomp_every and j % revcomp_every == revcomp_every - 1:
+            r = comp[r[::-1]]
+        reads.append(r.tobytes())
+    return reads, starts
 
 
 def unpack_kmer(x, k):

@@ -79,5 +79,35 @@ def main():
             port.close()
 
 
+SEED_CASES = [("rand20k", 16), ("gc1991", 16), ("tandem50", 16), ("ssw100k_slice", 16), ("repeat_tailA", 21)]
+
+
+def main_seeds():
+    """seeds.<genome>.k<k>.npz: the align.cpp:259-300 seed loop driven through the unmodified reference's own methods
+    (oracle/ref_harness.cpp ref_seed_batch) on simulated reads; `defined` masks the slots on which the reference itself
+    reads out of bounds (countHitsLeft on the last rank)."""
+    G = genomes()
+    with tempfile.TemporaryDirectory(dir="/dev/shm") as tmp:
+        for name, k in SEED_CASES:
+            g = G[name]
+            fa = os.path.join(tmp, f"{name}.fa")
+            O.write_fasta(fa, g)
+            ref = O.Ref(fa, os.path.join(tmp, name + ".sa"), os.path.join(tmp, f"{name}.k{k}.sap"), k=k)
+            reads, _ = O.simulate_reads(g, 150, min(150, len(g) // 4))
+            reads += [b"ACGT", g[100:100 + k], g[7:7 + k + 1], b"N" * 60, g[5:155].lower(), g[-150:], g[:150]]
+            rp, sp, lf, rt = ref.seed_batch(reads, 7, 32)
+            defined = ~((rp >= 0) & (sp == len(g) - 1))
+            out = os.path.join(HERE, f"seeds.{name}.k{k}.npz")
+            np.savez_compressed(out, genome=np.frombuffer(g, dtype=np.uint8), k=k, num_seeds=7, max_hits=32,
+                                reads=np.frombuffer(b"".join(reads), dtype=np.uint8),
+                                read_lens=np.array([len(r) for r in reads], dtype=np.uint32),
+                                ref_pos=rp, sa_pos=sp, left=lf, right=rt, defined=defined)
+            print(f"seeds.{name}.k{k}: reads={len(reads)} hits={(rp >= 0).sum()} of {rp.size} "
+                  f"max left/right={lf.max()}/{rt.max()} undefined={(~defined).sum()} -> {os.path.getsize(out) // 1024} KiB")
+            ref.close()
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) < 2 or sys.argv[1] != "seeds":
+        main()
+    main_seeds()

@@ -11,7 +11,9 @@ import pytest
 import _oracle as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "*.npz")))
+FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("seeds."))
+SEED_FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "seeds.*.npz")))
+SEED_IDS = [os.path.basename(p)[:-4] for p in SEED_FIXTURES]
 IDS = [os.path.basename(p)[:-4] for p in FIXTURES]
 
 
@@ -61,4 +63,40 @@ def test_cuda_reproduces_reference(path):
     assert np.array_equal(ix.plQueryBatch(d["strs"], d["string_kmers"]), d["string_answers"])
     for s, x, e in list(zip(d["strs"], d["string_kmers"], d["string_answers"]))[:8]:
         assert ix.plQuery(s, int(x), len(s)) == int(e)
+    ix.close()
+
+
+def _load_seeds(path):
+    z = np.load(path)
+    d = {k: z[k] for k in z.files}
+    d["genome"] = d["genome"].tobytes()
+    blob = d["reads"].tobytes()
+    offs = np.concatenate([[0], np.cumsum(d["read_lens"])]).astype(np.int64)
+    d["read_list"] = [blob[offs[i]:offs[i + 1]] for i in range(len(d["read_lens"]))]
+    return d
+
+
+def _check_seeds(d, got):
+    ok = d["defined"]
+    for a, what in zip(got, ("ref_pos", "sa_pos", "left", "right")):
+        assert np.array_equal(a[ok], d[what][ok]), what
+    assert (d["ref_pos"] >= 0).sum() > 50
+
+
+@pytest.mark.parametrize("path", SEED_FIXTURES, ids=SEED_IDS)
+def test_oracle_port_reproduces_reference_seed_loop(oracle_built, path):
+    """align.cpp:259-300 through the reference's own methods (golden) == the oracle's restatement."""
+    d = _load_seeds(path)
+    port = O.Port.from_memory(d["genome"], k=int(d["k"]))
+    _check_seeds(d, port.seed_batch(d["read_list"], int(d["num_seeds"]), int(d["max_hits"])))
+    port.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", SEED_FIXTURES, ids=SEED_IDS)
+def test_cuda_reproduces_reference_seed_loop(path):
+    import sapling_b200 as S
+    d = _load_seeds(path)
+    ix = S.Sapling.from_memory(d["genome"], None, k=int(d["k"]), flags=S.QUIET | S.KEEP_BUILD)
+    _check_seeds(d, ix.seedBatch(d["read_list"], int(d["num_seeds"]), int(d["max_hits"])))
     ix.close()

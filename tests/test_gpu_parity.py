@@ -208,3 +208,48 @@ def test_layout_and_hint_variants_agree(S, oracle_built, monkeypatch):
             assert [int(p) for p in pred] == [port.predict(int(x)) for x in kmers[:500]]
             ix.close()
         port.close()
+
+
+def test_k32_cross_checked_by_equal_range(S, oracle_built):
+    """k=32 has no reference oracle (the reference's signed 64-bit hash breaks there): unsigned arithmetic on
+    the GPU, validated against the independent match-range oracle (the contract of libdivsufsort's sa_search)."""
+    g = GENOMES["rand200k"]
+    k = 32
+    ix = S.Sapling.from_memory(g, None, k=k)
+    kmers, pos = O.present_queries(g, k, 20000)
+    mixed = O.mutate_queries(kmers, k)          # odd entries carry 1-2 substitutions
+    got = ix.queryBatch(mixed)
+    port = O.Port.from_memory(g, sa=ix.rev(), k=21)  # only its suffix array / equal_range are used
+    isa = port.isa
+    spelled = O.kmers_at(g, np.clip(got, 0, len(g) - k), k)
+    present = np.arange(len(mixed)) % 2 == 0
+    assert (got[present] >= 0).all() and np.array_equal(spelled[present], mixed[present])   # sapling_example's self-check
+    for i in list(range(0, 2000, 2)) + list(range(1, 2000, 2)):
+        lb, ub = port.equal_range(O.unpack_kmer(int(mixed[i]), k))
+        if got[i] >= 0 and got[i] + k <= len(g) and spelled[i] == mixed[i]:
+            assert lb <= isa[got[i]] < ub
+        else:
+            assert i % 2 == 1 and lb == ub, "a k-mer that occurs must be found"
+    assert ix.verify_device is not None
+    ix.close()
+    port.close()
+
+
+@pytest.mark.parametrize("name,k", [("rand200k", 16), ("rand200k", 21), ("gc1991", 16), ("tandem50", 16), ("repeat_tailA", 21),
+                                    ("gc0110", 11)])
+def test_seed_batch_matches_align_seed_loop(S, oracle_built, name, k):
+    """sapling_b200_seed_batch == the oracle's restatement of align.cpp:259-300 (itself pinned to the reference's own
+    methods, tests/test_cpu_host.py): hit positions, ranks and left/right hit counts, both strands."""
+    g = GENOMES[name]
+    reads, _ = O.simulate_reads(g, 300, min(150, len(g) // 4))
+    reads += [b"ACGT", g[100:100 + k], g[7:7 + k + 1], b"N" * 60, g[5:155].lower(), g[-150:], g[:150]]
+    port = O.Port.from_memory(g, k=k)
+    ix = S.Sapling.from_memory(g, None, k=k, flags=S.QUIET | S.KEEP_BUILD)
+    for num_seeds, max_hits in ((7, 32), (1, 4), (3, 1000)):
+        exp = port.seed_batch(reads, num_seeds, max_hits)
+        got = ix.seedBatch(reads, num_seeds, max_hits)
+        for a, b, what in zip(got, exp, ("ref_pos", "sa_pos", "left", "right")):
+            assert np.array_equal(a, b), (name, k, num_seeds, max_hits, what)
+    assert (exp[0] >= 0).any()
+    ix.close()
+    port.close()
