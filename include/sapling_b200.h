@@ -32,6 +32,10 @@ typedef struct sapling_b200_index sapling_b200_index;
 #define SAPLING_B200_KEEP_BUILD 4u   /* keep ISA / k-prefix runs on the device after construction
                                         (needed by count_hits / sa_rank) */
 
+#define SAPLING_B200_INLINE 8u       /* build the inline-prefix suffix array (16 B per base: rank -> {position, leading
+                                        bases}) whatever the genome size; default: only for genomes >= 400 Mbp */
+#define SAPLING_B200_NO_INLINE 16u   /* never build it */
+
 /* ---- construction -------------------------------------------------------------------------- */
 
 /* Sapling::Sapling(refFn, saFn, sapFn, numBuckets, maxMem, k, errorFn)   sapling_api.h:492-676.

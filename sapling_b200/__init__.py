@@ -11,3 +11,5 @@ from .api import (Sapling, SaplingError, kmerize, kmerize_adjusted, lib, lib_pat
 QUIET = 1
 NO_COMPAT = 2
 KEEP_BUILD = 4
+INLINE = 8
+NO_INLINE = 16

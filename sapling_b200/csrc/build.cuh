@@ -16,8 +16,13 @@ int synth_genome_packed(uint64_t seed, uint64_t n, uint64_t* d_packed, cudaStrea
 int unpack_genome(const uint64_t* d_packed, uint64_t n, char* d_ascii, cudaStream_t st);
 
 // ---- suffix array (sa_build.cu) ----
+// d_ext (optional, n entries): also filled, from the sort keys (27 leading bases per suffix) -- no extra gather
 int build_suffix_array(const uint64_t* d_genome, uint64_t n, uint32_t* d_sa, uint32_t* d_isa, cudaStream_t st,
-                       int* rounds_out);
+                       int* rounds_out, ExtEntry* d_ext = nullptr);
+constexpr int kExtBasesFromSort = 27;
+// ext[r] = {sa[r], 32 leading bases of that suffix} by a gather over the packed genome (for suffix arrays that were
+// loaded rather than built here)
+int build_ext_by_gather(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, ExtEntry* d_ext, cudaStream_t st);
 int invert_permutation(const uint32_t* d_src, uint64_t n, uint32_t* d_dst, cudaStream_t st);
 // sufcheck-style validation: counts adjacent pairs that are out of order / undecided within
 // max_chars, and positions where isa[sa[r]] != r.

@@ -60,6 +60,8 @@ struct sapling_b200_index {
 
   uint64_t* d_genome = nullptr;
   uint32_t* d_sa = nullptr;
+  ExtEntry* d_ext = nullptr;   // inline-prefix suffix array (large genomes; see want_ext)
+  int ext_bases = 0;
   uint32_t* d_isa = nullptr;   // only with KEEP_BUILD
   uint8_t* d_kflag = nullptr;  // only with KEEP_BUILD
   ModelEntry* d_model = nullptr;
@@ -94,6 +96,8 @@ struct sapling_b200_index {
     IndexView v;
     v.genome = d_genome;
     v.sa = d_sa;
+    v.ext = d_ext;
+    v.ext_bases = ext_bases;
     v.model = d_model;
     v.n = n;
     v.k = k;
@@ -129,6 +133,7 @@ struct sapling_b200_index {
     if (m1) cudaFreeHost(m1);
     cudaFree(d_genome);
     cudaFree(d_sa);
+    cudaFree(d_ext);
     cudaFree(d_isa);
     cudaFree(d_kflag);
     cudaFree(d_model);
@@ -405,6 +410,20 @@ int finish_model_checks(sapling_b200_index* ix) {
   return 0;
 }
 
+// Inline-prefix suffix array: trades 16 bytes of HBM per base for one DRAM line per probe instead of two.  It pays
+// once the packed genome no longer lives in L2 (measured: c3, 3.1 Gbp); below that the plain layout is as fast and
+// four times smaller.  SAPLING_B200_INLINE / _NO_INLINE (flags) or SAPLING_B200_INLINE=0|1 (environment) override.
+bool want_ext(const sapling_b200_index* ix) {
+  if (ix->flags & SAPLING_B200_NO_INLINE) return false;
+  if (const char* e = getenv("SAPLING_B200_INLINE")) return atoi(e) != 0;
+  if (ix->flags & SAPLING_B200_INLINE) return true;
+  if (ix->n < 400000000ull) return false;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+  // the entries themselves + the transient peak of the GPU suffix-array and model builders (~34 bytes per base)
+  return (double)free_b > 50.0 * (double)ix->n + 2e9;
+}
+
 // builds whatever is missing: SA (+ISA), kflags, model.  model_given: d_model & stats already set.
 int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, const Say& say) {
   const uint64_t n = ix->n;
@@ -412,8 +431,16 @@ int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, 
   if (!ix->d_sa) {
     say("Building suffix array\n");
     if (alloc_sa(ix, n) || dev_alloc(ix, &ix->d_isa, n)) return -1;
-    if (build_suffix_array(ix->d_genome, n, ix->d_sa, ix->d_isa, 0, &ix->sa_rounds)) return -1;
+    if (want_ext(ix)) {
+      if (dev_alloc(ix, &ix->d_ext, n)) return -1;
+      ix->ext_bases = kExtBasesFromSort;
+    }
+    if (build_suffix_array(ix->d_genome, n, ix->d_sa, ix->d_isa, 0, &ix->sa_rounds, ix->d_ext)) return -1;
     say("Built suffix array of size %llu\n", (unsigned long long)n);
+  } else if (!ix->d_ext && want_ext(ix)) {
+    if (dev_alloc(ix, &ix->d_ext, n)) return -1;
+    ix->ext_bases = 32;
+    if (build_ext_by_gather(ix->d_genome, n, ix->d_sa, ix->d_ext, 0)) return -1;
   }
   const bool need_build_arrays = !model_given || keep;
   if (need_build_arrays) {

@@ -27,9 +27,20 @@ struct __align__(16) ModelEntry {
 
 // Everything the query kernels read; passed by value as a kernel argument (lives in the
 // constant bank, so the scalars cost no memory traffic).
+// Inline-prefix suffix array ("ext"): rank -> {text position, the first ext_bases bases of that suffix}.  One 16-byte
+// entry answers a whole probe (rev[r] AND the suffix compare) from a single DRAM line, where the plain layout needs the
+// suffix-array line and then a dependent packed-genome line.  Used for genomes too large for L2.
+struct __align__(16) ExtEntry {
+  uint32_t pos;
+  uint32_t reserved;
+  uint64_t prefix;  // bases left-aligned, zero padded (same convention as load_bases32)
+};
+
 struct IndexView {
   const uint64_t* genome;
   const uint32_t* sa;
+  const ExtEntry* ext;  // nullptr: not built
+  int ext_bases;        // how many leading bases ext[].prefix holds (27 from the GPU builder's sort keys, 32 from a gather)
   const ModelEntry* model;
   uint64_t n;
   int k;
@@ -79,6 +90,7 @@ struct L2Policies {
 };
 inline L2Policies make_policies(unsigned) { return L2Policies{0, 0, 0}; }
 inline uint64_t ld_u64_pol(const uint64_t* p, uint64_t) { return *p; }
+inline uint4 ld_u32x4_pol(const uint4* p, uint64_t) { return *p; }
 inline uint32_t ld_u32_pol(const uint32_t* p, uint64_t) { return *p; }
 inline uint2 ld_u32x2_pol(const uint2* p, uint64_t) { return *p; }
 inline longlong2 ld_s64x2_pol(const longlong2* p, uint64_t) { return *p; }

@@ -99,6 +99,26 @@ kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
   }
 }
 
+// Inline-prefix variant: every probe is one 16-byte ExtEntry {position, leading bases}; the packed genome is not
+// touched at all (k <= ix.ext_bases).  For indexes whose genome does not fit L2 this halves the DRAM lines per query.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
+    KmerQuery q;
+    q.q = x << lsh;
+    q.k = (uint32_t)ix.k;
+    const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
+    const long long r = pl_query_from<false, false, KmerQuery, SaDirect, true, true>(ix, q, pred, 0, pol, SaDirect());
+    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
+    else out[i] = r;
+  }
+}
+
 // Traffic attribution (tools/ncu_hints.sh, SAPLING_B200_STAGES=1|2): the same kernel cut short after the model
 // lookup (1) or after the suffix-array sector fetch (2); never used to answer queries.
 __global__ void __launch_bounds__(kQueryThreads, 4)
@@ -380,11 +400,12 @@ inline int query_grid(size_t nq, int blocks_per_sm) {
 
 // Experiment knob (tools/gpu_experiments.py): SAPLING_B200_QV = resident blocks per SM the kernel is
 // compiled for (4: <=64 regs, 5, 6: <=40 regs, 8: <=32 regs).  Default chosen by measurement.
-static int query_variant(const IndexView& ix) {
+static int query_variant(const IndexView& ix, bool inline_layout) {
   const char* e = getenv("SAPLING_B200_QV");  // read per launch so one process can sweep variants
   // Measured (profiles/r1_experiments.md): while the genome and model mostly hit L2 more resident warps help (5
   // blocks/SM at c2: +8 %); once every access is a DRAM line and a TLB miss fewer do better (3 blocks/SM at c3: +9 %).
-  int v = e ? atoi(e) : (ix.n > 1000000000ull ? 3 : 5);
+  // The inline-prefix kernel is best at 4 (profiles/r1_c3_inline.md).
+  int v = e ? atoi(e) : (inline_layout ? 4 : (ix.n > 1000000000ull ? 3 : 5));
   if (v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
   return v;
 }
@@ -401,7 +422,9 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const bool pipelined = ix.narrow != nullptr && pe && atoi(pe) == 1;
   const bool line = le && atoi(le) == 1;
   const bool sector = !(se && atoi(se) == 0) && !pipelined && !line;
-  const int qv = query_variant(ix);
+  const char* ie = getenv("SAPLING_B200_INLINE_QUERY");  // 0 = ignore the inline-prefix array even if resident
+  const bool inl = ix.ext != nullptr && ix.k <= ix.ext_bases && !(ie && atoi(ie) == 0);
+  const int qv = query_variant(ix, inl);
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
       kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));
@@ -410,7 +433,14 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     }
   }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
-  if (sector) {
+  if (inl) {
+    switch (qv) {
+      case 3: SB_LAUNCH(kmer_query_inline_kernel, 3); break;
+      case 5: SB_LAUNCH(kmer_query_inline_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_inline_kernel, 6); break;
+      default: SB_LAUNCH(kmer_query_inline_kernel, 4); break;
+    }
+  } else if (sector) {
     switch (qv) {
       case 3: SB_LAUNCH(kmer_query_sector_kernel, 3); break;
       case 5: SB_LAUNCH(kmer_query_sector_kernel, 5); break;

@@ -41,7 +41,10 @@ struct KmerQuery {
   __device__ __forceinline__ uint32_t length() const { return k; }
   __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start,
                                                uint64_t pol) const {
-    const uint64_t g = load_bases_upto_pol(ix.genome, idx, k, pol);
+    return compare(ix, idx, load_bases_upto_pol(ix.genome, idx, k, pol), start);
+  }
+  // g = the bases of the suffix at idx, left-aligned (at least k of them, or up to the end of the text)
+  __device__ __forceinline__ ProbeResult compare(const IndexView& ix, uint64_t idx, uint64_t g, uint32_t start) const {
     uint64_t diff = q ^ g;
     if (start) diff &= (~0ull) >> (2u * start);  // getLcp trusts the first `start` characters
     const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
@@ -63,6 +66,9 @@ struct KmerQuery {
 struct StringQuery {
   const uint64_t* __restrict__ w;
   uint32_t slen_, length_;
+  __device__ __forceinline__ ProbeResult compare(const IndexView&, uint64_t, uint64_t, uint32_t) const {
+    return ProbeResult{};  // strings never use the inline-prefix path
+  }
   __device__ __forceinline__ uint32_t slen() const { return slen_; }
   __device__ __forceinline__ uint32_t length() const { return length_; }
   __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start,
@@ -191,7 +197,7 @@ struct SaSector {
 
 // The replay from a known prediction.  kHaveFirst: idx0 = rev[pred] was already loaded by the caller
 // (software-pipelined kernels issue that load one query ahead).
-template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true>
+template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true, bool kInline = false>
 __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
                                                    const uint64_t idx0, const L2Policies& pol, const Sa& sa) {
   const uint64_t n = ix.n;
@@ -205,9 +211,16 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
   int state = ST_PRED;
 
   for (;;) {
-    const uint64_t idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)sa.ld(ix, r, pol.sa);
+    uint64_t idx, g = 0;
+    if (kInline) {  // one 16-byte entry holds rev[r] and the bases to compare
+      const uint4 e = ld_u32x4_pol(reinterpret_cast<const uint4*>(ix.ext + r), pol.sa);
+      idx = e.x;
+      g = ((uint64_t)e.w << 32) | e.z;
+    } else {
+      idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)sa.ld(ix, r, pol.sa);
+    }
     if (state == ST_FINAL) return (long long)idx;
-    const ProbeResult pr = qy.probe(ix, idx, start, pol.genome);
+    const ProbeResult pr = kInline ? qy.compare(ix, idx, g, start) : qy.probe(ix, idx, start, pol.genome);
     const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
     bool to_search = false;
     switch (state) {

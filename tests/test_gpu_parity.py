@@ -253,3 +253,25 @@ def test_seed_batch_matches_align_seed_loop(S, oracle_built, name, k):
     assert (exp[0] >= 0).any()
     ix.close()
     port.close()
+
+
+@pytest.mark.parametrize("name", ["rand200k", "gc1991", "tandem50", "repeat_tailA", "polyC"])
+def test_inline_prefix_suffix_array(S, oracle_built, name):
+    """The inline-prefix suffix array (rank -> {position, leading bases}; default for genomes >= 400 Mbp) returns the
+    oracle's answers on both build paths: from the GPU suffix-array builder's sort keys (27 bases) and by gather for a
+    suffix array that was supplied (32 bases)."""
+    g = GENOMES[name]
+    for k, nb in ((21, -1), (16, 8), (11, -1), (27, 10), (31, 12)):
+        if len(g) < 4 * k:
+            continue
+        port = O.Port.from_memory(g, nb=nb, k=k)
+        kmers = F.query_mix(g, k, 6000, seed=3)
+        exp = port.query_batch(kmers, nthreads=4)
+        a = S.Sapling.from_memory(g, None, numBuckets=nb, k=k, flags=S.QUIET | S.INLINE)        # sort-key prefixes
+        b = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k, flags=S.QUIET | S.INLINE)     # gathered prefixes
+        c = S.Sapling.from_memory(g, None, numBuckets=nb, k=k, flags=S.QUIET | S.NO_INLINE)
+        assert a.device_bytes() >= c.device_bytes() + 16 * len(g)
+        for ix in (a, b, c):
+            assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb)
+            ix.close()
+        port.close()
