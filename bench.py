@@ -119,6 +119,30 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Pin this rank to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is allocated, so
+    that the end-to-end path copies from node-local memory (8 ranks x 2 directions of PCIe traffic otherwise cross the
+    socket interconnect).  Best effort: silently keeps the inherited affinity when sysfs does not say."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -341,6 +365,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -391,6 +416,7 @@ def main():
     total_ms = max_over_ranks(total_ms, dist, "cuda")
     value = world * nq * args.steps / (total_ms * 1e-3)
     kernel_ms = sum(step_ms) / len(step_ms)
+    kernel_name, kernel_bps = ix.query_kernel()
 
     # correctness of the timed output (self-check of sapling_example.cpp:144-154, on the device)
     last = (args.steps - 1) % nbatch
@@ -405,6 +431,7 @@ def main():
     ix.queryBatch(h_kmers, out=h_out)  # warm-up (allocates staging)
     ix.queryBatch(h_kmers, out=h_out)
     barrier()
+    launches0 = ix.launch_count()
     t0 = time.perf_counter()
     for s in range(e2e_steps):
         ix.queryBatch(h_kmers, out=h_out)
@@ -412,8 +439,7 @@ def main():
     e2e_s = time.perf_counter() - t0
     e2e_s = max_over_ranks(e2e_s, dist, "cuda")
     e2e_value = world * nq * e2e_steps / e2e_s
-    chunk = 1 << 22
-    e2e_launches = e2e_steps * ((nq + chunk - 1) // chunk)
+    e2e_launches = ix.launch_count() - launches0
 
     if rank != 0:
         if dist is not None:
@@ -438,11 +464,11 @@ def main():
         p_src = "counted by the oracle on this query set"
     bytes_per_query = 16 + 32 * (2 + probes_per_q)
     achieved = nq * bytes_per_query / (kernel_ms * 1e-3) / 1e9
-    traffic = None
+    traffic = None  # DRAM bytes per launch of THIS kernel on THIS workload from the committed ncu --set full capture
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            traffic = json.load(open(tp)).get(f"{args.workload}:{kernel_name}")
         except Exception:
             traffic = None
     gather = None
@@ -462,11 +488,11 @@ def main():
                    "seeds": {"genome": hex(SEED_G), "queries": hex(SEED_Q)}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_query": bytes_per_query,
-                     "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": "kmer_query_sector_kernel",
-                     "kernel_ms": kernel_ms, "random_sector_gather_gbs": gather},
+                     "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": kernel_name,
+                     "blocks_per_sm": kernel_bps, "kernel_ms": kernel_ms, "random_sector_gather_gbs": gather},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8,
-                "steps": e2e_steps, "api": "sapling_b200_query_batch (pinned host buffers)"},
+                "steps": e2e_steps, "api": "sapling_b200_query_batch (pinned host buffers)", "numa_node": numa_node},
         "gpu_launches": args.steps, "e2e_gpu_launches": e2e_launches,
         "clocks": clocks, "self_check": {"matching": int(n_match), "minus1": int(n_m1), "of": nq},
         "parity": parity,

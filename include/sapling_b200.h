@@ -35,6 +35,10 @@ typedef struct sapling_b200_index sapling_b200_index;
 #define SAPLING_B200_INLINE 8u       /* build the inline-prefix suffix array (16 B per base: rank -> {position, leading
                                         bases}) whatever the genome size; default: only for genomes >= 400 Mbp */
 #define SAPLING_B200_NO_INLINE 16u   /* never build it */
+#define SAPLING_B200_PACKED 32u      /* build the rank lines (16 B per base: one 128-byte DRAM line holds the positions
+                                        and leading bases of the 16 ranks around a prediction) whatever the genome
+                                        size; default: for genomes >= 50 Mbp when HBM allows */
+#define SAPLING_B200_NO_PACKED 64u   /* never build them */
 
 /* ---- construction -------------------------------------------------------------------------- */
 
@@ -96,6 +100,11 @@ int sapling_b200_check_sa(const sapling_b200_index *ix, uint32_t max_chars, uint
                           uint64_t *undecided, uint64_t *bad_perm);
 /* Device memory held by the index, in bytes. */
 uint64_t sapling_b200_device_bytes(const sapling_b200_index *ix);
+/* Number of k-mer query kernels launched through this handle so far (both batch entry points). */
+uint64_t sapling_b200_launch_count(const sapling_b200_index *ix);
+/* Name of the CUDA kernel sapling_b200_query_batch(_dev) launches for this index (which layout it reads depends on
+ * the genome size and the flags), and the resident blocks per SM it is compiled for. */
+const char *sapling_b200_query_kernel(const sapling_b200_index *ix, int *blocks_per_sm);
 
 /* ---- hashing (host, no GPU) ---------------------------------------------------------------- */
 

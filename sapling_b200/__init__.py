@@ -13,3 +13,5 @@ NO_COMPAT = 2
 KEEP_BUILD = 4
 INLINE = 8
 NO_INLINE = 16
+PACKED = 32
+NO_PACKED = 64

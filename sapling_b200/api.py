@@ -39,6 +39,8 @@ SYMBOLS = {
     "sapling_b200_write_sap": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sapling_b200_write_sa": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sapling_b200_device_bytes": (C.c_uint64, [C.c_void_p]),
+    "sapling_b200_launch_count": (C.c_uint64, [C.c_void_p]),
+    "sapling_b200_query_kernel": (C.c_char_p, [C.c_void_p, C.POINTER(C.c_int)]),
     "sapling_b200_kmerize": (C.c_int64, [C.c_int, C.c_char_p]),
     "sapling_b200_kmerize_adjusted": (C.c_int64, [C.c_int, C.c_int, C.c_char_p]),
     "sapling_b200_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -222,6 +224,15 @@ class Sapling:
 
     def device_bytes(self):
         return int(self._L.sapling_b200_device_bytes(self._h))
+
+    def launch_count(self):
+        return int(self._L.sapling_b200_launch_count(self._h))
+
+    def query_kernel(self):
+        """(name of the CUDA kernel queryBatch launches for this index, resident blocks per SM it is compiled for)."""
+        b = C.c_int(0)
+        name = self._L.sapling_b200_query_kernel(self._h, C.byref(b))
+        return (name or b"").decode(), b.value
 
     def _ck(self, rc):
         if rc != 0:

@@ -23,6 +23,9 @@ constexpr int kExtBasesFromSort = 27;
 // ext[r] = {sa[r], 32 leading bases of that suffix} by a gather over the packed genome (for suffix arrays that were
 // loaded rather than built here)
 int build_ext_by_gather(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, ExtEntry* d_ext, cudaStream_t st);
+// rank lines (common.cuh IndexView): d_packed must hold packed_sectors(n, shift) * 32 bytes
+int build_rank_lines(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, int bases, int shift,
+                     uint32_t* d_packed, cudaStream_t st);
 int invert_permutation(const uint32_t* d_src, uint64_t n, uint32_t* d_dst, cudaStream_t st);
 // sufcheck-style validation: counts adjacent pairs that are out of order / undecided within
 // max_chars, and positions where isa[sa[r]] != r.

@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -19,7 +20,8 @@
 namespace sb {
 
 // launchers in query.cu
-int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st);
+int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
+                      const char** name_out = nullptr);
 int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint64_t* d_word_off,
                         const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
                         long long* d_out, cudaStream_t st);
@@ -60,8 +62,10 @@ struct sapling_b200_index {
 
   uint64_t* d_genome = nullptr;
   uint32_t* d_sa = nullptr;
-  ExtEntry* d_ext = nullptr;   // inline-prefix suffix array (large genomes; see want_ext)
+  ExtEntry* d_ext = nullptr;   // inline-prefix suffix array (see want_ext)
   int ext_bases = 0;
+  uint32_t* d_packed = nullptr;  // rank lines (common.cuh IndexView; see want_packed)
+  int packed_bases = 0, packed_shift = 3;
   uint32_t* d_isa = nullptr;   // only with KEEP_BUILD
   uint8_t* d_kflag = nullptr;  // only with KEEP_BUILD
   ModelEntry* d_model = nullptr;
@@ -77,8 +81,11 @@ struct sapling_b200_index {
   // Chunks flow through three streams (upload, kernel, download) chained by events, kSlots chunks in flight, so
   // that both copy engines and the SMs stay busy at once: the host-fed rate is then set by PCIe (measured on the
   // bench box: 50 GB/s per direction with both directions active -> 6.2 G queries/s at 8 B in + 8 B out).
-  static constexpr size_t kChunk = 1u << 22;  // queries per chunk
-  static constexpr int kSlots = 4;
+  // A batch is cut into ~64 chunks (256 Ki .. 2 Mi queries each): the first upload and the last download are the only
+  // copies not overlapped with anything, so the finer the cut the closer the batch runs to the PCIe rate.
+  static constexpr size_t kChunk = 1u << 21;  // slot capacity, queries
+  static constexpr int kSlots = 6;
+  std::atomic<uint64_t> launches{0};  // query kernels launched through this handle (sapling_b200_launch_count)
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};  // 0 upload, 1 kernel, 2 download
   cudaEvent_t ev_up[kSlots] = {}, ev_k[kSlots] = {}, ev_down[kSlots] = {};
   uint64_t* d_in[kSlots] = {};
@@ -98,6 +105,9 @@ struct sapling_b200_index {
     v.sa = d_sa;
     v.ext = d_ext;
     v.ext_bases = ext_bases;
+    v.packed = d_packed;
+    v.packed_bases = packed_bases;
+    v.packed_shift = packed_shift;
     v.model = d_model;
     v.n = n;
     v.k = k;
@@ -134,6 +144,7 @@ struct sapling_b200_index {
     cudaFree(d_genome);
     cudaFree(d_sa);
     cudaFree(d_ext);
+    cudaFree(d_packed);
     cudaFree(d_isa);
     cudaFree(d_kflag);
     cudaFree(d_model);
@@ -413,10 +424,45 @@ int finish_model_checks(sapling_b200_index* ix) {
 // Inline-prefix suffix array: trades 16 bytes of HBM per base for one DRAM line per probe instead of two.  It pays
 // once the packed genome no longer lives in L2 (measured: c3, 3.1 Gbp); below that the plain layout is as fast and
 // four times smaller.  SAPLING_B200_INLINE / _NO_INLINE (flags) or SAPLING_B200_INLINE=0|1 (environment) override.
+// Rank lines (common.cuh IndexView): 16 bytes of HBM per base (8 with SAPLING_B200_PACKED_SHIFT=4) so that one
+// 128-byte DRAM line answers a whole query.  Pays as soon as the index no longer lives in L2.
+// SAPLING_B200_PACKED / _NO_PACKED (flags) or SAPLING_B200_PACKED=0|1 (environment) override the default.
+constexpr uint64_t kPackedMinGenome = 50000000ull;
+int packed_shift_setting() {
+  const char* e = getenv("SAPLING_B200_PACKED_SHIFT");
+  return (e && atoi(e) == 4) ? 4 : 3;
+}
+bool want_packed(const sapling_b200_index* ix) {
+  if (ix->flags & SAPLING_B200_NO_PACKED) return false;
+  if (const char* e = getenv("SAPLING_B200_PACKED")) return atoi(e) != 0;
+  if (ix->flags & SAPLING_B200_PACKED) return true;
+  if (ix->flags & SAPLING_B200_INLINE) return false;  // the caller asked for the other layout
+  if (ix->n < kPackedMinGenome) return false;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
+  // the lines are allocated after the suffix-array builder has released its transients (~34 bytes per base); the
+  // model builder then needs ~14 more next to them
+  return (double)free_b > (14.0 + 9.0 + (packed_shift_setting() == 3 ? 16.0 : 8.0)) * (double)ix->n + 2e9 &&
+         (double)free_b > 40.0 * (double)ix->n + 2e9;
+}
+
+int build_packed(sapling_b200_index* ix) {
+  if (ix->d_packed || !want_packed(ix)) return 0;
+  ix->packed_shift = packed_shift_setting();
+  ix->packed_bases = packed_bases_for(ix->n);
+  if (const char* e = getenv("SAPLING_B200_PACKED_BASES")) {  // test knob: force escapes / the long-query fallback
+    const int b = atoi(e);
+    if (b >= 4 && b <= 32) ix->packed_bases = b;
+  }
+  if (dev_alloc(ix, &ix->d_packed, packed_sectors(ix->n, ix->packed_shift) * 8)) return -1;
+  return build_rank_lines(ix->d_genome, ix->n, ix->d_sa, ix->packed_bases, ix->packed_shift, ix->d_packed, 0);
+}
+
 bool want_ext(const sapling_b200_index* ix) {
   if (ix->flags & SAPLING_B200_NO_INLINE) return false;
   if (const char* e = getenv("SAPLING_B200_INLINE")) return atoi(e) != 0;
   if (ix->flags & SAPLING_B200_INLINE) return true;
+  if (want_packed(ix)) return false;  // the rank lines supersede it
   if (ix->n < 400000000ull) return false;
   size_t free_b = 0, total_b = 0;
   if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -442,6 +488,7 @@ int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, 
     ix->ext_bases = 32;
     if (build_ext_by_gather(ix->d_genome, n, ix->d_sa, ix->d_ext, 0)) return -1;
   }
+  if (build_packed(ix)) return -1;
   const bool need_build_arrays = !model_given || keep;
   if (need_build_arrays) {
     if (!ix->d_isa) {
@@ -789,11 +836,24 @@ int sapling_b200_check_sa(const sapling_b200_index* ix, uint32_t max_chars, uint
 
 uint64_t sapling_b200_device_bytes(const sapling_b200_index* ix) { return ix ? ix->device_bytes : 0; }
 
+uint64_t sapling_b200_launch_count(const sapling_b200_index* ix) {
+  return ix ? ix->launches.load(std::memory_order_relaxed) : 0;
+}
+
+const char* sapling_b200_query_kernel(const sapling_b200_index* ix, int* blocks_per_sm) {
+  if (!ix) return "";
+  const char* name = "";
+  const int qv = launch_kmer_query(ix->view(), nullptr, 0, nullptr, nullptr, &name);
+  if (blocks_per_sm) *blocks_per_sm = qv;
+  return name;
+}
+
 // ---------------------------------------------------------------------------------------------
 
 int sapling_b200_query_batch_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, int64_t* d_out,
                                  void* stream) {
   if (!ix) { set_error("null index"); return -1; }
+  if (nq) ix->launches.fetch_add(1, std::memory_order_relaxed);
   return launch_kmer_query(ix->view(), d_kmers, nq, reinterpret_cast<long long*>(d_out),
                            static_cast<cudaStream_t>(stream));
 }
@@ -807,7 +867,13 @@ int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size
   const bool pin_in = is_pinned(kmers), pin_out = is_pinned(out);
   if ((!pin_in || !pin_out) && ensure_pinned(ix)) return -1;
   const IndexView v = ix->view();
-  const size_t CH = sapling_b200_index::kChunk;
+  size_t CH = ((nq / 64 + 65535) / 65536) * 65536;
+  if (CH < (1u << 18)) CH = 1u << 18;
+  if (CH > sapling_b200_index::kChunk) CH = sapling_b200_index::kChunk;
+  if (const char* e = getenv("SAPLING_B200_CHUNK_LOG2")) {  // experiment knob
+    const int l = atoi(e);
+    if (l >= 12 && (1ull << l) <= sapling_b200_index::kChunk) CH = 1ull << l;
+  }
   const int NS = sapling_b200_index::kSlots;
   const size_t nchunks = (nq + CH - 1) / CH;
   cudaStream_t s_up = ix->streams[0], s_k = ix->streams[1], s_down = ix->streams[2];
@@ -834,6 +900,7 @@ int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size
       SB_CUDA_CHECK(cudaEventRecord(ix->ev_up[s], s_up));
       SB_CUDA_CHECK(cudaStreamWaitEvent(s_k, ix->ev_up[s], 0));
       if (launch_kmer_query(v, ix->d_in[s], m, ix->d_out[s], s_k)) return -1;
+      ix->launches.fetch_add(1, std::memory_order_relaxed);
       SB_CUDA_CHECK(cudaEventRecord(ix->ev_k[s], s_k));
       SB_CUDA_CHECK(cudaStreamWaitEvent(s_down, ix->ev_k[s], 0));
       void* dst = pin_out ? (void*)(out + o) : (void*)ix->h_out[s];

@@ -36,11 +36,29 @@ struct __align__(16) ExtEntry {
   uint64_t prefix;  // bases left-aligned, zero padded (same convention as load_bases32)
 };
 
+// Rank lines ("packed" suffix array): the layout built around the one fact that decides this kernel on B200 -- an L2
+// miss fills a whole 128-byte DRAM line whatever the width of the load (profiles/r1_gather_dram_granularity.txt), so
+// the cost of a query is the number of distinct LINES it touches.  A rank line holds 16 consecutive ranks as four
+// self-contained 32-byte sectors; a sector answers four whole probes (rev[r] AND the suffix compare) on its own:
+//   v[0..1]  P0  = the first `packed_bases` bases of the suffix at the sector's first rank, as a 2*packed_bases-bit integer
+//   v[2..3]  D   = three 21-bit deltas d1,d2,d3 (bits 0-20, 21-41, 42-62): P_j = P0 + d_j   (suffixes are sorted, so d_j >= 0)
+//                  d_j == kPackedEscape, or bit 63 for entry 0: "compare this entry against the packed genome instead"
+//                  (delta overflow, or a suffix that ends within 32 bases of the end of the text)
+//   v[4..7]  the four text positions (the reference's rev[r])
+// Line L starts at rank L << packed_shift.  packed_shift == 4: lines tile the ranks.  packed_shift == 3: consecutive
+// lines overlap by half, so that the window [predicted - mostUnder, predicted + mostOver] of a typical query lies inside
+// ONE line (the "anchor" line) instead of straddling two with probability 1/4.
+constexpr uint32_t kPackedEscape = 0x1FFFFFu;
+constexpr int kPackedDeltaBits = 21;
+
 struct IndexView {
   const uint64_t* genome;
   const uint32_t* sa;
   const ExtEntry* ext;  // nullptr: not built
   int ext_bases;        // how many leading bases ext[].prefix holds (27 from the GPU builder's sort keys, 32 from a gather)
+  const uint32_t* packed;  // rank lines (see above); nullptr: not built
+  int packed_bases;        // leading bases per entry (<= 32)
+  int packed_shift;        // 3 or 4
   const ModelEntry* model;
   uint64_t n;
   int k;
@@ -94,6 +112,14 @@ inline uint4 ld_u32x4_pol(const uint4* p, uint64_t) { return *p; }
 inline uint32_t ld_u32_pol(const uint32_t* p, uint64_t) { return *p; }
 inline uint2 ld_u32x2_pol(const uint2* p, uint64_t) { return *p; }
 inline longlong2 ld_s64x2_pol(const longlong2* p, uint64_t) { return *p; }
+struct U32x8 {
+  uint32_t v[8];
+};
+inline U32x8 ld_u32x8_pol(const uint32_t* p, uint64_t) {
+  U32x8 r;
+  for (int i = 0; i < 8; i++) r.v[i] = p[i];
+  return r;
+}
 #else
 struct L2Policies {
   uint64_t genome, model, sa;
@@ -158,6 +184,50 @@ __device__ __forceinline__ uint64_t load_bases32(const uint64_t* __restrict__ ge
   if (o == 0) return hi;
   const uint64_t lo = __ldg(genome + w + 1);
   return (hi << o) | (lo >> (64u - o));
+}
+
+// One rank-line sector (see IndexView): ranks r0 .. r0+3 -> eight 32-bit words.  Shared by the build kernel
+// (sa_build.cu) and by the host simulation of the query code (tests/sim).
+__device__ __forceinline__ void pack_rank_sector(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ sa,
+                                                 uint64_t n, int bases, uint64_t r0, uint32_t out[8]) {
+  uint64_t P[4];
+  bool esc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const uint64_t r = r0 + (uint64_t)j;
+    if (r < n) {
+      const uint64_t pos = __ldg(sa + r);
+      out[4 + j] = (uint32_t)pos;
+      P[j] = load_bases32(genome, pos) >> (64 - 2 * bases);
+      esc[j] = n - pos < 32;  // the suffix ends inside the window: its compare needs the end-of-text rules
+    } else {  // padding past the last rank: never read by a query
+      out[4 + j] = 0;
+      P[j] = j ? P[j - 1] : 0;
+      esc[j] = true;
+    }
+  }
+  uint64_t D = esc[0] ? (1ull << 63) : 0ull;
+#pragma unroll
+  for (int j = 1; j < 4; j++) {
+    // suffixes are sorted, so P is non-decreasing except where a short suffix was zero-padded: those are escapes
+    const uint64_t d = P[j] >= P[0] ? P[j] - P[0] : (uint64_t)kPackedEscape;
+    const uint64_t f = (esc[j] || d >= (uint64_t)kPackedEscape) ? (uint64_t)kPackedEscape : d;
+    D |= f << (kPackedDeltaBits * (j - 1));
+  }
+  out[0] = (uint32_t)P[0];
+  out[1] = (uint32_t)(P[0] >> 32);
+  out[2] = (uint32_t)D;
+  out[3] = (uint32_t)(D >> 32);
+}
+// sectors in a rank-line array over n ranks (one extra line so that the last anchor line is whole)
+inline uint64_t packed_sectors(uint64_t n, int shift) { return (((n + (1ull << shift) - 1) >> shift) + 2) * 4; }
+// how many leading bases a 21-bit delta can carry: the mean gap between consecutive distinct prefixes, 4^bases / n,
+// must stay well (16x) below 2^21 or escapes stop being rare
+inline int packed_bases_for(uint64_t n) {
+  int lg = 0;
+  while ((1ull << (lg + 1)) <= n) lg++;
+  int b = (lg + 17) / 2;
+  return b < 8 ? 8 : (b > 32 ? 32 : b);
 }
 
 // Same, but only `need` (<=32) leading bases are required: skips the second word when the first

@@ -70,7 +70,8 @@ kmer_query_pipelined_kernel(const IndexView ix, const uint64_t* __restrict__ kme
     KmerQuery q;
     q.q = x0 << lsh;
     q.k = (uint32_t)ix.k;
-    const long long r = pl_query_from<false, true>(ix, q, pred0, idx0, pol, SaDirect());
+    SaDirect sad;
+    const long long r = pl_query_from<false, true>(ix, q, pred0, idx0, pol, sad);
     __stcs(out + i, r);
     x0 = x1; x1 = x2; x2 = x3;
     pred0 = pred1; idx0 = idx1; m1 = m2;
@@ -113,7 +114,31 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     q.q = x << lsh;
     q.k = (uint32_t)ix.k;
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
-    const long long r = pl_query_from<false, false, KmerQuery, SaDirect, true, true>(ix, q, pred, 0, pol, SaDirect());
+    SaDirect sad;
+    const long long r = pl_query_from<false, false, KmerQuery, SaDirect, true, 1>(ix, q, pred, 0, pol, sad);
+    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
+    else out[i] = r;
+  }
+}
+
+// Rank-line variant: every probe is answered by a 32-byte sector {4 positions, 4 prefixes}, and the sectors a typical
+// query needs share one 128-byte DRAM line (query.cuh SaPacked); the packed genome is read only for escaped entries
+// and for queries longer than the entries' prefix.
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
+    KmerQuery q;
+    q.q = x << lsh;
+    q.k = (uint32_t)ix.k;
+    const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
+    SaPacked sa;
+    sa.anchor(ix, pred);
+    const long long r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
     if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
     else out[i] = r;
   }
@@ -410,8 +435,10 @@ static int query_variant(const IndexView& ix, bool inline_layout) {
   return v;
 }
 
-int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st) {
-  if (nq == 0) return 0;
+// name_out != nullptr: only report which kernel a batch would run on (introspection for bench.py), launch nothing
+int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
+                      const char** name_out) {
+  if (nq == 0 && !name_out) return 0;
   const char* gm = getenv("SAPLING_B200_GRID_MULT");  // grid = 148 * blocks/SM * mult (experiment knob)
   const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 2) : 2;
   // Measured on the c2 workload (profiles/r1_experiments.md): the plain one-thread-per-query kernel at 4 blocks/SM
@@ -424,7 +451,9 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const bool sector = !(se && atoi(se) == 0) && !pipelined && !line;
   const char* ie = getenv("SAPLING_B200_INLINE_QUERY");  // 0 = ignore the inline-prefix array even if resident
   const bool inl = ix.ext != nullptr && ix.k <= ix.ext_bases && !(ie && atoi(ie) == 0);
-  const int qv = query_variant(ix, inl);
+  const char* pe2 = getenv("SAPLING_B200_PACKED_QUERY");  // 0 = ignore the rank lines even if resident
+  const bool packed = ix.packed != nullptr && !(pe2 && atoi(pe2) == 0);
+  const int qv = query_variant(ix, inl || packed);
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
       kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));
@@ -432,8 +461,21 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
       return 0;
     }
   }
+  if (name_out) {
+    *name_out = packed ? "kmer_query_packed_kernel" : inl ? "kmer_query_inline_kernel" : sector ? "kmer_query_sector_kernel"
+                : (line && pipelined) ? "kmer_query_line_pipelined_kernel" : line ? "kmer_query_line_kernel"
+                : pipelined ? "kmer_query_pipelined_kernel" : "kmer_query_kernel";
+    return qv;
+  }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
-  if (inl) {
+  if (packed) {
+    switch (qv) {
+      case 3: SB_LAUNCH(kmer_query_packed_kernel, 3); break;
+      case 5: SB_LAUNCH(kmer_query_packed_kernel, 5); break;
+      case 6: SB_LAUNCH(kmer_query_packed_kernel, 6); break;
+      default: SB_LAUNCH(kmer_query_packed_kernel, 4); break;
+    }
+  } else if (inl) {
     switch (qv) {
       case 3: SB_LAUNCH(kmer_query_inline_kernel, 3); break;
       case 5: SB_LAUNCH(kmer_query_inline_kernel, 5); break;

@@ -39,6 +39,7 @@ struct KmerQuery {
   uint32_t k;
   __device__ __forceinline__ uint32_t slen() const { return k; }
   __device__ __forceinline__ uint32_t length() const { return k; }
+  __device__ __forceinline__ uint64_t head() const { return q; }  // first 32 bases, left-aligned
   __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start,
                                                uint64_t pol) const {
     return compare(ix, idx, load_bases_upto_pol(ix.genome, idx, k, pol), start);
@@ -71,6 +72,7 @@ struct StringQuery {
   }
   __device__ __forceinline__ uint32_t slen() const { return slen_; }
   __device__ __forceinline__ uint32_t length() const { return length_; }
+  __device__ __forceinline__ uint64_t head() const { return w[0]; }
   __device__ __forceinline__ ProbeResult probe(const IndexView& ix, uint64_t idx, uint32_t start,
                                                uint64_t pol) const {
     const uint64_t room = ix.n - idx;
@@ -127,6 +129,40 @@ static unsigned long long g_sim_skip_tried = 0, g_sim_skip_ok = 0;
 struct SaDirect {
   __device__ __forceinline__ uint32_t ld(const IndexView& ix, uint64_t r, uint64_t pol) const {
     return ld_u32_pol(ix.sa + r, pol);
+  }
+};
+
+// Rank-line reader (layout: common.cuh IndexView).  The query's anchor line is the one that contains
+// [predicted - min(mostUnder, 4), +16 ranks): with overlapping lines (packed_shift 3) every rank the typical replay
+// touches is served by that ONE 128-byte DRAM line; ranks outside it are read from the line that starts at or
+// below them.  The last sector read stays in registers (the replay often asks for neighbouring ranks in turn).
+struct SaPacked {
+  uint64_t abase;  // first rank of the anchor line
+  uint64_t cur;    // first rank of the sector held in e (multiple of 4); ~0: none
+  U32x8 e;
+  __device__ __forceinline__ void anchor(const IndexView& ix, uint64_t pred) {
+    const uint64_t back = (uint64_t)(ix.mostUnder < 4 ? ix.mostUnder : 4);
+    const uint64_t lo = ix.packed_shift == 3 ? (pred > back ? pred - back : 0) : pred;
+    abase = (lo >> ix.packed_shift) << ix.packed_shift;
+    cur = ~0ull;
+  }
+  // rev[r]; *g = the entry's leading bases left-aligned; *esc = compare against the packed genome instead
+  __device__ __forceinline__ uint64_t get(const IndexView& ix, uint64_t r, uint64_t pol, uint64_t* g, bool* esc) {
+    const uint64_t s4 = r & ~3ull;
+    if (s4 != cur) {
+      const uint64_t first = (r - abase < 16) ? abase : ((r >> ix.packed_shift) << ix.packed_shift);
+      const uint64_t sector = (first >> ix.packed_shift) * 4 + ((r - first) >> 2);
+      e = ld_u32x8_pol(ix.packed + sector * 8, pol);
+      cur = s4;
+    }
+    const unsigned j = (unsigned)r & 3u;
+    const uint64_t P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
+    const uint64_t D = ((uint64_t)e.v[3] << 32) | e.v[2];
+    const uint64_t d = j ? ((D >> (kPackedDeltaBits * (j - 1))) & (uint64_t)kPackedEscape) : 0ull;
+    *esc = j ? (d == (uint64_t)kPackedEscape) : ((D >> 63) != 0);
+    *g = (P0 + d) << (64 - 2 * ix.packed_bases);
+    const uint32_t a = (j & 1u) ? e.v[5] : e.v[4], b = (j & 1u) ? e.v[7] : e.v[6];
+    return (uint64_t)((j & 2u) ? b : a);
   }
 };
 
@@ -197,9 +233,10 @@ struct SaSector {
 
 // The replay from a known prediction.  kHaveFirst: idx0 = rev[pred] was already loaded by the caller
 // (software-pipelined kernels issue that load one query ahead).
-template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true, bool kInline = false>
+// kMode: 0 = {suffix array, packed genome}; 1 = inline-prefix entries (ExtEntry); 2 = rank lines (SaPacked).
+template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true, int kMode = 0>
 __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
-                                                   const uint64_t idx0, const L2Policies& pol, const Sa& sa) {
+                                                   const uint64_t idx0, const L2Policies& pol, Sa& sa) {
   const uint64_t n = ix.n;
   const uint64_t nm1 = n - 1;
   const uint32_t slen = qy.slen(), length = qy.length();
@@ -212,15 +249,22 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
 
   for (;;) {
     uint64_t idx, g = 0;
-    if (kInline) {  // one 16-byte entry holds rev[r] and the bases to compare
+    bool use_genome = true;
+    if constexpr (kMode == 1) {  // one 16-byte entry holds rev[r] and the bases to compare
       const uint4 e = ld_u32x4_pol(reinterpret_cast<const uint4*>(ix.ext + r), pol.sa);
       idx = e.x;
       g = ((uint64_t)e.w << 32) | e.z;
+      use_genome = false;
+    } else if constexpr (kMode == 2) {  // one 32-byte sector holds four such entries
+      idx = sa.get(ix, r, pol.sa, &g, &use_genome);
+      // an entry carries packed_bases bases: a longer query that agrees on all of them is decided by the genome
+      if (!use_genome && (int)length > ix.packed_bases)
+        use_genome = ((qy.head() ^ g) >> (64 - 2 * ix.packed_bases)) == 0;
     } else {
       idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)sa.ld(ix, r, pol.sa);
     }
     if (state == ST_FINAL) return (long long)idx;
-    const ProbeResult pr = kInline ? qy.compare(ix, idx, g, start) : qy.probe(ix, idx, start, pol.genome);
+    const ProbeResult pr = use_genome ? qy.probe(ix, idx, start, pol.genome) : qy.compare(ix, idx, g, start);
     const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
     bool to_search = false;
     switch (state) {
@@ -377,7 +421,8 @@ template <bool kGallop, typename Query>
 __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& qy, uint64_t kmer) {
   const L2Policies pol = make_policies(ix.hints);
   const uint64_t pred = clamp_prediction(ix, predict_rank(ix, kmer, pol.model));  // :161
-  return pl_query_from<kGallop, false>(ix, qy, pred, 0, pol, SaDirect());
+  SaDirect sa;
+  return pl_query_from<kGallop, false>(ix, qy, pred, 0, pol, sa);
 }
 
 }  // namespace sb

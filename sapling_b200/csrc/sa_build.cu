@@ -130,6 +130,20 @@ __global__ void sa_invert(const uint32_t* __restrict__ src, uint64_t n, uint32_t
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[src[i]] = (uint32_t)i;
 }
 
+// rank lines (common.cuh IndexView): one thread per 32-byte sector
+__global__ void rank_lines_kernel(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ sa, uint64_t n,
+                                  int bases, int shift, uint64_t sectors, uint32_t* __restrict__ out) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < sectors; s += stride) {
+    const uint64_t r0 = ((s >> 2) << shift) + ((s & 3u) << 2);
+    uint32_t v[8];
+    pack_rank_sector(genome, sa, n, bases, r0, v);
+    uint4* dst = reinterpret_cast<uint4*>(out + s * 8);
+    dst[0] = make_uint4(v[0], v[1], v[2], v[3]);
+    dst[1] = make_uint4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 struct MaxOp {
   __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
 };
@@ -159,6 +173,14 @@ int invert_permutation(const uint32_t* d_src, uint64_t n, uint32_t* d_dst, cudaS
 // d_sa (out): rank -> position.  d_isa (out): position -> rank.  Both uint32[n], caller-allocated.
 int build_ext_by_gather(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, ExtEntry* d_ext, cudaStream_t st) {
   ext_gather<<<grid_for(n), 256, 0, st>>>(d_genome, d_sa, n, d_ext);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int build_rank_lines(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, int bases, int shift,
+                     uint32_t* d_packed, cudaStream_t st) {
+  const uint64_t sectors = packed_sectors(n, shift);
+  rank_lines_kernel<<<grid_for(sectors), 256, 0, st>>>(d_genome, d_sa, n, bases, shift, sectors, d_packed);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -46,6 +46,44 @@ void sim_kmer_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* m
   }
 }
 
+// rank lines (common.cuh IndexView) built by the same pack_rank_sector the build kernel runs, then the packed-mode
+// replay.  out_packed may be NULL; otherwise it receives packed_sectors(n, shift) * 8 words (to compare with the GPU's).
+void sim_kmer_batch_packed(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
+                           const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
+                           unsigned long long* oob, int bases, int shift, uint32_t* out_packed,
+                           unsigned long long* n_escapes) {
+  const uint64_t sectors = sb::packed_sectors(n, shift);
+  uint32_t* packed = out_packed ? out_packed : new uint32_t[sectors * 8];
+  unsigned long long esc = 0;
+  for (uint64_t s = 0; s < sectors; s++) {
+    const uint64_t r0 = ((s >> 2) << shift) + ((s & 3u) << 2);
+    sb::pack_rank_sector(genome, sa, n, bases, r0, packed + s * 8);
+    const uint64_t D = ((uint64_t)packed[s * 8 + 3] << 32) | packed[s * 8 + 2];
+    if (r0 < n) {
+      esc += (D >> 63);
+      for (int j = 1; j < 4; j++) esc += ((D >> (21 * (j - 1))) & 0x1FFFFFu) == 0x1FFFFFu && r0 + j < n;
+    }
+  }
+  if (n_escapes) *n_escapes = esc;
+  sb::IndexView ix;
+  ix.genome = genome; ix.sa = sa; ix.ext = nullptr; ix.ext_bases = 0;
+  ix.packed = packed; ix.packed_bases = bases; ix.packed_shift = shift;
+  ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
+  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
+  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
+  ix.compat = compat; ix.oob_counter = oob;
+  ix.narrow = nullptr; ix.last_x = 0; ix.last_y = 0; ix.hints = 0;
+  const sb::L2Policies pol = sb::make_policies(0);
+  for (size_t i = 0; i < nq; i++) {
+    sb::KmerQuery q; q.q = kmers[i] << (64 - 2 * k); q.k = (uint32_t)k;
+    const uint64_t pred = sb::clamp_prediction(ix, sb::predict_rank(ix, kmers[i], pol.model));
+    sb::SaPacked sp;
+    sp.anchor(ix, pred);
+    out[i] = sb::pl_query_from<false, false, sb::KmerQuery, sb::SaPacked, true, 2>(ix, q, pred, 0, pol, sp);
+  }
+  if (!out_packed) delete[] packed;
+}
+
 void sim_string_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                       const int* five, int compat, const uint64_t* words, const uint64_t* word_off,
                       const uint32_t* slens, const uint32_t* lengths, const int64_t* kmers, size_t nq, int64_t* out,

@@ -82,7 +82,48 @@ def _sim():
     L.sim_string_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
                                    O.u64p, O.u32p, O.u32p, O.i64p, C.c_size_t, O.i64p, C.POINTER(C.c_uint64),
                                    C.c_void_p, O.i64p]
+    L.sim_kmer_batch_packed.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
+                                        C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_void_p,
+                                        C.POINTER(C.c_uint64)]
     return L
+
+
+@pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])
+def test_rank_line_query_code_on_host_matches_oracle(oracle_built, name):
+    """The rank-line layout (common.cuh pack_rank_sector + query.cuh SaPacked, the default for genomes >= 50 Mbp)
+    compiled for the host == oracle: overlapping and tiling lines, prefixes shorter than / as long as / longer than k
+    (genome fallback on ties), prefixes wide enough that 21-bit deltas overflow (escapes), suffixes at the end of the
+    text, and the collapsed left window of SURVEY F5."""
+    L = _sim()
+    g = F.small_genomes()[name]
+    n = len(g)
+    escapes = 0
+    for k, nb in ((21, -1), (11, 4), (31, 10), (16, -1)):
+        if n < 4 * k:
+            continue
+        base = O.Port.from_memory(g, nb=nb, k=k)
+        packed, sa = F.pack_genome(g), base.sa
+        model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
+        kmers = F.query_mix(g, k, 3000)
+        # every suffix of the last 40 positions as a query too (short suffixes are escaped entries)
+        tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(max(0, n - 40), n)], dtype=np.uint64)
+        kmers = np.concatenate([kmers, tail])
+        f0 = list(base.five)
+        for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30]):
+            port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
+            five = np.array(five_t, dtype=np.int32)
+            exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
+            for bases in (6, 12, 16, 21, 32):
+                for shift in (3, 4):
+                    out = np.empty(len(kmers), dtype=np.int64)
+                    c, e = C.c_uint64(0), C.c_uint64(0)
+                    L.sim_kmer_batch_packed(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c),
+                                            bases, shift, None, C.byref(e))
+                    assert np.array_equal(out, exp) and c.value == oob, (name, k, nb, five_t, bases, shift)
+                    escapes += e.value
+            port.close()
+        base.close()
+    assert escapes > 0  # at least the short suffixes at the end of the text
 
 
 @pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])

@@ -275,3 +275,37 @@ def test_inline_prefix_suffix_array(S, oracle_built, name):
             assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb)
             ix.close()
         port.close()
+
+
+@pytest.mark.parametrize("name", ["rand200k", "gc1991", "gc0110", "tandem50", "repeat_tailA", "polyC"])
+def test_rank_line_layout(S, oracle_built, name, monkeypatch):
+    """The rank-line layout (one 32-byte sector = four {position, prefix} entries; default for genomes >= 50 Mbp)
+    returns the oracle's answers: overlapping (shift 3) and tiling (shift 4) lines, prefixes shorter than / equal to /
+    longer than k (the first falls back to the packed genome on ties, the last overflows the 21-bit deltas and
+    escapes), every resident-blocks variant of the kernel, and suffixes at the very end of the text."""
+    g = GENOMES[name]
+    for k, nb in ((21, -1), (16, 8), (11, -1), (31, 12)):
+        if len(g) < 4 * k:
+            continue
+        port = O.Port.from_memory(g, nb=nb, k=k)
+        kmers = F.query_mix(g, k, 6000, seed=7)
+        tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(len(g) - 40, len(g))], dtype=np.uint64)
+        kmers = np.concatenate([kmers, tail])
+        exp = port.query_batch(kmers, nthreads=4)
+        plain = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k, flags=S.QUIET | S.NO_PACKED | S.NO_INLINE)
+        assert plain.query_kernel()[0] == "kmer_query_sector_kernel"
+        for shift in ("3", "4"):
+            for bases in ("0", "8", "14", "32"):   # 0 = the default for this genome size
+                monkeypatch.setenv("SAPLING_B200_PACKED_SHIFT", shift)
+                monkeypatch.setenv("SAPLING_B200_PACKED_BASES", bases)
+                ix = S.Sapling.from_memory(g, port.sa if bases != "8" else None, numBuckets=nb, k=k,
+                                           flags=S.QUIET | S.PACKED)
+                assert ix.query_kernel()[0] == "kmer_query_packed_kernel"
+                assert ix.device_bytes() >= plain.device_bytes() + (16 if shift == "3" else 8) * len(g)
+                for qv in ("3", "4", "5", "6"):
+                    monkeypatch.setenv("SAPLING_B200_QV", qv)
+                    assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb, shift, bases, qv)
+                monkeypatch.delenv("SAPLING_B200_QV")
+                ix.close()
+        plain.close()
+        port.close()
