@@ -81,10 +81,11 @@ struct sapling_b200_index {
   // Chunks flow through three streams (upload, kernel, download) chained by events, kSlots chunks in flight, so
   // that both copy engines and the SMs stay busy at once: the host-fed rate is then set by PCIe (measured on the
   // bench box: 50 GB/s per direction with both directions active -> 6.2 G queries/s at 8 B in + 8 B out).
-  // A batch is cut into ~64 chunks (256 Ki .. 2 Mi queries each): the first upload and the last download are the only
-  // copies not overlapped with anything, so the finer the cut the closer the batch runs to the PCIe rate.
-  static constexpr size_t kChunk = 1u << 21;  // slot capacity, queries
-  static constexpr int kSlots = 6;
+  // Chunk size: the first upload and the last download are not overlapped with anything (favours small chunks), but
+  // every chunk costs ~40 us of copy-engine / cross-stream latency (favours large ones).  Measured on B200 (c2, 50 M
+  // queries): 4 Mi queries per chunk 5.4 G q/s, 2 Mi 5.3, 0.8 Mi 4.5 (profiles/r1u_*); the optimum grows like sqrt(nq).
+  static constexpr size_t kChunk = 1u << 22;  // slot capacity, queries
+  static constexpr int kSlots = 4;
   std::atomic<uint64_t> launches{0};  // query kernels launched through this handle (sapling_b200_launch_count)
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};  // 0 upload, 1 kernel, 2 download
   cudaEvent_t ev_up[kSlots] = {}, ev_k[kSlots] = {}, ev_down[kSlots] = {};
@@ -867,9 +868,8 @@ int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size
   const bool pin_in = is_pinned(kmers), pin_out = is_pinned(out);
   if ((!pin_in || !pin_out) && ensure_pinned(ix)) return -1;
   const IndexView v = ix->view();
-  size_t CH = ((nq / 64 + 65535) / 65536) * 65536;
-  if (CH < (1u << 18)) CH = 1u << 18;
-  if (CH > sapling_b200_index::kChunk) CH = sapling_b200_index::kChunk;
+  size_t CH = 1u << 18;  // ~sqrt(2 * nq * 1e5) rounded to a power of two, within [256 Ki, 4 Mi]
+  while (CH < sapling_b200_index::kChunk && (double)(2 * CH) * (double)(2 * CH) <= 8.0 * (double)nq * 1e5) CH *= 2;
   if (const char* e = getenv("SAPLING_B200_CHUNK_LOG2")) {  // experiment knob
     const int l = atoi(e);
     if (l >= 12 && (1ull << l) <= sapling_b200_index::kChunk) CH = 1ull << l;

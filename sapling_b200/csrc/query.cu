@@ -144,6 +144,104 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
   }
 }
 
+// Lane-refill variant of the rank-line kernel.  In the kernels above a warp holds 32 queries and runs until the
+// slowest of them is answered: the replay takes 1 to ~6 probes (mean 2.3), so on average barely half the lanes of an
+// issued instruction do useful work (ncu: 17 active threads per warp instruction) and every query pays the dependent
+// latency of the k-mer load, the model load and the longest probe chain in its warp.  Here a lane that finishes takes
+// the next query at once:
+//   * each warp owns a contiguous slice of the batch and reads it in 32-k-mer blocks, one coalesced load per block,
+//     two blocks ahead (registers; lanes fetch their k-mer with a shuffle);
+//   * every lane keeps a STANDBY query whose model checkpoints were requested when the standby slot was filled and are
+//     consumed only when the current query finishes, at least one probe later -- so the k-mer and model loads never sit
+//     on the critical path;
+//   * one loop iteration = one probe (one rank-line sector) for every lane of the warp.
+// Needs the narrow model layout.  Results are written straight to out[query index].
+template <int kMinBlocks>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_packed_refill_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq,
+                                long long* __restrict__ out) {
+  using Rp = Replay<false, false, KmerQuery, SaPacked, true, 2>;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const size_t warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  const size_t gw = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // slice of this warp: whole 32-query blocks, the last warp takes the ragged tail
+  const size_t blocks_total = (nq + 31) >> 5;
+  const size_t per = (blocks_total + warps - 1) / warps;
+  const size_t begin = gw * per * 32 < nq ? gw * per * 32 : nq;
+  const size_t end = (gw + 1) * per * 32 < nq ? (gw + 1) * per * 32 : nq;
+  if (begin >= end) return;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  auto load_block = [&](size_t first) -> uint64_t {  // k-mer (first + lane), clamped inside the slice
+    const size_t i = first + lane;
+    return __ldcs(kmers + (i < end ? i : end - 1));
+  };
+  uint64_t blk0 = load_block(begin), blk1 = load_block(begin + 32), blk2 = load_block(begin + 64);
+  size_t blk_first = begin;  // query index of blk0's lane 0
+  size_t next = begin;       // next query index to hand out (warp-uniform)
+
+  bool cur_valid = false, sb_valid = false;
+  size_t cur_qi = 0, sb_qi = 0;
+  uint64_t sb_x = 0;
+  NarrowPair sb_m;
+  sb_m.e0 = make_uint2(0, 0);
+  sb_m.e1 = make_uint2(0, 0);
+  KmerQuery q;
+  q.q = 0;
+  q.k = (uint32_t)ix.k;
+  Rp rp;
+  rp.begin(0);
+  SaPacked sa;
+  sa.abase = 0;
+  sa.cur = ~0ull;
+
+  for (;;) {
+    // A: a lane without a current query promotes its standby (its checkpoints were requested an iteration ago or more)
+    if (!cur_valid && sb_valid) {
+      const uint64_t pred = clamp_prediction(ix, narrow_finish(ix, sb_x, sb_m, pol.model));
+      q.q = sb_x << lsh;
+      cur_qi = sb_qi;
+      rp.begin(pred);
+      sa.anchor(ix, pred);
+      cur_valid = true;
+      sb_valid = false;
+    }
+    // B: lanes with an empty standby slot take the next query indices, in lane order
+    const unsigned want = __ballot_sync(0xffffffffu, !sb_valid);
+    if (want && next < end) {
+      const size_t mine = next + (size_t)__popc(want & lt_mask);
+      const unsigned off = (unsigned)(mine - blk_first);  // < 64: at most 32 indices handed out per iteration
+      const uint64_t a = __shfl_sync(0xffffffffu, blk0, (int)(off & 31u));
+      const uint64_t b = __shfl_sync(0xffffffffu, blk1, (int)(off & 31u));
+      if (!sb_valid && mine < end) {
+        sb_x = off < 32u ? a : b;
+        sb_qi = mine;
+        sb_m = narrow_load(ix, sb_x, pol.model);  // asynchronous: not consumed before step A of a later iteration
+        sb_valid = true;
+      }
+      next += (size_t)__popc(want);
+      if (next > end) next = end;
+      if (next - blk_first >= 32) {  // blk0 is used up: rotate, fetch two blocks ahead
+        blk0 = blk1;
+        blk1 = blk2;
+        blk_first += 32;
+        blk2 = load_block(blk_first + 64);
+      }
+    }
+    // C: done when no lane holds a query any more
+    if (!__any_sync(0xffffffffu, cur_valid || sb_valid)) break;
+    // D: one probe
+    if (cur_valid) {
+      long long res;
+      if (rp.step(ix, q, 0, pol, sa, &res)) {
+        __stcs(out + cur_qi, res);
+        cur_valid = false;
+      }
+    }
+  }
+}
+
 // Traffic attribution (tools/ncu_hints.sh, SAPLING_B200_STAGES=1|2): the same kernel cut short after the model
 // lookup (1) or after the suffix-array sector fetch (2); never used to answer queries.
 __global__ void __launch_bounds__(kQueryThreads, 4)
@@ -431,7 +529,7 @@ static int query_variant(const IndexView& ix, bool inline_layout) {
   // blocks/SM at c2: +8 %); once every access is a DRAM line and a TLB miss fewer do better (3 blocks/SM at c3: +9 %).
   // The inline-prefix kernel is best at 4 (profiles/r1_c3_inline.md).
   int v = e ? atoi(e) : (inline_layout ? 4 : (ix.n > 1000000000ull ? 3 : 5));
-  if (v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
+  if (v != 2 && v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
   return v;
 }
 
@@ -453,6 +551,8 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const bool inl = ix.ext != nullptr && ix.k <= ix.ext_bases && !(ie && atoi(ie) == 0);
   const char* pe2 = getenv("SAPLING_B200_PACKED_QUERY");  // 0 = ignore the rank lines even if resident
   const bool packed = ix.packed != nullptr && !(pe2 && atoi(pe2) == 0);
+  const char* re = getenv("SAPLING_B200_REFILL");  // 0 = one query per lane per pass (no lane refill)
+  const bool refill = packed && ix.narrow != nullptr && !(re && atoi(re) == 0);
   const int qv = query_variant(ix, inl || packed);
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
@@ -462,13 +562,25 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     }
   }
   if (name_out) {
-    *name_out = packed ? "kmer_query_packed_kernel" : inl ? "kmer_query_inline_kernel" : sector ? "kmer_query_sector_kernel"
+    *name_out = refill ? "kmer_query_packed_refill_kernel" : packed ? "kmer_query_packed_kernel" : inl ? "kmer_query_inline_kernel" : sector ? "kmer_query_sector_kernel"
                 : (line && pipelined) ? "kmer_query_line_pipelined_kernel" : line ? "kmer_query_line_kernel"
                 : pipelined ? "kmer_query_pipelined_kernel" : "kmer_query_kernel";
     return qv;
   }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
-  if (packed) {
+  if (refill) {
+    // persistent: every warp streams through one contiguous slice of the batch, so one resident wave (unless
+    // SAPLING_B200_GRID_MULT says otherwise)
+#define SB_LAUNCH_R(bps) \
+  kmer_query_packed_refill_kernel<bps><<<query_grid(nq, bps * (gm ? mult : 1)), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
+    switch (qv) {
+      case 2: SB_LAUNCH_R(2); break;
+      case 3: SB_LAUNCH_R(3); break;
+      case 5: SB_LAUNCH_R(5); break;
+      default: SB_LAUNCH_R(4); break;
+    }
+#undef SB_LAUNCH_R
+  } else if (packed) {
     switch (qv) {
       case 3: SB_LAUNCH(kmer_query_packed_kernel, 3); break;
       case 5: SB_LAUNCH(kmer_query_packed_kernel, 5); break;

@@ -234,20 +234,33 @@ struct SaSector {
 // The replay from a known prediction.  kHaveFirst: idx0 = rev[pred] was already loaded by the caller
 // (software-pipelined kernels issue that load one query ahead).
 // kMode: 0 = {suffix array, packed genome}; 1 = inline-prefix entries (ExtEntry); 2 = rank lines (SaPacked).
+//
+// The replay of one query as an explicit state: begin() after the prediction, then step() once per probe until it
+// returns true.  pl_query_from() below simply loops; the lane-refill kernel (query.cu) interleaves the steps of
+// different queries on one lane so that a warp never waits for its slowest query.
 template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true, int kMode = 0>
-__device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
-                                                   const uint64_t idx0, const L2Policies& pol, Sa& sa) {
-  const uint64_t n = ix.n;
-  const uint64_t nm1 = n - 1;
-  const uint32_t slen = qy.slen(), length = qy.length();
-  // (int)predicted of :209/:225 -- wraps negative for predicted >= 2^31
-  const int32_t p32 = (int32_t)(uint32_t)pred;
+struct Replay {
+  uint64_t pred, lo, hi, r;
+  uint32_t loLcp, hiLcp, lcp0, start;
+  int state;
 
-  uint64_t lo = 0, hi = 0, r = pred;
-  uint32_t loLcp = 0, hiLcp = 0, lcp0 = 0, start = 0;
-  int state = ST_PRED;
+  __device__ __forceinline__ void begin(uint64_t predicted) {
+    pred = predicted;
+    lo = 0;
+    hi = 0;
+    r = predicted;
+    loLcp = hiLcp = lcp0 = start = 0;
+    state = ST_PRED;
+  }
 
-  for (;;) {
+  // one probe; true when the query is answered (*result = the reference's return value)
+  __device__ __forceinline__ bool step(const IndexView& ix, const Query& qy, const uint64_t idx0, const L2Policies& pol,
+                                       Sa& sa, long long* result) {
+    const uint64_t n = ix.n;
+    const uint64_t nm1 = n - 1;
+    const uint32_t slen = qy.slen(), length = qy.length();
+    // (int)predicted of :209/:225 -- wraps negative for predicted >= 2^31
+    const int32_t p32 = (int32_t)(uint32_t)pred;
     uint64_t idx, g = 0;
     bool use_genome = true;
     if constexpr (kMode == 1) {  // one 16-byte entry holds rev[r] and the bases to compare
@@ -263,13 +276,13 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
     } else {
       idx = (kHaveFirst && state == ST_PRED) ? idx0 : (uint64_t)sa.ld(ix, r, pol.sa);
     }
-    if (state == ST_FINAL) return (long long)idx;
+    if (state == ST_FINAL) { *result = (long long)idx; return true; }
     const ProbeResult pr = use_genome ? qy.probe(ix, idx, start, pol.genome) : qy.compare(ix, idx, g, start);
     const bool small = pr.at_end || pr.q_gt;  // "suffix too small" test of :143,:167,:175,:214
     bool to_search = false;
     switch (state) {
       case ST_PRED:
-        if (pr.lcp == length) return (long long)idx;  // :164
+        if (pr.lcp == length) { *result = (long long)idx; return true; }  // :164
         lcp0 = pr.lcp;
         if (small) {  // :167-172
           lo = pred;
@@ -291,7 +304,7 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
         }
         break;
       case ST_R1:
-        if (pr.lcp == length) return (long long)idx;  // :174
+        if (pr.lcp == length) { *result = (long long)idx; return true; }  // :174
         if (small) {                                  // :175-181
           lo = hi;
           loLcp = pr.lcp;
@@ -307,7 +320,7 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
         break;
       case ST_R2:
       case ST_RG:
-        if (pr.lcp == (state == ST_R2 ? length : slen)) return (long long)idx;  // :183 / :194
+        if (pr.lcp == (state == ST_R2 ? length : slen)) { *result = (long long)idx; return true; }  // :183 / :194
         // :184-196 (reference loops forever once hi is pinned at n-1; we stop there)
         if (kGallop && slen > (uint32_t)ix.k && !pr.at_end && pr.q_gt && hi != nm1) {
           lo = hi;
@@ -322,7 +335,7 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
         }
         break;
       case ST_L1:
-        if (pr.lcp == slen) return (long long)idx;  // :213
+        if (pr.lcp == slen) { *result = (long long)idx; return true; }  // :213
         if (small) {                                // :214-219
           hiLcp = lcp0;
           loLcp = pr.lcp;
@@ -369,7 +382,7 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
         break;
       case ST_L2:
       case ST_LG:
-        if (pr.lcp == slen) return (long long)idx;  // :228 / :239
+        if (pr.lcp == slen) { *result = (long long)idx; return true; }  // :228 / :239
         // :229-241 (reference underflows lo below rank 0; we stop at 0)
         if (kGallop && slen > (uint32_t)ix.k && !pr.at_end && pr.q_lt && lo != 0) {
           hi = lo;
@@ -392,8 +405,8 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
         to_search = true;
         break;
       default:  // ST_BS, probed mid == r  (:139-152)
-        if (pr.lcp == slen) return (long long)idx;  // :141 then :247 (rev[mid] == idx)
-        if (lo + 1 >= hi) return -1;                // :142
+        if (pr.lcp == slen) { *result = (long long)idx; return true; }  // :141 then :247 (rev[mid] == idx)
+        if (lo + 1 >= hi) { *result = -1; return true; }                // :142
         if (small) {
           lo = r;
           loLcp = pr.lcp;
@@ -414,7 +427,19 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
         state = ST_BS;
       }
     }
+    return false;
   }
+};
+
+template <bool kGallop, bool kHaveFirst, typename Query, typename Sa, bool kSkip = true, int kMode = 0>
+__device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Query& qy, const uint64_t pred,
+                                                   const uint64_t idx0, const L2Policies& pol, Sa& sa) {
+  Replay<kGallop, kHaveFirst, Query, Sa, kSkip, kMode> rp;
+  rp.begin(pred);
+  long long result;
+  while (!rp.step(ix, qy, idx0, pol, sa, &result)) {
+  }
+  return result;
 }
 
 template <bool kGallop, typename Query>

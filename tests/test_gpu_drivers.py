@@ -42,3 +42,49 @@ def test_unmodified_sapling_example_runs_on_the_shim(tmp_path):
         assert open(fa_ref, "rb").read() == open(fa_b, "rb").read(), ext
     # the queries both drivers generated (unseeded rand(), same sequence) are identical
     assert open(tmp_path / "ref" / "queries.out").read() == open(tmp_path / "b200" / "queries.out").read()
+
+
+def _write_fastq(path, reads):
+    with open(path, "wb") as f:
+        for i, r in enumerate(reads):
+            f.write(b"@read%d some comment\n" % i + r + b"\n+\n" + bytes(33 + (j * 7 + i) % 40 for j in range(len(r))) + b"\n")
+
+
+ALIGN_REF = os.path.join(REFDIR, "align_ref")
+ALIGN_B200 = os.path.join(O.ROOT, "sapling_b200", "bin", "align_b200")
+
+
+@pytest.mark.skipif(not (os.path.exists(ALIGN_REF) and os.path.exists(ALIGN_B200)),
+                    reason="align drivers not prebuilt (need /root/reference at build time)")
+@pytest.mark.parametrize("case", ["random_two_chr", "repeats", "few_seeds"])
+def test_batched_gpu_seeded_align_writes_the_reference_sam(tmp_path, case):
+    """BASELINE configs[4]: sapling_b200/host/align_b200.cpp (GPU seed batch -> host SSW, multi-threaded, blocked) must
+    write the same SAM records as the reference's align.cpp (run unmodified through oracle/ref_align_harness.cpp, which
+    only fills the Sapling::sa the snapshot forgets)."""
+    import _fixtures as F
+    if case == "repeats":
+        g = F.small_genomes()["repeat_tailA"] + O.synth_genome(O.SEED_G + 31, 60_000) + F.small_genomes()["tandem50"]
+        text = b">rep1\n" + g + b"\n"
+        args = ["sapling_k=12", "max_hits=8"]
+    else:
+        a, b = O.synth_genome(O.SEED_G + 29, 150_000), O.synth_genome(O.SEED_G + 30, 90_000)
+        g = a + b
+        text = b">chrA first\n" + a[:70_000] + b"\nNNNNNNNN\n" + a[70_000:] + b"\n>chrB\n" + b + b"\n"
+        args = ["num_seeds=3", "flanking_sequence=5"] if case == "few_seeds" else []
+    reads, _ = O.simulate_reads(g, 400, 150)
+    reads += [g[1000:1150], g[-150:], g[:150], g[5000:5040], b"ACGTACGTACGTACGTACGT" * 5, g[300:450].replace(b"A", b"N", 3)]
+    outs = {}
+    for tag, binary, extra in (("ref", ALIGN_REF, []), ("b200", ALIGN_B200, ["batch=97", "threads=4"])):
+        d = tmp_path / tag
+        d.mkdir()
+        fa, fq, sam = str(d / "g.fa"), str(d / "r.fq"), str(d / "out.sam")
+        open(fa, "wb").write(text)
+        _write_fastq(fq, reads)
+        p = subprocess.run([binary, fq, fa, sam] + args + extra, cwd=str(d), capture_output=True, text=True, timeout=900)
+        assert p.returncode == 0, (tag, p.stdout[-1000:], p.stderr[-2000:])
+        outs[tag] = [l for l in open(sam) if not l.startswith("@PG")]
+    n_sq = 1 if case == "repeats" else 2
+    assert len(outs["ref"]) == len(reads) + 1 + n_sq   # @HD + one @SQ per FASTA record + one line per read
+    assert outs["ref"] == outs["b200"]
+    aligned = sum(1 for l in outs["ref"] if not l.startswith("@") and l.split("\t")[1] != "4")
+    assert aligned > 0.9 * 400

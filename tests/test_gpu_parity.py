@@ -300,12 +300,19 @@ def test_rank_line_layout(S, oracle_built, name, monkeypatch):
                 monkeypatch.setenv("SAPLING_B200_PACKED_BASES", bases)
                 ix = S.Sapling.from_memory(g, port.sa if bases != "8" else None, numBuckets=nb, k=k,
                                            flags=S.QUIET | S.PACKED)
-                assert ix.query_kernel()[0] == "kmer_query_packed_kernel"
                 assert ix.device_bytes() >= plain.device_bytes() + (16 if shift == "3" else 8) * len(g)
-                for qv in ("3", "4", "5", "6"):
-                    monkeypatch.setenv("SAPLING_B200_QV", qv)
-                    assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb, shift, bases, qv)
-                monkeypatch.delenv("SAPLING_B200_QV")
+                for refill, kernel in (("1", "kmer_query_packed_refill_kernel"), ("0", "kmer_query_packed_kernel")):
+                    monkeypatch.setenv("SAPLING_B200_REFILL", refill)
+                    # the refill kernel reads the narrow model layout, which needs 2k - nb <= 31
+                    assert ix.query_kernel()[0] == (kernel if 2 * k - port.nb <= 31 else "kmer_query_packed_kernel")
+                    for qv in ("2", "3", "4", "5", "6"):
+                        monkeypatch.setenv("SAPLING_B200_QV", qv)
+                        assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb, shift, bases, refill, qv)
+                        # ragged batch sizes: fewer queries than lanes, than warps, one over a block boundary
+                        for m in (1, 31, 33, 257, 4097):
+                            assert np.array_equal(ix.queryBatch(kmers[:m]), exp[:m]), (name, k, m, refill, qv)
+                    monkeypatch.delenv("SAPLING_B200_QV")
+                monkeypatch.delenv("SAPLING_B200_REFILL")
                 ix.close()
         plain.close()
         port.close()

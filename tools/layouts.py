@@ -38,8 +38,10 @@ for lay in layouts:
         build_s = time.time() - t0
         for mut in (0, 0x5A911C0DE5EED003):
             ix.sample_queries_device(0x5A911C0DE5EED002, mut, 0, nq, d_k.data_ptr(), st)
-            for qv in (3, 4, 5, 6):
+            variants = [(0, 3), (0, 4), (0, 5)] + ([(1, 2), (1, 3), (1, 4), (1, 5)] if lay.startswith("packed") else [])
+            for refill, qv in variants:
                 os.environ["SAPLING_B200_QV"] = str(qv)
+                os.environ["SAPLING_B200_REFILL"] = str(refill)
                 for _ in range(2):
                     ix.queryBatchDevice(d_k.data_ptr(), nq, d_o.data_ptr(), st)
                 torch.cuda.synchronize()
@@ -53,11 +55,12 @@ for lay in layouts:
                 if mut not in ref:
                     ref[mut] = d_o.clone()
                 rows.append({"genome_bp": n, "queries": nq, "layout": lay, "kernel": ix.query_kernel()[0], "hints": hints,
-                             "mutated_half": bool(mut), "blocks_per_sm": qv, "ms": round(ms, 3),
+                             "refill": refill, "mutated_half": bool(mut), "blocks_per_sm": qv, "ms": round(ms, 3),
                              "Gq_per_s": round(nq / ms / 1e6, 2), "same_results": bool(torch.equal(d_o, ref[mut])),
                              "device_MB": round(ix.device_bytes() / 1e6), "build_s": round(build_s, 2)})
                 print(rows[-1], flush=True)
             os.environ.pop("SAPLING_B200_QV", None)
+            os.environ.pop("SAPLING_B200_REFILL", None)
         ix.close()
         del ix
         torch.cuda.empty_cache()
