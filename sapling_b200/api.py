@@ -41,6 +41,7 @@ SYMBOLS = {
     "sapling_b200_device_bytes": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_launch_count": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_query_kernel": (C.c_char_p, [C.c_void_p, C.POINTER(C.c_int)]),
+    "sapling_b200_query_partition_bits": (C.c_int, [C.c_void_p, C.c_size_t]),
     "sapling_b200_kmerize": (C.c_int64, [C.c_int, C.c_char_p]),
     "sapling_b200_kmerize_adjusted": (C.c_int64, [C.c_int, C.c_int, C.c_char_p]),
     "sapling_b200_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -227,6 +228,10 @@ class Sapling:
 
     def launch_count(self):
         return int(self._L.sapling_b200_launch_count(self._h))
+
+    def partition_bits(self, nq):
+        """Top k-mer bits a device batch of nq queries is partitioned by (0 = answered in the caller's order)."""
+        return int(self._L.sapling_b200_query_partition_bits(self._h, nq))
 
     def query_kernel(self):
         """(name of the CUDA kernel queryBatch launches for this index, resident blocks per SM it is compiled for)."""

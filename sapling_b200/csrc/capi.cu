@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <map>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -16,12 +17,13 @@
 #include "../../include/sapling_b200.h"
 #include "build.cuh"
 #include "common.cuh"
+#include "partition.cuh"
 
 namespace sb {
 
 // launchers in query.cu
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
-                      const char** name_out = nullptr);
+                      const char** name_out = nullptr, const uint16_t* d_slot = nullptr);
 int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint64_t* d_word_off,
                         const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
                         long long* d_out, cudaStream_t st);
@@ -94,6 +96,14 @@ struct sapling_b200_index {
   uint64_t* h_in[kSlots] = {};
   long long* h_out[kSlots] = {};
 
+  // scratch of the partitioned batch path (partition.cu), one block per stream it was used on, grown on demand
+  struct PartWs {
+    void* p = nullptr;
+    size_t bytes = 0;
+  };
+  std::mutex mu_ws;
+  std::map<cudaStream_t, PartWs> part_ws;
+
   // single-query path (plQuery drop-in): one mapped pinned block, no per-call allocation
   std::mutex mu1;
   cudaStream_t s1 = nullptr;
@@ -129,6 +139,7 @@ struct sapling_b200_index {
 
   ~sapling_b200_index() {
     cudaSetDevice(device);
+    for (auto& kv : part_ws) cudaFree(kv.second.p);
     for (int i = 0; i < 3; i++)
       if (streams[i]) cudaStreamDestroy(streams[i]);
     for (int i = 0; i < kSlots; i++) {
@@ -851,12 +862,83 @@ const char* sapling_b200_query_kernel(const sapling_b200_index* ix, int* blocks_
 
 // ---------------------------------------------------------------------------------------------
 
+// How many top k-mer bits to partition a batch of nq queries by; 0 = answer it in the caller's order.
+// The slice of the index one bin maps to (suffix array or rank lines + model, both monotone in the k-mer) should fit
+// the part of L2 that data shared by all SMs gets (~48 MB, profiles/r1_experiments.md section 1) with room for the
+// genome and the streams; each bin should still receive enough queries to amortise its line fills.
+// SAPLING_B200_PART=0 disables, SAPLING_B200_PART_BITS forces a bin count, SAPLING_B200_PART_MIN sets the smallest batch.
+static int partition_bits(const sapling_b200_index* ix, size_t nq) {
+  if (const char* e = getenv("SAPLING_B200_PART")) {
+    if (atoi(e) == 0) return 0;
+  }
+  size_t min_nq = (size_t)1 << 22;
+  if (const char* e = getenv("SAPLING_B200_PART_MIN")) min_nq = (size_t)atoll(e);
+  if (nq < min_nq || nq >= (1ull << 32)) return 0;
+  const int kbits = 2 * ix->k;
+  int bits;
+  if (const char* e = getenv("SAPLING_B200_PART_BITS")) {
+    bits = atoi(e);
+  } else {
+    const double sa_bytes = ix->d_packed ? (double)packed_sectors(ix->n, ix->packed_shift) * 32.0
+                            : ix->d_ext  ? 16.0 * (double)ix->n
+                                         : 4.0 * (double)ix->n;
+    const double model_bytes = (ix->d_narrow ? 8.0 : 16.0) * (double)(1ull << ix->nb);
+    const double slice = 16e6;
+    bits = 1;
+    while (bits < kPartMaxBits && (sa_bytes + model_bytes) / (double)(1ull << bits) > slice) bits++;
+    while (bits > 0 && (nq >> bits) < 4096) bits--;
+    if (bits < 3) return 0;
+  }
+  if (bits > kPartMaxBits) bits = kPartMaxBits;
+  if (bits > kbits) bits = kbits;
+  return bits < 1 ? 0 : bits;
+}
+
+// One batch of k-mers already on the device -> answers, enqueued on st.
+static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint64_t* d_kmers, size_t nq, long long* d_out,
+                          cudaStream_t st) {
+  if (nq == 0) return 0;
+  const int bits = partition_bits(ix, nq);
+  if (bits == 0) {
+    ix->launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_kmer_query(v, d_kmers, nq, d_out, st);
+  }
+  void* ws = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ix->mu_ws);
+    sapling_b200_index::PartWs& w = ix->part_ws[st];
+    const size_t need = partition_workspace_bytes(nq, bits);
+    if (w.bytes < need) {
+      if (w.p) { cudaFree(w.p); ix->device_bytes -= w.bytes; }  // cudaFree waits for work that still uses the block
+      w.p = nullptr;
+      w.bytes = 0;
+      if (cudaMalloc(&w.p, need) != cudaSuccess) {
+        cudaGetLastError();
+        w.p = nullptr;  // no room for the scratch: answer in the caller's order instead
+      } else {
+        w.bytes = need;
+        ix->device_bytes += need;
+      }
+    }
+    ws = w.p;
+  }
+  if (!ws) {
+    ix->launches.fetch_add(1, std::memory_order_relaxed);
+    return launch_kmer_query(v, d_kmers, nq, d_out, st);
+  }
+  ix->launches.fetch_add(6, std::memory_order_relaxed);
+  return launch_partitioned_query(v, d_kmers, nq, d_out, ws, bits, st);
+}
+
+int sapling_b200_query_partition_bits(const sapling_b200_index* ix, size_t nq) {
+  return ix ? partition_bits(ix, nq) : 0;
+}
+
 int sapling_b200_query_batch_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, int64_t* d_out,
                                  void* stream) {
   if (!ix) { set_error("null index"); return -1; }
-  if (nq) ix->launches.fetch_add(1, std::memory_order_relaxed);
-  return launch_kmer_query(ix->view(), d_kmers, nq, reinterpret_cast<long long*>(d_out),
-                           static_cast<cudaStream_t>(stream));
+  return run_kmer_batch(ix, ix->view(), d_kmers, nq, reinterpret_cast<long long*>(d_out),
+                        static_cast<cudaStream_t>(stream));
 }
 
 int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size_t nq, int64_t* out) {
@@ -899,8 +981,7 @@ int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size
       SB_CUDA_CHECK(cudaMemcpyAsync(ix->d_in[s], src, m * 8, cudaMemcpyHostToDevice, s_up));
       SB_CUDA_CHECK(cudaEventRecord(ix->ev_up[s], s_up));
       SB_CUDA_CHECK(cudaStreamWaitEvent(s_k, ix->ev_up[s], 0));
-      if (launch_kmer_query(v, ix->d_in[s], m, ix->d_out[s], s_k)) return -1;
-      ix->launches.fetch_add(1, std::memory_order_relaxed);
+      if (run_kmer_batch(ix, v, ix->d_in[s], m, ix->d_out[s], s_k)) return -1;
       SB_CUDA_CHECK(cudaEventRecord(ix->ev_k[s], s_k));
       SB_CUDA_CHECK(cudaStreamWaitEvent(s_down, ix->ev_k[s], 0));
       void* dst = pin_out ? (void*)(out + o) : (void*)ix->h_out[s];

@@ -1,0 +1,199 @@
+// partition.cu -- batch partitioning around the query kernel.
+//
+// Why.  A k-mer's bucket (top nb bits) and its suffix-array rank are both monotone in the k-mer value, so the top
+// bits of a query say which SLICE of the model table and of the suffix array (or rank lines) it will touch.  An
+// unordered batch gathers from the whole multi-GB index at once: every model read and every suffix-array read is a
+// TLB miss plus a 128-byte DRAM line fill that no other query reuses (profiles/r1_experiments.md sections 1-2).  If
+// the batch is first partitioned by the top `pbits` bits of the k-mer and the query kernel then walks the partitioned
+// array in order, the ~150 k queries in flight at any moment all fall into one or two slices: the model slice and
+// (for a fine enough partition) the suffix-array slice are L2 resident, a DRAM line is filled at most once per batch
+// and shared by all queries that need it, and the SMs touch a handful of 2 MB pages instead of thousands.
+// The price is three streaming passes (42 bytes per query); the reference's per-query arithmetic is untouched --
+// the same Replay code answers every query, only the order in which queries are answered changes.
+//
+//   A  part_hist_kernel     chunk c (kPartChunk queries) x bin -> count            cnt[bin][c]
+//   S  part_scan_*          exclusive scan over chunks per bin, then over bins     off[bin][c], bin_start[bin]
+//   B  part_scatter_kernel  k-mer -> part_kmer[bin_start + off + local rank], its index inside the chunk -> part_slot
+//   Q  query kernel (query.cu) over part_kmer in order; result word = slot << 48 | answer
+//   U  part_unpermute_kernel  chunk c gathers its answers bin by bin into shared memory, writes out[] coalesced
+#include "partition.cuh"
+
+namespace sb {
+
+namespace {
+
+constexpr int kHistThreads = 512;
+constexpr int kUnpermThreads = 1024;
+
+__device__ __forceinline__ uint32_t bin_of(uint64_t x, int pshift, uint32_t nbins) {
+  const uint64_t b = x >> pshift;
+  return b < (uint64_t)nbins ? (uint32_t)b : nbins - 1;  // a k-mer with bits above 2k set: still a valid array slot
+}
+
+// A: per-chunk histogram.  cnt is bin-major with rows of nchunks + 1 entries.
+__global__ void __launch_bounds__(kHistThreads)
+part_hist_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
+                 uint32_t* __restrict__ cnt) {
+  extern __shared__ uint32_t sh[];
+  const size_t c = blockIdx.x;
+  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) sh[b] = 0;
+  __syncthreads();
+  const size_t base = c * kPartChunk;
+  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
+  for (uint32_t i = threadIdx.x; i < m; i += kHistThreads) atomicAdd(&sh[bin_of(__ldg(kmers + base + i), pshift, nbins)], 1u);
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cnt[(size_t)b * (nchunks + 1) + c] = sh[b];
+}
+
+// S1: one block per bin: exclusive scan of its row in place, row total stored at [nchunks]
+__global__ void __launch_bounds__(256)
+part_scan_rows_kernel(uint32_t* __restrict__ cnt, size_t nchunks) {
+  __shared__ uint32_t part[256];
+  uint32_t* row = cnt + (size_t)blockIdx.x * (nchunks + 1);
+  const size_t per = (nchunks + 255) / 256;
+  const size_t lo = (size_t)threadIdx.x * per < nchunks ? (size_t)threadIdx.x * per : nchunks;
+  const size_t hi = lo + per < nchunks ? lo + per : nchunks;
+  uint32_t s = 0;
+  for (size_t i = lo; i < hi; i++) s += row[i];
+  part[threadIdx.x] = s;
+  __syncthreads();
+  // Hillis-Steele inclusive scan over the 256 partial sums
+  for (int d = 1; d < 256; d <<= 1) {
+    const uint32_t v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[threadIdx.x] - s;  // exclusive prefix of this thread's segment
+  for (size_t i = lo; i < hi; i++) {
+    const uint32_t v = row[i];
+    row[i] = run;
+    run += v;
+  }
+  if (threadIdx.x == 255) row[nchunks] = part[255];
+}
+
+// S2: one block: bin_start = exclusive scan of the row totals (nbins <= 2048)
+__global__ void __launch_bounds__(1024)
+part_scan_bins_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, uint32_t* __restrict__ bin_start) {
+  __shared__ uint32_t a[2048];
+  for (uint32_t b = threadIdx.x; b < 2048; b += 1024) a[b] = b < nbins ? cnt[(size_t)b * (nchunks + 1) + nchunks] : 0u;
+  __syncthreads();
+  for (int d = 1; d < 2048; d <<= 1) {
+    uint32_t v[2];
+    for (int j = 0; j < 2; j++) {
+      const uint32_t b = threadIdx.x + 1024u * j;
+      v[j] = b >= (unsigned)d ? a[b - d] : 0u;
+    }
+    __syncthreads();
+    for (int j = 0; j < 2; j++) a[threadIdx.x + 1024u * j] += v[j];
+    __syncthreads();
+  }
+  for (uint32_t b = threadIdx.x; b < nbins; b += 1024) bin_start[b] = b ? a[b - 1] : 0u;
+  if (threadIdx.x == 0) bin_start[nbins] = a[nbins - 1];
+}
+
+// B: scatter.  The order of a chunk's queries inside one bin is whatever the shared-memory atomics make it: the slot
+// travels with the query, so the un-permute pass does not care.
+__global__ void __launch_bounds__(kHistThreads)
+part_scatter_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
+                    const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
+                    uint64_t* __restrict__ part_kmer, uint16_t* __restrict__ part_slot) {
+  extern __shared__ uint32_t cur[];
+  const size_t c = blockIdx.x;
+  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cur[b] = bin_start[b] + off[(size_t)b * (nchunks + 1) + c];
+  __syncthreads();
+  const size_t base = c * kPartChunk;
+  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
+  for (uint32_t i = threadIdx.x; i < m; i += kHistThreads) {
+    const uint64_t x = __ldcs(kmers + base + i);
+    const uint32_t pos = atomicAdd(&cur[bin_of(x, pshift, nbins)], 1u);
+    part_kmer[pos] = x;
+    part_slot[pos] = (uint16_t)i;
+  }
+}
+
+// U: chunk c collects its answers.  Warp w walks bins w, w+32, ...; the run (bin, c) is read coalesced by the lanes.
+__global__ void __launch_bounds__(kUnpermThreads)
+part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
+                      const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start, long long* __restrict__ out) {
+  extern __shared__ long long buf[];
+  const size_t c = blockIdx.x;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  // bounds of this warp's runs, two bins per lane (nbins <= 2048 = 32 warps x 32 lanes x 2)
+  uint32_t lo[2], hi[2];
+#pragma unroll
+  for (int j = 0; j < 2; j++) {
+    const uint32_t b = warp + 32u * (lane + 32u * j);
+    if (b < nbins) {
+      const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+      const uint32_t s = bin_start[b];
+      lo[j] = s + row[0];
+      hi[j] = s + row[1];
+    } else {
+      lo[j] = hi[j] = 0;
+    }
+  }
+  const uint32_t per_warp = (nbins + 31u - warp) / 32u;  // bins warp, warp+32, ... below nbins
+#pragma unroll 4
+  for (uint32_t t = 0; t < per_warp; t++) {
+    const uint32_t a = __shfl_sync(0xffffffffu, t < 32u ? lo[0] : lo[1], (int)(t & 31u));
+    const uint32_t e = __shfl_sync(0xffffffffu, t < 32u ? hi[0] : hi[1], (int)(t & 31u));
+    for (uint32_t p = a + lane; p < e; p += 32u) {
+      const unsigned long long v = (unsigned long long)__ldcs(res + p);
+      buf[v >> 48] = (long long)(v << 16) >> 16;  // sign-extend the 48-bit answer
+    }
+  }
+  __syncthreads();
+  const size_t base = c * kPartChunk;
+  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
+  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) __stcs(out + base + i, buf[i]);
+}
+
+}  // namespace
+
+size_t partition_workspace_bytes(size_t nq, int pbits) {
+  const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
+  const size_t nbins = (size_t)1 << pbits;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  return up(nq * 8) + up(nq * 8) + up(nq * 2) + up(nbins * (nchunks + 1) * 4) + up((nbins + 1) * 4);
+}
+
+int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, void* ws,
+                             int pbits, cudaStream_t st) {
+  if (nq == 0) return 0;
+  if (pbits < 1 || pbits > kPartMaxBits || pbits > 2 * ix.k || nq >= (1ull << 32)) {
+    set_error("launch_partitioned_query: pbits=%d nq=%zu out of range", pbits, nq);
+    return -1;
+  }
+  static bool attr_set = false;  // benign race: the attribute is idempotent
+  if (!attr_set) {
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kPartChunk * sizeof(long long))));
+    attr_set = true;
+  }
+  const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
+  const uint32_t nbins = 1u << pbits;
+  const int pshift = 2 * ix.k - pbits;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  char* p = static_cast<char*>(ws);
+  uint64_t* part_kmer = reinterpret_cast<uint64_t*>(p); p += up(nq * 8);
+  long long* res = reinterpret_cast<long long*>(p); p += up(nq * 8);
+  uint16_t* part_slot = reinterpret_cast<uint16_t*>(p); p += up(nq * 2);
+  uint32_t* cnt = reinterpret_cast<uint32_t*>(p); p += up((size_t)nbins * (nchunks + 1) * 4);
+  uint32_t* bin_start = reinterpret_cast<uint32_t*>(p);
+
+  part_hist_kernel<<<(unsigned)nchunks, kHistThreads, nbins * 4, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt);
+  part_scan_rows_kernel<<<nbins, 256, 0, st>>>(cnt, nchunks);
+  part_scan_bins_kernel<<<1, 1024, 0, st>>>(cnt, nchunks, nbins, bin_start);
+  part_scatter_kernel<<<(unsigned)nchunks, kHistThreads, nbins * 4, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt,
+                                                                          bin_start, part_kmer, part_slot);
+  SB_CUDA_CHECK(cudaGetLastError());
+  if (launch_kmer_query(ix, part_kmer, nq, res, st, nullptr, part_slot)) return -1;
+  part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, kPartChunk * sizeof(long long), st>>>(
+      res, nq, nbins, nchunks, cnt, bin_start, d_out);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sb

@@ -1,0 +1,25 @@
+// partition.cuh -- partitioned batch queries (partition.cu): the batch is bucketed by the top bits of the k-mer so that
+// the query kernel walks the index slice by slice.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace sb {
+
+constexpr uint32_t kPartChunk = 16384;  // queries per partition chunk: slots fit 16 bits, a chunk's answers fit shared memory
+constexpr int kPartMaxBits = 11;        // at most 2048 slices
+
+// bytes of device scratch launch_partitioned_query needs for nq queries and 2^pbits slices
+size_t partition_workspace_bytes(size_t nq, int pbits);
+// partition -> query -> un-permute, all enqueued on st.  nq < 2^32.  out[i] = the reference's plQuery answer for kmers[i].
+int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, void* ws,
+                             int pbits, cudaStream_t st);
+
+// query.cu
+int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
+                      const char** name_out, const uint16_t* d_slot);
+
+}  // namespace sb

@@ -78,11 +78,22 @@ kmer_query_pipelined_kernel(const IndexView ix, const uint64_t* __restrict__ kme
   }
 }
 
+// Result store shared by the production kernels.  slot != nullptr: the batch was partitioned (partition.cu); the
+// query's position inside its chunk rides in the top 16 bits of the result word (an answer is -1 or < 2^32, so 48
+// bits hold it) and the un-permute pass puts it back in the caller's order.
+__device__ __forceinline__ void store_result(const IndexView& ix, long long* __restrict__ out,
+                                             const uint16_t* __restrict__ slot, size_t i, long long r) {
+  if (slot) r = (long long)(((unsigned long long)__ldcs(slot + i) << 48) | ((unsigned long long)r & 0xFFFFFFFFFFFFull));
+  if (slot || (ix.hints & HINT_IO_STREAM)) __stcs(out + i, r);
+  else out[i] = r;
+}
+
 // Sector-cached variant (default): the 8 suffix-array ranks around rev[predicted] come in one 256-bit load and stay
 // in registers (query.cuh SaSector); works with either model layout.
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
-kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+                         const uint16_t* __restrict__ slot) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
@@ -94,9 +105,8 @@ kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
     SaSector sa;
     sa.fill(ix, pred, pol.sa);
-    const long long r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
-    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
-    else out[i] = r;
+    long long r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
+    store_result(ix, out, slot, i, r);
   }
 }
 
@@ -104,7 +114,8 @@ kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 // touched at all (k <= ix.ext_bases).  For indexes whose genome does not fit L2 this halves the DRAM lines per query.
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
-kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+                         const uint16_t* __restrict__ slot) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
@@ -115,9 +126,8 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     q.k = (uint32_t)ix.k;
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
     SaDirect sad;
-    const long long r = pl_query_from<false, false, KmerQuery, SaDirect, true, 1>(ix, q, pred, 0, pol, sad);
-    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
-    else out[i] = r;
+    long long r = pl_query_from<false, false, KmerQuery, SaDirect, true, 1>(ix, q, pred, 0, pol, sad);
+    store_result(ix, out, slot, i, r);
   }
 }
 
@@ -126,7 +136,8 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 // and for queries longer than the entries' prefix.
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
-kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
+kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+                         const uint16_t* __restrict__ slot) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
@@ -138,9 +149,8 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
     SaPacked sa;
     sa.anchor(ix, pred);
-    const long long r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
-    if (ix.hints & HINT_IO_STREAM) __stcs(out + i, r);
-    else out[i] = r;
+    long long r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
+    store_result(ix, out, slot, i, r);
   }
 }
 
@@ -534,8 +544,9 @@ static int query_variant(const IndexView& ix, bool inline_layout) {
 }
 
 // name_out != nullptr: only report which kernel a batch would run on (introspection for bench.py), launch nothing
+// d_slot != nullptr: partitioned batch (partition.cu) -- results carry their chunk slot in the top 16 bits
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
-                      const char** name_out) {
+                      const char** name_out, const uint16_t* d_slot) {
   if (nq == 0 && !name_out) return 0;
   const char* gm = getenv("SAPLING_B200_GRID_MULT");  // grid = 148 * blocks/SM * mult (experiment knob)
   const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 2) : 2;
@@ -551,8 +562,10 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const bool inl = ix.ext != nullptr && ix.k <= ix.ext_bases && !(ie && atoi(ie) == 0);
   const char* pe2 = getenv("SAPLING_B200_PACKED_QUERY");  // 0 = ignore the rank lines even if resident
   const bool packed = ix.packed != nullptr && !(pe2 && atoi(pe2) == 0);
-  const char* re = getenv("SAPLING_B200_REFILL");  // 0 = one query per lane per pass (no lane refill)
-  const bool refill = packed && ix.narrow != nullptr && !(re && atoi(re) == 0);
+  // 1 = lane-refill kernel.  Measured slower than one query per lane per pass at every size (profiles/r1v_layouts.md:
+  // c2 13.8 vs 18.2 G q/s, c3 9.9 vs 11.3), so it is opt-in.
+  const char* re = getenv("SAPLING_B200_REFILL");
+  const bool refill = packed && ix.narrow != nullptr && re && atoi(re) == 1 && !d_slot;
   const int qv = query_variant(ix, inl || packed);
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
@@ -568,6 +581,12 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     return qv;
   }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
+#define SB_LAUNCH_S(kernel, bps) \
+  kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot)
+  if (d_slot && !(packed || inl || sector)) {
+    set_error("partitioned batches need the sector, inline or rank-line kernel");
+    return -1;
+  }
   if (refill) {
     // persistent: every warp streams through one contiguous slice of the batch, so one resident wave (unless
     // SAPLING_B200_GRID_MULT says otherwise)
@@ -582,24 +601,24 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 #undef SB_LAUNCH_R
   } else if (packed) {
     switch (qv) {
-      case 3: SB_LAUNCH(kmer_query_packed_kernel, 3); break;
-      case 5: SB_LAUNCH(kmer_query_packed_kernel, 5); break;
-      case 6: SB_LAUNCH(kmer_query_packed_kernel, 6); break;
-      default: SB_LAUNCH(kmer_query_packed_kernel, 4); break;
+      case 3: SB_LAUNCH_S(kmer_query_packed_kernel, 3); break;
+      case 5: SB_LAUNCH_S(kmer_query_packed_kernel, 5); break;
+      case 6: SB_LAUNCH_S(kmer_query_packed_kernel, 6); break;
+      default: SB_LAUNCH_S(kmer_query_packed_kernel, 4); break;
     }
   } else if (inl) {
     switch (qv) {
-      case 3: SB_LAUNCH(kmer_query_inline_kernel, 3); break;
-      case 5: SB_LAUNCH(kmer_query_inline_kernel, 5); break;
-      case 6: SB_LAUNCH(kmer_query_inline_kernel, 6); break;
-      default: SB_LAUNCH(kmer_query_inline_kernel, 4); break;
+      case 3: SB_LAUNCH_S(kmer_query_inline_kernel, 3); break;
+      case 5: SB_LAUNCH_S(kmer_query_inline_kernel, 5); break;
+      case 6: SB_LAUNCH_S(kmer_query_inline_kernel, 6); break;
+      default: SB_LAUNCH_S(kmer_query_inline_kernel, 4); break;
     }
   } else if (sector) {
     switch (qv) {
-      case 3: SB_LAUNCH(kmer_query_sector_kernel, 3); break;
-      case 5: SB_LAUNCH(kmer_query_sector_kernel, 5); break;
-      case 6: SB_LAUNCH(kmer_query_sector_kernel, 6); break;
-      default: SB_LAUNCH(kmer_query_sector_kernel, 4); break;
+      case 3: SB_LAUNCH_S(kmer_query_sector_kernel, 3); break;
+      case 5: SB_LAUNCH_S(kmer_query_sector_kernel, 5); break;
+      case 6: SB_LAUNCH_S(kmer_query_sector_kernel, 6); break;
+      default: SB_LAUNCH_S(kmer_query_sector_kernel, 4); break;
     }
   } else if (line && pipelined) {
     switch (qv) {
@@ -632,6 +651,7 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     }
   }
 #undef SB_LAUNCH
+#undef SB_LAUNCH_S
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

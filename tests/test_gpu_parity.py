@@ -316,3 +316,38 @@ def test_rank_line_layout(S, oracle_built, name, monkeypatch):
                 ix.close()
         plain.close()
         port.close()
+
+
+@pytest.mark.parametrize("name", ["rand200k", "gc0110", "tandem50", "repeat_tailA", "polyC"])
+def test_partitioned_batch(S, oracle_built, name, monkeypatch):
+    """The partitioned batch path (partition.cu: bucket the batch by the top bits of the k-mer, answer it slice by
+    slice, put the answers back in the caller's order) returns exactly what the oracle returns for the caller's order:
+    every layout, bin counts from 2 to 2048 (more bins than buckets included), batches smaller than one partition
+    chunk, ragged last chunks, several chunks, k-mers that all fall into one bin."""
+    g = GENOMES[name]
+    for k, nb in ((21, -1), (16, 8), (11, 4), (31, 12)):
+        if len(g) < 4 * k:
+            continue
+        port = O.Port.from_memory(g, nb=nb, k=k)
+        base = F.query_mix(g, k, 6000, seed=11)
+        kmers = np.concatenate([base, base[::-1], np.sort(base), np.full(3000, base[0], dtype=np.uint64)] * 2)  # 42000 > 2 chunks
+        exp = port.query_batch(kmers, nthreads=4)
+        for flags in (S.NO_PACKED | S.NO_INLINE, S.PACKED, S.INLINE | S.NO_PACKED):
+            ix = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k, flags=S.QUIET | flags)
+            monkeypatch.setenv("SAPLING_B200_PART", "0")
+            assert ix.partition_bits(len(kmers)) == 0
+            plain = ix.queryBatch(kmers)
+            assert np.array_equal(plain, exp)
+            monkeypatch.setenv("SAPLING_B200_PART", "1")
+            monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
+            for bits in (1, 3, 8, 11):
+                monkeypatch.setenv("SAPLING_B200_PART_BITS", str(bits))
+                assert ix.partition_bits(len(kmers)) == min(bits, 2 * k)
+                for m in (len(kmers), 16384, 16385, 32767, 1, 33, 5000):
+                    assert np.array_equal(ix.queryBatch(kmers[:m]), exp[:m]), (name, k, nb, flags, bits, m)
+            monkeypatch.delenv("SAPLING_B200_PART_BITS")
+            assert ix.oob_count() >= 0
+            ix.close()
+        port.close()
+    monkeypatch.delenv("SAPLING_B200_PART_MIN", raising=False)
+    monkeypatch.delenv("SAPLING_B200_PART", raising=False)
