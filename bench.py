@@ -415,8 +415,19 @@ def main():
     step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
     total_ms = max_over_ranks(total_ms, dist, "cuda")
     value = world * nq * args.steps / (total_ms * 1e-3)
-    kernel_ms = sum(step_ms) / len(step_ms)
+    step_mean_ms = sum(step_ms) / len(step_ms)
     kernel_name, kernel_bps = ix.query_kernel()
+    part_bits = ix.partition_bits(nq)
+    launches_per_step = 6 if part_bits else 1
+    # the query kernel on its own: the same steps again with CUDA events recorded by the library on the launching
+    # stream around each stage (a partitioned step is histogram+scans, scatter, QUERY KERNEL, un-permute)
+    ix.profile(True)
+    for s in range(args.steps):
+        ix.queryBatchDevice(d_kmers[s % nbatch].data_ptr(), nq, d_out.data_ptr(), stream)
+    calls, stage_sum = ix.stage_ms()
+    ix.profile(False)
+    stage_ms = [x / max(calls, 1) for x in stage_sum]
+    kernel_ms = stage_ms[2] if calls else step_mean_ms
 
     # correctness of the timed output (self-check of sapling_example.cpp:144-154, on the device)
     last = (args.steps - 1) % nbatch
@@ -489,11 +500,15 @@ def main():
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src, "bytes_per_query": bytes_per_query,
                      "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": kernel_name,
-                     "blocks_per_sm": kernel_bps, "kernel_ms": kernel_ms, "random_sector_gather_gbs": gather},
+                     "blocks_per_sm": kernel_bps, "kernel_ms": kernel_ms, "step_ms": step_mean_ms,
+                     "kernel_share_of_step": kernel_ms / step_mean_ms if step_mean_ms else None,
+                     "partition_bits": part_bits,
+                     "stage_ms": dict(zip(("hist_scan", "scatter", "query_kernel", "unpermute"), stage_ms)),
+                     "random_sector_gather_gbs": gather},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8,
                 "steps": e2e_steps, "api": "sapling_b200_query_batch (pinned host buffers)", "numa_node": numa_node},
-        "gpu_launches": args.steps, "e2e_gpu_launches": e2e_launches,
+        "gpu_launches": args.steps * launches_per_step, "e2e_gpu_launches": e2e_launches,
         "clocks": clocks, "self_check": {"matching": int(n_match), "minus1": int(n_m1), "of": nq},
         "parity": parity,
     }

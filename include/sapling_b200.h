@@ -109,6 +109,13 @@ const char *sapling_b200_query_kernel(const sapling_b200_index *ix, int *blocks_
  * walks it (2^bits slices of the index); 0 = the batch is answered in the caller's order.
  * The answers are the same either way. */
 int sapling_b200_query_partition_bits(const sapling_b200_index *ix, size_t nq);
+/* Stage timing of sapling_b200_query_batch_dev (measurement only; bench.py's roofline uses it to time the query kernel
+ * on its own when the batch is partitioned).  While profiling is on, every call records CUDA events on its launching
+ * stream around its stages.  sapling_b200_stage_ms waits for the profiled calls, returns how many there were and the
+ * SUM of their stage times in milliseconds: ms[0] histogram + scans, ms[1] scatter, ms[2] the query kernel,
+ * ms[3] un-permute (an unpartitioned call only has ms[2]); the list is then cleared. */
+int sapling_b200_profile(sapling_b200_index *ix, int on);
+int sapling_b200_stage_ms(sapling_b200_index *ix, double ms[4]);
 
 /* ---- hashing (host, no GPU) ---------------------------------------------------------------- */
 

@@ -42,6 +42,8 @@ SYMBOLS = {
     "sapling_b200_launch_count": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_query_kernel": (C.c_char_p, [C.c_void_p, C.POINTER(C.c_int)]),
     "sapling_b200_query_partition_bits": (C.c_int, [C.c_void_p, C.c_size_t]),
+    "sapling_b200_profile": (C.c_int, [C.c_void_p, C.c_int]),
+    "sapling_b200_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "sapling_b200_kmerize": (C.c_int64, [C.c_int, C.c_char_p]),
     "sapling_b200_kmerize_adjusted": (C.c_int64, [C.c_int, C.c_int, C.c_char_p]),
     "sapling_b200_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
@@ -232,6 +234,18 @@ class Sapling:
     def partition_bits(self, nq):
         """Top k-mer bits a device batch of nq queries is partitioned by (0 = answered in the caller's order)."""
         return int(self._L.sapling_b200_query_partition_bits(self._h, nq))
+
+    def profile(self, on=True):
+        """Record CUDA events around the stages of every queryBatchDevice call (read them with stage_ms)."""
+        self._ck(self._L.sapling_b200_profile(self._h, 1 if on else 0))
+
+    def stage_ms(self):
+        """(profiled calls, [histogram+scans, scatter, query kernel, un-permute] summed over them, ms); clears the list."""
+        ms = (C.c_double * 4)()
+        calls = self._L.sapling_b200_stage_ms(self._h, ms)
+        if calls < 0:
+            raise SaplingError(_err())
+        return calls, [float(x) for x in ms]
 
     def query_kernel(self):
         """(name of the CUDA kernel queryBatch launches for this index, resident blocks per SM it is compiled for)."""

@@ -23,7 +23,8 @@ namespace sb {
 
 // launchers in query.cu
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
-                      const char** name_out = nullptr, const uint16_t* d_slot = nullptr);
+                      const char** name_out = nullptr, const uint16_t* d_slot = nullptr,
+                      unsigned long long* d_tiles = nullptr);
 int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint64_t* d_word_off,
                         const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
                         long long* d_out, cudaStream_t st);
@@ -104,6 +105,15 @@ struct sapling_b200_index {
   std::mutex mu_ws;
   std::map<cudaStream_t, PartWs> part_ws;
 
+  // stage timing (sapling_b200_profile / sapling_b200_stage_ms): five events per profiled call, see run_kmer_batch
+  std::mutex mu_prof;
+  bool profiling = false;
+  struct ProfCall {
+    cudaEvent_t ev[5];
+    bool partitioned;
+  };
+  std::vector<ProfCall> prof_calls;
+
   // single-query path (plQuery drop-in): one mapped pinned block, no per-call allocation
   std::mutex mu1;
   cudaStream_t s1 = nullptr;
@@ -140,6 +150,8 @@ struct sapling_b200_index {
   ~sapling_b200_index() {
     cudaSetDevice(device);
     for (auto& kv : part_ws) cudaFree(kv.second.p);
+    for (auto& c : prof_calls)
+      for (int i = 0; i < 5; i++) cudaEventDestroy(c.ev[i]);
     for (int i = 0; i < 3; i++)
       if (streams[i]) cudaStreamDestroy(streams[i]);
     for (int i = 0; i < kSlots; i++) {
@@ -899,10 +911,37 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
                           cudaStream_t st) {
   if (nq == 0) return 0;
   const int bits = partition_bits(ix, nq);
-  if (bits == 0) {
-    ix->launches.fetch_add(1, std::memory_order_relaxed);
-    return launch_kmer_query(v, d_kmers, nq, d_out, st);
+  cudaEvent_t* ev = nullptr;
+  {
+    std::lock_guard<std::mutex> lock(ix->mu_prof);
+    if (ix->profiling) {
+      sapling_b200_index::ProfCall c;
+      for (int i = 0; i < 5; i++) SB_CUDA_CHECK(cudaEventCreate(&c.ev[i]));
+      c.partitioned = bits != 0;
+      ix->prof_calls.push_back(c);
+      ev = ix->prof_calls.back().ev;  // stays valid: the vector is only touched under mu_prof and read after a sync
+    }
   }
+  cudaEvent_t evs[5];
+  if (ev) {
+    for (int i = 0; i < 5; i++) evs[i] = ev[i];
+    ev = evs;
+  }
+  auto plain = [&]() -> int {
+    ix->launches.fetch_add(1, std::memory_order_relaxed);
+    if (ev) {  // unpartitioned call: stages 0, 1 and 3 are empty
+      cudaEventRecord(ev[0], st);
+      cudaEventRecord(ev[1], st);
+      cudaEventRecord(ev[2], st);
+    }
+    const int rc = launch_kmer_query(v, d_kmers, nq, d_out, st);
+    if (ev) {
+      cudaEventRecord(ev[3], st);
+      cudaEventRecord(ev[4], st);
+    }
+    return rc;
+  };
+  if (bits == 0) return plain();
   void* ws = nullptr;
   {
     std::lock_guard<std::mutex> lock(ix->mu_ws);
@@ -922,12 +961,36 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
     }
     ws = w.p;
   }
-  if (!ws) {
-    ix->launches.fetch_add(1, std::memory_order_relaxed);
-    return launch_kmer_query(v, d_kmers, nq, d_out, st);
-  }
+  if (!ws) return plain();
   ix->launches.fetch_add(6, std::memory_order_relaxed);
-  return launch_partitioned_query(v, d_kmers, nq, d_out, ws, bits, st);
+  return launch_partitioned_query(v, d_kmers, nq, d_out, ws, bits, st, ev);
+}
+
+int sapling_b200_profile(sapling_b200_index* ix, int on) {
+  if (!ix) { set_error("null index"); return -1; }
+  std::lock_guard<std::mutex> lock(ix->mu_prof);
+  ix->profiling = on != 0;
+  return 0;
+}
+
+int sapling_b200_stage_ms(sapling_b200_index* ix, double ms[4]) {
+  if (!ix) { set_error("null index"); return -1; }
+  std::lock_guard<std::mutex> lock(ix->mu_prof);
+  for (int i = 0; i < 4; i++) ms[i] = 0.0;
+  int calls = 0;
+  for (auto& c : ix->prof_calls) {
+    if (cudaEventSynchronize(c.ev[4]) == cudaSuccess) {
+      for (int i = 0; i < 4; i++) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, c.ev[i], c.ev[i + 1]) == cudaSuccess) ms[i] += (double)t;
+      }
+      calls++;
+    }
+    cudaGetLastError();
+    for (int i = 0; i < 5; i++) cudaEventDestroy(c.ev[i]);
+  }
+  ix->prof_calls.clear();
+  return calls;
 }
 
 int sapling_b200_query_partition_bits(const sapling_b200_index* ix, size_t nq) {

@@ -15,6 +15,50 @@ namespace {
 
 constexpr int kQueryThreads = 256;
 
+// Which query a lane answers next.
+//   tiles == nullptr: grid-stride over the batch (k-mer reads and result writes coalesced; the order in which blocks
+//     reach which part of the batch does not matter for an unordered batch).
+//   tiles != nullptr: the batch is partitioned (partition.cu) and must be WALKED IN ORDER for the partition to pay: a
+//     warp takes the next 32 queries from a global counter, so the queries in flight on the whole GPU are always the
+//     ~300 k that follow each other in the partitioned array -- one or two slices of the index.  With a static
+//     grid-stride schedule the blocks drift apart by several slices and the slices fall out of L2 and of TLB reach
+//     again (ncu, profiles/r1y: 273 DRAM bytes per query where the partitioned order needs ~150).  The counter for the
+//     next tile is bumped before the current tile is answered, so its round trip never sits on the critical path.
+struct QueryCursor {
+  size_t i, stride;
+  unsigned long long next_tile;
+  unsigned long long* tiles;
+  __device__ __forceinline__ void init(unsigned long long* t) {
+    tiles = t;
+    if (tiles) {
+      unsigned long long a = 0, b = 0;
+      if ((threadIdx.x & 31u) == 0) {
+        a = atomicAdd(tiles, 32ull);
+        b = atomicAdd(tiles, 32ull);
+      }
+      i = (size_t)__shfl_sync(0xffffffffu, a, 0) + (threadIdx.x & 31u);
+      next_tile = __shfl_sync(0xffffffffu, b, 0);
+      stride = 0;
+    } else {
+      stride = (size_t)gridDim.x * blockDim.x;
+      i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+      next_tile = 0;
+    }
+  }
+  // warp-uniform in tile mode (a tile is in range when its first query is)
+  __device__ __forceinline__ bool more(size_t nq) const { return tiles ? (i - (threadIdx.x & 31u)) < nq : i < nq; }
+  __device__ __forceinline__ void next() {
+    if (tiles) {
+      unsigned long long b = 0;
+      if ((threadIdx.x & 31u) == 0) b = atomicAdd(tiles, 32ull);
+      i = (size_t)next_tile + (threadIdx.x & 31u);
+      next_tile = __shfl_sync(0xffffffffu, b, 0);
+    } else {
+      i += stride;
+    }
+  }
+};
+
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out) {
@@ -93,11 +137,13 @@ __device__ __forceinline__ void store_result(const IndexView& ix, long long* __r
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
-                         const uint16_t* __restrict__ slot) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+                         const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+  QueryCursor cur;
+  for (cur.init(tiles); cur.more(nq); cur.next()) {
+    const size_t i = cur.i;
+    if (i >= nq) continue;  // ragged last tile
     const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
     KmerQuery q;
     q.q = x << lsh;
@@ -115,11 +161,13 @@ kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
-                         const uint16_t* __restrict__ slot) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+                         const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+  QueryCursor cur;
+  for (cur.init(tiles); cur.more(nq); cur.next()) {
+    const size_t i = cur.i;
+    if (i >= nq) continue;  // ragged last tile
     const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
     KmerQuery q;
     q.q = x << lsh;
@@ -137,11 +185,13 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 template <int kMinBlocks>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
-                         const uint16_t* __restrict__ slot) {
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
+                         const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+  QueryCursor cur;
+  for (cur.init(tiles); cur.more(nq); cur.next()) {
+    const size_t i = cur.i;
+    if (i >= nq) continue;  // ragged last tile
     const uint64_t x = (ix.hints & HINT_IO_STREAM) ? __ldcs(kmers + i) : __ldg(kmers + i);
     KmerQuery q;
     q.q = x << lsh;
@@ -151,6 +201,71 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     sa.anchor(ix, pred);
     long long r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
     store_result(ix, out, slot, i, r);
+  }
+}
+
+// In-order, software-pipelined kernel of the partitioned batch path (partition.cu).  Same replay as the kernels above;
+// what differs is what is in flight while a lane replays query t of its warp's tile sequence:
+//   * the warp's tiles come from the global in-order counter (QueryCursor explains why the order matters), claimed three
+//     ahead;
+//   * the k-mers of tile t+2 and the model checkpoints of tile t+1 are already requested, so the two dependent round trips
+//     that head every query in the kernels above (k-mer -> checkpoints -> first suffix-array read; 14 % of all stall
+//     samples in profiles/r1y) overlap with the probes of the previous tile;
+//   * the slot of the query (partition.cu) is requested before the replay and consumed after it.
+// Needs the narrow model layout.  kMode as in Replay: 0 = {suffix array sector, packed genome}, 1 = inline-prefix
+// entries, 2 = rank lines.
+template <int kMinBlocks, int kMode>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+                          const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  const size_t last = nq - 1;
+  auto claim = [&]() -> size_t {
+    unsigned long long a = 0;
+    if (lane == 0) a = atomicAdd(tiles, 32ull);
+    return (size_t)__shfl_sync(0xffffffffu, a, 0);
+  };
+  auto kmer_at = [&](size_t t) {  // past the end: the last k-mer again (loaded, predicted for, never answered)
+    const size_t i = t + lane;
+    return __ldcs(kmers + (i < last ? i : last));
+  };
+  size_t t0 = claim(), t1 = claim(), t2 = claim();
+  if (t0 >= nq) return;
+  uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1);
+  NarrowPair m0 = narrow_load(ix, x0, pol.model);
+  while (t0 < nq) {
+    const uint64_t x2 = kmer_at(t2);
+    const NarrowPair m1 = narrow_load(ix, x1, pol.model);
+    const size_t i = t0 + lane;
+    if (i < nq) {
+      const unsigned long long sl = (unsigned long long)__ldcs(slot + i);
+      const uint64_t pred = clamp_prediction(ix, narrow_finish(ix, x0, m0, pol.model));
+      KmerQuery q;
+      q.q = x0 << lsh;
+      q.k = (uint32_t)ix.k;
+      long long r;
+      if constexpr (kMode == 2) {
+        SaPacked sa;
+        sa.anchor(ix, pred);
+        r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
+      } else if constexpr (kMode == 1) {
+        SaDirect sad;
+        r = pl_query_from<false, false, KmerQuery, SaDirect, true, 1>(ix, q, pred, 0, pol, sad);
+      } else {
+        SaSector sa;
+        sa.fill(ix, pred, pol.sa);
+        r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
+      }
+      __stcs(out + i, (long long)((sl << 48) | ((unsigned long long)r & 0xFFFFFFFFFFFFull)));
+    }
+    x0 = x1;
+    x1 = x2;
+    m0 = m1;
+    t0 = t1;
+    t1 = t2;
+    t2 = claim();
   }
 }
 
@@ -546,7 +661,7 @@ static int query_variant(const IndexView& ix, bool inline_layout) {
 // name_out != nullptr: only report which kernel a batch would run on (introspection for bench.py), launch nothing
 // d_slot != nullptr: partitioned batch (partition.cu) -- results carry their chunk slot in the top 16 bits
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
-                      const char** name_out, const uint16_t* d_slot) {
+                      const char** name_out, const uint16_t* d_slot, unsigned long long* d_tiles) {
   if (nq == 0 && !name_out) return 0;
   const char* gm = getenv("SAPLING_B200_GRID_MULT");  // grid = 148 * blocks/SM * mult (experiment knob)
   const int mult = gm ? (atoi(gm) > 0 ? atoi(gm) : 2) : 2;
@@ -582,10 +697,30 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
 #define SB_LAUNCH_S(kernel, bps) \
-  kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot)
+  kernel<bps><<<query_grid(nq, bps * (d_tiles ? 1 : mult)), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles)
   if (d_slot && !(packed || inl || sector)) {
     set_error("partitioned batches need the sector, inline or rank-line kernel");
     return -1;
+  }
+  const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");  // 0 = in-order tiles without the software pipeline
+  if (d_tiles && d_slot && ix.narrow != nullptr && (packed || inl || sector) && !(oe && atoi(oe) == 0)) {
+#define SB_LAUNCH_O(bps, mode) \
+  kmer_query_ordered_kernel<bps, mode><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles)
+    const int mode = packed ? 2 : inl ? 1 : 0;
+    switch (qv * 10 + mode) {
+      case 30: SB_LAUNCH_O(3, 0); break;
+      case 31: SB_LAUNCH_O(3, 1); break;
+      case 32: SB_LAUNCH_O(3, 2); break;
+      case 50: SB_LAUNCH_O(5, 0); break;
+      case 51: SB_LAUNCH_O(5, 1); break;
+      case 52: SB_LAUNCH_O(5, 2); break;
+      case 41: SB_LAUNCH_O(4, 1); break;
+      case 42: SB_LAUNCH_O(4, 2); break;
+      default: SB_LAUNCH_O(4, 0); break;
+    }
+#undef SB_LAUNCH_O
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
   }
   if (refill) {
     // persistent: every warp streams through one contiguous slice of the batch, so one resident wave (unless

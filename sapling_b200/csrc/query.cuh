@@ -145,6 +145,8 @@ struct SaPacked {
     const uint64_t lo = ix.packed_shift == 3 ? (pred > back ? pred - back : 0) : pred;
     abase = (lo >> ix.packed_shift) << ix.packed_shift;
     cur = ~0ull;
+    // (Prefetching the other three sectors of the anchor line into L1 here was measured and rejected: prefetch.global.L1
+    // is slower than the demand loads it saves, 2.6 -> 6.7 ms per 50 M queries at c2; gpurun r1z.)
   }
   // rev[r]; *g = the entry's leading bases left-aligned; *esc = compare against the packed genome instead
   __device__ __forceinline__ uint64_t get(const IndexView& ix, uint64_t r, uint64_t pol, uint64_t* g, bool* esc) {

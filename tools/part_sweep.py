@@ -54,15 +54,23 @@ for lay in layouts:
                     e1.record()
                     torch.cuda.synchronize()
                     ms = e0.elapsed_time(e1) / 4
+                    ix.profile(True)  # stage breakdown, separately from the timed loop
+                    for _ in range(3):
+                        ix.queryBatchDevice(d_k.data_ptr(), nq, d_o.data_ptr(), st)
+                    calls, stage = ix.stage_ms()
+                    ix.profile(False)
+                    stage = [round(x / max(calls, 1), 3) for x in stage]
                     if mut not in ref:
                         ref[mut] = d_o.clone()
                     rows.append({"genome_bp": n, "queries": nq, "layout": lay, "kernel": ix.query_kernel()[0], "hints": hints,
                                  "part_bits": bits, "mutated_half": bool(mut), "blocks_per_sm": qv, "ms": round(ms, 3),
                                  "Gq_per_s": round(nq / ms / 1e6, 2), "same_results": bool(torch.equal(d_o, ref[mut])),
-                                 "device_MB": round(ix.device_bytes() / 1e6), "build_s": round(build_s, 2)})
+                                 "device_MB": round(ix.device_bytes() / 1e6), "build_s": round(build_s, 2),
+                                 "stage_ms": dict(zip(("hist_scan", "scatter", "query", "unpermute"), stage)),
+                                 "scatter": os.environ.get("SAPLING_B200_PART_SCATTER", "1")})
                     r = rows[-1]
                     print(n, lay, "hints", hints, "mut", int(bool(mut)), "bits", bits, "bps", qv, r["ms"], "ms", r["Gq_per_s"],
-                          "Gq/s", r["same_results"], flush=True)
+                          "Gq/s", r["same_results"], "stages", stage, flush=True)
         ix.close()
         del ix
         torch.cuda.empty_cache()
