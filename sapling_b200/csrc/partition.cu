@@ -117,15 +117,54 @@ part_scatter_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, u
   }
 }
 
+// Block-wide exclusive scan of 2048 counters in shared memory; thread t owns the kPer = 2048 / kThreads consecutive
+// counters from t * kPer.  On return a[b] = sum of the counts before b; own[j] holds the thread's own exclusive starts.
+template <int kThreads>
+__device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t (&own)[2048 / kThreads]) {
+  constexpr int kPer = 2048 / kThreads;
+  const uint32_t b0 = (uint32_t)kPer * threadIdx.x;
+  uint32_t c[kPer];
+  uint32_t total = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    c[j] = a[b0 + j];
+    total += c[j];
+  }
+  uint32_t incl = total;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+    if ((threadIdx.x & 31u) >= (unsigned)d) incl += v;
+  }
+  if ((threadIdx.x & 31u) == 31u) wsum[threadIdx.x >> 5] = incl;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t w = threadIdx.x < kThreads / 32 ? wsum[threadIdx.x] : 0u;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+      if (threadIdx.x >= (unsigned)d) w += v;
+    }
+    wsum[threadIdx.x] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  uint32_t run = ((threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0u) + incl - total;
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    own[j] = run;
+    a[b0 + j] = run;
+    run += c[j];
+  }
+}
+
 // B': the same scatter staged through shared memory.  The direct scatter above sends every warp store to 32 different
 // lines (measured: 1.0 ms per 50 M queries, 40 % of the query kernel's own time).  Here a block first sorts its chunk
 // by bin inside shared memory -- each thread keeps its 16 k-mers in registers, the shared-memory atomic that counts the
 // bin also hands out the query's rank inside (chunk, bin) -- and then writes the sorted chunk out in order: consecutive
 // threads store consecutive addresses for as long as the bin lasts (chunk / bins queries on average).
-constexpr int kScatterThreads = 1024;  // 16 k-mers per thread in registers
+constexpr int kScatterThreads = 512;  // 16 k-mers per thread in registers, two blocks per SM
 constexpr int kScatterPer = kPartChunk / kScatterThreads;
-static_assert(kScatterThreads * 2 == 2048, "the scan gives each thread two of the 2048 bin slots");
-__global__ void __launch_bounds__(kScatterThreads)
+__global__ void __launch_bounds__(kScatterThreads, 2)
 part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
                            const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
                            uint64_t* __restrict__ part_kmer, uint16_t* __restrict__ part_slot) {
@@ -150,35 +189,16 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
     }
   }
   __syncthreads();
-  // exclusive scan of the bin counts: thread t owns bins 2t and 2t+1; warp shuffles, then the 32 warp totals
+  // exclusive scan of the bin counts -> first sorted index of every bin; then where the bin's run goes in part_kmer
   __shared__ uint32_t wsum[32];
-  const uint32_t b0 = 2u * threadIdx.x;
-  const uint32_t c0 = lstart[b0], c1 = lstart[b0 + 1];
-  uint32_t incl = c0 + c1;
-#pragma unroll
-  for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-    if ((threadIdx.x & 31u) >= (unsigned)d) incl += v;
-  }
-  if ((threadIdx.x & 31u) == 31u) wsum[threadIdx.x >> 5] = incl;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    uint32_t w = wsum[threadIdx.x];
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
-      if (threadIdx.x >= (unsigned)d) w += v;
-    }
-    wsum[threadIdx.x] = w;  // inclusive over warps
-  }
-  __syncthreads();
   {
-    const uint32_t wbase = (threadIdx.x >> 5) ? wsum[(threadIdx.x >> 5) - 1] : 0u;
-    const uint32_t first0 = wbase + incl - (c0 + c1), first1 = first0 + c0;
-    lstart[b0] = first0;
-    lstart[b0 + 1] = first1;
-    gdelta[b0] = b0 < nbins ? bin_start[b0] + off[(size_t)b0 * (nchunks + 1) + c] - first0 : 0u;
-    gdelta[b0 + 1] = b0 + 1 < nbins ? bin_start[b0 + 1] + off[(size_t)(b0 + 1) * (nchunks + 1) + c] - first1 : 0u;
+    uint32_t own[2048 / kScatterThreads];
+    scan_2048<kScatterThreads>(lstart, wsum, own);
+#pragma unroll
+    for (int j = 0; j < 2048 / kScatterThreads; j++) {
+      const uint32_t b = (uint32_t)(2048 / kScatterThreads) * threadIdx.x + j;
+      gdelta[b] = b < nbins ? bin_start[b] + off[(size_t)b * (nchunks + 1) + c] - own[j] : 0u;
+    }
   }
   __syncthreads();
 #pragma unroll
@@ -236,8 +256,61 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
   for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) __stcs(out + base + i, buf[i]);
 }
 
+// U': the same un-permute with the work split by ELEMENT instead of by bin.  Above, a warp walks whole (bin, chunk) runs,
+// which leaves most lanes idle once runs are shorter than a warp (2048 bins: 8 queries per run, 4.3 ms per 250 M
+// queries against 1.2 ms at 256 bins).  Here the block first scans the chunk's run lengths, then thread i of the chunk's
+// sorted order finds its run by binary search over the scanned starts in shared memory: neighbouring threads read
+// neighbouring answers whatever the run length.
+constexpr int kFlatThreads = 512;  // two blocks per SM
+__global__ void __launch_bounds__(kFlatThreads, 2)
+part_unpermute_flat_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
+                           const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
+                           long long* __restrict__ out) {
+  extern __shared__ long long buf[];                                   // [kPartChunk] answers in the caller's order
+  uint32_t* lstart = reinterpret_cast<uint32_t*>(buf + kPartChunk);    // [2048] first sorted index of the bin's run
+  uint32_t* gdelta = lstart + 2048;                                    // [2048] position in res - sorted index
+  __shared__ uint32_t wsum[32];
+  const size_t c = blockIdx.x;
+  const size_t base = c * kPartChunk;
+  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
+  constexpr int kPer = 2048 / kFlatThreads;
+  uint32_t gpos[kPer];
+#pragma unroll
+  for (int j = 0; j < kPer; j++) {
+    const uint32_t b = (uint32_t)kPer * threadIdx.x + j;
+    uint32_t len = 0;
+    gpos[j] = 0;
+    if (b < nbins) {
+      const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+      const uint32_t r0 = row[0];
+      len = row[1] - r0;
+      gpos[j] = bin_start[b] + r0;
+    }
+    lstart[b] = len;
+  }
+  __syncthreads();
+  {
+    uint32_t own[kPer];
+    scan_2048<kFlatThreads>(lstart, wsum, own);
+#pragma unroll
+    for (int j = 0; j < kPer; j++) gdelta[(uint32_t)kPer * threadIdx.x + j] = gpos[j] - own[j];
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < m; i += kFlatThreads) {
+    uint32_t b = 0;  // last bin whose run starts at or before i (empty runs share their start with the next one)
+#pragma unroll
+    for (uint32_t step = 1024; step; step >>= 1)
+      if (lstart[b + step] <= i) b += step;
+    const unsigned long long v = (unsigned long long)__ldcs(res + gdelta[b] + i);
+    buf[v >> 48] = (long long)(v << 16) >> 16;
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < m; i += kFlatThreads) __stcs(out + base + i, buf[i]);
+}
+
 }  // namespace
 
+constexpr size_t kUnpermFlatSmem = (size_t)kPartChunk * sizeof(long long) + 2 * 2048 * 4;
 constexpr size_t kScatterSmem = (size_t)kPartChunk * 12 + 2 * 2048 * 4;
 
 size_t partition_workspace_bytes(size_t nq, int pbits) {
@@ -258,6 +331,8 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   if (!attr_set) {
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kPartChunk * sizeof(long long))));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kUnpermFlatSmem));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kScatterSmem));
     attr_set = true;
@@ -293,8 +368,14 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   if (ev) cudaEventRecord(ev[2], st);
   if (launch_kmer_query(ix, part_kmer, nq, res, st, nullptr, part_slot, in_order ? tiles : nullptr)) return -1;
   if (ev) cudaEventRecord(ev[3], st);
-  part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, kPartChunk * sizeof(long long), st>>>(
-      res, nq, nbins, nchunks, cnt, bin_start, d_out);
+  const char* ue = getenv("SAPLING_B200_PART_UNPERMUTE");  // 0 = the run-per-warp un-permute (kept for A/B measurements)
+  if (ue && atoi(ue) == 0) {
+    part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, kPartChunk * sizeof(long long), st>>>(
+        res, nq, nbins, nchunks, cnt, bin_start, d_out);
+  } else {
+    part_unpermute_flat_kernel<<<(unsigned)nchunks, kFlatThreads, kUnpermFlatSmem, st>>>(res, nq, nbins, nchunks, cnt,
+                                                                                          bin_start, d_out);
+  }
   if (ev) cudaEventRecord(ev[4], st);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;

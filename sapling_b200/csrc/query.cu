@@ -134,7 +134,7 @@ __device__ __forceinline__ void store_result(const IndexView& ix, long long* __r
 
 // Sector-cached variant (default): the 8 suffix-array ranks around rev[predicted] come in one 256-bit load and stay
 // in registers (query.cuh SaSector); works with either model layout.
-template <int kMinBlocks>
+template <int kMinBlocks, bool kLean>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                          const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -149,16 +149,23 @@ kmer_query_sector_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     q.q = x << lsh;
     q.k = (uint32_t)ix.k;
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
-    SaSector sa;
-    sa.fill(ix, pred, pol.sa);
-    long long r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
+    long long r;
+    if constexpr (kLean) {
+      SaSector32 sa;
+      sa.fill(ix, (uint32_t)pred, pol.sa);
+      r = kmer_replay32<0, true>(ix, q.q, (uint32_t)pred, pol, sa);
+    } else {
+      SaSector sa;
+      sa.fill(ix, pred, pol.sa);
+      r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
+    }
     store_result(ix, out, slot, i, r);
   }
 }
 
 // Inline-prefix variant: every probe is one 16-byte ExtEntry {position, leading bases}; the packed genome is not
 // touched at all (k <= ix.ext_bases).  For indexes whose genome does not fit L2 this halves the DRAM lines per query.
-template <int kMinBlocks>
+template <int kMinBlocks, bool kLean>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                          const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -173,8 +180,14 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     q.q = x << lsh;
     q.k = (uint32_t)ix.k;
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
-    SaDirect sad;
-    long long r = pl_query_from<false, false, KmerQuery, SaDirect, true, 1>(ix, q, pred, 0, pol, sad);
+    long long r;
+    if constexpr (kLean) {
+      SaNone32 none;
+      r = kmer_replay32<1, true>(ix, q.q, (uint32_t)pred, pol, none);
+    } else {
+      SaDirect sad;
+      r = pl_query_from<false, false, KmerQuery, SaDirect, true, 1>(ix, q, pred, 0, pol, sad);
+    }
     store_result(ix, out, slot, i, r);
   }
 }
@@ -182,7 +195,7 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 // Rank-line variant: every probe is answered by a 32-byte sector {4 positions, 4 prefixes}, and the sectors a typical
 // query needs share one 128-byte DRAM line (query.cuh SaPacked); the packed genome is read only for escaped entries
 // and for queries longer than the entries' prefix.
-template <int kMinBlocks>
+template <int kMinBlocks, int kVariant>  // 0: general Replay, 1: lean replay, 2: lean replay + anchor line in shared memory
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                          const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -197,9 +210,22 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     q.q = x << lsh;
     q.k = (uint32_t)ix.k;
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
-    SaPacked sa;
-    sa.anchor(ix, pred);
-    long long r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
+    long long r;
+    if constexpr (kVariant == 2) {
+      __shared__ uint4 lines[kQueryThreads * kLineSlotU4];
+      SaLine32 sa;
+      sa.sm = lines + threadIdx.x * kLineSlotU4;
+      sa.anchor(ix, (uint32_t)pred, pol.sa);
+      r = kmer_replay32<2, true>(ix, q.q, (uint32_t)pred, pol, sa);
+    } else if constexpr (kVariant == 1) {
+      SaPacked32 sa;
+      sa.anchor(ix, (uint32_t)pred);
+      r = kmer_replay32<2, true>(ix, q.q, (uint32_t)pred, pol, sa);
+    } else {
+      SaPacked sa;
+      sa.anchor(ix, pred);
+      r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
+    }
     store_result(ix, out, slot, i, r);
   }
 }
@@ -213,8 +239,8 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 //     samples in profiles/r1y) overlap with the probes of the previous tile;
 //   * the slot of the query (partition.cu) is requested before the replay and consumed after it.
 // Needs the narrow model layout.  kMode as in Replay: 0 = {suffix array sector, packed genome}, 1 = inline-prefix
-// entries, 2 = rank lines.
-template <int kMinBlocks, int kMode>
+// entries, 2 = rank lines, 3 = rank lines with the anchor line staged in shared memory (SaLine32; lean replay only).
+template <int kMinBlocks, int kMode, bool kLean>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -246,7 +272,24 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       q.q = x0 << lsh;
       q.k = (uint32_t)ix.k;
       long long r;
-      if constexpr (kMode == 2) {
+      if constexpr (kLean && kMode == 3) {
+        __shared__ uint4 lines[kQueryThreads * kLineSlotU4];
+        SaLine32 sa;
+        sa.sm = lines + threadIdx.x * kLineSlotU4;
+        sa.anchor(ix, (uint32_t)pred, pol.sa);
+        r = kmer_replay32<2, true>(ix, q.q, (uint32_t)pred, pol, sa);
+      } else if constexpr (kLean && kMode == 2) {
+        SaPacked32 sa;
+        sa.anchor(ix, (uint32_t)pred);
+        r = kmer_replay32<2, true>(ix, q.q, (uint32_t)pred, pol, sa);
+      } else if constexpr (kLean && kMode == 1) {
+        SaNone32 none;
+        r = kmer_replay32<1, true>(ix, q.q, (uint32_t)pred, pol, none);
+      } else if constexpr (kLean) {
+        SaSector32 sa;
+        sa.fill(ix, (uint32_t)pred, pol.sa);
+        r = kmer_replay32<0, true>(ix, q.q, (uint32_t)pred, pol, sa);
+      } else if constexpr (kMode >= 2) {
         SaPacked sa;
         sa.anchor(ix, pred);
         r = pl_query_from<false, false, KmerQuery, SaPacked, true, 2>(ix, q, pred, 0, pol, sa);
@@ -682,6 +725,10 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const char* re = getenv("SAPLING_B200_REFILL");
   const bool refill = packed && ix.narrow != nullptr && re && atoi(re) == 1 && !d_slot;
   const int qv = query_variant(ix, inl || packed);
+  const char* lne = getenv("SAPLING_B200_LEAN");  // 0 = the general Replay instead of kmer_replay32 (A/B measurements)
+  const bool lean = lean_eligible(ix) && !(lne && atoi(lne) == 0);
+  const char* lse = getenv("SAPLING_B200_LINE_SMEM");  // 0 = rank-line sectors fetched probe by probe (A/B measurements)
+  const bool line_smem = lean && packed && !(lse && atoi(lse) == 0);
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
       kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));
@@ -696,18 +743,35 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     return qv;
   }
 #define SB_LAUNCH(kernel, bps) kernel<bps><<<query_grid(nq, bps * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out)
-#define SB_LAUNCH_S(kernel, bps) \
-  kernel<bps><<<query_grid(nq, bps * (d_tiles ? 1 : mult)), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles)
+#define SB_LAUNCH_S(kernel, bps)                                                                                       \
+  do {                                                                                                                \
+    if (lean)                                                                                                         \
+      kernel<bps, true><<<query_grid(nq, bps * (d_tiles ? 1 : mult)), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out,  \
+                                                                                              d_slot, d_tiles);      \
+    else                                                                                                              \
+      kernel<bps, false><<<query_grid(nq, bps * (d_tiles ? 1 : mult)), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, \
+                                                                                               d_slot, d_tiles);     \
+  } while (0)
   if (d_slot && !(packed || inl || sector)) {
     set_error("partitioned batches need the sector, inline or rank-line kernel");
     return -1;
   }
   const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");  // 0 = in-order tiles without the software pipeline
   if (d_tiles && d_slot && ix.narrow != nullptr && (packed || inl || sector) && !(oe && atoi(oe) == 0)) {
-#define SB_LAUNCH_O(bps, mode) \
-  kmer_query_ordered_kernel<bps, mode><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles)
-    const int mode = packed ? 2 : inl ? 1 : 0;
+#define SB_LAUNCH_O(bps, mode)                                                                                       \
+  do {                                                                                                               \
+    if (lean)                                                                                                        \
+      kmer_query_ordered_kernel<bps, mode, true><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, \
+                                                                                                d_slot, d_tiles);   \
+    else                                                                                                             \
+      kmer_query_ordered_kernel<bps, mode, false><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(                    \
+          ix, d_kmers, nq, d_out, d_slot, d_tiles);                                                                  \
+  } while (0)
+    const int mode = packed ? (line_smem ? 3 : 2) : inl ? 1 : 0;
     switch (qv * 10 + mode) {
+      case 33: SB_LAUNCH_O(3, 3); break;
+      case 43: SB_LAUNCH_O(4, 3); break;
+      case 53: SB_LAUNCH_O(5, 3); break;
       case 30: SB_LAUNCH_O(3, 0); break;
       case 31: SB_LAUNCH_O(3, 1); break;
       case 32: SB_LAUNCH_O(3, 2); break;
@@ -735,12 +799,20 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     }
 #undef SB_LAUNCH_R
   } else if (packed) {
+#define SB_LAUNCH_P(bps)                                                                                             \
+  do {                                                                                                               \
+    const int g = query_grid(nq, bps * (d_tiles ? 1 : mult));                                                        \
+    if (line_smem) kmer_query_packed_kernel<bps, 2><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles); \
+    else if (lean) kmer_query_packed_kernel<bps, 1><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles); \
+    else kmer_query_packed_kernel<bps, 0><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);       \
+  } while (0)
     switch (qv) {
-      case 3: SB_LAUNCH_S(kmer_query_packed_kernel, 3); break;
-      case 5: SB_LAUNCH_S(kmer_query_packed_kernel, 5); break;
-      case 6: SB_LAUNCH_S(kmer_query_packed_kernel, 6); break;
-      default: SB_LAUNCH_S(kmer_query_packed_kernel, 4); break;
+      case 3: SB_LAUNCH_P(3); break;
+      case 5: SB_LAUNCH_P(5); break;
+      case 6: SB_LAUNCH_P(6); break;
+      default: SB_LAUNCH_P(4); break;
     }
+#undef SB_LAUNCH_P
   } else if (inl) {
     switch (qv) {
       case 3: SB_LAUNCH_S(kmer_query_inline_kernel, 3); break;

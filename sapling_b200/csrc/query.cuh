@@ -444,6 +444,286 @@ __device__ __forceinline__ long long pl_query_from(const IndexView& ix, const Qu
   return result;
 }
 
+// ---- lean k-mer replay --------------------------------------------------------------------------------------------
+// The same replay specialised for what the batch kernels actually answer: a k-mer (s.length() == length == k <= 32, so no
+// gallop loops) against an index with n < 2^32 ranks.  Ranks, windows and LCPs are 32-bit, and the nine cases of
+// Replay::step collapse into ONE straight-line update, because every probe after the first either moves the low bound
+// (lo = r, loLcp = lcp) or the high bound (hi = r, hiLcp = lcp) of the pair binarySearch is finally called with:
+//   R1 (r == hi)  small: lo = hi, loLcp = lcp, then widen hi (:175-181)      else: hiLcp = lcp, search   (:199-204; loLcp
+//                                                                                   already holds the first probe's lcp)
+//   L1 (r == lo)  small: loLcp = lcp, search (:214-219; hiLcp already holds it)  else: hi = lo, hiLcp = lcp, then widen lo
+//   R2 (r == hi)  hiLcp = lcp, search (:197)         L2 (r == lo)  loLcp = lcp, search (:242)
+//   BS            small: lo = mid, loLcp = lcp       else: hi = mid, hiLcp = lcp    (:143-152)
+//   SKIP          verified: lo = cand, loLcp = lcp   else: nothing                  (long-window shortcut, see Replay)
+// A warp whose lanes sit in different cases therefore executes one instruction stream instead of one per case
+// (ncu, profiles/r1y: 15 of 32 lanes active per instruction, 43 warp instructions per query with Replay::step).
+// "Suffix too small" (:143) needs no base extraction: with the first `start` bases masked out of both words, the first
+// differing base decides the unsigned comparison of the words.
+// Preconditions (checked by the launcher, which otherwise uses Replay): n <= 2^32 - 16, error bounds >= 0.
+constexpr uint64_t kLeanMaxN = 0xFFFFFFF0ull;
+
+struct SaPacked32 {
+  uint32_t abase;  // first rank of the anchor line
+  uint32_t cur;    // first rank of the sector held in e (a multiple of 4); 0xFFFFFFFF: none
+  U32x8 e;
+  __device__ __forceinline__ void anchor(const IndexView& ix, uint32_t pred) {
+    const uint32_t back = (uint32_t)(ix.mostUnder < 4 ? ix.mostUnder : 4);
+    const uint32_t lo = ix.packed_shift == 3 ? (pred > back ? pred - back : 0u) : pred;
+    abase = (lo >> ix.packed_shift) << ix.packed_shift;
+    cur = 0xFFFFFFFFu;
+  }
+  __device__ __forceinline__ uint32_t get(const IndexView& ix, uint32_t r, uint64_t pol, uint64_t* g, bool* esc) {
+    const uint32_t s4 = r & ~3u;
+    if (s4 != cur) {
+      const uint32_t first = (r - abase < 16u) ? abase : ((r >> ix.packed_shift) << ix.packed_shift);
+      const uint32_t sector = ((first >> ix.packed_shift) << 2) + ((r - first) >> 2);
+      e = ld_u32x8_pol(ix.packed + (uint64_t)sector * 8u, pol);
+      cur = s4;
+    }
+    const unsigned j = r & 3u;
+    const uint64_t P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
+    const uint64_t D = ((uint64_t)e.v[3] << 32) | e.v[2];
+    const uint64_t d = j ? ((D >> (kPackedDeltaBits * (j - 1))) & (uint64_t)kPackedEscape) : 0ull;
+    *esc = j ? (d == (uint64_t)kPackedEscape) : ((D >> 63) != 0);
+    *g = (P0 + d) << (64 - 2 * ix.packed_bases);
+    const uint32_t a = (j & 1u) ? e.v[5] : e.v[4], b = (j & 1u) ? e.v[7] : e.v[6];
+    return (j & 2u) ? b : a;
+  }
+};
+
+// Anchor line staged in shared memory.  SaPacked32 above fetches the sectors of the anchor line one probe at a time and
+// counts on L2 to still hold the line for the later ones.  Once the batch is walked in order that stops being true in a
+// bistable way (gpurun r2b, c3: the same kernel takes 10 or 15.6 ms per 250 M queries depending on how many warps are
+// resident): with ~5 TB/s of line fills streaming through L2 a line survives about as long as one query lasts, and when
+// it does not, every later probe of the query refetches 128 bytes from DRAM and the queries get slower still.  Here the
+// thread requests all four sectors of its anchor line at once (four independent 256-bit loads: one DRAM line fill, one
+// latency instead of up to four dependent ones), parks them in its own 144-byte shared-memory slot and answers every
+// probe inside the line from there; only ranks outside the anchor line (the long left chains of SURVEY F5, windows that
+// straddle two tiling lines) still go to global memory, through a one-sector register cache as before.
+// Slot stride 144 = 128 + 16 bytes: the 16-byte accesses of 8 consecutive lanes then fall into 8 different bank groups.
+constexpr int kLineSlotU4 = 9;  // uint4 per thread slot
+struct SaLine32 {
+  uint4* sm;       // this thread's slot
+  uint32_t abase;  // first rank of the anchor line
+  uint32_t cur;    // first rank of the sector held in e (outside the anchor line); 0xFFFFFFFF: none
+  U32x8 e;
+  __device__ __forceinline__ void anchor(const IndexView& ix, uint32_t pred, uint64_t pol) {
+    const uint32_t back = (uint32_t)(ix.mostUnder < 4 ? ix.mostUnder : 4);
+    const uint32_t lo = ix.packed_shift == 3 ? (pred > back ? pred - back : 0u) : pred;
+    abase = (lo >> ix.packed_shift) << ix.packed_shift;
+    cur = 0xFFFFFFFFu;
+    const uint32_t* line = ix.packed + (uint64_t)(abase >> ix.packed_shift) * 32u;
+    const U32x8 s0 = ld_u32x8_pol(line, pol), s1 = ld_u32x8_pol(line + 8, pol);
+    const U32x8 s2 = ld_u32x8_pol(line + 16, pol), s3 = ld_u32x8_pol(line + 24, pol);
+    sm[0] = make_uint4(s0.v[0], s0.v[1], s0.v[2], s0.v[3]);
+    sm[1] = make_uint4(s0.v[4], s0.v[5], s0.v[6], s0.v[7]);
+    sm[2] = make_uint4(s1.v[0], s1.v[1], s1.v[2], s1.v[3]);
+    sm[3] = make_uint4(s1.v[4], s1.v[5], s1.v[6], s1.v[7]);
+    sm[4] = make_uint4(s2.v[0], s2.v[1], s2.v[2], s2.v[3]);
+    sm[5] = make_uint4(s2.v[4], s2.v[5], s2.v[6], s2.v[7]);
+    sm[6] = make_uint4(s3.v[0], s3.v[1], s3.v[2], s3.v[3]);
+    sm[7] = make_uint4(s3.v[4], s3.v[5], s3.v[6], s3.v[7]);
+  }
+  __device__ __forceinline__ uint32_t get(const IndexView& ix, uint32_t r, uint64_t pol, uint64_t* g, bool* esc) {
+    const unsigned j = r & 3u;
+    uint64_t P0, D;
+    uint32_t pos;
+    const uint32_t off = r - abase;
+    if (off < 16u) {
+      const uint4 h = sm[2u * (off >> 2)];
+      P0 = ((uint64_t)h.y << 32) | h.x;
+      D = ((uint64_t)h.w << 32) | h.z;
+      pos = reinterpret_cast<const uint32_t*>(sm + 2u * (off >> 2) + 1u)[j];
+    } else {
+      const uint32_t s4 = r & ~3u;
+      if (s4 != cur) {
+        const uint32_t first = (r >> ix.packed_shift) << ix.packed_shift;
+        const uint32_t sector = ((first >> ix.packed_shift) << 2) + ((r - first) >> 2);
+        e = ld_u32x8_pol(ix.packed + (uint64_t)sector * 8u, pol);
+        cur = s4;
+      }
+      P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
+      D = ((uint64_t)e.v[3] << 32) | e.v[2];
+      const uint32_t a = (j & 1u) ? e.v[5] : e.v[4], b = (j & 1u) ? e.v[7] : e.v[6];
+      pos = (j & 2u) ? b : a;
+    }
+    const uint64_t d = j ? ((D >> (kPackedDeltaBits * (j - 1))) & (uint64_t)kPackedEscape) : 0ull;
+    *esc = j ? (d == (uint64_t)kPackedEscape) : ((D >> 63) != 0);
+    *g = (P0 + d) << (64 - 2 * ix.packed_bases);
+    return pos;
+  }
+};
+
+struct SaSector32 {
+  U32x8 e;
+  uint32_t base;  // first rank of the cached sector (multiple of 8)
+  __device__ __forceinline__ void fill(const IndexView& ix, uint32_t pred, uint64_t pol) {
+    base = pred & ~7u;
+    e = ld_u32x8_pol(ix.sa + base, pol);  // the SA allocation is padded to whole lines
+  }
+  __device__ __forceinline__ uint32_t ld(const IndexView& ix, uint32_t r, uint64_t pol) const {
+    if ((r & ~7u) == base) {
+      const unsigned j = r & 7u;
+      const uint32_t a = (j & 1u) ? e.v[1] : e.v[0], b = (j & 1u) ? e.v[3] : e.v[2];
+      const uint32_t c = (j & 1u) ? e.v[5] : e.v[4], d = (j & 1u) ? e.v[7] : e.v[6];
+      const uint32_t ab = (j & 2u) ? b : a, cd = (j & 2u) ? d : c;
+      return (j & 4u) ? cd : ab;
+    }
+    return ld_u32_pol(ix.sa + r, pol);
+  }
+};
+
+struct SaNone32 {};  // kMode 1 reads ExtEntry directly
+
+__device__ __forceinline__ uint32_t lean_uhadd(uint32_t a, uint32_t b) {  // floor((a + b) / 2) without overflow
+#ifdef SB_HOST_SIM
+  return (uint32_t)(((uint64_t)a + b) >> 1);
+#else
+  return __uhadd(a, b);
+#endif
+}
+__device__ __forceinline__ uint32_t lean_add_clamped(uint32_t a, uint32_t b, uint32_t top) {  // min(a + b, top), a <= top
+  const uint32_t t = a + b;
+  return (t < a || t > top) ? top : t;
+}
+
+// q = the k bases left-aligned; pred < n.  kMode: 0 = {suffix-array sector, packed genome}, 1 = inline-prefix entries,
+// 2 = rank lines.  Returns plQuery's answer (sapling_api.h:159-248).
+template <int kMode, bool kSkip, typename Sa>
+__device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const uint64_t q, const uint32_t pred,
+                                                   const L2Policies& pol, Sa& sa) {
+  enum : int { S_PRED = 0, S_R1, S_R2, S_L1, S_L2, S_BS, S_FINAL, S_SKIP };
+  const uint32_t k = (uint32_t)ix.k;
+  const uint32_t n32 = (uint32_t)ix.n, nm1 = n32 - 1u;
+  uint32_t lo = 0, hi = 0, r = pred, loLcp = 0, hiLcp = 0, start = 0;
+  int state = S_PRED;
+  for (;;) {
+    // ---- one probe: rev[r] and the leading bases of that suffix --------------------------------------------------
+    uint32_t idx;
+    uint64_t g;
+    if constexpr (kMode == 1) {
+      const uint4 e = ld_u32x4_pol(reinterpret_cast<const uint4*>(ix.ext + r), pol.sa);
+      idx = e.x;
+      g = ((uint64_t)e.w << 32) | e.z;
+      if (state == S_FINAL) return (long long)idx;
+    } else if constexpr (kMode == 2) {
+      bool esc;
+      idx = sa.get(ix, r, pol.sa, &g, &esc);
+      if (state == S_FINAL) return (long long)idx;
+      // an entry carries packed_bases bases: a longer k-mer that agrees on all of them is decided by the genome
+      if (!esc && (int)k > ix.packed_bases) esc = ((q ^ g) >> (64 - 2 * ix.packed_bases)) == 0;
+      if (esc) g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
+    } else {
+      idx = sa.ld(ix, r, pol.sa);
+      if (state == S_FINAL) return (long long)idx;
+      g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
+    }
+    // ---- getLcp from `start` (:115-120) and the "suffix too small" test (:143) ------------------------------------
+    const uint64_t mask = (~0ull) >> (2u * start);  // start < k <= 32
+    const uint64_t qm = q & mask, gm = g & mask;
+    const uint64_t diff = qm ^ gm;
+    const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
+    const uint32_t room = n32 - idx;  // characters left in the text
+    const uint32_t leff = room < k ? room : k;
+    const uint32_t lcp = m < leff ? m : leff;
+    const bool small = (lcp == room) || (qm > gm);
+    const bool match = lcp == k;
+
+    if (state == S_PRED) {  // :162-172 / :209-211
+      if (match) return (long long)idx;
+      if (small) {
+        lo = pred;
+        loLcp = lcp;
+        hi = lean_add_clamped(pred, (uint32_t)ix.mostOver, nm1);
+        r = hi;
+        state = S_R1;
+      } else {
+        hi = pred;
+        hiLcp = lcp;
+        if (ix.compat) {  // (int)predicted - mostUnder (:209): wraps negative for predicted >= 2^31
+          const int32_t v = (int32_t)(pred - (uint32_t)ix.mostUnder);
+          lo = (uint32_t)(v > 0 ? v : 0);
+        } else {
+          const uint32_t d = (uint32_t)ix.mostUnder;
+          lo = pred > d ? pred - d : 0u;
+        }
+        r = lo;
+        state = S_L1;
+      }
+      continue;
+    }
+    if (state != S_SKIP && match) return (long long)idx;      // :174 :183 :213 :228 :141
+    if (state == S_BS && lo + 1u >= hi) return -1;            // :142
+    {
+      const bool to_lo = state == S_R2 ? false : (state == S_L2 ? true : small);
+      const bool upd = !(state == S_SKIP && (!small || match));  // unverified shortcut: assume nothing
+      if (upd) {
+        if (to_lo) {
+          lo = r;
+          loLcp = lcp;
+        } else {
+          hi = r;
+          hiLcp = lcp;
+        }
+      }
+    }
+    if (state == S_R1 && small) {  // :180-181
+      hi = lean_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
+      r = hi;
+      state = S_R2;
+      continue;
+    }
+    if (state == S_L1 && !small) {  // :225-226
+      if (ix.compat) {
+        const int32_t v = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
+        lo = (uint32_t)(v > 0 ? v : 0);
+      } else {
+        const uint32_t d = (uint32_t)ix.maxUnder + 1u;
+        lo = pred > d ? pred - d : 0u;
+      }
+      r = lo;
+      state = S_L2;
+      continue;
+    }
+    if (kSkip && state == S_L1) {  // small: the long-window shortcut (see Replay::step)
+      const uint32_t guard = (uint32_t)ix.maxUnder + 1u;
+      if ((uint64_t)(hi - lo) > 4ull * guard + 64ull) {
+        uint32_t cand = lo;
+        for (;;) {
+          const uint32_t mid = lean_uhadd(cand, hi);
+          if (hi - mid < guard) break;
+          cand = mid;
+        }
+        if (cand != lo) {
+          SB_SIM_COUNT(g_sim_skip_tried);
+          r = cand;
+          start = 0;
+          state = S_SKIP;
+          continue;
+        }
+      }
+    }
+#ifdef SB_HOST_SIM
+    if (state == S_SKIP && small && !match) SB_SIM_COUNT(g_sim_skip_ok);
+#endif
+    // top of binarySearch (:136-140)
+    if (hi - lo == 2u) {
+      r = lo + 1u;
+      state = S_FINAL;
+    } else {
+      r = lean_uhadd(lo, hi);
+      start = loLcp < hiLcp ? loLcp : hiLcp;
+      state = S_BS;
+    }
+  }
+}
+
+// whether kmer_replay32 may answer queries on this index
+__host__ __device__ inline bool lean_eligible(const IndexView& ix) {
+  return ix.n <= kLeanMaxN && ix.k >= 1 && ix.k <= 32 && ix.maxOver >= 0 && ix.maxUnder >= 0 && ix.mostOver >= 0 &&
+         ix.mostUnder >= 0;
+}
+
 template <bool kGallop, typename Query>
 __device__ __forceinline__ long long pl_query(const IndexView& ix, const Query& qy, uint64_t kmer) {
   const L2Policies pol = make_policies(ix.hints);

@@ -84,6 +84,74 @@ void sim_kmer_batch_packed(const uint64_t* genome, const uint32_t* sa, const int
   if (!out_packed) delete[] packed;
 }
 
+// The lean 32-bit k-mer replay (query.cuh kmer_replay32) on the three layouts.  mode 0: suffix-array sector + packed
+// genome; 1: inline-prefix entries (ext_bases leading bases, k <= ext_bases); 2: rank lines (bases, shift).
+int sim_kmer_batch_lean(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
+                        const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
+                        unsigned long long* oob, int mode, int bases, int shift) {
+  sb::IndexView ix;
+  ix.genome = genome; ix.sa = sa; ix.ext = nullptr; ix.ext_bases = 0;
+  ix.packed = nullptr; ix.packed_bases = bases; ix.packed_shift = shift;
+  ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
+  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
+  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
+  ix.compat = compat; ix.oob_counter = oob;
+  ix.narrow = nullptr; ix.last_x = 0; ix.last_y = 0; ix.hints = 0;
+  if (!sb::lean_eligible(ix)) return -1;
+  uint32_t* packed = nullptr;
+  sb::ExtEntry* ext = nullptr;
+  // the device arrays are padded to whole lines; sectors are read whole
+  uint32_t* sa_pad = new uint32_t[sb::sa_alloc_entries(n) + 16]();
+  memcpy(sa_pad, sa, n * sizeof(uint32_t));
+  ix.sa = sa_pad;
+  if (mode == 2 || mode == 3) {
+    const uint64_t sectors = sb::packed_sectors(n, shift);
+    packed = new uint32_t[sectors * 8];
+    for (uint64_t s = 0; s < sectors; s++) {
+      const uint64_t r0 = ((s >> 2) << shift) + ((s & 3u) << 2);
+      sb::pack_rank_sector(genome, sa, n, bases, r0, packed + s * 8);
+    }
+    ix.packed = packed;
+  } else if (mode == 1) {
+    ext = new sb::ExtEntry[n];
+    for (uint64_t r = 0; r < n; r++) {
+      ext[r].pos = sa[r];
+      ext[r].reserved = 0;
+      const uint64_t w = sb::load_bases32(genome, sa[r]);
+      ext[r].prefix = bases >= 32 ? w : (w >> (64 - 2 * bases)) << (64 - 2 * bases);
+    }
+    ix.ext = ext;
+    ix.ext_bases = bases;
+  }
+  const sb::L2Policies pol = sb::make_policies(0);
+  for (size_t i = 0; i < nq; i++) {
+    const uint64_t q = kmers[i] << (64 - 2 * k);
+    const uint32_t pred = (uint32_t)sb::clamp_prediction(ix, sb::predict_rank(ix, kmers[i], pol.model));
+    if (mode == 2) {
+      sb::SaPacked32 sp;
+      sp.anchor(ix, pred);
+      out[i] = sb::kmer_replay32<2, true>(ix, q, pred, pol, sp);
+    } else if (mode == 3) {  // anchor line staged in the thread's shared-memory slot
+      uint4 slot[sb::kLineSlotU4];
+      sb::SaLine32 sl;
+      sl.sm = slot;
+      sl.anchor(ix, pred, pol.sa);
+      out[i] = sb::kmer_replay32<2, true>(ix, q, pred, pol, sl);
+    } else if (mode == 1) {
+      sb::SaNone32 none;
+      out[i] = sb::kmer_replay32<1, true>(ix, q, pred, pol, none);
+    } else {
+      sb::SaSector32 ss;
+      ss.fill(ix, pred, pol.sa);
+      out[i] = sb::kmer_replay32<0, true>(ix, q, pred, pol, ss);
+    }
+  }
+  delete[] packed;
+  delete[] ext;
+  delete[] sa_pad;
+  return 0;
+}
+
 void sim_string_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                       const int* five, int compat, const uint64_t* words, const uint64_t* word_off,
                       const uint32_t* slens, const uint32_t* lengths, const int64_t* kmers, size_t nq, int64_t* out,

@@ -85,7 +85,62 @@ def _sim():
     L.sim_kmer_batch_packed.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
                                         C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_void_p,
                                         C.POINTER(C.c_uint64)]
+    L.sim_kmer_batch_lean.restype = C.c_int
+    L.sim_kmer_batch_lean.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
+                                      C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
     return L
+
+
+@pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])
+def test_lean_kmer_replay_on_host_matches_oracle(oracle_built, name):
+    """query.cuh kmer_replay32 (32-bit ranks, the nine cases of the replay folded into one update; what the batch
+    kernels run) compiled for the host == oracle, on all three layouts: suffix-array sector + packed genome, inline
+    prefixes, rank lines (overlapping / tiling, prefixes shorter than k, escapes); the model's own error bounds, bounds
+    that collapse the left window to rank 0 (long-window shortcut), tiny bounds; compat and 64-bit-safe
+    window arithmetic."""
+    L = _sim()
+    g = F.small_genomes()[name]
+    n = len(g)
+    for k, nb in ((21, -1), (11, 4), (31, 10), (16, -1), (32, 12)):
+        if n < 4 * k:
+            continue
+        if k == 32:
+            continue  # oracle-undefined (SURVEY F4)
+        base = O.Port.from_memory(g, nb=nb, k=k)
+        packed, sa = F.pack_genome(g), base.sa
+        model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
+        kmers = F.query_mix(g, k, 3000)
+        tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(max(0, n - 40), n)], dtype=np.uint64)
+        kmers = np.concatenate([kmers, tail])
+        f0 = list(base.five)
+        for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30], [2, 2, 1, 1, 1],
+                       [1, 40, 1, 9, 30]):
+            port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
+            five = np.array(five_t, dtype=np.int32)
+            exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
+            cases = [(0, 0, 3), (2, 6, 3), (2, 12, 4), (2, 21, 3), (2, 32, 4), (2, 16, 4),
+                     (3, 6, 4), (3, 12, 3), (3, 21, 4), (3, 32, 3), (3, 16, 3)]
+            cases += [(1, b, 3) for b in (27, 32) if k <= b]
+            for mode, bases, shift in cases:
+                out = np.empty(len(kmers), dtype=np.int64)
+                c = C.c_uint64(0)
+                rc = L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c),
+                                           mode, bases, shift)
+                assert rc == 0
+                bad = np.nonzero(out != exp)[0]
+                assert len(bad) == 0 and c.value == oob, (name, k, nb, five_t, mode, bases, shift, bad[:5], out[bad[:5]],
+                                                          exp[bad[:5]])
+            # 64-bit-safe window arithmetic (SAPLING_B200_NO_COMPAT) has no oracle: lean replay == general replay
+            gen = np.empty(len(kmers), dtype=np.int64)
+            last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
+            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), gen, C.byref(c), None, last)
+            for mode, bases, shift in cases[:3]:
+                out = np.empty(len(kmers), dtype=np.int64)
+                assert L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), out,
+                                             C.byref(c), mode, bases, shift) == 0
+                assert np.array_equal(out, gen), (name, k, nb, five_t, mode, "no-compat")
+            port.close()
+        base.close()
 
 
 @pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])

@@ -343,7 +343,7 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
             for bits in (1, 3, 8, 11):
                 monkeypatch.setenv("SAPLING_B200_PART_BITS", str(bits))
                 assert ix.partition_bits(len(kmers)) == min(bits, 2 * k)
-                for m in (len(kmers), 16384, 16385, 32767, 1, 33, 5000):
+                for m in (len(kmers), 8192, 8193, 16384, 16385, 32767, 1, 33, 5000):
                     assert np.array_equal(ix.queryBatch(kmers[:m]), exp[:m]), (name, k, nb, flags, bits, m)
             monkeypatch.delenv("SAPLING_B200_PART_BITS")
             assert ix.oob_count() >= 0
@@ -351,3 +351,53 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
         port.close()
     monkeypatch.delenv("SAPLING_B200_PART_MIN", raising=False)
     monkeypatch.delenv("SAPLING_B200_PART", raising=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["rand200k", "gc0110", "tandem50"])
+def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch):
+    """Every selectable variant of the batch path returns the oracle's answers: the lean 32-bit replay against the
+    general one, the anchor line staged in shared memory against sector-by-sector fetches, the in-order tile schedule
+    with and without the software pipeline against the static grid-stride schedule, the staged against the direct
+    scatter and the flat against the run-per-warp un-permute -- on all three index layouts, collapsed left windows
+     included."""
+    g = GENOMES[name]
+    for k, nb, five_fn in ((21, -1, None), (16, 8, lambda f: [f[0], f[1], f[2], f[3], 1 << 30]), (31, 12, None)):
+        if len(g) < 4 * k:
+            continue
+        base = O.Port.from_memory(g, nb=nb, k=k)
+        five = list(base.five) if five_fn is None else five_fn(list(base.five))
+        port = O.Port.from_parts(g, base.sa, k, base.nb, base.xlist, base.ylist, five)
+        q0 = F.query_mix(g, k, 6000, seed=5)
+        kmers = np.concatenate([q0, np.sort(q0), q0[::-1]] * 2)  # 36000: several partition chunks
+        exp = port.query_batch(kmers, nthreads=4)
+        for flags in (S.NO_PACKED | S.NO_INLINE, S.PACKED, S.INLINE | S.NO_PACKED):
+            for shift in (("3", "4") if flags == S.PACKED else ("3",)):
+                monkeypatch.setenv("SAPLING_B200_PACKED_SHIFT", shift)
+                ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, five, flags=S.QUIET | flags)
+                for part in ("0", "1"):
+                    monkeypatch.setenv("SAPLING_B200_PART", part)
+                    monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
+                    monkeypatch.setenv("SAPLING_B200_PART_BITS", "5")
+                    for lean, line_smem in (("1", "1"), ("1", "0"), ("0", "0")):
+                        monkeypatch.setenv("SAPLING_B200_LEAN", lean)
+                        monkeypatch.setenv("SAPLING_B200_LINE_SMEM", line_smem)
+                        combos = ((("1", "1", "1", "1"), ("1", "0", "1", "1"), ("0", "1", "0", "0"), ("0", "1", "1", "0"))
+                                  if part == "1" else (("1", "1", "1", "1"),))
+                        for tiles, pipe, scat, unp in combos:
+                            monkeypatch.setenv("SAPLING_B200_PART_TILES", tiles)
+                            monkeypatch.setenv("SAPLING_B200_ORDERED_PIPE", pipe)
+                            monkeypatch.setenv("SAPLING_B200_PART_SCATTER", scat)
+                            monkeypatch.setenv("SAPLING_B200_PART_UNPERMUTE", unp)
+                            for qv in ("3", "4", "5"):
+                                monkeypatch.setenv("SAPLING_B200_QV", qv)
+                                got = ix.queryBatch(kmers)
+                                assert np.array_equal(got, exp), (name, k, flags, shift, part, lean, line_smem, tiles,
+                                                                  pipe, scat, unp, qv)
+                            assert np.array_equal(ix.queryBatch(kmers[:8191]), exp[:8191])
+                ix.close()
+        port.close()
+        base.close()
+    for v in ("PART", "PART_MIN", "PART_BITS", "LEAN", "LINE_SMEM", "PART_TILES", "ORDERED_PIPE", "PART_SCATTER",
+              "PART_UNPERMUTE", "QV", "PACKED_SHIFT"):
+        monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
