@@ -78,7 +78,8 @@ enum : unsigned {
   HINT_GENOME_KEEP = 1u,   // packed genome loads: L2 evict_last
   HINT_MODEL_KEEP = 2u,    // model loads: L2 evict_last
   HINT_SA_STREAM = 4u,     // suffix-array loads: L2 evict_first
-  HINT_IO_STREAM = 8u      // k-mer reads / result writes: ld.cs / st.cs
+  HINT_IO_STREAM = 8u,     // k-mer reads / result writes: ld.cs / st.cs
+  HINT_SA_KEEP = 16u       // suffix-array / rank-line loads: L2 evict_last (wins over HINT_SA_STREAM)
 };
 
 #define SB_CUDA_CHECK(expr)                                                          \
@@ -132,7 +133,7 @@ __device__ __forceinline__ L2Policies make_policies(unsigned hints) {
   L2Policies p;
   p.genome = (hints & HINT_GENOME_KEEP) ? keep : normal;
   p.model = (hints & HINT_MODEL_KEEP) ? keep : normal;
-  p.sa = (hints & HINT_SA_STREAM) ? first : normal;
+  p.sa = (hints & HINT_SA_KEEP) ? keep : (hints & HINT_SA_STREAM) ? first : normal;
   return p;
 }
 __device__ __forceinline__ uint64_t ld_u64_pol(const uint64_t* p, uint64_t pol) {

@@ -162,9 +162,9 @@ __device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t 
 // by bin inside shared memory -- each thread keeps its 16 k-mers in registers, the shared-memory atomic that counts the
 // bin also hands out the query's rank inside (chunk, bin) -- and then writes the sorted chunk out in order: consecutive
 // threads store consecutive addresses for as long as the bin lasts (chunk / bins queries on average).
-constexpr int kScatterThreads = 512;  // 16 k-mers per thread in registers, two blocks per SM
+constexpr int kScatterThreads = kPartChunk / 16;  // 16 k-mers per thread in registers
 constexpr int kScatterPer = kPartChunk / kScatterThreads;
-__global__ void __launch_bounds__(kScatterThreads, 2)
+__global__ void __launch_bounds__(kScatterThreads)
 part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
                            const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
                            uint64_t* __restrict__ part_kmer, uint16_t* __restrict__ part_slot) {
@@ -261,8 +261,8 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
 // queries against 1.2 ms at 256 bins).  Here the block first scans the chunk's run lengths, then thread i of the chunk's
 // sorted order finds its run by binary search over the scanned starts in shared memory: neighbouring threads read
 // neighbouring answers whatever the run length.
-constexpr int kFlatThreads = 512;  // two blocks per SM
-__global__ void __launch_bounds__(kFlatThreads, 2)
+constexpr int kFlatThreads = kPartChunk / 16;
+__global__ void __launch_bounds__(kFlatThreads)
 part_unpermute_flat_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
                            const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
                            long long* __restrict__ out) {

@@ -727,8 +727,8 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const int qv = query_variant(ix, inl || packed);
   const char* lne = getenv("SAPLING_B200_LEAN");  // 0 = the general Replay instead of kmer_replay32 (A/B measurements)
   const bool lean = lean_eligible(ix) && !(lne && atoi(lne) == 0);
-  const char* lse = getenv("SAPLING_B200_LINE_SMEM");  // 0 = rank-line sectors fetched probe by probe (A/B measurements)
-  const bool line_smem = lean && packed && !(lse && atoi(lse) == 0);
+  const char* lse = getenv("SAPLING_B200_LINE_SMEM");  // 1 = anchor line staged in shared memory (measured slower: opt-in)
+  const bool line_smem = lean && packed && lse && atoi(lse) == 1;
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
       kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));

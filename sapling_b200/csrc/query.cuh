@@ -491,7 +491,10 @@ struct SaPacked32 {
   }
 };
 
-// Anchor line staged in shared memory.  SaPacked32 above fetches the sectors of the anchor line one probe at a time and
+// Anchor line staged in shared memory -- MEASURED SLOWER, opt-in (SAPLING_B200_LINE_SMEM=1); kept because the result is
+// instructive: four sector requests per query instead of ~2.5 cost more than the dependent round trips they remove
+// (gpurun r2c: c2 2.5 -> 4.9 ms unpartitioned, 1.6 -> 2.1 ms partitioned; c3 partitioned 12.3 ms, stable, against
+// 10.1-15.8 ms).  The idea was: SaPacked32 above fetches the sectors of the anchor line one probe at a time and
 // counts on L2 to still hold the line for the later ones.  Once the batch is walked in order that stops being true in a
 // bistable way (gpurun r2b, c3: the same kernel takes 10 or 15.6 ms per 250 M queries depending on how many warps are
 // resident): with ~5 TB/s of line fills streaming through L2 a line survives about as long as one query lasts, and when
