@@ -416,7 +416,7 @@ def main():
     total_ms = max_over_ranks(total_ms, dist, "cuda")
     value = world * nq * args.steps / (total_ms * 1e-3)
     step_mean_ms = sum(step_ms) / len(step_ms)
-    kernel_name, kernel_bps = ix.query_kernel()
+    kernel_name, kernel_bps = ix.query_kernel(nq)
     part_bits = ix.partition_bits(nq)
     launches_per_step = 6 if part_bits else 1
     # the query kernel on its own: the same steps again with CUDA events recorded by the library on the launching

@@ -105,6 +105,9 @@ uint64_t sapling_b200_launch_count(const sapling_b200_index *ix);
 /* Name of the CUDA kernel sapling_b200_query_batch(_dev) launches for this index (which layout it reads depends on
  * the genome size and the flags), and the resident blocks per SM it is compiled for. */
 const char *sapling_b200_query_kernel(const sapling_b200_index *ix, int *blocks_per_sm);
+/* The same for a batch of nq queries: a batch large enough to be partitioned (next entry) runs the in-order
+ * kernel over the partitioned k-mers instead. */
+const char *sapling_b200_query_kernel_for(const sapling_b200_index *ix, size_t nq, int *blocks_per_sm);
 /* How many top k-mer bits sapling_b200_query_batch_dev partitions a batch of nq queries by before the query kernel
  * walks it (2^bits slices of the index); 0 = the batch is answered in the caller's order.
  * The answers are the same either way. */

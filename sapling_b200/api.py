@@ -41,6 +41,7 @@ SYMBOLS = {
     "sapling_b200_device_bytes": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_launch_count": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_query_kernel": (C.c_char_p, [C.c_void_p, C.POINTER(C.c_int)]),
+    "sapling_b200_query_kernel_for": (C.c_char_p, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "sapling_b200_query_partition_bits": (C.c_int, [C.c_void_p, C.c_size_t]),
     "sapling_b200_profile": (C.c_int, [C.c_void_p, C.c_int]),
     "sapling_b200_stage_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -247,10 +248,14 @@ class Sapling:
             raise SaplingError(_err())
         return calls, [float(x) for x in ms]
 
-    def query_kernel(self):
-        """(name of the CUDA kernel queryBatch launches for this index, resident blocks per SM it is compiled for)."""
+    def query_kernel(self, nq=None):
+        """(name of the CUDA kernel queryBatch launches for this index, resident blocks per SM it is compiled for);
+        with nq: for a batch of that many queries (a partitioned batch runs the in-order kernel)."""
         b = C.c_int(0)
-        name = self._L.sapling_b200_query_kernel(self._h, C.byref(b))
+        if nq is None:
+            name = self._L.sapling_b200_query_kernel(self._h, C.byref(b))
+        else:
+            name = self._L.sapling_b200_query_kernel_for(self._h, int(nq), C.byref(b))
         return (name or b"").decode(), b.value
 
     def _ck(self, rc):

@@ -413,7 +413,9 @@ int finish_model_checks(sapling_b200_index* ix) {
   // query-side layout + L2 residency policy (experiment knobs: SAPLING_B200_NARROW=0, SAPLING_B200_HINTS=<bits>)
   const char* e_narrow = getenv("SAPLING_B200_NARROW");
   const char* e_hints = getenv("SAPLING_B200_HINTS");
-  ix->hints = e_hints ? (unsigned)atoi(e_hints) : (HINT_GENOME_KEEP | HINT_MODEL_KEEP | HINT_SA_STREAM | HINT_IO_STREAM);
+  // measured (gpurun r2d / r2e): with the batch partitioned the suffix-array slice is what L2 should hold -- evict_last on
+  // it makes the c3 kernel time stable at 10.0-10.1 ms per 250 M queries where the other policies flip between 10 and 16
+  ix->hints = e_hints ? (unsigned)atoi(e_hints) : (HINT_GENOME_KEEP | HINT_MODEL_KEEP | HINT_SA_KEEP | HINT_IO_STREAM);
   if (const char* e_persist = getenv("SAPLING_B200_L2_PERSIST_MB")) {
     // optional: widen the L2 set-aside that evict_last ("persisting") lines may occupy
     cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(e_persist) << 20);
@@ -454,7 +456,9 @@ int finish_model_checks(sapling_b200_index* ix) {
 constexpr uint64_t kPackedMinGenome = 50000000ull;
 int packed_shift_setting() {
   const char* e = getenv("SAPLING_B200_PACKED_SHIFT");
-  return (e && atoi(e) == 4) ? 4 : 3;
+  // measured (gpurun r2c / r2e, tools/part_sweep.py): tiling lines (shift 4) answer a partitioned batch faster than the
+  // overlapping ones at half the memory (c3: 10.1 against 12.9 ms per 250 M queries); shift 3 stays selectable
+  return (e && atoi(e) == 3) ? 3 : 4;
 }
 bool want_packed(const sapling_b200_index* ix) {
   if (ix->flags & SAPLING_B200_NO_PACKED) return false;
@@ -995,6 +999,20 @@ int sapling_b200_stage_ms(sapling_b200_index* ix, double ms[4]) {
 
 int sapling_b200_query_partition_bits(const sapling_b200_index* ix, size_t nq) {
   return ix ? partition_bits(ix, nq) : 0;
+}
+
+const char* sapling_b200_query_kernel_for(const sapling_b200_index* ix, size_t nq, int* blocks_per_sm) {
+  if (!ix) return "";
+  if (partition_bits(ix, nq) == 0) return sapling_b200_query_kernel(ix, blocks_per_sm);
+  const char* te = getenv("SAPLING_B200_PART_TILES");
+  const bool in_order = !(te && atoi(te) == 0);
+  // non-null dummies: "this batch arrives partitioned, with an in-order tile counter" (nothing is launched)
+  static const uint16_t slot_tag = 0;
+  static unsigned long long tile_tag = 0;
+  const char* name = "";
+  const int qv = launch_kmer_query(ix->view(), nullptr, 0, nullptr, nullptr, &name, &slot_tag, in_order ? &tile_tag : nullptr);
+  if (blocks_per_sm) *blocks_per_sm = qv;
+  return name;
 }
 
 int sapling_b200_query_batch_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, int64_t* d_out,

@@ -691,12 +691,14 @@ inline int query_grid(size_t nq, int blocks_per_sm) {
 
 // Experiment knob (tools/gpu_experiments.py): SAPLING_B200_QV = resident blocks per SM the kernel is
 // compiled for (4: <=64 regs, 5, 6: <=40 regs, 8: <=32 regs).  Default chosen by measurement.
-static int query_variant(const IndexView& ix, bool inline_layout) {
+static int query_variant(const IndexView& ix, bool inline_layout, bool partitioned) {
   const char* e = getenv("SAPLING_B200_QV");  // read per launch so one process can sweep variants
   // Measured (profiles/r1_experiments.md): while the genome and model mostly hit L2 more resident warps help (5
   // blocks/SM at c2: +8 %); once every access is a DRAM line and a TLB miss fewer do better (3 blocks/SM at c3: +9 %).
   // The inline-prefix kernel is best at 4 (profiles/r1_c3_inline.md).
-  int v = e ? atoi(e) : (inline_layout ? 4 : (ix.n > 1000000000ull ? 3 : 5));
+  // A partitioned batch (in-order tiles, the slice of the index in L2) is latency- and issue-bound rather than DRAM-bound:
+  // 5 blocks/SM (gpurun r2d / r2e: c2 1.55 against 1.63 ms per 50 M, c3 10.1 against 10.7 ms per 250 M).
+  int v = e ? atoi(e) : (partitioned ? 5 : inline_layout ? 4 : (ix.n > 1000000000ull ? 3 : 5));
   if (v != 2 && v != 3 && v != 4 && v != 5 && v != 6 && v != 8) v = 4;
   return v;
 }
@@ -724,7 +726,7 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   // c2 13.8 vs 18.2 G q/s, c3 9.9 vs 11.3), so it is opt-in.
   const char* re = getenv("SAPLING_B200_REFILL");
   const bool refill = packed && ix.narrow != nullptr && re && atoi(re) == 1 && !d_slot;
-  const int qv = query_variant(ix, inl || packed);
+  const int qv = query_variant(ix, inl || packed, d_slot != nullptr);
   const char* lne = getenv("SAPLING_B200_LEAN");  // 0 = the general Replay instead of kmer_replay32 (A/B measurements)
   const bool lean = lean_eligible(ix) && !(lne && atoi(lne) == 0);
   const char* lse = getenv("SAPLING_B200_LINE_SMEM");  // 1 = anchor line staged in shared memory (measured slower: opt-in)
@@ -736,8 +738,10 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
       return 0;
     }
   }
+  const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");  // 0 = in-order tiles without the software pipeline
+  const bool ordered = d_tiles && d_slot && ix.narrow != nullptr && (packed || inl || sector) && !(oe && atoi(oe) == 0);
   if (name_out) {
-    *name_out = refill ? "kmer_query_packed_refill_kernel" : packed ? "kmer_query_packed_kernel" : inl ? "kmer_query_inline_kernel" : sector ? "kmer_query_sector_kernel"
+    *name_out = ordered ? "kmer_query_ordered_kernel" : refill ? "kmer_query_packed_refill_kernel" : packed ? "kmer_query_packed_kernel" : inl ? "kmer_query_inline_kernel" : sector ? "kmer_query_sector_kernel"
                 : (line && pipelined) ? "kmer_query_line_pipelined_kernel" : line ? "kmer_query_line_kernel"
                 : pipelined ? "kmer_query_pipelined_kernel" : "kmer_query_kernel";
     return qv;
@@ -756,8 +760,7 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
     set_error("partitioned batches need the sector, inline or rank-line kernel");
     return -1;
   }
-  const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");  // 0 = in-order tiles without the software pipeline
-  if (d_tiles && d_slot && ix.narrow != nullptr && (packed || inl || sector) && !(oe && atoi(oe) == 0)) {
+  if (ordered) {
 #define SB_LAUNCH_O(bps, mode)                                                                                       \
   do {                                                                                                               \
     if (lean)                                                                                                        \
