@@ -159,9 +159,13 @@ __device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t 
 
 // B': the same scatter staged through shared memory.  The direct scatter above sends every warp store to 32 different
 // lines (measured: 1.0 ms per 50 M queries, 40 % of the query kernel's own time).  Here a block first sorts its chunk
-// by bin inside shared memory -- each thread keeps its 16 k-mers in registers, the shared-memory atomic that counts the
-// bin also hands out the query's rank inside (chunk, bin) -- and then writes the sorted chunk out in order: consecutive
-// threads store consecutive addresses for as long as the bin lasts (chunk / bins queries on average).
+// by bin inside shared memory and then writes the sorted chunk out in order: consecutive threads store consecutive
+// addresses for as long as the bin lasts (chunk / bins queries on average).
+// The (chunk, bin) counts are already known -- pass A wrote them, the scan turned them into offsets -- so the block
+// does not count again: it requests its column of the offset table together with its k-mers (each thread keeps 16 of
+// them in registers), scans the run lengths into run starts, and then ONE shared-memory atomic per k-mer hands out the
+// k-mer's place in the sorted chunk.  (The version measured in gpurun r2d counted with returning atomics, kept the
+// ranks in shared memory and re-read the run starts: 9 shared-memory operations per k-mer against 6 here.)
 constexpr int kScatterThreads = kPartChunk / 16;  // 16 k-mers per thread in registers
 constexpr int kScatterPer = kPartChunk / kScatterThreads;
 __global__ void __launch_bounds__(kScatterThreads)
@@ -171,43 +175,57 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);                         // [kPartChunk] k-mers sorted by bin
   uint16_t* ss = reinterpret_cast<uint16_t*>(sk + kPartChunk);                  // [kPartChunk] their slots
-  uint32_t* lstart = reinterpret_cast<uint32_t*>(ss + kPartChunk);              // [2048] first sorted index of the bin
+  uint32_t* lstart = reinterpret_cast<uint32_t*>(ss + kPartChunk);              // [2048] next free sorted index of the bin
   uint32_t* gdelta = lstart + 2048;                                             // [2048] global position - sorted index
-  uint16_t* srank = reinterpret_cast<uint16_t*>(gdelta + 2048);                 // [kPartChunk] rank inside (chunk, bin)
+  __shared__ uint32_t wsum[32];
   const size_t c = blockIdx.x;
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t b = threadIdx.x; b < 2048; b += kScatterThreads) lstart[b] = 0;
-  __syncthreads();
   uint64_t x[kScatterPer];
 #pragma unroll
   for (int j = 0; j < kScatterPer; j++) {
     const uint32_t i = threadIdx.x + (uint32_t)j * kScatterThreads;
-    if (i < m) {
-      x[j] = __ldcs(kmers + base + i);
-      srank[i] = (uint16_t)atomicAdd(&lstart[bin_of(x[j], pshift, nbins)], 1u);
+    x[j] = i < m ? __ldcs(kmers + base + i) : 0ull;
+  }
+  constexpr int kBins = 2048 / kScatterThreads;  // bins per thread
+  uint32_t gpos[kBins];
+#pragma unroll
+  for (int j = 0; j < kBins; j++) {
+    const uint32_t b = (uint32_t)kBins * threadIdx.x + j;
+    uint32_t len = 0;
+    gpos[j] = 0;
+    if (b < nbins) {
+      const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+      const uint32_t r0 = __ldg(row);
+      len = __ldg(row + 1) - r0;
+      gpos[j] = __ldg(bin_start + b) + r0;
     }
+    lstart[b] = len;
   }
   __syncthreads();
-  // exclusive scan of the bin counts -> first sorted index of every bin; then where the bin's run goes in part_kmer
-  __shared__ uint32_t wsum[32];
   {
-    uint32_t own[2048 / kScatterThreads];
-    scan_2048<kScatterThreads>(lstart, wsum, own);
+    uint32_t own[kBins];
+    scan_2048<kScatterThreads>(lstart, wsum, own);  // run lengths -> first sorted index of every run
 #pragma unroll
-    for (int j = 0; j < 2048 / kScatterThreads; j++) {
-      const uint32_t b = (uint32_t)(2048 / kScatterThreads) * threadIdx.x + j;
-      gdelta[b] = b < nbins ? bin_start[b] + off[(size_t)b * (nchunks + 1) + c] - own[j] : 0u;
-    }
+    for (int j = 0; j < kBins; j++) gdelta[(uint32_t)kBins * threadIdx.x + j] = gpos[j] - own[j];
   }
   __syncthreads();
+  // four atomics in flight per thread, then their four stores (more would spill: the 16 k-mers hold 32 registers)
 #pragma unroll
-  for (int j = 0; j < kScatterPer; j++) {
-    const uint32_t i = threadIdx.x + (uint32_t)j * kScatterThreads;
-    if (i < m) {
-      const uint32_t p = lstart[bin_of(x[j], pshift, nbins)] + (uint32_t)srank[i];
-      sk[p] = x[j];
-      ss[p] = (uint16_t)i;
+  for (int h = 0; h < kScatterPer; h += 4) {
+    uint32_t p[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
+      p[j] = i < m ? atomicAdd(&lstart[bin_of(x[h + j], pshift, nbins)], 1u) : 0u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
+      if (i < m) {
+        sk[p[j]] = x[h + j];
+        ss[p[j]] = (uint16_t)i;
+      }
     }
   }
   __syncthreads();
@@ -308,10 +326,52 @@ part_unpermute_flat_kernel(const long long* __restrict__ res, size_t nq, uint32_
   for (uint32_t i = threadIdx.x; i < m; i += kFlatThreads) __stcs(out + base + i, buf[i]);
 }
 
+// U'': lane GROUPS per run.  The flat kernel above pays an 11-step binary search in shared memory per element (ncu r2d:
+// 3 warp instructions per answer, a third of the issue slots, 1.95 ms per 250 M answers where the bytes alone take 0.7).
+// Here kGroup lanes (a power of two near half the mean run length) own a run: they read its bounds once and then
+// kGroup consecutive answers per step -- no scan, no search, and neighbouring lanes still read neighbouring addresses.
+// The bounds of kBatch runs are requested before the first answer is, so the two dependent loads overlap across runs.
+template <int kGroup>
+__global__ void __launch_bounds__(kUnpermThreads)
+part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
+                            const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
+                            long long* __restrict__ out) {
+  extern __shared__ long long buf[];  // [kPartChunk] answers in the caller's order
+  constexpr uint32_t kGroups = kUnpermThreads / kGroup;
+  constexpr int kBatch = 4;
+  const size_t c = blockIdx.x;
+  const uint32_t g = threadIdx.x / kGroup, l = threadIdx.x % kGroup;
+  for (uint32_t b0 = g; b0 < nbins; b0 += kGroups * kBatch) {
+    uint32_t lo[kBatch], hi[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; j++) {
+      const uint32_t b = b0 + (uint32_t)j * kGroups;
+      lo[j] = hi[j] = 0;
+      if (b < nbins) {
+        const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+        const uint32_t s = __ldg(bin_start + b);
+        lo[j] = s + __ldg(row);
+        hi[j] = s + __ldg(row + 1);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < kBatch; j++) {
+      for (uint32_t p = lo[j] + l; p < hi[j]; p += kGroup) {
+        const unsigned long long v = (unsigned long long)__ldcs(res + p);
+        buf[v >> 48] = (long long)(v << 16) >> 16;  // sign-extend the 48-bit answer
+      }
+    }
+  }
+  __syncthreads();
+  const size_t base = c * kPartChunk;
+  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
+  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) __stcs(out + base + i, buf[i]);
+}
+
 }  // namespace
 
 constexpr size_t kUnpermFlatSmem = (size_t)kPartChunk * sizeof(long long) + 2 * 2048 * 4;
-constexpr size_t kScatterSmem = (size_t)kPartChunk * 12 + 2 * 2048 * 4;
+constexpr size_t kScatterSmem = (size_t)kPartChunk * 10 + 2 * 2048 * 4;
 
 size_t partition_workspace_bytes(size_t nq, int pbits) {
   const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
@@ -335,6 +395,12 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
                                        (int)kUnpermFlatSmem));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kScatterSmem));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kPartChunk * sizeof(long long))));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kPartChunk * sizeof(long long))));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(kPartChunk * sizeof(long long))));
     attr_set = true;
   }
   const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
@@ -368,10 +434,20 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   if (ev) cudaEventRecord(ev[2], st);
   if (launch_kmer_query(ix, part_kmer, nq, res, st, nullptr, part_slot, in_order ? tiles : nullptr)) return -1;
   if (ev) cudaEventRecord(ev[3], st);
-  const char* ue = getenv("SAPLING_B200_PART_UNPERMUTE");  // 0 = the run-per-warp un-permute (kept for A/B measurements)
-  if (ue && atoi(ue) == 0) {
-    part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, kPartChunk * sizeof(long long), st>>>(
-        res, nq, nbins, nchunks, cnt, bin_start, d_out);
+  // 0 = the run-per-warp un-permute, 1 = the flat one (both kept for A/B measurements); default: lane groups per run,
+  // the group about half the mean run length (a whole warp from 64 answers per run: that is the run-per-warp kernel)
+  const char* ue = getenv("SAPLING_B200_PART_UNPERMUTE");
+  const uint32_t mean_run = kPartChunk >> pbits;
+  const size_t ubytes = kPartChunk * sizeof(long long);
+  if ((ue && atoi(ue) == 0) || (!ue && mean_run >= 64)) {
+    part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
+  } else if (!ue || atoi(ue) != 1) {
+    if (mean_run >= 32)
+      part_unpermute_group_kernel<16><<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
+    else if (mean_run >= 16)
+      part_unpermute_group_kernel<8><<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
+    else
+      part_unpermute_group_kernel<4><<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
   } else {
     part_unpermute_flat_kernel<<<(unsigned)nchunks, kFlatThreads, kUnpermFlatSmem, st>>>(res, nq, nbins, nchunks, cnt,
                                                                                           bin_start, d_out);

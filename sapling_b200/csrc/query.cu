@@ -195,7 +195,8 @@ kmer_query_inline_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 // Rank-line variant: every probe is answered by a 32-byte sector {4 positions, 4 prefixes}, and the sectors a typical
 // query needs share one 128-byte DRAM line (query.cuh SaPacked); the packed genome is read only for escaped entries
 // and for queries longer than the entries' prefix.
-template <int kMinBlocks, int kVariant>  // 0: general Replay, 1: lean replay, 2: lean replay + anchor line in shared memory
+template <int kMinBlocks, int kVariant>  // 0: general Replay, 1: lean replay, 2: lean replay + anchor line in shared memory,
+                                         // 3: flat replay (tiling lines only)
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                          const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -211,7 +212,9 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
     q.k = (uint32_t)ix.k;
     const uint64_t pred = clamp_prediction(ix, predict_rank(ix, x, pol.model));
     long long r;
-    if constexpr (kVariant == 2) {
+    if constexpr (kVariant == 3) {
+      r = kmer_replay_flat<true>(ix, q.q, (uint32_t)pred, pol);
+    } else if constexpr (kVariant == 2) {
       __shared__ uint4 lines[kQueryThreads * kLineSlotU4];
       SaLine32 sa;
       sa.sm = lines + threadIdx.x * kLineSlotU4;
@@ -239,7 +242,8 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 //     samples in profiles/r1y) overlap with the probes of the previous tile;
 //   * the slot of the query (partition.cu) is requested before the replay and consumed after it.
 // Needs the narrow model layout.  kMode as in Replay: 0 = {suffix array sector, packed genome}, 1 = inline-prefix
-// entries, 2 = rank lines, 3 = rank lines with the anchor line staged in shared memory (SaLine32; lean replay only).
+// entries, 2 = rank lines, 3 = rank lines with the anchor line staged in shared memory (SaLine32; lean replay only),
+// 4 = tiling rank lines answered by kmer_replay_flat (lean only).
 template <int kMinBlocks, int kMode, bool kLean>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
@@ -272,7 +276,9 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       q.q = x0 << lsh;
       q.k = (uint32_t)ix.k;
       long long r;
-      if constexpr (kLean && kMode == 3) {
+      if constexpr (kLean && kMode == 4) {
+        r = kmer_replay_flat<true>(ix, q.q, (uint32_t)pred, pol);
+      } else if constexpr (kLean && kMode == 3) {
         __shared__ uint4 lines[kQueryThreads * kLineSlotU4];
         SaLine32 sa;
         sa.sm = lines + threadIdx.x * kLineSlotU4;
@@ -731,6 +737,8 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const bool lean = lean_eligible(ix) && !(lne && atoi(lne) == 0);
   const char* lse = getenv("SAPLING_B200_LINE_SMEM");  // 1 = anchor line staged in shared memory (measured slower: opt-in)
   const bool line_smem = lean && packed && lse && atoi(lse) == 1;
+  const char* fe = getenv("SAPLING_B200_FLAT");  // 0 = kmer_replay32 instead of kmer_replay_flat (A/B measurements)
+  const bool flat = lean && packed && ix.packed_shift == 4 && !line_smem && !(fe && atoi(fe) == 0);
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
       kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));
@@ -770,8 +778,12 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
       kmer_query_ordered_kernel<bps, mode, false><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(                    \
           ix, d_kmers, nq, d_out, d_slot, d_tiles);                                                                  \
   } while (0)
-    const int mode = packed ? (line_smem ? 3 : 2) : inl ? 1 : 0;
+    const int mode = packed ? (flat ? 4 : line_smem ? 3 : 2) : inl ? 1 : 0;
     switch (qv * 10 + mode) {
+      case 34: SB_LAUNCH_O(3, 4); break;
+      case 44: SB_LAUNCH_O(4, 4); break;
+      case 54: SB_LAUNCH_O(5, 4); break;
+      case 64: SB_LAUNCH_O(6, 4); break;
       case 33: SB_LAUNCH_O(3, 3); break;
       case 43: SB_LAUNCH_O(4, 3); break;
       case 53: SB_LAUNCH_O(5, 3); break;
@@ -805,7 +817,8 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 #define SB_LAUNCH_P(bps)                                                                                             \
   do {                                                                                                               \
     const int g = query_grid(nq, bps * (d_tiles ? 1 : mult));                                                        \
-    if (line_smem) kmer_query_packed_kernel<bps, 2><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles); \
+    if (flat) kmer_query_packed_kernel<bps, 3><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);  \
+    else if (line_smem) kmer_query_packed_kernel<bps, 2><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles); \
     else if (lean) kmer_query_packed_kernel<bps, 1><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles); \
     else kmer_query_packed_kernel<bps, 0><<<g, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);       \
   } while (0)

@@ -721,6 +721,115 @@ __device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const ui
   }
 }
 
+// ---- flat k-mer replay on tiling rank lines --------------------------------------------------------------------------
+// kmer_replay32 once more, for the layout and the kernel the partitioned batch path runs (rank lines with
+// packed_shift == 4, so sector = rank >> 2 and no anchor line), written so that the compiler has nothing to branch on.
+// ncu of the in-order kernel (profiles/r2f_*): 77-79 % of the issue slots busy, 16-18 of 32 lanes active per
+// instruction, a ~215-instruction loop body full of per-state branches -- the kernel is bound by instruction issue, and
+// lanes in different states of the replay serialise.  Here the state is ONE-HOT, every transition is a select on
+// predicates all lanes compute, the three ways out of the loop are one test, and only the two rare paths (an escaped
+// entry that needs the genome, the long-window shortcut) remain real branches.  Same probes in the same order, so the
+// same answers (tests: host simulation against the oracle, GPU variants against each other).
+template <bool kSkip>
+__device__ __forceinline__ long long kmer_replay_flat(const IndexView& ix, const uint64_t q, const uint32_t pred,
+                                                      const L2Policies& pol) {
+  enum : uint32_t { F_PRED = 1u, F_R1 = 2u, F_R2 = 4u, F_L1 = 8u, F_L2 = 16u, F_BS = 32u, F_FINAL = 64u, F_SKIP = 128u };
+  const uint32_t k = (uint32_t)ix.k;
+  const uint32_t n32 = (uint32_t)ix.n, nm1 = n32 - 1u;
+  const unsigned gsh = 64u - 2u * (unsigned)ix.packed_bases;
+  const bool tie_possible = (int)k > ix.packed_bases;  // an entry holds fewer bases than the k-mer: ties go to the genome
+  uint32_t lo = 0, hi = 0, r = pred, loLcp = 0, hiLcp = 0, start = 0, st = F_PRED;
+  uint32_t cur = 0xFFFFFFFFu;
+  U32x8 e;
+#pragma unroll
+  for (int i = 0; i < 8; i++) e.v[i] = 0;
+  for (;;) {
+    // ---- one probe: rev[r] and the leading bases of that suffix, from the sector r >> 2 ---------------------------
+    const uint32_t sec = r >> 2;
+    if (sec != cur) {
+      e = ld_u32x8_pol(ix.packed + (uint64_t)sec * 8u, pol.sa);
+      cur = sec;
+    }
+    const unsigned j = r & 3u;
+    const uint64_t P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
+    const uint64_t D = ((uint64_t)e.v[3] << 32) | e.v[2];
+    // entry 0 reads as delta 0 with bit 63 as its escape flag; entries 1-3 are 21-bit fields, all ones = escape
+    const uint64_t dj = (D >> ((kPackedDeltaBits * j - kPackedDeltaBits) & 63u)) & (uint64_t)kPackedEscape;
+    const uint64_t d = j ? dj : 0ull;
+    bool esc = j ? (dj == (uint64_t)kPackedEscape) : ((D >> 63) != 0);
+    uint64_t g = (P0 + d) << gsh;
+    const uint32_t ia = (j & 1u) ? e.v[5] : e.v[4], ib = (j & 1u) ? e.v[7] : e.v[6];
+    const uint32_t idx = (j & 2u) ? ib : ia;
+    const bool fin = (st & F_FINAL) != 0;
+    if (tie_possible) esc = esc || (((q ^ g) >> gsh) == 0);
+    if (esc && !fin) g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);  // rare
+    // ---- getLcp from `start` (:115-120) and the "suffix too small" test (:143) ------------------------------------
+    const uint64_t mask = (~0ull) >> (2u * start);  // start < k <= 32
+    const uint64_t qm = q & mask, gm = g & mask;
+    const uint64_t diff = qm ^ gm;
+    const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
+    const uint32_t room = n32 - idx;  // characters left in the text
+    const uint32_t leff = room < k ? room : k;
+    const uint32_t lcp = m < leff ? m : leff;
+    const bool small = (lcp == room) || (qm > gm);
+    const bool match = lcp == k;
+    // ---- the three ways out: rev[lo + 1] unverified (:137-139), a verified match (:141 :174 :183 :213 :228), and
+    //      an empty search interval (:142) -- in this order of precedence
+    const bool hit = fin || (match && !(st & F_SKIP));
+    const bool miss = (st & F_BS) && (lo + 1u >= hi);
+    if (hit || miss) return hit ? (long long)idx : -1ll;
+    // ---- every probe moves one bound of the pair binarySearch is finally called with (see kmer_replay32) ---------
+    const bool to_lo = (st & F_R2) ? false : ((st & F_L2) ? true : small);
+    const bool upd = !((st & F_SKIP) && (!small || match));  // unverified shortcut: assume nothing
+    const bool set_lo = upd && to_lo, set_hi = upd && !to_lo;
+    lo = set_lo ? r : lo;
+    loLcp = set_lo ? lcp : loLcp;
+    hi = set_hi ? r : hi;
+    hiLcp = set_hi ? lcp : hiLcp;
+    // ---- what to probe next ----------------------------------------------------------------------------------------
+    const bool first = (st & F_PRED) != 0;
+    const bool widen_hi = small && (st & (F_PRED | F_R1));    // :165-166 (mostOver), :180-181 (maxOver + 1)
+    const bool widen_lo = !small && (st & (F_PRED | F_L1));   // :209-210 (mostUnder), :225-226 (maxUnder + 1)
+    const uint32_t d_over = first ? (uint32_t)ix.mostOver : (uint32_t)ix.maxOver + 1u;
+    const uint32_t d_under = first ? (uint32_t)ix.mostUnder : (uint32_t)ix.maxUnder + 1u;
+    const uint32_t up = lean_add_clamped(pred, d_over, nm1);
+    // (int)predicted - d (:209 :225) wraps negative for predicted >= 2^31 in the reference: compat keeps that
+    const int32_t dv = (int32_t)(pred - d_under);
+    const uint32_t down = ix.compat ? (uint32_t)(dv > 0 ? dv : 0) : (pred > d_under ? pred - d_under : 0u);
+    if (kSkip && (st & F_L1) && small) {  // the long-window shortcut (see Replay::step); rare unless ranks >= 2^31
+      const uint32_t guard = (uint32_t)ix.maxUnder + 1u;
+      if ((uint64_t)(hi - lo) > 4ull * guard + 64ull) {
+        uint32_t cand = lo;
+        for (;;) {
+          const uint32_t mid = lean_uhadd(cand, hi);
+          if (hi - mid < guard) break;
+          cand = mid;
+        }
+        if (cand != lo) {
+          SB_SIM_COUNT(g_sim_skip_tried);
+          r = cand;
+          start = 0;
+          st = F_SKIP;
+          continue;
+        }
+      }
+    }
+#ifdef SB_HOST_SIM
+    if ((st & F_SKIP) && small && !match) SB_SIM_COUNT(g_sim_skip_ok);
+#endif
+    hi = widen_hi ? up : hi;
+    lo = widen_lo ? down : lo;
+    const bool two = (hi - lo) == 2u;  // top of binarySearch (:136-140)
+    const uint32_t r_bs = two ? lo + 1u : lean_uhadd(lo, hi);
+    const uint32_t st_bs = two ? (uint32_t)F_FINAL : (uint32_t)F_BS;
+    const uint32_t lcp_min = loLcp < hiLcp ? loLcp : hiLcp;
+    r = widen_hi ? hi : (widen_lo ? lo : r_bs);
+    // PRED -> R1 -> R2 is a shift; PRED -> L1 -> L2 is 8 then a shift
+    st = widen_hi ? (st << 1) : (widen_lo ? (first ? (uint32_t)F_L1 : (uint32_t)F_L2) : st_bs);
+    start = (widen_hi || widen_lo || two) ? start : lcp_min;
+  }
+}
+
 // whether kmer_replay32 may answer queries on this index
 __host__ __device__ inline bool lean_eligible(const IndexView& ix) {
   return ix.n <= kLeanMaxN && ix.k >= 1 && ix.k <= 32 && ix.maxOver >= 0 && ix.maxUnder >= 0 && ix.mostOver >= 0 &&

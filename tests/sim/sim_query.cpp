@@ -104,7 +104,8 @@ int sim_kmer_batch_lean(const uint64_t* genome, const uint32_t* sa, const int64_
   uint32_t* sa_pad = new uint32_t[sb::sa_alloc_entries(n) + 16]();
   memcpy(sa_pad, sa, n * sizeof(uint32_t));
   ix.sa = sa_pad;
-  if (mode == 2 || mode == 3) {
+  if (mode == 4 && shift != 4) return -2;  // the flat replay reads tiling lines only
+  if (mode == 2 || mode == 3 || mode == 4) {
     const uint64_t sectors = sb::packed_sectors(n, shift);
     packed = new uint32_t[sectors * 8];
     for (uint64_t s = 0; s < sectors; s++) {
@@ -127,7 +128,9 @@ int sim_kmer_batch_lean(const uint64_t* genome, const uint32_t* sa, const int64_
   for (size_t i = 0; i < nq; i++) {
     const uint64_t q = kmers[i] << (64 - 2 * k);
     const uint32_t pred = (uint32_t)sb::clamp_prediction(ix, sb::predict_rank(ix, kmers[i], pol.model));
-    if (mode == 2) {
+    if (mode == 4) {
+      out[i] = sb::kmer_replay_flat<true>(ix, q, pred, pol);
+    } else if (mode == 2) {
       sb::SaPacked32 sp;
       sp.anchor(ix, pred);
       out[i] = sb::kmer_replay32<2, true>(ix, q, pred, pol, sp);

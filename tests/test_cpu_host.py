@@ -119,7 +119,8 @@ def test_lean_kmer_replay_on_host_matches_oracle(oracle_built, name):
             five = np.array(five_t, dtype=np.int32)
             exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
             cases = [(0, 0, 3), (2, 6, 3), (2, 12, 4), (2, 21, 3), (2, 32, 4), (2, 16, 4),
-                     (3, 6, 4), (3, 12, 3), (3, 21, 4), (3, 32, 3), (3, 16, 3)]
+                     (3, 6, 4), (3, 12, 3), (3, 21, 4), (3, 32, 3), (3, 16, 3),
+                     (4, 6, 4), (4, 12, 4), (4, 21, 4), (4, 32, 4), (4, 16, 4), (4, 24, 4)]
             cases += [(1, b, 3) for b in (27, 32) if k <= b]
             for mode, bases, shift in cases:
                 out = np.empty(len(kmers), dtype=np.int64)
@@ -134,7 +135,7 @@ def test_lean_kmer_replay_on_host_matches_oracle(oracle_built, name):
             gen = np.empty(len(kmers), dtype=np.int64)
             last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
             L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), gen, C.byref(c), None, last)
-            for mode, bases, shift in cases[:3]:
+            for mode, bases, shift in cases[:3] + [(4, 12, 4), (4, 21, 4)]:
                 out = np.empty(len(kmers), dtype=np.int64)
                 assert L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), out,
                                              C.byref(c), mode, bases, shift) == 0

@@ -340,7 +340,7 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
             assert np.array_equal(plain, exp)
             monkeypatch.setenv("SAPLING_B200_PART", "1")
             monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
-            for bits in (1, 3, 8, 11):
+            for bits in (1, 3, 8, 9, 10, 11):  # un-permute: run-per-warp up to 8, then lane groups of 16, 8, 4
                 monkeypatch.setenv("SAPLING_B200_PART_BITS", str(bits))
                 assert ix.partition_bits(len(kmers)) == min(bits, 2 * k)
                 for m in (len(kmers), 8192, 8193, 16384, 16385, 32767, 1, 33, 5000):
@@ -359,7 +359,7 @@ def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch)
     """Every selectable variant of the batch path returns the oracle's answers: the lean 32-bit replay against the
     general one, the anchor line staged in shared memory against sector-by-sector fetches, the in-order tile schedule
     with and without the software pipeline against the static grid-stride schedule, the staged against the direct
-    scatter and the flat against the run-per-warp un-permute -- on all three index layouts, collapsed left windows
+    scatter, the flat and the lane-group against the run-per-warp un-permute, the flat replay against the lean one -- on all three index layouts, collapsed left windows
      included."""
     g = GENOMES[name]
     for k, nb, five_fn in ((21, -1, None), (16, 8, lambda f: [f[0], f[1], f[2], f[3], 1 << 30]), (31, 12, None)):
@@ -382,9 +382,11 @@ def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch)
                     for lean, line_smem in (("1", "1"), ("1", "0"), ("0", "0")):
                         monkeypatch.setenv("SAPLING_B200_LEAN", lean)
                         monkeypatch.setenv("SAPLING_B200_LINE_SMEM", line_smem)
-                        combos = ((("1", "1", "1", "1"), ("1", "0", "1", "1"), ("0", "1", "0", "0"), ("0", "1", "1", "0"))
-                                  if part == "1" else (("1", "1", "1", "1"),))
-                        for tiles, pipe, scat, unp in combos:
+                        combos = ((("1", "1", "1", "1", "1"), ("1", "0", "1", "2", "1"), ("0", "1", "0", "0", "1"),
+                                   ("0", "1", "1", "0", "0"), ("1", "1", "1", "2", "0"))
+                                  if part == "1" else (("1", "1", "1", "1", "1"), ("1", "1", "1", "1", "0")))
+                        for tiles, pipe, scat, unp, flat in combos:
+                            monkeypatch.setenv("SAPLING_B200_FLAT", flat)  # kmer_replay_flat / kmer_replay32 (tiling lines)
                             monkeypatch.setenv("SAPLING_B200_PART_TILES", tiles)
                             monkeypatch.setenv("SAPLING_B200_ORDERED_PIPE", pipe)
                             monkeypatch.setenv("SAPLING_B200_PART_SCATTER", scat)
@@ -393,11 +395,11 @@ def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch)
                                 monkeypatch.setenv("SAPLING_B200_QV", qv)
                                 got = ix.queryBatch(kmers)
                                 assert np.array_equal(got, exp), (name, k, flags, shift, part, lean, line_smem, tiles,
-                                                                  pipe, scat, unp, qv)
+                                                                  pipe, scat, unp, flat, qv)
                             assert np.array_equal(ix.queryBatch(kmers[:8191]), exp[:8191])
                 ix.close()
         port.close()
         base.close()
     for v in ("PART", "PART_MIN", "PART_BITS", "LEAN", "LINE_SMEM", "PART_TILES", "ORDERED_PIPE", "PART_SCATTER",
-              "PART_UNPERMUTE", "QV", "PACKED_SHIFT"):
+              "PART_UNPERMUTE", "QV", "PACKED_SHIFT", "FLAT"):
         monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
