@@ -899,7 +899,7 @@ static int partition_bits(const sapling_b200_index* ix, size_t nq) {
                             : ix->d_ext  ? 16.0 * (double)ix->n
                                          : 4.0 * (double)ix->n;
     const double model_bytes = (ix->d_narrow ? 8.0 : 16.0) * (double)(1ull << ix->nb);
-    const double slice = 16e6;
+    const double slice = 32e6;  // measured (gpurun r2f): c3 10 bits (26 MB slices) 15.0 ms per step, 11 bits 15.9, 9 bits bistable
     bits = 1;
     while (bits < kPartMaxBits && (sa_bytes + model_bytes) / (double)(1ull << bits) > slice) bits++;
     while (bits > 0 && (nq >> bits) < 4096) bits--;

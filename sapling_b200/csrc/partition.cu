@@ -238,10 +238,12 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
 }
 
 // U: chunk c collects its answers.  Warp w walks bins w, w+32, ...; the run (bin, c) is read coalesced by the lanes.
-__global__ void __launch_bounds__(kUnpermThreads)
+__global__ void __launch_bounds__(kUnpermThreads, 2)
 part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
                       const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start, long long* __restrict__ out) {
-  extern __shared__ long long buf[];
+  // answers staged as 32 bits (a position < n <= 2^32 - 16, or 0xFFFFFFFF for -1): 64 KB per chunk, so that two blocks
+  // share an SM and one block's loads overlap the other's stores
+  extern __shared__ uint32_t buf32[];
   const size_t c = blockIdx.x;
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   // bounds of this warp's runs, two bins per lane (nbins <= 2048 = 32 warps x 32 lanes x 2)
@@ -265,13 +267,16 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
     const uint32_t e = __shfl_sync(0xffffffffu, t < 32u ? hi[0] : hi[1], (int)(t & 31u));
     for (uint32_t p = a + lane; p < e; p += 32u) {
       const unsigned long long v = (unsigned long long)__ldcs(res + p);
-      buf[v >> 48] = (long long)(v << 16) >> 16;  // sign-extend the 48-bit answer
+      buf32[v >> 48] = (uint32_t)v;  // the low 32 bits of the 48-bit answer: -1 reads back as 0xFFFFFFFF
     }
   }
   __syncthreads();
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) __stcs(out + base + i, buf[i]);
+  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) {
+    const uint32_t v = buf32[i];
+    __stcs(out + base + i, v == 0xFFFFFFFFu ? -1ll : (long long)v);
+  }
 }
 
 // U': the same un-permute with the work split by ELEMENT instead of by bin.  Above, a warp walks whole (bin, chunk) runs,
@@ -332,11 +337,11 @@ part_unpermute_flat_kernel(const long long* __restrict__ res, size_t nq, uint32_
 // kGroup consecutive answers per step -- no scan, no search, and neighbouring lanes still read neighbouring addresses.
 // The bounds of kBatch runs are requested before the first answer is, so the two dependent loads overlap across runs.
 template <int kGroup>
-__global__ void __launch_bounds__(kUnpermThreads)
+__global__ void __launch_bounds__(kUnpermThreads, 2)
 part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
                             const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
                             long long* __restrict__ out) {
-  extern __shared__ long long buf[];  // [kPartChunk] answers in the caller's order
+  extern __shared__ uint32_t buf32[];  // [kPartChunk] answers in the caller's order, 32 bits each (see part_unpermute_kernel)
   constexpr uint32_t kGroups = kUnpermThreads / kGroup;
   constexpr int kBatch = 4;
   const size_t c = blockIdx.x;
@@ -358,14 +363,17 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
     for (int j = 0; j < kBatch; j++) {
       for (uint32_t p = lo[j] + l; p < hi[j]; p += kGroup) {
         const unsigned long long v = (unsigned long long)__ldcs(res + p);
-        buf[v >> 48] = (long long)(v << 16) >> 16;  // sign-extend the 48-bit answer
+        buf32[v >> 48] = (uint32_t)v;
       }
     }
   }
   __syncthreads();
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) __stcs(out + base + i, buf[i]);
+  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) {
+    const uint32_t v = buf32[i];
+    __stcs(out + base + i, v == 0xFFFFFFFFu ? -1ll : (long long)v);
+  }
 }
 
 }  // namespace
@@ -390,17 +398,23 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   static bool attr_set = false;  // benign race: the attribute is idempotent
   if (!attr_set) {
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(long long))));
+                                       (int)(kPartChunk * sizeof(uint32_t))));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kUnpermFlatSmem));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kScatterSmem));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(long long))));
+                                       (int)(kPartChunk * sizeof(uint32_t))));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(long long))));
+                                       (int)(kPartChunk * sizeof(uint32_t))));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(long long))));
+                                       (int)(kPartChunk * sizeof(uint32_t))));
+    // two 64 KB un-permute blocks per SM need the large shared-memory carve-out
+    cudaFuncSetAttribute(part_unpermute_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(part_unpermute_group_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(part_unpermute_group_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaFuncSetAttribute(part_unpermute_group_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    cudaGetLastError();
     attr_set = true;
   }
   const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
@@ -438,7 +452,7 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   // the group about half the mean run length (a whole warp from 64 answers per run: that is the run-per-warp kernel)
   const char* ue = getenv("SAPLING_B200_PART_UNPERMUTE");
   const uint32_t mean_run = kPartChunk >> pbits;
-  const size_t ubytes = kPartChunk * sizeof(long long);
+  const size_t ubytes = kPartChunk * sizeof(uint32_t);
   if ((ue && atoi(ue) == 0) || (!ue && mean_run >= 64)) {
     part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
   } else if (!ue || atoi(ue) != 1) {

@@ -737,8 +737,11 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   const bool lean = lean_eligible(ix) && !(lne && atoi(lne) == 0);
   const char* lse = getenv("SAPLING_B200_LINE_SMEM");  // 1 = anchor line staged in shared memory (measured slower: opt-in)
   const bool line_smem = lean && packed && lse && atoi(lse) == 1;
-  const char* fe = getenv("SAPLING_B200_FLAT");  // 0 = kmer_replay32 instead of kmer_replay_flat (A/B measurements)
-  const bool flat = lean && packed && ix.packed_shift == 4 && !line_smem && !(fe && atoi(fe) == 0);
+  // 1 = kmer_replay_flat instead of kmer_replay32.  Measured slower (gpurun r2g: c2 1.72 against 1.55 ms per 50 M
+  // partitioned queries, c3 10.7 against 10.0 ms per 250 M): a lane executes ~155 instructions per probe where the branchy
+  // replay executes ~110 on its path, and that costs more than the convergence wins back.  Opt-in.
+  const char* fe = getenv("SAPLING_B200_FLAT");
+  const bool flat = lean && packed && ix.packed_shift == 4 && !line_smem && fe && atoi(fe) == 1;
   if (const char* sg = getenv("SAPLING_B200_STAGES")) {
     if (atoi(sg) == 1 || atoi(sg) == 2) {
       kmer_query_stages_kernel<<<query_grid(nq, 4 * mult), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, atoi(sg));

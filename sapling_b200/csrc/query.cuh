@@ -475,8 +475,13 @@ struct SaPacked32 {
   __device__ __forceinline__ uint32_t get(const IndexView& ix, uint32_t r, uint64_t pol, uint64_t* g, bool* esc) {
     const uint32_t s4 = r & ~3u;
     if (s4 != cur) {
-      const uint32_t first = (r - abase < 16u) ? abase : ((r >> ix.packed_shift) << ix.packed_shift);
-      const uint32_t sector = ((first >> ix.packed_shift) << 2) + ((r - first) >> 2);
+      uint32_t sector;
+      if (ix.packed_shift == 4) {  // tiling lines: sector s holds ranks 4s .. 4s+3 (uniform branch, hoisted out of the loop)
+        sector = r >> 2;
+      } else {
+        const uint32_t first = (r - abase < 16u) ? abase : ((r >> ix.packed_shift) << ix.packed_shift);
+        sector = ((first >> ix.packed_shift) << 2) + ((r - first) >> 2);
+      }
       e = ld_u32x8_pol(ix.packed + (uint64_t)sector * 8u, pol);
       cur = s4;
     }
@@ -486,8 +491,17 @@ struct SaPacked32 {
     const uint64_t d = j ? ((D >> (kPackedDeltaBits * (j - 1))) & (uint64_t)kPackedEscape) : 0ull;
     *esc = j ? (d == (uint64_t)kPackedEscape) : ((D >> 63) != 0);
     *g = (P0 + d) << (64 - 2 * ix.packed_bases);
+    return pos_of(j);
+  }
+  __device__ __forceinline__ uint32_t pos_of(unsigned j) const {
     const uint32_t a = (j & 1u) ? e.v[5] : e.v[4], b = (j & 1u) ? e.v[7] : e.v[6];
     return (j & 2u) ? b : a;
+  }
+  // rev[r] if the sector in registers holds it (binarySearch's unverified rev[lo + 1] usually falls into it)
+  __device__ __forceinline__ bool cached_pos(uint32_t r, uint32_t* idx) const {
+    if ((r & ~3u) != cur) return false;
+    *idx = pos_of(r & 3u);
+    return true;
   }
 };
 
@@ -555,6 +569,12 @@ struct SaLine32 {
     *g = (P0 + d) << (64 - 2 * ix.packed_bases);
     return pos;
   }
+  __device__ __forceinline__ bool cached_pos(uint32_t r, uint32_t* idx) const {
+    const uint32_t off = r - abase;
+    if (off >= 16u) return false;
+    *idx = reinterpret_cast<const uint32_t*>(sm + 2u * (off >> 2) + 1u)[r & 3u];
+    return true;
+  }
 };
 
 struct SaSector32 {
@@ -574,9 +594,20 @@ struct SaSector32 {
     }
     return ld_u32_pol(ix.sa + r, pol);
   }
+  __device__ __forceinline__ bool cached_pos(uint32_t r, uint32_t* idx) const {
+    if ((r & ~7u) != base) return false;
+    const unsigned j = r & 7u;
+    const uint32_t a = (j & 1u) ? e.v[1] : e.v[0], b = (j & 1u) ? e.v[3] : e.v[2];
+    const uint32_t c = (j & 1u) ? e.v[5] : e.v[4], d = (j & 1u) ? e.v[7] : e.v[6];
+    const uint32_t ab = (j & 2u) ? b : a, cd = (j & 2u) ? d : c;
+    *idx = (j & 4u) ? cd : ab;
+    return true;
+  }
 };
 
-struct SaNone32 {};  // kMode 1 reads ExtEntry directly
+struct SaNone32 {  // kMode 1 reads ExtEntry directly
+  __device__ __forceinline__ bool cached_pos(uint32_t, uint32_t*) const { return false; }
+};
 
 __device__ __forceinline__ uint32_t lean_uhadd(uint32_t a, uint32_t b) {  // floor((a + b) / 2) without overflow
 #ifdef SB_HOST_SIM
@@ -712,6 +743,8 @@ __device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const ui
     // top of binarySearch (:136-140)
     if (hi - lo == 2u) {
       r = lo + 1u;
+      uint32_t pos;
+      if (sa.cached_pos(r, &pos)) return (long long)pos;  // rev[lo + 1] without another trip round the loop
       state = S_FINAL;
     } else {
       r = lean_uhadd(lo, hi);
@@ -722,6 +755,8 @@ __device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const ui
 }
 
 // ---- flat k-mer replay on tiling rank lines --------------------------------------------------------------------------
+// MEASURED SLOWER than kmer_replay32 (gpurun r2g, see launch_kmer_query) and therefore opt-in (SAPLING_B200_FLAT=1); kept
+// because the reason is instructive and the variant is covered by the parity tests.
 // kmer_replay32 once more, for the layout and the kernel the partitioned batch path runs (rank lines with
 // packed_shift == 4, so sector = rank >> 2 and no anchor line), written so that the compiler has nothing to branch on.
 // ncu of the in-order kernel (profiles/r2f_*): 77-79 % of the issue slots busy, 16-18 of 32 lanes active per
