@@ -623,134 +623,163 @@ __device__ __forceinline__ uint32_t lean_add_clamped(uint32_t a, uint32_t b, uin
 
 // q = the k bases left-aligned; pred < n.  kMode: 0 = {suffix-array sector, packed genome}, 1 = inline-prefix entries,
 // 2 = rank lines.  Returns plQuery's answer (sapling_api.h:159-248).
-template <int kMode, bool kSkip, typename Sa>
-__device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const uint64_t q, const uint32_t pred,
-                                                   const L2Policies& pol, Sa& sa) {
-  enum : int { S_PRED = 0, S_R1, S_R2, S_L1, S_L2, S_BS, S_FINAL, S_SKIP };
+// One probe of the lean replay and the transition it causes; true = answered (*result).  kKnown tells the compiler
+// which state the call can be in: >= 0 exactly that state, -2 "R1 or L1" (the second probe of every query), -1 anything.
+// kmer_replay32 peels the first two probes with it, so their code carries no dispatch on the state and none of the
+// transitions that cannot happen there -- the kernel is bound by instruction issue (profiles/r2f_*), not by memory.
+enum : int { S_PRED = 0, S_R1, S_R2, S_L1, S_L2, S_BS, S_FINAL, S_SKIP };
+struct Lean32 {
+  uint32_t lo, hi, r, loLcp, hiLcp, start;
+  int state;
+};
+template <int kMode, bool kSkip, int kKnown, typename Sa>
+__device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q, const uint32_t pred, const L2Policies& pol,
+                                          Sa& sa, Lean32& s, long long* result) {
   const uint32_t k = (uint32_t)ix.k;
   const uint32_t n32 = (uint32_t)ix.n, nm1 = n32 - 1u;
-  uint32_t lo = 0, hi = 0, r = pred, loLcp = 0, hiLcp = 0, start = 0;
-  int state = S_PRED;
-  for (;;) {
-    // ---- one probe: rev[r] and the leading bases of that suffix --------------------------------------------------
-    uint32_t idx;
-    uint64_t g;
-    if constexpr (kMode == 1) {
-      const uint4 e = ld_u32x4_pol(reinterpret_cast<const uint4*>(ix.ext + r), pol.sa);
-      idx = e.x;
-      g = ((uint64_t)e.w << 32) | e.z;
-      if (state == S_FINAL) return (long long)idx;
-    } else if constexpr (kMode == 2) {
-      bool esc;
-      idx = sa.get(ix, r, pol.sa, &g, &esc);
-      if (state == S_FINAL) return (long long)idx;
-      // an entry carries packed_bases bases: a longer k-mer that agrees on all of them is decided by the genome
-      if (!esc && (int)k > ix.packed_bases) esc = ((q ^ g) >> (64 - 2 * ix.packed_bases)) == 0;
-      if (esc) g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
-    } else {
-      idx = sa.ld(ix, r, pol.sa);
-      if (state == S_FINAL) return (long long)idx;
-      g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
-    }
-    // ---- getLcp from `start` (:115-120) and the "suffix too small" test (:143) ------------------------------------
-    const uint64_t mask = (~0ull) >> (2u * start);  // start < k <= 32
-    const uint64_t qm = q & mask, gm = g & mask;
-    const uint64_t diff = qm ^ gm;
-    const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
-    const uint32_t room = n32 - idx;  // characters left in the text
-    const uint32_t leff = room < k ? room : k;
-    const uint32_t lcp = m < leff ? m : leff;
-    const bool small = (lcp == room) || (qm > gm);
-    const bool match = lcp == k;
+  const int state = kKnown >= 0 ? kKnown : s.state;
+#ifndef SB_HOST_SIM
+  if (kKnown == -2) __builtin_assume(state == S_R1 || state == S_L1);
+#endif
+  uint32_t& lo = s.lo;
+  uint32_t& hi = s.hi;
+  uint32_t& r = s.r;
+  uint32_t& loLcp = s.loLcp;
+  uint32_t& hiLcp = s.hiLcp;
+  uint32_t& start = s.start;
+  // ---- one probe: rev[r] and the leading bases of that suffix ----------------------------------------------------
+  uint32_t idx;
+  uint64_t g;
+  if constexpr (kMode == 1) {
+    const uint4 e = ld_u32x4_pol(reinterpret_cast<const uint4*>(ix.ext + r), pol.sa);
+    idx = e.x;
+    g = ((uint64_t)e.w << 32) | e.z;
+    if (state == S_FINAL) { *result = (long long)idx; return true; }
+  } else if constexpr (kMode == 2) {
+    bool esc;
+    idx = sa.get(ix, r, pol.sa, &g, &esc);
+    if (state == S_FINAL) { *result = (long long)idx; return true; }
+    // an entry carries packed_bases bases: a longer k-mer that agrees on all of them is decided by the genome
+    if (!esc && (int)k > ix.packed_bases) esc = ((q ^ g) >> (64 - 2 * ix.packed_bases)) == 0;
+    if (esc) g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
+  } else {
+    idx = sa.ld(ix, r, pol.sa);
+    if (state == S_FINAL) { *result = (long long)idx; return true; }
+    g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
+  }
+  // ---- getLcp from `start` (:115-120) and the "suffix too small" test (:143) --------------------------------------
+  const uint32_t st0 = (kKnown == S_PRED || kKnown == -2) ? 0u : start;  // the first two probes compare from base 0
+  const uint64_t mask = (~0ull) >> (2u * st0);  // start < k <= 32
+  const uint64_t qm = q & mask, gm = g & mask;
+  const uint64_t diff = qm ^ gm;
+  const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
+  const uint32_t room = n32 - idx;  // characters left in the text
+  const uint32_t leff = room < k ? room : k;
+  const uint32_t lcp = m < leff ? m : leff;
+  const bool small = (lcp == room) || (qm > gm);
+  const bool match = lcp == k;
 
-    if (state == S_PRED) {  // :162-172 / :209-211
-      if (match) return (long long)idx;
-      if (small) {
-        lo = pred;
-        loLcp = lcp;
-        hi = lean_add_clamped(pred, (uint32_t)ix.mostOver, nm1);
-        r = hi;
-        state = S_R1;
-      } else {
-        hi = pred;
-        hiLcp = lcp;
-        if (ix.compat) {  // (int)predicted - mostUnder (:209): wraps negative for predicted >= 2^31
-          const int32_t v = (int32_t)(pred - (uint32_t)ix.mostUnder);
-          lo = (uint32_t)(v > 0 ? v : 0);
-        } else {
-          const uint32_t d = (uint32_t)ix.mostUnder;
-          lo = pred > d ? pred - d : 0u;
-        }
-        r = lo;
-        state = S_L1;
-      }
-      continue;
-    }
-    if (state != S_SKIP && match) return (long long)idx;      // :174 :183 :213 :228 :141
-    if (state == S_BS && lo + 1u >= hi) return -1;            // :142
-    {
-      const bool to_lo = state == S_R2 ? false : (state == S_L2 ? true : small);
-      const bool upd = !(state == S_SKIP && (!small || match));  // unverified shortcut: assume nothing
-      if (upd) {
-        if (to_lo) {
-          lo = r;
-          loLcp = lcp;
-        } else {
-          hi = r;
-          hiLcp = lcp;
-        }
-      }
-    }
-    if (state == S_R1 && small) {  // :180-181
-      hi = lean_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
+  if (state == S_PRED) {  // :162-172 / :209-211
+    if (match) { *result = (long long)idx; return true; }
+    if (small) {
+      lo = pred;
+      loLcp = lcp;
+      hi = lean_add_clamped(pred, (uint32_t)ix.mostOver, nm1);
       r = hi;
-      state = S_R2;
-      continue;
-    }
-    if (state == S_L1 && !small) {  // :225-226
-      if (ix.compat) {
-        const int32_t v = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
+      s.state = S_R1;
+    } else {
+      hi = pred;
+      hiLcp = lcp;
+      if (ix.compat) {  // (int)predicted - mostUnder (:209): wraps negative for predicted >= 2^31
+        const int32_t v = (int32_t)(pred - (uint32_t)ix.mostUnder);
         lo = (uint32_t)(v > 0 ? v : 0);
       } else {
-        const uint32_t d = (uint32_t)ix.maxUnder + 1u;
+        const uint32_t d = (uint32_t)ix.mostUnder;
         lo = pred > d ? pred - d : 0u;
       }
       r = lo;
-      state = S_L2;
-      continue;
+      s.state = S_L1;
     }
-    if (kSkip && state == S_L1) {  // small: the long-window shortcut (see Replay::step)
-      const uint32_t guard = (uint32_t)ix.maxUnder + 1u;
-      if ((uint64_t)(hi - lo) > 4ull * guard + 64ull) {
-        uint32_t cand = lo;
-        for (;;) {
-          const uint32_t mid = lean_uhadd(cand, hi);
-          if (hi - mid < guard) break;
-          cand = mid;
-        }
-        if (cand != lo) {
-          SB_SIM_COUNT(g_sim_skip_tried);
-          r = cand;
-          start = 0;
-          state = S_SKIP;
-          continue;
-        }
+    return false;
+  }
+  if (state != S_SKIP && match) { *result = (long long)idx; return true; }   // :174 :183 :213 :228 :141
+  if (state == S_BS && lo + 1u >= hi) { *result = -1; return true; }          // :142
+  {
+    const bool to_lo = state == S_R2 ? false : (state == S_L2 ? true : small);
+    const bool upd = !(state == S_SKIP && (!small || match));  // unverified shortcut: assume nothing
+    if (upd) {
+      if (to_lo) {
+        lo = r;
+        loLcp = lcp;
+      } else {
+        hi = r;
+        hiLcp = lcp;
       }
     }
-#ifdef SB_HOST_SIM
-    if (state == S_SKIP && small && !match) SB_SIM_COUNT(g_sim_skip_ok);
-#endif
-    // top of binarySearch (:136-140)
-    if (hi - lo == 2u) {
-      r = lo + 1u;
-      uint32_t pos;
-      if (sa.cached_pos(r, &pos)) return (long long)pos;  // rev[lo + 1] without another trip round the loop
-      state = S_FINAL;
+  }
+  if (state == S_R1 && small) {  // :180-181
+    hi = lean_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
+    r = hi;
+    s.state = S_R2;
+    return false;
+  }
+  if (state == S_L1 && !small) {  // :225-226
+    if (ix.compat) {
+      const int32_t v = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
+      lo = (uint32_t)(v > 0 ? v : 0);
     } else {
-      r = lean_uhadd(lo, hi);
-      start = loLcp < hiLcp ? loLcp : hiLcp;
-      state = S_BS;
+      const uint32_t d = (uint32_t)ix.maxUnder + 1u;
+      lo = pred > d ? pred - d : 0u;
     }
+    r = lo;
+    s.state = S_L2;
+    return false;
+  }
+  if (kSkip && state == S_L1) {  // small: the long-window shortcut (see Replay::step)
+    const uint32_t guard = (uint32_t)ix.maxUnder + 1u;
+    if ((uint64_t)(hi - lo) > 4ull * guard + 64ull) {
+      uint32_t cand = lo;
+      for (;;) {
+        const uint32_t mid = lean_uhadd(cand, hi);
+        if (hi - mid < guard) break;
+        cand = mid;
+      }
+      if (cand != lo) {
+        SB_SIM_COUNT(g_sim_skip_tried);
+        r = cand;
+        start = 0;
+        s.state = S_SKIP;
+        return false;
+      }
+    }
+  }
+#ifdef SB_HOST_SIM
+  if (state == S_SKIP && small && !match) SB_SIM_COUNT(g_sim_skip_ok);
+#endif
+  // top of binarySearch (:136-140)
+  if (hi - lo == 2u) {
+    r = lo + 1u;
+    uint32_t pos;
+    if (sa.cached_pos(r, &pos)) { *result = (long long)pos; return true; }  // rev[lo + 1] without another trip round the loop
+    s.state = S_FINAL;
+  } else {
+    r = lean_uhadd(lo, hi);
+    start = loLcp < hiLcp ? loLcp : hiLcp;
+    s.state = S_BS;
+  }
+  return false;
+}
+
+template <int kMode, bool kSkip, typename Sa>
+__device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const uint64_t q, const uint32_t pred,
+                                                   const L2Policies& pol, Sa& sa) {
+  Lean32 s;
+  s.lo = 0; s.hi = 0; s.r = pred; s.loLcp = 0; s.hiLcp = 0; s.start = 0; s.state = S_PRED;
+  long long result = 0;
+  if (lean_step<kMode, kSkip, S_PRED>(ix, q, pred, pol, sa, s, &result)) return result;  // probe 1: rev[predicted]
+  if (lean_step<kMode, kSkip, -2>(ix, q, pred, pol, sa, s, &result)) return result;      // probe 2: the mostOver / mostUnder bound
+  for (;;) {
+    if (lean_step<kMode, kSkip, -1>(ix, q, pred, pol, sa, s, &result)) return result;
   }
 }
 
