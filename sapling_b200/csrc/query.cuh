@@ -624,9 +624,13 @@ __device__ __forceinline__ uint32_t lean_add_clamped(uint32_t a, uint32_t b, uin
 // q = the k bases left-aligned; pred < n.  kMode: 0 = {suffix-array sector, packed genome}, 1 = inline-prefix entries,
 // 2 = rank lines.  Returns plQuery's answer (sapling_api.h:159-248).
 // One probe of the lean replay and the transition it causes; true = answered (*result).  kKnown tells the compiler
-// which state the call can be in: >= 0 exactly that state, -2 "R1 or L1" (the second probe of every query), -1 anything.
-// kmer_replay32 peels the first two probes with it, so their code carries no dispatch on the state and none of the
-// transitions that cannot happen there -- the kernel is bound by instruction issue (profiles/r2f_*), not by memory.
+// which states the call can be in, so that each call site carries only the transitions that can happen there -- the
+// kernel is bound by instruction issue (profiles/r2f_*), not by memory:
+//   S_PRED  the first probe, rev[predicted]
+//   -2      R1 or L1: the second probe of every query (the mostOver / mostUnder bound)
+//   -3      anything but PRED, R1, L1: the third probe (R2, L2, the long-window shortcut, or already binarySearch)
+//   -4      BS or FINAL: every probe after the third (R2, L2 and SKIP all lead into binarySearch)
+//   -1      anything (not used by kmer_replay32; kept for callers that resume a replay)
 enum : int { S_PRED = 0, S_R1, S_R2, S_L1, S_L2, S_BS, S_FINAL, S_SKIP };
 struct Lean32 {
   uint32_t lo, hi, r, loLcp, hiLcp, start;
@@ -635,12 +639,13 @@ struct Lean32 {
 template <int kMode, bool kSkip, int kKnown, typename Sa>
 __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q, const uint32_t pred, const L2Policies& pol,
                                           Sa& sa, Lean32& s, long long* result) {
+  constexpr bool may_pred = kKnown == -1 || kKnown == S_PRED;
+  constexpr bool may_first = kKnown == -1 || kKnown == -2;                  // R1, L1
+  constexpr bool may_second = kKnown == -1 || kKnown == -3;                 // R2, L2, SKIP
+  constexpr bool may_search = kKnown == -1 || kKnown == -3 || kKnown == -4;  // BS, FINAL
   const uint32_t k = (uint32_t)ix.k;
   const uint32_t n32 = (uint32_t)ix.n, nm1 = n32 - 1u;
   const int state = kKnown >= 0 ? kKnown : s.state;
-#ifndef SB_HOST_SIM
-  if (kKnown == -2) __builtin_assume(state == S_R1 || state == S_L1);
-#endif
   uint32_t& lo = s.lo;
   uint32_t& hi = s.hi;
   uint32_t& r = s.r;
@@ -654,17 +659,17 @@ __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q,
     const uint4 e = ld_u32x4_pol(reinterpret_cast<const uint4*>(ix.ext + r), pol.sa);
     idx = e.x;
     g = ((uint64_t)e.w << 32) | e.z;
-    if (state == S_FINAL) { *result = (long long)idx; return true; }
+    if (may_search && state == S_FINAL) { *result = (long long)idx; return true; }
   } else if constexpr (kMode == 2) {
     bool esc;
     idx = sa.get(ix, r, pol.sa, &g, &esc);
-    if (state == S_FINAL) { *result = (long long)idx; return true; }
+    if (may_search && state == S_FINAL) { *result = (long long)idx; return true; }
     // an entry carries packed_bases bases: a longer k-mer that agrees on all of them is decided by the genome
     if (!esc && (int)k > ix.packed_bases) esc = ((q ^ g) >> (64 - 2 * ix.packed_bases)) == 0;
     if (esc) g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
   } else {
     idx = sa.ld(ix, r, pol.sa);
-    if (state == S_FINAL) { *result = (long long)idx; return true; }
+    if (may_search && state == S_FINAL) { *result = (long long)idx; return true; }
     g = load_bases_upto_pol(ix.genome, (uint64_t)idx, k, pol.genome);
   }
   // ---- getLcp from `start` (:115-120) and the "suffix too small" test (:143) --------------------------------------
@@ -679,7 +684,7 @@ __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q,
   const bool small = (lcp == room) || (qm > gm);
   const bool match = lcp == k;
 
-  if (state == S_PRED) {  // :162-172 / :209-211
+  if (may_pred && state == S_PRED) {  // :162-172 / :209-211
     if (match) { *result = (long long)idx; return true; }
     if (small) {
       lo = pred;
@@ -702,11 +707,12 @@ __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q,
     }
     return false;
   }
-  if (state != S_SKIP && match) { *result = (long long)idx; return true; }   // :174 :183 :213 :228 :141
-  if (state == S_BS && lo + 1u >= hi) { *result = -1; return true; }          // :142
+  const bool is_skip = may_second && state == S_SKIP;
+  if (!is_skip && match) { *result = (long long)idx; return true; }                          // :174 :183 :213 :228 :141
+  if (may_search && (kKnown == -4 || state == S_BS) && lo + 1u >= hi) { *result = -1; return true; }  // :142
   {
-    const bool to_lo = state == S_R2 ? false : (state == S_L2 ? true : small);
-    const bool upd = !(state == S_SKIP && (!small || match));  // unverified shortcut: assume nothing
+    const bool to_lo = (may_second && state == S_R2) ? false : ((may_second && state == S_L2) ? true : small);
+    const bool upd = !(is_skip && (!small || match));  // unverified shortcut: assume nothing
     if (upd) {
       if (to_lo) {
         lo = r;
@@ -717,13 +723,13 @@ __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q,
       }
     }
   }
-  if (state == S_R1 && small) {  // :180-181
+  if (may_first && state == S_R1 && small) {  // :180-181
     hi = lean_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
     r = hi;
     s.state = S_R2;
     return false;
   }
-  if (state == S_L1 && !small) {  // :225-226
+  if (may_first && state == S_L1 && !small) {  // :225-226
     if (ix.compat) {
       const int32_t v = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
       lo = (uint32_t)(v > 0 ? v : 0);
@@ -735,7 +741,7 @@ __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q,
     s.state = S_L2;
     return false;
   }
-  if (kSkip && state == S_L1) {  // small: the long-window shortcut (see Replay::step)
+  if (kSkip && may_first && state == S_L1) {  // small: the long-window shortcut (see Replay::step)
     const uint32_t guard = (uint32_t)ix.maxUnder + 1u;
     if ((uint64_t)(hi - lo) > 4ull * guard + 64ull) {
       uint32_t cand = lo;
@@ -754,7 +760,7 @@ __device__ __forceinline__ bool lean_step(const IndexView& ix, const uint64_t q,
     }
   }
 #ifdef SB_HOST_SIM
-  if (state == S_SKIP && small && !match) SB_SIM_COUNT(g_sim_skip_ok);
+  if (is_skip && small && !match) SB_SIM_COUNT(g_sim_skip_ok);
 #endif
   // top of binarySearch (:136-140)
   if (hi - lo == 2u) {
@@ -778,8 +784,9 @@ __device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const ui
   long long result = 0;
   if (lean_step<kMode, kSkip, S_PRED>(ix, q, pred, pol, sa, s, &result)) return result;  // probe 1: rev[predicted]
   if (lean_step<kMode, kSkip, -2>(ix, q, pred, pol, sa, s, &result)) return result;      // probe 2: the mostOver / mostUnder bound
+  if (lean_step<kMode, kSkip, -3>(ix, q, pred, pol, sa, s, &result)) return result;      // probe 3: R2 / L2 / shortcut / search
   for (;;) {
-    if (lean_step<kMode, kSkip, -1>(ix, q, pred, pol, sa, s, &result)) return result;
+    if (lean_step<kMode, kSkip, -4>(ix, q, pred, pol, sa, s, &result)) return result;    // binarySearch
   }
 }
 
