@@ -475,11 +475,15 @@ def main():
         p_src = "counted by the oracle on this query set"
     bytes_per_query = 16 + 32 * (2 + probes_per_q)
     achieved = nq * bytes_per_query / (kernel_ms * 1e-3) / 1e9
-    traffic = None  # DRAM bytes per launch of THIS kernel on THIS workload from the committed ncu --set full capture
+    # DRAM bytes per launch of THIS kernel on THIS workload (dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    # ncu --set full capture)
+    traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(f"{args.workload}:{kernel_name}")
+            t = json.load(open(tp)).get(f"{args.workload}:{kernel_name}")
+            if t:
+                traffic, traffic_src = float(t["per_launch_bytes"]), t.get("source")
         except Exception:
             traffic = None
     gather = None
@@ -498,7 +502,12 @@ def main():
                    f"{ix.device_bytes() // 1_000_000} MB index gathered)",
                    "seeds": {"genome": hex(SEED_G), "queries": hex(SEED_Q)}},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "peak_source": peak_src, "bytes_per_query": bytes_per_query,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "dram_gbs_from_traffic": (traffic / (kernel_ms * 1e-3) / 1e9) if traffic else None,
+                     "note": ("achieved counts the REFERENCE algorithm's bytes per query (SURVEY 8d); a partitioned batch "
+                              "shares index lines between queries, so the kernel's own DRAM traffic is lower and the kernel "
+                              "is bound by instruction issue (DESIGN.md 4.2)") if part_bits else None,
+                     "peak_source": peak_src, "bytes_per_query": bytes_per_query,
                      "probes_per_query": probes_per_q, "probes_source": p_src, "kernel": kernel_name,
                      "blocks_per_sm": kernel_bps, "kernel_ms": kernel_ms, "step_ms": step_mean_ms,
                      "kernel_share_of_step": kernel_ms / step_mean_ms if step_mean_ms else None,

@@ -330,6 +330,15 @@ __device__ __forceinline__ uint64_t predict_rank(const IndexView& ix, uint64_t x
   return interpolate((long long)x, lo.x, lo.y, hi.x, hi.y);
 }
 
+// Partitioned batches (partition.cu, query.cu kmer_query_ordered_kernel).
+// For k <= 25 the 14-bit slot of a query rides in bits 50-63 of its partitioned k-mer word (2k + 14 <= 64): one shared-
+// memory store, one global store and one load per query instead of two of each (the scatter is bound by exactly those:
+// ncu r2k, stalls mio_throttle + lg_throttle).  The slot pointer then carries this tag instead of an array.
+constexpr int kSlotShift = 50;
+constexpr uint64_t kSlotKmerMask = (1ull << kSlotShift) - 1ull;
+__host__ __device__ inline const uint16_t* slot_in_kmer_tag() { return reinterpret_cast<const uint16_t*>(uintptr_t(1)); }
+
+
 __host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t z) {
   z += 0x9E3779B97F4A7C15ull;
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;

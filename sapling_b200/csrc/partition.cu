@@ -47,32 +47,44 @@ part_hist_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint
   for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cnt[(size_t)b * (nchunks + 1) + c] = sh[b];
 }
 
-// S1: one block per bin: exclusive scan of its row in place, row total stored at [nchunks]
+// S1: one block per bin: exclusive scan of its row in place, row total stored at [nchunks].  The row is walked in tiles
+// of 1024 counts, thread t holding counts 4t .. 4t+3 of the tile: neighbouring threads read neighbouring words (the
+// version measured in gpurun r2k gave each thread one contiguous 60-count segment -- 240-byte strides between lanes --
+// and the two scan kernels took 0.23 ms of the 0.56 ms "histogram + scans" stage at c3).
 __global__ void __launch_bounds__(256)
 part_scan_rows_kernel(uint32_t* __restrict__ cnt, size_t nchunks) {
-  __shared__ uint32_t part[256];
+  __shared__ uint32_t wsum[8];
+  __shared__ uint32_t carry_s;
   uint32_t* row = cnt + (size_t)blockIdx.x * (nchunks + 1);
-  const size_t per = (nchunks + 255) / 256;
-  const size_t lo = (size_t)threadIdx.x * per < nchunks ? (size_t)threadIdx.x * per : nchunks;
-  const size_t hi = lo + per < nchunks ? lo + per : nchunks;
-  uint32_t s = 0;
-  for (size_t i = lo; i < hi; i++) s += row[i];
-  part[threadIdx.x] = s;
-  __syncthreads();
-  // Hillis-Steele inclusive scan over the 256 partial sums
-  for (int d = 1; d < 256; d <<= 1) {
-    const uint32_t v = threadIdx.x >= (unsigned)d ? part[threadIdx.x - d] : 0u;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  for (size_t t0 = 0; t0 < nchunks; t0 += 1024) {
+    const size_t i0 = t0 + 4u * threadIdx.x;
+    uint32_t v[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) v[j] = i0 + j < nchunks ? row[i0 + j] : 0u;
+    const uint32_t total = v[0] + v[1] + v[2] + v[3];
+    uint32_t incl = total;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= (unsigned)d) incl += u;
+    }
+    if (lane == 31u) wsum[warp] = incl;
     __syncthreads();
-    part[threadIdx.x] += v;
+    uint32_t before = carry;  // counts of the tiles before this one + of the warps before this one
+    for (unsigned w = 0; w < warp; w++) before += wsum[w];
+    uint32_t run = before + incl - total;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (i0 + j < nchunks) row[i0 + j] = run;
+      run += v[j];
+    }
+    if (threadIdx.x == 255) carry_s = run;  // the last thread's running sum = everything up to the end of the tile
     __syncthreads();
+    carry = carry_s;
   }
-  uint32_t run = part[threadIdx.x] - s;  // exclusive prefix of this thread's segment
-  for (size_t i = lo; i < hi; i++) {
-    const uint32_t v = row[i];
-    row[i] = run;
-    run += v;
-  }
-  if (threadIdx.x == 255) row[nchunks] = part[255];
+  if (threadIdx.x == 0) row[nchunks] = carry;
 }
 
 // S2: one block: bin_start = exclusive scan of the row totals (nbins <= 2048)
@@ -168,6 +180,7 @@ __device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t 
 // ranks in shared memory and re-read the run starts: 9 shared-memory operations per k-mer against 6 here.)
 constexpr int kScatterThreads = kPartChunk / 16;  // 16 k-mers per thread in registers
 constexpr int kScatterPer = kPartChunk / kScatterThreads;
+template <bool kSlotInKmer>
 __global__ void __launch_bounds__(kScatterThreads)
 part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
                            const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
@@ -186,6 +199,7 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
   for (int j = 0; j < kScatterPer; j++) {
     const uint32_t i = threadIdx.x + (uint32_t)j * kScatterThreads;
     x[j] = i < m ? __ldcs(kmers + base + i) : 0ull;
+    if (kSlotInKmer) x[j] = (x[j] & kSlotKmerMask) | ((uint64_t)i << kSlotShift);
   }
   constexpr int kBins = 2048 / kScatterThreads;  // bins per thread
   uint32_t gpos[kBins];
@@ -217,23 +231,23 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
-      p[j] = i < m ? atomicAdd(&lstart[bin_of(x[h + j], pshift, nbins)], 1u) : 0u;
+      p[j] = i < m ? atomicAdd(&lstart[bin_of(kSlotInKmer ? (x[h + j] & kSlotKmerMask) : x[h + j], pshift, nbins)], 1u) : 0u;
     }
 #pragma unroll
     for (int j = 0; j < 4; j++) {
       const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
       if (i < m) {
         sk[p[j]] = x[h + j];
-        ss[p[j]] = (uint16_t)i;
+        if (!kSlotInKmer) ss[p[j]] = (uint16_t)i;
       }
     }
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < m; i += kScatterThreads) {
     const uint64_t v = sk[i];
-    const uint32_t g = gdelta[bin_of(v, pshift, nbins)] + i;
+    const uint32_t g = gdelta[bin_of(kSlotInKmer ? (v & kSlotKmerMask) : v, pshift, nbins)] + i;
     part_kmer[g] = v;
-    part_slot[g] = ss[i];
+    if (!kSlotInKmer) part_slot[g] = ss[i];
   }
 }
 
@@ -343,7 +357,7 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
                             long long* __restrict__ out) {
   extern __shared__ uint32_t buf32[];  // [kPartChunk] answers in the caller's order, 32 bits each (see part_unpermute_kernel)
   constexpr uint32_t kGroups = kUnpermThreads / kGroup;
-  constexpr int kBatch = 4;
+  constexpr int kBatch = 8;
   const size_t c = blockIdx.x;
   const uint32_t g = threadIdx.x / kGroup, l = threadIdx.x % kGroup;
   for (uint32_t b0 = g; b0 < nbins; b0 += kGroups * kBatch) {
@@ -401,7 +415,9 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
                                        (int)(kPartChunk * sizeof(uint32_t))));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kUnpermFlatSmem));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)kScatterSmem));
+    SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)kScatterSmem));
     SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)(kPartChunk * sizeof(uint32_t))));
@@ -437,16 +453,26 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   part_scan_bins_kernel<<<1, 1024, 0, st>>>(cnt, nchunks, nbins, bin_start, tiles);
   if (ev) cudaEventRecord(ev[1], st);
   const char* se = getenv("SAPLING_B200_PART_SCATTER");  // 0 = the direct scatter (kept for A/B measurements)
-  if (se && atoi(se) == 0) {
+  // slots inside the k-mer words: only the in-order pipelined kernel reads that format (query.cu), k <= 25
+  const char* ke = getenv("SAPLING_B200_SLOT_IN_KMER");  // 0 = separate slot array (A/B measurements)
+  const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");
+  const bool slot_in_kmer = 2 * ix.k + 14 <= 64 && in_order && ix.narrow != nullptr && !(oe && atoi(oe) == 0) &&
+                            !(se && atoi(se) == 0) && !(ke && atoi(ke) == 0);
+  if (slot_in_kmer) {
+    part_scatter_staged_kernel<true><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
+        d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
+  } else if (se && atoi(se) == 0) {
     part_scatter_kernel<<<(unsigned)nchunks, kHistThreads, nbins * 4, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt,
                                                                             bin_start, part_kmer, part_slot);
   } else {
-    part_scatter_staged_kernel<<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
+    part_scatter_staged_kernel<false><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
   }
   SB_CUDA_CHECK(cudaGetLastError());
   if (ev) cudaEventRecord(ev[2], st);
-  if (launch_kmer_query(ix, part_kmer, nq, res, st, nullptr, part_slot, in_order ? tiles : nullptr)) return -1;
+  if (launch_kmer_query(ix, part_kmer, nq, res, st, nullptr, slot_in_kmer ? slot_in_kmer_tag() : part_slot,
+                        in_order ? tiles : nullptr))
+    return -1;
   if (ev) cudaEventRecord(ev[3], st);
   // 0 = the run-per-warp un-permute, 1 = the flat one (both kept for A/B measurements); default: lane groups per run,
   // the group about half the mean run length (a whole warp from 64 answers per run: that is the run-per-warp kernel)

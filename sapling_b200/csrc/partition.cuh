@@ -12,6 +12,7 @@ namespace sb {
 constexpr uint32_t kPartChunk = 16384;  // queries per partition chunk: slots fit 16 bits, a chunk is staged in shared memory
                                         // (8192 with two blocks per SM was measured: no faster, and twice the count table)
 constexpr int kPartMaxBits = 11;        // at most 2048 slices
+// (kSlotShift, kSlotKmerMask, slot_in_kmer_tag: common.cuh)
 
 // bytes of device scratch launch_partitioned_query needs for nq queries and 2^pbits slices
 size_t partition_workspace_bytes(size_t nq, int pbits);

@@ -273,19 +273,22 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     const size_t i = t + lane;
     return __ldcs(kmers + (i < last ? i : last));
   };
+  // partition.cuh: the slot may ride in bits 50-63 of the k-mer word (uniform for the launch)
+  const bool in_kmer = slot == slot_in_kmer_tag();
+  const uint64_t kmask = in_kmer ? kSlotKmerMask : ~0ull;
   size_t t0 = claim(), t1 = claim(), t2 = claim();
   if (t0 >= nq) return;
   uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1);
-  NarrowPair m0 = narrow_load(ix, x0, pol.model);
+  NarrowPair m0 = narrow_load(ix, x0 & kmask, pol.model);
   while (t0 < nq) {
     const uint64_t x2 = kmer_at(t2);
-    const NarrowPair m1 = narrow_load(ix, x1, pol.model);
+    const NarrowPair m1 = narrow_load(ix, x1 & kmask, pol.model);
     const size_t i = t0 + lane;
     if (i < nq) {
-      const unsigned long long sl = (unsigned long long)__ldcs(slot + i);
-      const uint64_t pred = clamp_prediction(ix, narrow_finish(ix, x0, m0, pol.model));
+      const unsigned long long sl = in_kmer ? (unsigned long long)(x0 >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
+      const uint64_t pred = clamp_prediction(ix, narrow_finish(ix, x0 & kmask, m0, pol.model));
       KmerQuery q;
-      q.q = x0 << lsh;
+      q.q = (x0 & kmask) << lsh;
       q.k = (uint32_t)ix.k;
       long long r;
       if constexpr (kLean && kMode == 4) {
@@ -779,6 +782,10 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
       kernel<bps, false><<<query_grid(nq, bps * (d_tiles ? 1 : mult)), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, \
                                                                                                d_slot, d_tiles);     \
   } while (0)
+  if (d_slot == slot_in_kmer_tag() && !ordered) {
+    set_error("slots inside the k-mer words are only read by the in-order pipelined kernel");
+    return -1;
+  }
   if (d_slot && !(packed || inl || sector)) {
     set_error("partitioned batches need the sector, inline or rank-line kernel");
     return -1;
