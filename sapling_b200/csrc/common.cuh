@@ -303,6 +303,24 @@ __device__ __forceinline__ NarrowPair narrow_load(const IndexView& ix, uint64_t 
 __device__ __forceinline__ uint64_t narrow_finish(const IndexView& ix, uint64_t x, const NarrowPair& p, uint64_t pol) {
   const uint64_t b = x >> ix.shift;
   const uint64_t B = 1ull << ix.nb;
+  // Common case -- both buckets hold a k-mer and b is not the last bucket: the three differences the interpolation needs
+  // fit 32 bits (the narrow layout implies shift <= 31: xoff < 2^31, ranks < 2^32), so they are formed from the entries'
+  // offsets without rebuilding the 64-bit checkpoints.  Same real values, hence the same doubles as interpolate() below.
+  if (!((p.e0.x | p.e1.x) & kNarrowFill) && b + 1 != B) {
+    const uint32_t xl = (uint32_t)x & ((1u << ix.shift) - 1u);          // x - (b << shift)
+    const int32_t dx = (int32_t)xl - (int32_t)p.e0.x;                    // x - xlo
+    const uint32_t den = (1u << ix.shift) + p.e1.x - p.e0.x;             // xhi - xlo in [1, 2^32)
+    const uint32_t dy = p.e1.y - p.e0.y;                                 // yhi - ylo
+    const double num = (double)(dx == 0 ? 1 : dx);                       // see interpolate(): 0 / d takes the slow path
+    const double frac = __ddiv_rn(num, (double)den);
+    const double rise = __dmul_rn((double)dy, frac);
+    const double base = __dadd_rn(0.5, (double)p.e0.y);
+    const double sum = __dadd_rn(base, rise);
+    long long r = __double2ll_rz(sum);
+    if (dx == 0) r = (long long)p.e0.y;
+    if (r < 0) r = 0;
+    return (uint64_t)r;
+  }
   long long xhi, yhi;
   if (b + 1 == B) {
     xhi = ix.last_x;

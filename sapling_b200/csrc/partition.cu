@@ -357,7 +357,7 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
                             long long* __restrict__ out) {
   extern __shared__ uint32_t buf32[];  // [kPartChunk] answers in the caller's order, 32 bits each (see part_unpermute_kernel)
   constexpr uint32_t kGroups = kUnpermThreads / kGroup;
-  constexpr int kBatch = 8;
+  constexpr int kBatch = 4;  // 8 was measured slower (spills at the 32-register cap of two 1024-thread blocks per SM)
   const size_t c = blockIdx.x;
   const uint32_t g = threadIdx.x / kGroup, l = threadIdx.x % kGroup;
   for (uint32_t b0 = g; b0 < nbins; b0 += kGroups * kBatch) {

@@ -251,40 +251,42 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   const unsigned lane = threadIdx.x & 31u;
   const unsigned lsh = 64u - 2u * (unsigned)ix.k;
   const L2Policies pol = make_policies(ix.hints);
-  const size_t last = nq - 1;
+  // a partitioned batch has fewer than 2^32 queries (launch_partitioned_query): indices are 32-bit
+  const uint32_t nq32 = (uint32_t)nq, last = nq32 - 1u;
   // tiles are claimed from the global in-order counter four at a time (128 consecutive queries per atomic): the claim
   // with its shuffles and reconvergence was 42 warp instructions per tile (ncu r2f, SASS page)
   constexpr unsigned kSpan = 4;
-  unsigned long long span_next = 0;
+  uint32_t span_next = 0;
   unsigned span_left = 0;  // warp-uniform
-  auto claim = [&]() -> size_t {
+  auto claim = [&]() -> uint32_t {
     if (span_left == 0) {
       unsigned long long a = 0;
       if (lane == 0) a = atomicAdd(tiles, 32ull * kSpan);
-      span_next = __shfl_sync(0xffffffffu, a, 0);
+      a = __shfl_sync(0xffffffffu, a, 0);
+      span_next = a < 0xFFFFFE00ull ? (uint32_t)a : 0xFFFFFE00u;  // past the end either way; keeps t + lane from wrapping
       span_left = kSpan;
     }
-    const size_t t = (size_t)span_next;
-    span_next += 32ull;
+    const uint32_t t = span_next;
+    span_next += 32u;
     span_left--;
     return t;
   };
-  auto kmer_at = [&](size_t t) {  // past the end: the last k-mer again (loaded, predicted for, never answered)
-    const size_t i = t + lane;
+  auto kmer_at = [&](uint32_t t) {  // past the end: the last k-mer again (loaded, predicted for, never answered)
+    const uint32_t i = t + lane;
     return __ldcs(kmers + (i < last ? i : last));
   };
   // partition.cuh: the slot may ride in bits 50-63 of the k-mer word (uniform for the launch)
   const bool in_kmer = slot == slot_in_kmer_tag();
   const uint64_t kmask = in_kmer ? kSlotKmerMask : ~0ull;
-  size_t t0 = claim(), t1 = claim(), t2 = claim();
-  if (t0 >= nq) return;
+  uint32_t t0 = claim(), t1 = claim(), t2 = claim();
+  if (t0 >= nq32) return;
   uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1);
   NarrowPair m0 = narrow_load(ix, x0 & kmask, pol.model);
-  while (t0 < nq) {
+  while (t0 < nq32) {
     const uint64_t x2 = kmer_at(t2);
     const NarrowPair m1 = narrow_load(ix, x1 & kmask, pol.model);
-    const size_t i = t0 + lane;
-    if (i < nq) {
+    const uint32_t i = t0 + lane;
+    if (i < nq32) {
       const unsigned long long sl = in_kmer ? (unsigned long long)(x0 >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
       const uint64_t pred = clamp_prediction(ix, narrow_finish(ix, x0 & kmask, m0, pol.model));
       KmerQuery q;
