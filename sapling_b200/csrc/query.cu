@@ -243,7 +243,8 @@ kmer_query_packed_kernel(const IndexView ix, const uint64_t* __restrict__ kmers,
 //   * the slot of the query (partition.cu) is requested before the replay and consumed after it.
 // Needs the narrow model layout.  kMode as in Replay: 0 = {suffix array sector, packed genome}, 1 = inline-prefix
 // entries, 2 = rank lines, 3 = rank lines with the anchor line staged in shared memory (SaLine32; lean replay only),
-// 4 = tiling rank lines answered by kmer_replay_flat (lean only).
+// 4 = tiling rank lines answered by kmer_replay_flat (lean only), 5 = rank lines, lean replay, unfinished queries parked
+// after three probes and resumed 32 at a time (needs the slot inside the k-mer word).
 template <int kMinBlocks, int kMode, bool kLean>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
@@ -278,6 +279,30 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   // partition.cuh: the slot may ride in bits 50-63 of the k-mer word (uniform for the launch)
   const bool in_kmer = slot == slot_in_kmer_tag();
   const uint64_t kmask = in_kmer ? kSlotKmerMask : ~0ull;
+  // kMode 5: per-warp queue of parked queries (structure of arrays: lane j of a drain reads word j of each array)
+  __shared__ uint32_t park_s[(kLean && kMode == 5) ? kQueryThreads / 32 : 1][7][(kLean && kMode == 5) ? 64 : 1];
+  uint32_t (*pk)[(kLean && kMode == 5) ? 64 : 1] = park_s[(kLean && kMode == 5) ? (threadIdx.x >> 5) : 0];
+  unsigned parked = 0;  // warp-uniform
+  Lean32 ps;
+  bool pending = false;
+  auto drain = [&](unsigned e) {  // resume parked query e in binarySearch and store its answer
+    const uint64_t w = ((uint64_t)pk[1][e] << 32) | pk[0][e];
+    Lean32 d;
+    d.lo = pk[2][e];
+    d.hi = pk[3][e];
+    d.r = pk[4][e];
+    const uint32_t c = pk[5][e];
+    d.loLcp = c & 0xFFu;
+    d.hiLcp = (c >> 8) & 0xFFu;
+    d.start = (c >> 16) & 0xFFu;
+    d.state = (int)(c >> 24);
+    const uint32_t qi = pk[6][e];
+    SaPacked32 sa;
+    sa.abase = 0xFFFFFFF0u;  // no anchor line: every rank resolves to its own line
+    sa.cur = 0xFFFFFFFFu;
+    const long long r = kmer_replay32_tail<2, true>(ix, (w & kmask) << lsh, pol, sa, d);
+    __stcs(out + qi, (long long)(((unsigned long long)(w >> kSlotShift) << 48) | ((unsigned long long)r & 0xFFFFFFFFFFFFull)));
+  };
   uint32_t t0 = claim(), t1 = claim(), t2 = claim();
   if (t0 >= nq32) return;
   uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1);
@@ -286,6 +311,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     const uint64_t x2 = kmer_at(t2);
     const NarrowPair m1 = narrow_load(ix, x1 & kmask, pol.model);
     const uint32_t i = t0 + lane;
+    pending = false;
     if (i < nq32) {
       const unsigned long long sl = in_kmer ? (unsigned long long)(x0 >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
       const uint64_t pred = clamp_prediction(ix, narrow_finish(ix, x0 & kmask, m0, pol.model));
@@ -293,7 +319,11 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       q.q = (x0 & kmask) << lsh;
       q.k = (uint32_t)ix.k;
       long long r;
-      if constexpr (kLean && kMode == 4) {
+      if constexpr (kLean && kMode == 5) {
+        SaPacked32 sa;
+        sa.anchor(ix, (uint32_t)pred);
+        pending = !kmer_replay32_head<2, true>(ix, q.q, (uint32_t)pred, pol, sa, ps, &r);
+      } else if constexpr (kLean && kMode == 4) {
         r = kmer_replay_flat<true>(ix, q.q, (uint32_t)pred, pol);
       } else if constexpr (kLean && kMode == 3) {
         __shared__ uint4 lines[kQueryThreads * kLineSlotU4];
@@ -324,7 +354,30 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
         sa.fill(ix, pred, pol.sa);
         r = pl_query_from<false, false>(ix, q, pred, 0, pol, sa);
       }
-      __stcs(out + i, (long long)((sl << 48) | ((unsigned long long)r & 0xFFFFFFFFFFFFull)));
+      if (!(kLean && kMode == 5) || !pending)
+        __stcs(out + i, (long long)((sl << 48) | ((unsigned long long)r & 0xFFFFFFFFFFFFull)));
+    }
+    if constexpr (kLean && kMode == 5) {
+      // park what is still searching: after three probes about a third of the lanes are, and the binarySearch loop used to
+      // run with ~10 of 32 lanes active (ncu r2k, SASS page: 375 of 726 warp instructions per tile at 10.9 lanes)
+      const unsigned pmask = __ballot_sync(0xffffffffu, pending);
+      if (pending) {
+        const unsigned pos = parked + (unsigned)__popc(pmask & ((1u << lane) - 1u));
+        pk[0][pos] = (uint32_t)x0;
+        pk[1][pos] = (uint32_t)(x0 >> 32);
+        pk[2][pos] = ps.lo;
+        pk[3][pos] = ps.hi;
+        pk[4][pos] = ps.r;
+        pk[5][pos] = ps.loLcp | (ps.hiLcp << 8) | (ps.start << 16) | ((uint32_t)ps.state << 24);
+        pk[6][pos] = t0 + lane;
+      }
+      parked += (unsigned)__popc(pmask);
+      __syncwarp();
+      if (parked >= 32u) {
+        parked -= 32u;
+        drain(parked + lane);
+        __syncwarp();
+      }
     }
     x0 = x1;
     x1 = x2;
@@ -332,6 +385,9 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     t0 = t1;
     t1 = t2;
     t2 = claim();
+  }
+  if constexpr (kLean && kMode == 5) {
+    if (lane < parked) drain(lane);
   }
 }
 
@@ -802,8 +858,15 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
       kmer_query_ordered_kernel<bps, mode, false><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(                    \
           ix, d_kmers, nq, d_out, d_slot, d_tiles);                                                                  \
   } while (0)
-    const int mode = packed ? (flat ? 4 : line_smem ? 3 : 2) : inl ? 1 : 0;
+    // parked binarySearch tails: rank lines, lean replay, slots inside the k-mer words (k <= 25); SAPLING_B200_PARK=0 disables
+    const char* pke = getenv("SAPLING_B200_PARK");
+    const bool park = lean && packed && !flat && !line_smem && d_slot == slot_in_kmer_tag() && !(pke && atoi(pke) == 0);
+    const int mode = packed ? (park ? 5 : flat ? 4 : line_smem ? 3 : 2) : inl ? 1 : 0;
     switch (qv * 10 + mode) {
+      case 35: SB_LAUNCH_O(3, 5); break;
+      case 45: SB_LAUNCH_O(4, 5); break;
+      case 55: SB_LAUNCH_O(5, 5); break;
+      case 65: SB_LAUNCH_O(6, 5); break;
       case 62: SB_LAUNCH_O(6, 2); break;
       case 34: SB_LAUNCH_O(3, 4); break;
       case 44: SB_LAUNCH_O(4, 4); break;

@@ -790,6 +790,26 @@ __device__ __forceinline__ long long kmer_replay32(const IndexView& ix, const ui
   }
 }
 
+// The same replay cut in two for the kernel that parks unfinished queries (query.cu kmer_query_ordered_kernel, kMode 5):
+// head = the first three probes, after which a query is answered or sits in binarySearch (state BS or FINAL);
+// tail = the binarySearch loop, resumed from a Lean32 with nothing cached in registers.
+template <int kMode, bool kSkip, typename Sa>
+__device__ __forceinline__ bool kmer_replay32_head(const IndexView& ix, const uint64_t q, const uint32_t pred,
+                                                   const L2Policies& pol, Sa& sa, Lean32& s, long long* result) {
+  s.lo = 0; s.hi = 0; s.r = pred; s.loLcp = 0; s.hiLcp = 0; s.start = 0; s.state = S_PRED;
+  if (lean_step<kMode, kSkip, S_PRED>(ix, q, pred, pol, sa, s, result)) return true;
+  if (lean_step<kMode, kSkip, -2>(ix, q, pred, pol, sa, s, result)) return true;
+  return lean_step<kMode, kSkip, -3>(ix, q, pred, pol, sa, s, result);
+}
+template <int kMode, bool kSkip, typename Sa>
+__device__ __forceinline__ long long kmer_replay32_tail(const IndexView& ix, const uint64_t q, const L2Policies& pol, Sa& sa,
+                                                        Lean32& s) {
+  long long result = 0;
+  for (;;) {
+    if (lean_step<kMode, kSkip, -4>(ix, q, 0u, pol, sa, s, &result)) return result;  // predicted is not used in binarySearch
+  }
+}
+
 // ---- flat k-mer replay on tiling rank lines --------------------------------------------------------------------------
 // MEASURED SLOWER than kmer_replay32 (gpurun r2g, see launch_kmer_query) and therefore opt-in (SAPLING_B200_FLAT=1); kept
 // because the reason is instructive and the variant is covered by the parity tests.

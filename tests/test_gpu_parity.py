@@ -382,10 +382,16 @@ def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch)
                     for lean, line_smem in (("1", "1"), ("1", "0"), ("0", "0")):
                         monkeypatch.setenv("SAPLING_B200_LEAN", lean)
                         monkeypatch.setenv("SAPLING_B200_LINE_SMEM", line_smem)
-                        combos = ((("1", "1", "1", "1", "1"), ("1", "0", "1", "2", "1"), ("0", "1", "0", "0", "1"),
-                                   ("0", "1", "1", "0", "0"), ("1", "1", "1", "2", "0"))
-                                  if part == "1" else (("1", "1", "1", "1", "1"), ("1", "1", "1", "1", "0")))
-                        for tiles, pipe, scat, unp, flat in combos:
+                        # last two: SLOT_IN_KMER (slot inside the partitioned k-mer word, k <= 25), PARK (unfinished
+                        # queries parked after three probes; needs the former)
+                        combos = ((("1", "1", "1", "1", "1", "1", "1"), ("1", "0", "1", "2", "1", "1", "1"),
+                                   ("0", "1", "0", "0", "1", "1", "1"), ("0", "1", "1", "0", "0", "1", "1"),
+                                   ("1", "1", "1", "2", "0", "1", "0"), ("1", "1", "1", "2", "0", "0", "1"),
+                                   ("1", "1", "1", "1", "0", "1", "1"))
+                                  if part == "1" else (("1", "1", "1", "1", "1", "1", "1"), ("1", "1", "1", "1", "0", "1", "1")))
+                        for tiles, pipe, scat, unp, flat, sik, park in combos:
+                            monkeypatch.setenv("SAPLING_B200_SLOT_IN_KMER", sik)
+                            monkeypatch.setenv("SAPLING_B200_PARK", park)
                             monkeypatch.setenv("SAPLING_B200_FLAT", flat)  # kmer_replay_flat / kmer_replay32 (tiling lines)
                             monkeypatch.setenv("SAPLING_B200_PART_TILES", tiles)
                             monkeypatch.setenv("SAPLING_B200_ORDERED_PIPE", pipe)
@@ -395,11 +401,11 @@ def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch)
                                 monkeypatch.setenv("SAPLING_B200_QV", qv)
                                 got = ix.queryBatch(kmers)
                                 assert np.array_equal(got, exp), (name, k, flags, shift, part, lean, line_smem, tiles,
-                                                                  pipe, scat, unp, flat, qv)
+                                                                  pipe, scat, unp, flat, sik, park, qv)
                             assert np.array_equal(ix.queryBatch(kmers[:8191]), exp[:8191])
                 ix.close()
         port.close()
         base.close()
     for v in ("PART", "PART_MIN", "PART_BITS", "LEAN", "LINE_SMEM", "PART_TILES", "ORDERED_PIPE", "PART_SCATTER",
-              "PART_UNPERMUTE", "QV", "PACKED_SHIFT", "FLAT"):
+              "PART_UNPERMUTE", "QV", "PACKED_SHIFT", "FLAT", "SLOT_IN_KMER", "PARK"):
         monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
