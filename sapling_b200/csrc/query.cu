@@ -858,9 +858,12 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
       kmer_query_ordered_kernel<bps, mode, false><<<query_grid(nq, bps), kQueryThreads, 0, st>>>(                    \
           ix, d_kmers, nq, d_out, d_slot, d_tiles);                                                                  \
   } while (0)
-    // parked binarySearch tails: rank lines, lean replay, slots inside the k-mer words (k <= 25); SAPLING_B200_PARK=0 disables
+    // parked binarySearch tails: rank lines, lean replay, slots inside the k-mer words (k <= 25).  MEASURED SLOWER once the
+    // binarySearch loop had been specialised (gpurun r2o: c2 1.26 against 1.13 ms per 50 M, c3 8.2 against 7.6 ms per 250 M:
+    // the queue traffic, the lost sector in registers and the scattered result stores cost more than the ~10 idle lanes
+    // of a ~60-instruction loop body).  Opt-in: SAPLING_B200_PARK=1.
     const char* pke = getenv("SAPLING_B200_PARK");
-    const bool park = lean && packed && !flat && !line_smem && d_slot == slot_in_kmer_tag() && !(pke && atoi(pke) == 0);
+    const bool park = lean && packed && !flat && !line_smem && d_slot == slot_in_kmer_tag() && pke && atoi(pke) == 1;
     const int mode = packed ? (park ? 5 : flat ? 4 : line_smem ? 3 : 2) : inl ? 1 : 0;
     switch (qv * 10 + mode) {
       case 35: SB_LAUNCH_O(3, 5); break;
