@@ -11,8 +11,9 @@
 // The price is three streaming passes (42 bytes per query); the reference's per-query arithmetic is untouched --
 // the same Replay code answers every query, only the order in which queries are answered changes.
 //
-//   A  part_hist_kernel     chunk c (kPartChunk queries) x bin -> count            cnt[bin][c]
-//   S  part_scan_*          exclusive scan over chunks per bin, then over bins     off[bin][c], bin_start[bin]
+//   A  part_hist_kernel     chunk c (kPartChunk queries) x bin -> count            cnt[c][bin]  (chunk-major: every
+//                           pass reads or writes whole rows; a bin-major table cost 1024 strided sectors per chunk)
+//   S  part_col*_kernel     exclusive scan down every column (over chunks), then over bins     off[c][bin], bin_start[bin]
 //   B  part_scatter_kernel  k-mer -> part_kmer[bin_start + off + local rank], its index inside the chunk -> part_slot
 //   Q  query kernel (query.cu) over part_kmer in order; result word = slot << 48 | answer
 //   U  part_unpermute_kernel  chunk c gathers its answers bin by bin into shared memory, writes out[] coalesced
@@ -32,7 +33,7 @@ __device__ __forceinline__ uint32_t bin_of(uint64_t x, int pshift, uint32_t nbin
   return b < (uint64_t)nbins ? (uint32_t)b : nbins - 1;  // a k-mer with bits above 2k set: still a valid array slot
 }
 
-// A: per-chunk histogram.  cnt is bin-major with rows of nchunks + 1 entries.
+// A: per-chunk histogram.  cnt is chunk-major: row c holds the nbins counts of chunk c (row nchunks: the totals).
 __global__ void __launch_bounds__(kHistThreads)
 part_hist_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
                  uint32_t* __restrict__ cnt) {
@@ -44,47 +45,46 @@ part_hist_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
   for (uint32_t i = threadIdx.x; i < m; i += kHistThreads) atomicAdd(&sh[bin_of(__ldg(kmers + base + i), pshift, nbins)], 1u);
   __syncthreads();
-  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cnt[(size_t)b * (nchunks + 1) + c] = sh[b];
+  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cnt[c * nbins + b] = sh[b];
 }
 
-// S1: one block per bin: exclusive scan of its row in place, row total stored at [nchunks].  The row is walked in tiles
-// of 1024 counts, thread t holding counts 4t .. 4t+3 of the tile: neighbouring threads read neighbouring words (the
-// version measured in gpurun r2k gave each thread one contiguous 60-count segment -- 240-byte strides between lanes --
-// and the two scan kernels took 0.23 ms of the 0.56 ms "histogram + scans" stage at c3).
-__global__ void __launch_bounds__(256)
-part_scan_rows_kernel(uint32_t* __restrict__ cnt, size_t nchunks) {
-  __shared__ uint32_t wsum[8];
-  __shared__ uint32_t carry_s;
-  uint32_t* row = cnt + (size_t)blockIdx.x * (nchunks + 1);
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t carry = 0;
-  for (size_t t0 = 0; t0 < nchunks; t0 += 1024) {
-    const size_t i0 = t0 + 4u * threadIdx.x;
-    uint32_t v[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) v[j] = i0 + j < nchunks ? row[i0 + j] : 0u;
-    const uint32_t total = v[0] + v[1] + v[2] + v[3];
-    uint32_t incl = total;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t u = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= (unsigned)d) incl += u;
-    }
-    if (lane == 31u) wsum[warp] = incl;
-    __syncthreads();
-    uint32_t before = carry;  // counts of the tiles before this one + of the warps before this one
-    for (unsigned w = 0; w < warp; w++) before += wsum[w];
-    uint32_t run = before + incl - total;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (i0 + j < nchunks) row[i0 + j] = run;
-      run += v[j];
-    }
-    if (threadIdx.x == 255) carry_s = run;  // the last thread's running sum = everything up to the end of the tile
-    __syncthreads();
-    carry = carry_s;
+// S1: exclusive scan down every column of cnt (over the chunks of one bin), in three small passes so that every access is
+// a coalesced row piece: the rows are cut into kScanSegs segments; (a) per-segment column sums, (b) a serial scan of the
+// kScanSegs sums per column (totals -> row nchunks), (c) each segment rewrites its rows as running sums.
+constexpr int kScanSegs = 64;
+__global__ void __launch_bounds__(128)
+part_colsum_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, size_t rows_per_seg,
+                   uint32_t* __restrict__ segsum) {
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t r0 = (size_t)blockIdx.y * rows_per_seg;
+  const size_t r1 = r0 + rows_per_seg < nchunks ? r0 + rows_per_seg : nchunks;
+  uint32_t sum = 0;
+  for (size_t r = r0; r < r1; r++) sum += __ldg(cnt + r * nbins + col);
+  segsum[(size_t)blockIdx.y * nbins + col] = sum;
+}
+__global__ void __launch_bounds__(128)
+part_segscan_kernel(uint32_t* __restrict__ segsum, uint32_t nbins, uint32_t* __restrict__ totals) {
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t run = 0;
+  for (int sg = 0; sg < kScanSegs; sg++) {
+    const uint32_t v = segsum[(size_t)sg * nbins + col];
+    segsum[(size_t)sg * nbins + col] = run;
+    run += v;
   }
-  if (threadIdx.x == 0) row[nchunks] = carry;
+  totals[col] = run;
+}
+__global__ void __launch_bounds__(128)
+part_colscan_kernel(uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, size_t rows_per_seg,
+                    const uint32_t* __restrict__ segsum) {
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t r0 = (size_t)blockIdx.y * rows_per_seg;
+  const size_t r1 = r0 + rows_per_seg < nchunks ? r0 + rows_per_seg : nchunks;
+  uint32_t run = segsum[(size_t)blockIdx.y * nbins + col];
+  for (size_t r = r0; r < r1; r++) {
+    const uint32_t v = cnt[r * nbins + col];
+    cnt[r * nbins + col] = run;
+    run += v;
+  }
 }
 
 // S2: one block: bin_start = exclusive scan of the row totals (nbins <= 2048)
@@ -93,7 +93,7 @@ part_scan_bins_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t
                       unsigned long long* __restrict__ tiles) {
   __shared__ uint32_t a[2048];
   if (threadIdx.x == 0) *tiles = 0;  // the query kernel's in-order tile counter (query.cu QueryCursor)
-  for (uint32_t b = threadIdx.x; b < 2048; b += 1024) a[b] = b < nbins ? cnt[(size_t)b * (nchunks + 1) + nchunks] : 0u;
+  for (uint32_t b = threadIdx.x; b < 2048; b += 1024) a[b] = b < nbins ? cnt[nchunks * nbins + b] : 0u;
   __syncthreads();
   for (int d = 1; d < 2048; d <<= 1) {
     uint32_t v[2];
@@ -117,7 +117,7 @@ part_scatter_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, u
                     uint64_t* __restrict__ part_kmer, uint16_t* __restrict__ part_slot) {
   extern __shared__ uint32_t cur[];
   const size_t c = blockIdx.x;
-  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cur[b] = bin_start[b] + off[(size_t)b * (nchunks + 1) + c];
+  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cur[b] = bin_start[b] + off[c * nbins + b];
   __syncthreads();
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
@@ -209,9 +209,9 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
     uint32_t len = 0;
     gpos[j] = 0;
     if (b < nbins) {
-      const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+      const uint32_t* row = off + c * nbins + b;  // rows c and c + 1 of the offset table: coalesced
       const uint32_t r0 = __ldg(row);
-      len = __ldg(row + 1) - r0;
+      len = __ldg(row + nbins) - r0;
       gpos[j] = __ldg(bin_start + b) + r0;
     }
     lstart[b] = len;
@@ -266,10 +266,10 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
   for (int j = 0; j < 2; j++) {
     const uint32_t b = warp + 32u * (lane + 32u * j);
     if (b < nbins) {
-      const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+      const uint32_t* row = off + c * nbins + b;
       const uint32_t s = bin_start[b];
       lo[j] = s + row[0];
-      hi[j] = s + row[1];
+      hi[j] = s + row[nbins];
     } else {
       lo[j] = hi[j] = 0;
     }
@@ -318,9 +318,9 @@ part_unpermute_flat_kernel(const long long* __restrict__ res, size_t nq, uint32_
     uint32_t len = 0;
     gpos[j] = 0;
     if (b < nbins) {
-      const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+      const uint32_t* row = off + c * nbins + b;
       const uint32_t r0 = row[0];
-      len = row[1] - r0;
+      len = row[nbins] - r0;
       gpos[j] = bin_start[b] + r0;
     }
     lstart[b] = len;
@@ -367,10 +367,10 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
       const uint32_t b = b0 + (uint32_t)j * kGroups;
       lo[j] = hi[j] = 0;
       if (b < nbins) {
-        const uint32_t* row = off + (size_t)b * (nchunks + 1) + c;
+        const uint32_t* row = off + c * nbins + b;
         const uint32_t s = __ldg(bin_start + b);
         lo[j] = s + __ldg(row);
-        hi[j] = s + __ldg(row + 1);
+        hi[j] = s + __ldg(row + nbins);
       }
     }
 #pragma unroll
@@ -399,7 +399,8 @@ size_t partition_workspace_bytes(size_t nq, int pbits) {
   const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
   const size_t nbins = (size_t)1 << pbits;
   auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  return up(nq * 8) + up(nq * 8) + up(nq * 2) + up(nbins * (nchunks + 1) * 4) + up((nbins + 1) * 4) + 256;
+  return up(nq * 8) + up(nq * 8) + up(nq * 2) + up(nbins * (nchunks + 1) * 4) + up((nbins + 1) * 4) + 256 +
+         up((size_t)kScanSegs * nbins * 4);
 }
 
 int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, void* ws,
@@ -443,13 +444,21 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   uint16_t* part_slot = reinterpret_cast<uint16_t*>(p); p += up(nq * 2);
   uint32_t* cnt = reinterpret_cast<uint32_t*>(p); p += up((size_t)nbins * (nchunks + 1) * 4);
   uint32_t* bin_start = reinterpret_cast<uint32_t*>(p); p += up((size_t)(nbins + 1) * 4);
-  unsigned long long* tiles = reinterpret_cast<unsigned long long*>(p);
+  unsigned long long* tiles = reinterpret_cast<unsigned long long*>(p); p += 256;
+  uint32_t* segsum = reinterpret_cast<uint32_t*>(p);
   const char* te = getenv("SAPLING_B200_PART_TILES");  // 0 = static grid-stride schedule (kept for A/B measurements)
   const bool in_order = !(te && atoi(te) == 0);
 
   if (ev) cudaEventRecord(ev[0], st);
   part_hist_kernel<<<(unsigned)nchunks, kHistThreads, nbins * 4, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt);
-  part_scan_rows_kernel<<<nbins, 256, 0, st>>>(cnt, nchunks);
+  {
+    const unsigned cw = nbins < 128u ? nbins : 128u;  // columns per block (nbins is a power of two)
+    const size_t rows_per_seg = (nchunks + kScanSegs - 1) / kScanSegs;
+    const dim3 grid(nbins / cw, kScanSegs);
+    part_colsum_kernel<<<grid, cw, 0, st>>>(cnt, nchunks, nbins, rows_per_seg, segsum);
+    part_segscan_kernel<<<nbins / cw, cw, 0, st>>>(segsum, nbins, cnt + nchunks * nbins);
+    part_colscan_kernel<<<grid, cw, 0, st>>>(cnt, nchunks, nbins, rows_per_seg, segsum);
+  }
   part_scan_bins_kernel<<<1, 1024, 0, st>>>(cnt, nchunks, nbins, bin_start, tiles);
   if (ev) cudaEventRecord(ev[1], st);
   const char* se = getenv("SAPLING_B200_PART_SCATTER");  // 0 = the direct scatter (kept for A/B measurements)
