@@ -125,7 +125,12 @@ def full(src, dst, nq=None):
         if h is not None:
             hd = lines[h]
             si, ii = hd.index("Source"), hd.index("# Samples")
-            body = [l for l in lines[h + 1:] if len(l) == len(hd)]
+            body = []
+            for l in lines[h + 1:]:  # a report with several kernels repeats the header: keep the first kernel only
+                if l and l[0] == "Address":
+                    break
+                if len(l) == len(hd):
+                    body.append(l)
             tot = sum(int(l[ii] or 0) for l in body)
             top = sorted(body, key=lambda l: -int(l[ii] or 0))[:14]
             f.write(f"\n## Hottest SASS instructions by warp-stall samples ({tot} samples)\n\n| samples | share | instruction |\n|---:|---:|---|\n")
