@@ -418,7 +418,7 @@ def main():
     step_mean_ms = sum(step_ms) / len(step_ms)
     kernel_name, kernel_bps = ix.query_kernel(nq)
     part_bits = ix.partition_bits(nq)
-    launches_per_step = 7 if part_bits else 1  # hist, column sums, segment + bin scan, column scan, scatter, QUERY, un-permute
+    launches_per_step = 8 if part_bits else 1  # hist, 3 column-scan passes, bin scan, scatter, QUERY, un-permute
     # the query kernel on its own: the same steps again with CUDA events recorded by the library on the launching
     # stream around each stage (a partitioned step is histogram+scans, scatter, QUERY KERNEL, un-permute)
     ix.profile(True)

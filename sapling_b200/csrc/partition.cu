@@ -50,8 +50,7 @@ part_hist_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint
 
 // S1: exclusive scan down every column of cnt (over the chunks of one bin), in three small passes so that every access is
 // a coalesced row piece: the rows are cut into kScanSegs segments; (a) per-segment column sums, (b) a serial scan of the
-// kScanSegs sums per column (totals -> row nchunks; inside part_scan_bins_kernel), (c) each segment rewrites its rows
-// as running sums.
+// kScanSegs sums per column (totals -> row nchunks), (c) each segment rewrites its rows as running sums.
 constexpr int kScanSegs = 64;
 __global__ void __launch_bounds__(128)
 part_colsum_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, size_t rows_per_seg,
@@ -62,6 +61,17 @@ part_colsum_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nb
   uint32_t sum = 0;
   for (size_t r = r0; r < r1; r++) sum += __ldg(cnt + r * nbins + col);
   segsum[(size_t)blockIdx.y * nbins + col] = sum;
+}
+__global__ void __launch_bounds__(128)
+part_segscan_kernel(uint32_t* __restrict__ segsum, uint32_t nbins, uint32_t* __restrict__ totals) {
+  const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t run = 0;
+  for (int sg = 0; sg < kScanSegs; sg++) {
+    const uint32_t v = segsum[(size_t)sg * nbins + col];
+    segsum[(size_t)sg * nbins + col] = run;
+    run += v;
+  }
+  totals[col] = run;
 }
 __global__ void __launch_bounds__(128)
 part_colscan_kernel(uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, size_t rows_per_seg,
@@ -77,25 +87,13 @@ part_colscan_kernel(uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, 
   }
 }
 
-// S2: one block: (b) of the column scan -- the kScanSegs segment sums of every column turned into segment starts, the
-// column totals stored as row nchunks -- and then bin_start = exclusive scan of those totals (nbins <= 2048)
+// S2: one block: bin_start = exclusive scan of the row totals (nbins <= 2048)
 __global__ void __launch_bounds__(1024)
-part_scan_bins_kernel(uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, uint32_t* __restrict__ segsum,
-                      uint32_t* __restrict__ bin_start, unsigned long long* __restrict__ tiles) {
+part_scan_bins_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t nbins, uint32_t* __restrict__ bin_start,
+                      unsigned long long* __restrict__ tiles) {
   __shared__ uint32_t a[2048];
   if (threadIdx.x == 0) *tiles = 0;  // the query kernel's in-order tile counter (query.cu QueryCursor)
-  for (uint32_t b = threadIdx.x; b < 2048; b += 1024) {
-    uint32_t run = 0;
-    if (b < nbins) {
-      for (int sg = 0; sg < kScanSegs; sg++) {
-        const uint32_t v = segsum[(size_t)sg * nbins + b];
-        segsum[(size_t)sg * nbins + b] = run;
-        run += v;
-      }
-      cnt[nchunks * nbins + b] = run;
-    }
-    a[b] = run;
-  }
+  for (uint32_t b = threadIdx.x; b < 2048; b += 1024) a[b] = b < nbins ? cnt[nchunks * nbins + b] : 0u;
   __syncthreads();
   for (int d = 1; d < 2048; d <<= 1) {
     uint32_t v[2];
@@ -458,9 +456,10 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
     const size_t rows_per_seg = (nchunks + kScanSegs - 1) / kScanSegs;
     const dim3 grid(nbins / cw, kScanSegs);
     part_colsum_kernel<<<grid, cw, 0, st>>>(cnt, nchunks, nbins, rows_per_seg, segsum);
-    part_scan_bins_kernel<<<1, 1024, 0, st>>>(cnt, nchunks, nbins, segsum, bin_start, tiles);
+    part_segscan_kernel<<<nbins / cw, cw, 0, st>>>(segsum, nbins, cnt + nchunks * nbins);
     part_colscan_kernel<<<grid, cw, 0, st>>>(cnt, nchunks, nbins, rows_per_seg, segsum);
   }
+  part_scan_bins_kernel<<<1, 1024, 0, st>>>(cnt, nchunks, nbins, bin_start, tiles);
   if (ev) cudaEventRecord(ev[1], st);
   const char* se = getenv("SAPLING_B200_PART_SCATTER");  // 0 = the direct scatter (kept for A/B measurements)
   // slots inside the k-mer words: only the in-order pipelined kernel reads that format (query.cu), k <= 25
