@@ -486,6 +486,23 @@ def main():
                 traffic, traffic_src = float(t["per_launch_bytes"]), t.get("source")
         except Exception:
             traffic = None
+    # Whole-step HBM bound of the partitioned pipeline: what one step has to move at the least -- the streams
+    # of passes A, B, Q, U (8 + 16 + 16 + 16 bytes per query) plus every index line that at least one query of the batch
+    # touches, once (rank lines 128 B per 16 ranks and the narrow model 8 B per bucket, Poisson coverage).  Unpartitioned: the
+    # per-query figure above, there is no sharing.
+    import math
+    if part_bits:
+        lines = n / 16.0
+        line_bytes = 128.0 * lines * (1.0 - math.exp(-nq / lines))
+        buckets = float(1 << ix.buckets)
+        model_bytes = 8.0 * buckets * (1.0 - math.exp(-nq / buckets))
+        step_bytes = 56.0 * nq + line_bytes + model_bytes
+    else:
+        step_bytes = bytes_per_query * nq
+    step_gbs = step_bytes / (step_mean_ms * 1e-3) / 1e9
+    roofline_step = {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                     "bytes_per_query": step_bytes / nq, "step_ms": step_mean_ms,
+                     "what": "minimum DRAM bytes of one whole step (all launches) / step time"}
     gather = None
     try:
         gather = S.gather_bench(12 << 30, 1 << 28, 3)
@@ -514,6 +531,7 @@ def main():
                      "partition_bits": part_bits,
                      "stage_ms": dict(zip(("hist_scan", "scatter", "query_kernel", "unpermute"), stage_ms)),
                      "random_sector_gather_gbs": gather},
+        "roofline_step": roofline_step,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8,
                 "steps": e2e_steps, "api": "sapling_b200_query_batch (pinned host buffers)", "numa_node": numa_node},

@@ -34,6 +34,11 @@ t1 = ["| workload | whole step, G q/s | kernel Q ms/launch | achieved GB/s (algo
       "| c2, 1×B200 " + roof(c2, 50e6), "| c3, 1×B200 " + roof(c3, 250e6)]
 
 
+def steproof(d):
+    r = d.get("roofline_step")
+    return f"{r['bytes_per_query']:.0f} B/query, {r['achieved']:.0f} GB/s = {r['frac']:.2f} of the copy bandwidth" if r else "—"
+
+
 def stages(d):
     s = d["roofline"]["stage_ms"]
     return f"{s['hist_scan']:.2f} / {s['scatter']:.2f} / {s['query_kernel']:.2f} / {s['unpermute']:.2f}"
@@ -49,6 +54,7 @@ t2 = ["| | c2 | c3 |", "|---|---:|---:|",
       f"| GPU device-resident, whole step | {c2['value'] / 1e9:.1f} G q/s ({c2['ms_per_step']:.3f} ms / 50 M) | "
       f"{c3['value'] / 1e9:.1f} G q/s ({c3['ms_per_step']:.2f} ms / 250 M) |",
       f"| stages A+S / B / Q / U, ms | {stages(c2)} | {stages(c3)} |",
+      f"| whole-step HBM bound (`roofline_step`) | {steproof(c2)} | {steproof(c3)} |",
       f"| partition bits | {c2['roofline']['partition_bits']} | {c3['roofline']['partition_bits']} |",
       f"| GPU end-to-end (host buffers, PCIe inside) | {c2['e2e']['value'] / 1e9:.2f} G q/s | {c3['e2e']['value'] / 1e9:.2f} G q/s |",
       f"| CPU, {c2['cpu_baseline']['cores']} threads | {c2['cpu_baseline']['value'] / 1e6:.1f} M q/s (unmodified reference; "
@@ -62,6 +68,6 @@ p = os.path.join(ROOT, "DESIGN.md")
 s = open(p).read()
 s = re.sub(r"<!-- ROOFLINE -->.*?<!-- /ROOFLINE -->", "<!-- ROOFLINE -->\n" + "\n".join(t1) + "\n<!-- /ROOFLINE -->", s, flags=re.S)
 s = re.sub(r"<!-- BENCH -->.*?<!-- /BENCH -->", "<!-- BENCH -->\n" + "\n".join(t2) + "\n<!-- /BENCH -->", s, flags=re.S)
-s = re.sub(r"profiles/r2[a-z]_", f"profiles/{tag}_", s)
+s = re.sub(r"profiles/r2[g-z]_", f"profiles/{tag}_", s)  # r2f stays: the "before" captures
 open(p, "w").write(s)
 print("\n".join(t1 + [""] + t2))
