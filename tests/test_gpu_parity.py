@@ -354,6 +354,38 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name,k", [("rand200k", 21), ("tandem50", 16), ("gc0110", 31)])
+def test_partitioned_large_batch(S, oracle_built, name, k, monkeypatch):
+    """A batch of many partition chunks (2.1 M queries = 129 chunks: the column scan of the offset table works in 64 row
+    segments of more than one row, the last chunk is ragged) answered through the partitioned path, with the slot inside
+    the k-mer word (k <= 25) and in the side array (k = 31), equals the same batch answered in the caller's order, and
+    its first 40 000 answers equal the oracle's."""
+    g = GENOMES[name]
+    port = O.Port.from_memory(g, k=k)
+    rng = np.random.default_rng(17)
+    q0 = F.query_mix(g, k, 40000, seed=23)
+    kmers = np.concatenate([q0, rng.choice(q0, size=2_100_000 - len(q0) + 777)])
+    exp_head = port.query_batch(q0, nthreads=4)
+    for flags in (S.PACKED, S.NO_PACKED | S.NO_INLINE):
+        ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, list(port.five), flags=S.QUIET | flags)
+        monkeypatch.setenv("SAPLING_B200_PART", "0")
+        plain = ix.queryBatch(kmers)
+        assert np.array_equal(plain[:len(q0)], exp_head)
+        monkeypatch.setenv("SAPLING_B200_PART", "1")
+        monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
+        monkeypatch.setenv("SAPLING_B200_CHUNK_LOG2", "22")  # the host entry point hands the whole batch to one call
+        for bits in (5, 10):
+            monkeypatch.setenv("SAPLING_B200_PART_BITS", str(bits))
+            assert ix.partition_bits(len(kmers)) == bits
+            got = ix.queryBatch(kmers)
+            assert np.array_equal(got, plain), (name, k, flags, bits, int((got != plain).sum()))
+        ix.close()
+    port.close()
+    for v in ("PART", "PART_MIN", "PART_BITS", "CHUNK_LOG2"):
+        monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ["rand200k", "gc0110", "tandem50"])
 def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch):
     """Every selectable variant of the batch path returns the oracle's answers: the lean 32-bit replay against the
