@@ -100,7 +100,8 @@ int sapling_b200_check_sa(const sapling_b200_index *ix, uint32_t max_chars, uint
                           uint64_t *undecided, uint64_t *bad_perm);
 /* Device memory held by the index, in bytes. */
 uint64_t sapling_b200_device_bytes(const sapling_b200_index *ix);
-/* Number of k-mer query kernels launched through this handle so far (both batch entry points). */
+/* Number of kernels launched for k-mer batches through this handle so far (both batch entry points; a partitioned batch
+ * is eight launches). */
 uint64_t sapling_b200_launch_count(const sapling_b200_index *ix);
 /* Name of the CUDA kernel sapling_b200_query_batch(_dev) launches for this index (which layout it reads depends on
  * the genome size and the flags), and the resident blocks per SM it is compiled for. */

@@ -966,7 +966,7 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
     ws = w.p;
   }
   if (!ws) return plain();
-  ix->launches.fetch_add(6, std::memory_order_relaxed);
+  ix->launches.fetch_add(8, std::memory_order_relaxed);  // histogram, three column-scan passes, bin scan, scatter, query, un-permute
   return launch_partitioned_query(v, d_kmers, nq, d_out, ws, bits, st, ev);
 }
 
