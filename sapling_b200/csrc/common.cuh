@@ -293,20 +293,20 @@ struct NarrowPair {
   uint2 e0, e1;
 };
 __device__ __forceinline__ NarrowPair narrow_load(const IndexView& ix, uint64_t x, uint64_t pol) {
-  const uint64_t b = x >> ix.shift;
-  const uint64_t B = 1ull << ix.nb;
+  const uint32_t b = (uint32_t)(x >> ix.shift);  // nb <= 31 (capi.cu): bucket numbers are 32-bit
+  const uint32_t last = (uint32_t)((1ull << ix.nb) - 1ull);
   NarrowPair p;
   p.e0 = ld_u32x2_pol(ix.narrow + b, pol);
-  p.e1 = ld_u32x2_pol(ix.narrow + (b + 1 < B ? b + 1 : b), pol);
+  p.e1 = ld_u32x2_pol(ix.narrow + (b < last ? b + 1u : b), pol);
   return p;
 }
 __device__ __forceinline__ uint64_t narrow_finish(const IndexView& ix, uint64_t x, const NarrowPair& p, uint64_t pol) {
-  const uint64_t b = x >> ix.shift;
+  const uint64_t b = (uint32_t)(x >> ix.shift);  // nb <= 31: fits 32 bits (the 64-bit type only serves the rare paths below)
   const uint64_t B = 1ull << ix.nb;
   // Common case -- both buckets hold a k-mer and b is not the last bucket: the three differences the interpolation needs
   // fit 32 bits (the narrow layout implies shift <= 31: xoff < 2^31, ranks < 2^32), so they are formed from the entries'
   // offsets without rebuilding the 64-bit checkpoints.  Same real values, hence the same doubles as interpolate() below.
-  if (!((p.e0.x | p.e1.x) & kNarrowFill) && b + 1 != B) {
+  if (!((p.e0.x | p.e1.x) & kNarrowFill) && (uint32_t)b != (uint32_t)(B - 1)) {
     const uint32_t xl = (uint32_t)x & ((1u << ix.shift) - 1u);          // x - (b << shift)
     const int32_t dx = (int32_t)xl - (int32_t)p.e0.x;                    // x - xlo
     const uint32_t den = (1u << ix.shift) + p.e1.x - p.e0.x;             // xhi - xlo in [1, 2^32)
