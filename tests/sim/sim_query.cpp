@@ -105,7 +105,7 @@ int sim_kmer_batch_lean(const uint64_t* genome, const uint32_t* sa, const int64_
   memcpy(sa_pad, sa, n * sizeof(uint32_t));
   ix.sa = sa_pad;
   if (mode == 4 && shift != 4) return -2;  // the flat replay reads tiling lines only
-  if (mode == 2 || mode == 3 || mode == 4) {
+  if (mode == 2 || mode == 3 || mode == 4 || mode == 5) {
     const uint64_t sectors = sb::packed_sectors(n, shift);
     packed = new uint32_t[sectors * 8];
     for (uint64_t s = 0; s < sectors; s++) {
@@ -130,6 +130,18 @@ int sim_kmer_batch_lean(const uint64_t* genome, const uint32_t* sa, const int64_
     const uint32_t pred = (uint32_t)sb::clamp_prediction(ix, sb::predict_rank(ix, kmers[i], pol.model));
     if (mode == 4) {
       out[i] = sb::kmer_replay_flat<true>(ix, q, pred, pol);
+    } else if (mode == 5) {  // the replay cut in two (parked tails): three probes, then binarySearch resumed cold
+      sb::SaPacked32 sp;
+      sp.anchor(ix, pred);
+      sb::Lean32 st;
+      long long r = 0;
+      if (!sb::kmer_replay32_head<2, true>(ix, q, pred, pol, sp, st, &r)) {
+        sb::SaPacked32 cold;
+        cold.abase = 0xFFFFFFF0u;
+        cold.cur = 0xFFFFFFFFu;
+        r = sb::kmer_replay32_tail<2, true>(ix, q, pol, cold, st);
+      }
+      out[i] = r;
     } else if (mode == 2) {
       sb::SaPacked32 sp;
       sp.anchor(ix, pred);

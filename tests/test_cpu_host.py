@@ -120,7 +120,8 @@ def test_lean_kmer_replay_on_host_matches_oracle(oracle_built, name):
             exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
             cases = [(0, 0, 3), (2, 6, 3), (2, 12, 4), (2, 21, 3), (2, 32, 4), (2, 16, 4),
                      (3, 6, 4), (3, 12, 3), (3, 21, 4), (3, 32, 3), (3, 16, 3),
-                     (4, 6, 4), (4, 12, 4), (4, 21, 4), (4, 32, 4), (4, 16, 4), (4, 24, 4)]
+                     (4, 6, 4), (4, 12, 4), (4, 21, 4), (4, 32, 4), (4, 16, 4), (4, 24, 4),
+                     (5, 6, 4), (5, 12, 3), (5, 21, 4), (5, 32, 3), (5, 24, 4)]
             cases += [(1, b, 3) for b in (27, 32) if k <= b]
             for mode, bases, shift in cases:
                 out = np.empty(len(kmers), dtype=np.int64)
