@@ -62,6 +62,13 @@ sapling_b200_index *sapling_b200_create_with_model(const char *genome, uint64_t 
                                                    int k, int nb, const int64_t *xlist,
                                                    const int64_t *ylist, const int *five, unsigned flags);
 
+/* Private index cache (not a reference format): the 2-bit genome, the 32-bit suffix array, the model, the
+ * error bounds and the chromosome table of an open index, written so that sapling_b200_open_cache restores the index
+ * with three sequential reads instead of cleaning a FASTA and inverting a 16-bytes-per-base .sa file (sapling_api.h:512-611).
+ * The restored index answers every entry point exactly like the one that was saved. */
+int sapling_b200_save_cache(const sapling_b200_index *ix, const char *path);
+sapling_b200_index *sapling_b200_open_cache(const char *path, unsigned flags);
+
 /* Synthetic genome generated on the device: base[i] = "ACGT"[splitmix64(seed+i)>>62]; suffix
  * array and model built on the GPU.  keep_host_genome != 0 also materialises the ASCII genome
  * on the host (needed for sapling_b200_genome()). */

@@ -40,6 +40,8 @@ SYMBOLS = {
     "sapling_b200_write_sa": (C.c_int, [C.c_void_p, C.c_char_p]),
     "sapling_b200_device_bytes": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_launch_count": (C.c_uint64, [C.c_void_p]),
+    "sapling_b200_save_cache": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "sapling_b200_open_cache": (C.c_void_p, [C.c_char_p, C.c_uint]),
     "sapling_b200_query_kernel": (C.c_char_p, [C.c_void_p, C.POINTER(C.c_int)]),
     "sapling_b200_query_kernel_for": (C.c_char_p, [C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "sapling_b200_query_partition_bits": (C.c_int, [C.c_void_p, C.c_size_t]),
@@ -166,6 +168,15 @@ class Sapling:
         L = lib()
         return cls(_handle=L.sapling_b200_create_synthetic(seed, n, numBuckets, maxMem, k,
                                                            1 if keep_host_genome else 0, flags) or 0)
+
+    @classmethod
+    def from_cache(cls, path, flags=1):
+        """Index restored from a private cache file written by save_cache."""
+        L = lib()
+        return cls(_handle=L.sapling_b200_open_cache(os.fsencode(path), flags) or 0)
+
+    def save_cache(self, path):
+        self._ck(self._L.sapling_b200_save_cache(self._h, os.fsencode(path)))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -702,6 +702,121 @@ sapling_b200_index* sapling_b200_open(const char* ref_fn, const char* sa_fn, con
   return ix;
 }
 
+// ---- private index cache ---------------------------------------------------------------------------------
+// The reference's files are what they are -- a .sa file is 16 bytes per base (50 GB at 3.1 Gbp) and has to be inverted,
+// the FASTA has to be cleaned and packed.  The cache holds the three arrays the device needs in the form it needs them
+// (2-bit genome, 32-bit suffix array, {x, y} model: 5.6 bytes per base at c3 instead of 17 + FASTA) plus the scalars, so
+// a later open is three sequential reads.  Native endianness, like the reference's own files.
+namespace {
+constexpr char kCacheMagic[8] = {'S', 'B', '2', '0', '0', 'I', 'D', 'X'};
+constexpr uint32_t kCacheVersion = 1;
+struct CacheHeader {
+  char magic[8];
+  uint32_t version, k, nb, maxMem;
+  int32_t five[5];
+  uint32_t n_chr;
+  uint64_t n, perfect, n_over, n_under, genome_words, model_entries;
+};
+int write_dev(FILE* f, const void* d, size_t bytes) {
+  std::vector<char> buf(std::min<size_t>(bytes, (size_t)64 << 20));
+  for (size_t o = 0; o < bytes; o += buf.size()) {
+    const size_t m = std::min(buf.size(), bytes - o);
+    SB_CUDA_CHECK(cudaMemcpy(buf.data(), static_cast<const char*>(d) + o, m, cudaMemcpyDeviceToHost));
+    if (fwrite(buf.data(), 1, m, f) != m) { set_error("index cache: short write"); return -1; }
+  }
+  return 0;
+}
+int read_dev(FILE* f, void* d, size_t bytes) {
+  std::vector<char> buf(std::min<size_t>(bytes, (size_t)64 << 20));
+  for (size_t o = 0; o < bytes; o += buf.size()) {
+    const size_t m = std::min(buf.size(), bytes - o);
+    if (fread(buf.data(), 1, m, f) != m) { set_error("index cache: file is truncated"); return -1; }
+    SB_CUDA_CHECK(cudaMemcpy(static_cast<char*>(d) + o, buf.data(), m, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
+}  // namespace
+
+int sapling_b200_save_cache(const sapling_b200_index* ix, const char* path) {
+  if (!ix || !path || !path[0]) { set_error("save_cache: null index or empty path"); return -1; }
+  cudaSetDevice(ix->device);
+  FILE* f = fopen(path, "wb");
+  if (!f) { set_error("cannot write index cache %s", path); return -1; }
+  CacheHeader h{};
+  memcpy(h.magic, kCacheMagic, 8);
+  h.version = kCacheVersion;
+  h.k = (uint32_t)ix->k; h.nb = (uint32_t)ix->nb; h.maxMem = (uint32_t)ix->maxMem;
+  h.five[0] = ix->stats.maxOver; h.five[1] = ix->stats.maxUnder; h.five[2] = ix->stats.meanError;
+  h.five[3] = ix->stats.mostOver; h.five[4] = ix->stats.mostUnder;
+  h.n_chr = (uint32_t)ix->chr_ends.size();
+  h.n = ix->n; h.perfect = ix->stats.perfect; h.n_over = ix->stats.nOver; h.n_under = ix->stats.nUnder;
+  h.genome_words = packed_words(ix->n);
+  h.model_entries = (1ull << ix->nb) + 1;
+  int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? 0 : -1;
+  for (const auto& ce : ix->chr_ends) {
+    const uint32_t len = (uint32_t)ce.second.size();
+    if (fwrite(&ce.first, 8, 1, f) != 1 || fwrite(&len, 4, 1, f) != 1 || (len && fwrite(ce.second.data(), 1, len, f) != len)) rc = -1;
+  }
+  if (rc) set_error("index cache: short write");
+  if (!rc) rc = write_dev(f, ix->d_genome, h.genome_words * 8);
+  if (!rc) rc = write_dev(f, ix->d_sa, ix->n * 4);
+  if (!rc) rc = write_dev(f, ix->d_model, h.model_entries * sizeof(ModelEntry));
+  if (!rc && fwrite(kCacheMagic, 8, 1, f) != 1) { set_error("index cache: short write"); rc = -1; }
+  if (fclose(f) != 0 && !rc) { set_error("index cache: close failed"); rc = -1; }
+  if (rc) remove(path);
+  return rc;
+}
+
+sapling_b200_index* sapling_b200_open_cache(const char* path, unsigned flags) {
+  FILE* f = path ? fopen(path, "rb") : nullptr;
+  if (!f) { set_error("cannot open index cache %s", path ? path : "(null)"); return nullptr; }
+  CacheHeader h{};
+  if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kCacheMagic, 8) != 0 || h.version != kCacheVersion) {
+    set_error("%s is not a sapling_b200 index cache (or another version of it)", path);
+    fclose(f);
+    return nullptr;
+  }
+  sapling_b200_index* ix = new_index(flags, (int)h.nb, (int)h.maxMem, (int)h.k);
+  if (!ix) { fclose(f); return nullptr; }
+  Say say(flags);
+  auto fail = [&]() { fclose(f); delete ix; return (sapling_b200_index*)nullptr; };
+  ix->n = h.n;
+  if (validate_params(ix)) return fail();
+  if (h.genome_words != packed_words(h.n) || h.model_entries != (1ull << h.nb) + 1 || h.nb < 1 || h.nb > 31) {
+    set_error("index cache %s: inconsistent header", path);
+    return fail();
+  }
+  ix->stats.maxOver = h.five[0]; ix->stats.maxUnder = h.five[1]; ix->stats.meanError = h.five[2];
+  ix->stats.mostOver = h.five[3]; ix->stats.mostUnder = h.five[4];
+  ix->stats.perfect = h.perfect; ix->stats.nOver = h.n_over; ix->stats.nUnder = h.n_under;
+  for (uint32_t i = 0; i < h.n_chr; i++) {
+    uint64_t end = 0;
+    uint32_t len = 0;
+    if (fread(&end, 8, 1, f) != 1 || fread(&len, 4, 1, f) != 1 || len > (1u << 20)) { set_error("index cache: bad chromosome table"); return fail(); }
+    std::string name(len, '\0');
+    if (len && fread(&name[0], 1, len, f) != len) { set_error("index cache: file is truncated"); return fail(); }
+    ix->chr_ends.emplace_back(end, name);
+  }
+  say("Reading index cache\n");
+  if (dev_alloc(ix, &ix->d_genome, h.genome_words) || read_dev(f, ix->d_genome, h.genome_words * 8)) return fail();
+  if (alloc_sa(ix, h.n) || read_dev(f, ix->d_sa, h.n * 4)) return fail();
+  if (dev_alloc(ix, &ix->d_model, h.model_entries) || read_dev(f, ix->d_model, h.model_entries * sizeof(ModelEntry))) return fail();
+  char tail[8];
+  if (fread(tail, 8, 1, f) != 1 || memcmp(tail, kCacheMagic, 8) != 0) { set_error("index cache %s: file is truncated", path); return fail(); }
+  {  // Sapling::reference for the callers that read it (sapling_b200_genome)
+    char* d_ascii = nullptr;
+    if (cudaMalloc(&d_ascii, h.n) != cudaSuccess) { cudaGetLastError(); set_error("cudaMalloc ascii genome failed"); return fail(); }
+    ix->genome.resize(h.n);
+    int rc = unpack_genome(ix->d_genome, h.n, d_ascii, 0);
+    if (!rc && cudaMemcpy(&ix->genome[0], d_ascii, h.n, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+    cudaFree(d_ascii);
+    if (rc) { set_error("index cache: genome download failed"); return fail(); }
+  }
+  if (build_missing(ix, true, nullptr, say)) return fail();
+  fclose(f);
+  return ix;
+}
+
 static sapling_b200_index* create_common(const char* genome, uint64_t n, const uint32_t* sa, int nb, int maxMem,
                                          int k, const int64_t* xlist, const int64_t* ylist, const int* five,
                                          unsigned flags) {

@@ -354,6 +354,50 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
 
 
 @pytest.mark.gpu
+def test_index_cache_round_trip(S, oracle_built, tmp_path):
+    """an index opened from the reference's files (two-record FASTA; .sa and .sap built and written on the
+    way), saved as a private cache and restored from it is the same index: scalars, chromosome table, genome, suffix
+    array, model, .sap bytes, and the answers to a mixed query batch (checked against the oracle too).  Damaged cache
+    files are refused."""
+    g = GENOMES["rand200k"]
+    half = len(g) // 2
+    fa = tmp_path / "two.fa"
+    with open(fa, "wb") as f:
+        for name, seq in ((b"chrA first record", g[:half]), (b"chrB", g[half:])):
+            f.write(b">" + name + b"\n")
+            for i in range(0, len(seq), 70):
+                f.write(seq[i:i + 70] + b"\n")
+    k = 21
+    a = S.Sapling(str(fa), str(tmp_path / "two.sa"), str(tmp_path / "two.sap"), k=k, flags=S.QUIET)
+    cache = tmp_path / "two.b200"
+    a.save_cache(str(cache))
+    b = S.Sapling.from_cache(str(cache), flags=S.QUIET)
+    assert (b.n, b.k, b.buckets, b.five, b.perfectPredictions) == (a.n, a.k, a.buckets, a.five, a.perfectPredictions)
+    assert b.chrEnds == a.chrEnds and len(a.chrEnds) == 2
+    assert b.reference == a.reference == g
+    assert np.array_equal(b.rev(), a.rev())
+    xa, ya = a.model()
+    xb, yb = b.model()
+    assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    b.write_sap(str(tmp_path / "restored.sap"))
+    assert open(tmp_path / "restored.sap", "rb").read() == open(tmp_path / "two.sap", "rb").read()
+    kmers = F.query_mix(g, k, 20000, seed=3)
+    port = O.Port.from_memory(g, k=k)
+    exp = port.query_batch(kmers, nthreads=4)
+    port.close()
+    assert np.array_equal(a.queryBatch(kmers), exp)
+    assert np.array_equal(b.queryBatch(kmers), exp)
+    assert b.plQuery(g[1000:1000 + k], S.kmerize(k, g[1000:1000 + k]), k) == a.plQuery(g[1000:1000 + k], S.kmerize(k, g[1000:1000 + k]), k)
+    a.close()
+    b.close()
+    raw = open(cache, "rb").read()
+    for bad in (raw[:len(raw) // 2], b"X" + raw[1:], raw[:-8] + b"garbage!"):
+        open(tmp_path / "bad.b200", "wb").write(bad)
+        with pytest.raises(S.SaplingError):
+            S.Sapling.from_cache(str(tmp_path / "bad.b200"), flags=S.QUIET)
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name,k", [("rand200k", 21), ("tandem50", 16), ("gc0110", 31)])
 def test_partitioned_large_batch(S, oracle_built, name, k, monkeypatch):
     """A batch of many partition chunks (2.1 M queries = 129 chunks: the column scan of the offset table works in 64 row
