@@ -66,6 +66,8 @@ sapling_b200_index *sapling_b200_create_with_model(const char *genome, uint64_t 
  * error bounds and the chromosome table of an open index, written so that sapling_b200_open_cache restores the index
  * with three sequential reads instead of cleaning a FASTA and inverting a 16-bytes-per-base .sa file (sapling_api.h:512-611).
  * The restored index answers every entry point exactly like the one that was saved. */
+/* With SAPLING_B200_CACHE=1 in the environment sapling_b200_open keeps such a cache as <sapFn>.b200 and opens from it when
+ * it is there and was built with the same k (and nb, if one is asked for); the cache is not checked against the FASTA. */
 int sapling_b200_save_cache(const sapling_b200_index *ix, const char *path);
 sapling_b200_index *sapling_b200_open_cache(const char *path, unsigned flags);
 

@@ -645,8 +645,21 @@ static sapling_b200_index* new_index(unsigned flags, int nb, int maxMem, int k) 
   return ix;
 }
 
+sapling_b200_index* sapling_b200_open_cache(const char* path, unsigned flags);
+int sapling_b200_save_cache(const sapling_b200_index* ix, const char* path);
+
 sapling_b200_index* sapling_b200_open(const char* ref_fn, const char* sa_fn, const char* sap_fn, int nb, int maxMem,
                                       int k, const char* err_fn, unsigned flags) {
+  // SAPLING_B200_CACHE=1: keep a private cache next to the .sap file (<sapFn>.b200) and open from it when it is there and
+  // was built with the same k (and nb, when one is asked for).  Opt-in: the cache is not checked against the FASTA.
+  const char* ce = getenv("SAPLING_B200_CACHE");
+  const bool use_cache = ce && atoi(ce) != 0 && sap_fn && sap_fn[0] && !(err_fn && err_fn[0]);
+  const std::string cache_fn = use_cache ? std::string(sap_fn) + ".b200" : std::string();
+  if (use_cache && file_exists(cache_fn.c_str())) {
+    sapling_b200_index* c = sapling_b200_open_cache(cache_fn.c_str(), flags);
+    if (c && c->k == (k == -1 ? 21 : k) && (nb == -1 || c->nb == nb)) return c;
+    if (c) delete c;  // another k / nb: rebuild from the reference's files below and replace the cache
+  }
   sapling_b200_index* ix = new_index(flags, nb, maxMem, k);
   if (!ix) return nullptr;
   Say say(flags);
@@ -699,6 +712,7 @@ sapling_b200_index* sapling_b200_open(const char* ref_fn, const char* sa_fn, con
     if (ix->d_isa) { cudaFree(ix->d_isa); ix->d_isa = nullptr; ix->device_bytes -= ix->n * 4; }
     if (ix->d_kflag) { cudaFree(ix->d_kflag); ix->d_kflag = nullptr; ix->device_bytes -= ix->n; }
   }
+  if (use_cache && sapling_b200_save_cache(ix, cache_fn.c_str())) say("%s\n", last_error());  // not fatal
   return ix;
 }
 

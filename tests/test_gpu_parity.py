@@ -354,7 +354,7 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
 
 
 @pytest.mark.gpu
-def test_index_cache_round_trip(S, oracle_built, tmp_path):
+def test_index_cache_round_trip(S, oracle_built, tmp_path, monkeypatch):
     """an index opened from the reference's files (two-record FASTA; .sa and .sap built and written on the
     way), saved as a private cache and restored from it is the same index: scalars, chromosome table, genome, suffix
     array, model, .sap bytes, and the answers to a mixed query batch (checked against the oracle too).  Damaged cache
@@ -390,6 +390,20 @@ def test_index_cache_round_trip(S, oracle_built, tmp_path):
     assert b.plQuery(g[1000:1000 + k], S.kmerize(k, g[1000:1000 + k]), k) == a.plQuery(g[1000:1000 + k], S.kmerize(k, g[1000:1000 + k]), k)
     a.close()
     b.close()
+    # the reference constructor with SAPLING_B200_CACHE=1: the first open leaves <sapFn>.b200, the second one reads it
+    monkeypatch.setenv("SAPLING_B200_CACHE", "1")
+    c1 = S.Sapling(str(fa), str(tmp_path / "two.sa"), str(tmp_path / "two.sap"), k=k, flags=S.QUIET)
+    assert os.path.exists(str(tmp_path / "two.sap") + ".b200")
+    os.rename(fa, str(fa) + ".gone")  # a cached open touches none of the reference's files
+    c2 = S.Sapling(str(fa), str(tmp_path / "two.sa"), str(tmp_path / "two.sap"), k=k, flags=S.QUIET)
+    assert np.array_equal(c1.queryBatch(kmers), exp) and np.array_equal(c2.queryBatch(kmers), exp)
+    assert c2.chrEnds == c1.chrEnds and c2.reference == g
+    os.rename(str(fa) + ".gone", fa)
+    c3 = S.Sapling(str(fa), str(tmp_path / "two.sa"), str(tmp_path / "k16.sap"), k=16, flags=S.QUIET)  # other k: own cache
+    assert c3.k == 16 and os.path.exists(str(tmp_path / "k16.sap") + ".b200")
+    for c in (c1, c2, c3):
+        c.close()
+    monkeypatch.delenv("SAPLING_B200_CACHE")
     raw = open(cache, "rb").read()
     for bad in (raw[:len(raw) // 2], b"X" + raw[1:], raw[:-8] + b"garbage!"):
         open(tmp_path / "bad.b200", "wb").write(bad)
