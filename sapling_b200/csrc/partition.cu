@@ -20,6 +20,7 @@
 #include "partition.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace sb {
 
@@ -468,8 +469,13 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   // slots inside the k-mer words: only the in-order pipelined kernel reads that format (query.cu), k <= 25
   const char* ke = getenv("SAPLING_B200_SLOT_IN_KMER");  // 0 = separate slot array (A/B measurements)
   const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");
-  const bool slot_in_kmer = 2 * ix.k + 14 <= 64 && in_order && ix.narrow != nullptr && !(oe && atoi(oe) == 0) &&
-                            !(se && atoi(se) == 0) && !(ke && atoi(ke) == 0);
+  bool slot_in_kmer = 2 * ix.k + 14 <= 64 && in_order && ix.narrow != nullptr && !(oe && atoi(oe) == 0) &&
+                      !(se && atoi(se) == 0) && !(ke && atoi(ke) == 0);
+  if (slot_in_kmer) {  // ask the launcher which kernel this batch would get: only the in-order pipelined one reads the format
+    const char* name = "";
+    launch_kmer_query(ix, nullptr, 0, nullptr, st, &name, slot_in_kmer_tag(), tiles);
+    slot_in_kmer = strcmp(name, "kmer_query_ordered_kernel") == 0;
+  }
   if (slot_in_kmer) {
     part_scatter_staged_kernel<true><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
