@@ -229,6 +229,64 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
     print(f"long-window shortcut: tried {tried.value}, accepted {ok.value}")
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_randomised_replay_against_oracle(oracle_built, seed):
+    """Randomised differential test of the device replay code (host simulation) against the oracle: random genome
+    recipes (uniform, skewed, short tandem units, planted repeats), random k, bucket count and error bounds (bounds
+    smaller than the model's true errors included: the replay must reproduce the reference's wrong answers too), every
+    replay variant and layout the batch kernels can run."""
+    L = _sim()
+    rng = np.random.default_rng(9000 + seed)
+    n = int(rng.integers(400, 6000))
+    kind = seed % 4
+    if kind == 0:
+        g = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)])
+    elif kind == 1:
+        w = rng.random(4) ** 3 + 1e-3
+        g = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.choice(4, size=n, p=w / w.sum())])
+    elif kind == 2:
+        unit = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(rng.integers(1, 9)))])
+        g = (unit * (n // len(unit) + 1))[:n]
+    else:
+        core = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n // 2)])
+        g = core + core[: n // 3] + b"A" * int(rng.integers(0, 40)) + core[n // 4:]
+        n = len(g)
+    k = int(rng.integers(6, 32))
+    nb = int(rng.integers(1, min(2 * k, 14) + 1))
+    base = O.Port.from_memory(g, nb=nb, k=k)
+    packed, sa = F.pack_genome(g), base.sa
+    model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
+    last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
+    narrow, nok = F.narrow_model(base.xlist, base.ylist, k, base.nb)
+    kmers = F.query_mix(g, k, 1500, seed=seed)
+    f0 = list(base.five)
+    bounds = [f0, [int(rng.integers(0, 6)), int(rng.integers(0, 6)), 1, int(rng.integers(0, 4)), int(rng.integers(0, 4))],
+              [f0[0], f0[1], f0[2], f0[3], 1 << 30]]
+    for five_t in bounds:
+        port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
+        five = np.array(five_t, dtype=np.int32)
+        exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
+        port.close()
+        for nptr in [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else []):
+            out = np.empty(len(kmers), dtype=np.int64)
+            c = C.c_uint64(0)
+            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last)
+            assert np.array_equal(out, exp) and c.value == oob, (seed, n, k, nb, five_t, "general", nptr is not None)
+        pb = int(rng.integers(4, 33))
+        cases = [(0, 0, 3), (2, pb, 3), (2, pb, 4), (3, pb, 3), (3, pb, 4), (4, pb, 4), (5, pb, 4), (5, pb, 3)]
+        cases += [(1, b, 3) for b in (27, 32) if k <= b]
+        for mode, bases, shift in cases:
+            out = np.empty(len(kmers), dtype=np.int64)
+            c = C.c_uint64(0)
+            rc = L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c),
+                                       mode, bases, shift)
+            assert rc == 0
+            bad = np.nonzero(out != exp)[0]
+            assert len(bad) == 0 and c.value == oob, (seed, n, k, nb, five_t, mode, bases, shift, bad[:5], out[bad[:5]],
+                                                      exp[bad[:5]])
+    base.close()
+
+
 def test_seed_batch_port_matches_reference_methods(oracle_built, tmp_path):
     """The oracle's restatement of the align.cpp seed loop == the same loop driven through the unmodified reference's
     own kmerize / plQuery / countHitsLeft/Right (oracle/ref_harness.cpp).  Needs /root/reference (skipped on the GPU box,
