@@ -69,12 +69,25 @@ def test_kmerize_host(built, oracle_built):
             assert S.kmerize_adjusted(k, L, s) == O.kmerize_adjusted(k, L, s)
 
 
+_SIM = None
+
+
 def _sim():
+    """The device query code compiled for the host (tests/sim/sim_query.cpp), built once per session and only when a
+    source is newer than the library; written under a temporary name first so that parallel test workers never load a
+    half-written file."""
+    global _SIM
+    if _SIM is not None:
+        return _SIM
     so = os.path.join(ROOT, "build", "libsim_query.so")
     src = os.path.join(ROOT, "tests", "sim", "sim_query.cpp")
+    deps = [src] + [os.path.join(ROOT, "sapling_b200", "csrc", f) for f in ("query.cuh", "common.cuh")]
     os.makedirs(os.path.dirname(so), exist_ok=True)
-    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w",
-                    "-I/usr/local/cuda/include", "-o", so, src], check=True)
+    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
+        tmp = f"{so}.{os.getpid()}.tmp"
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-w",
+                        "-I/usr/local/cuda/include", "-o", tmp, src], check=True)
+        os.replace(tmp, so)
     L = C.CDLL(so)
     i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
     L.sim_kmer_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
@@ -88,6 +101,7 @@ def _sim():
     L.sim_kmer_batch_lean.restype = C.c_int
     L.sim_kmer_batch_lean.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
                                       C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
+    _SIM = L
     return L
 
 
@@ -229,7 +243,7 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
     print(f"long-window shortcut: tried {tried.value}, accepted {ok.value}")
 
 
-@pytest.mark.parametrize("seed", range(12))
+@pytest.mark.parametrize("seed", range(40))
 def test_randomised_replay_against_oracle(oracle_built, seed):
     """Randomised differential test of the device replay code (host simulation) against the oracle: random genome
     recipes (uniform, skewed, short tandem units, planted repeats), random k, bucket count and error bounds (bounds
