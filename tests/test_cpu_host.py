@@ -301,6 +301,48 @@ def test_randomised_replay_against_oracle(oracle_built, seed):
     base.close()
 
 
+@pytest.mark.parametrize("seed", range(10))
+def test_randomised_string_queries_against_oracle(oracle_built, seed):
+    """The string form of the query (plQuery(s, kmer, length) with length != k: kmerizeAdjusted, the gallop loops
+    sapling_api.h:184-196,:229-241) on random genomes / k / nb, wide and narrow model layouts, against the oracle."""
+    L = _sim()
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(800, 5000))
+    if seed % 3 == 0:
+        g = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n)])
+    elif seed % 3 == 1:
+        unit = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=int(rng.integers(1, 9)))])
+        g = (unit * (n // len(unit) + 1))[:n]
+    else:
+        core = bytes(np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, size=n // 2)])
+        g = core + core[: n // 3] + b"A" * int(rng.integers(0, 40))
+        n = len(g)
+    k = int(rng.integers(11, 32))
+    nb = int(rng.integers(1, min(2 * k, 12) + 1))
+    base = O.Port.from_memory(g, nb=nb, k=k)
+    packed, sa = F.pack_genome(g), base.sa
+    model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
+    last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
+    narrow, nok = F.narrow_model(base.xlist, base.ylist, k, base.nb)
+    strs = F.var_len_strings(g, k, 20, seed=seed)
+    words, offs = F.pack_strings(strs)
+    slens = np.array([len(s) for s in strs], dtype=np.uint32)
+    km = np.array([O.kmerize_adjusted(k, len(s), s) for s in strs], dtype=np.int64)
+    f0 = list(base.five)
+    for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30]):
+        port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
+        five = np.array(five_t, dtype=np.int32)
+        exp = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
+        port.close()
+        for nptr in [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else []):
+            out = np.empty(len(strs), dtype=np.int64)
+            c = C.c_uint64(0)
+            L.sim_string_batch(packed, sa, model, n, k, base.nb, five, 1, words, offs, slens, slens, km, len(strs), out,
+                               C.byref(c), nptr, last)
+            assert np.array_equal(out, exp), (seed, n, k, nb, five_t, nptr is not None)
+    base.close()
+
+
 def test_seed_batch_port_matches_reference_methods(oracle_built, tmp_path):
     """The oracle's restatement of the align.cpp seed loop == the same loop driven through the unmodified reference's
     own kmerize / plQuery / countHitsLeft/Right (oracle/ref_harness.cpp).  Needs /root/reference (skipped on the GPU box,
