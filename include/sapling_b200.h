@@ -193,6 +193,10 @@ int sapling_b200_sample_queries_dev(sapling_b200_index *ix, uint64_t seed, uint6
  * and the number of -1 answers. */
 int sapling_b200_verify_dev(sapling_b200_index *ix, const uint64_t *d_kmers, const int64_t *d_out,
                             size_t nq, uint64_t *n_match, uint64_t *n_minus1, void *stream);
+/* P of SURVEY 8d measured on the device: the total number of getLcp calls (sapling_api.h:115-120) the REFERENCE's
+ * plQuery makes for these queries (the literal probe sequence, none of this library's shortcuts). */
+int sapling_b200_count_probes_dev(sapling_b200_index *ix, const uint64_t *d_kmers, size_t nq, uint64_t *n_probes,
+                                  void *stream);
 /* Random 32-byte-sector gather over `bytes` of scratch HBM: returns achieved GB/s (the
  * "HBM random-sector roofline" denominator). */
 int sapling_b200_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double *gbps);

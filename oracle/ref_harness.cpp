@@ -47,6 +47,42 @@ void *ref_open(const char *ref_fn, const char *sa_fn, const char *sap_fn, int nb
   return s;
 }
 
+/* The same struct filled member by member instead of through the constructor (which needs a FASTA, a 16n-byte .sa
+   file and ~29n bytes of RAM, sapling_api.h:559-611: ~90 GB and ~1 h at 3.1 Gbp).  Every member plQuery reads is public
+   (sapling_api.h:19-68): reference, n, k, buckets, rev, xlist, ylist and the five error bounds.  The caller streams the
+   parts in chunks (ref_parts_*), so peak host memory is the struct itself (~10.4 bytes per base + 16 per bucket);
+   plQuery / queryPiecewiseLinear / binarySearch / getLcp are then the untouched reference code. */
+void *ref_from_parts(uint64_t n, int k, int nb, const int *five) {
+  Sapling *s = new Sapling();
+  s->n = (size_t)n;
+  s->k = k;
+  s->buckets = nb;
+  s->maxOver = five[0]; s->maxUnder = five[1]; s->meanError = five[2];
+  s->mostOver = five[3]; s->mostUnder = five[4];
+  for (int i = 0; i < 256; i++) s->vals[i] = 0; /* sapling_api.h:494-498 */
+  s->vals['A'] = 0; s->vals['C'] = 1; s->vals['G'] = 2; s->vals['T'] = 3;
+  s->reference.resize((size_t)n);
+  s->rev.resize((size_t)n);
+  const size_t count = ((size_t)1 << nb) + 1;
+  s->xlist = new long long[count];
+  s->ylist = new long long[count];
+  return s;
+}
+void ref_parts_genome(void *h, uint64_t first, uint64_t count, const char *bases) {
+  std::memcpy(&((Sapling *)h)->reference[(size_t)first], bases, (size_t)count);
+}
+void ref_parts_rev(void *h, uint64_t first, uint64_t count, const uint32_t *rev32, int nthreads) {
+  size_t *dst = ((Sapling *)h)->rev.data() + first;
+  if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for num_threads(nthreads) schedule(static)
+  for (size_t i = 0; i < (size_t)count; i++) dst[i] = rev32[i];
+}
+void ref_parts_model(void *h, uint64_t first, uint64_t count, const long long *xs, const long long *ys) {
+  Sapling *s = (Sapling *)h;
+  std::memcpy(s->xlist + first, xs, (size_t)count * sizeof(long long));
+  std::memcpy(s->ylist + first, ys, (size_t)count * sizeof(long long));
+}
+
 void ref_close(void *h) { delete (Sapling *)h; } /* the reference leaks xlist/ylist; so do we */
 
 void ref_info(void *h, uint64_t *n, int *k, int *nb, int *five, uint64_t *perfect) {

@@ -61,6 +61,7 @@ SYMBOLS = {
     "sapling_b200_oob_count": (C.c_uint64, [C.c_void_p]),
     "sapling_b200_sample_queries_dev": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]),
     "sapling_b200_verify_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p]),
+    "sapling_b200_count_probes_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64), C.c_void_p]),
     "sapling_b200_check_sa": (C.c_int, [C.c_void_p, C.c_uint32] + [C.POINTER(C.c_uint64)] * 3),
     "sapling_b200_gather_bench": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.POINTER(C.c_double)]),
     "sapling_b200_gather_bench2": (C.c_int, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
@@ -370,6 +371,12 @@ class Sapling:
         a, b = C.c_uint64(0), C.c_uint64(0)
         self._ck(self._L.sapling_b200_verify_dev(self._h, d_kmers_ptr, d_out_ptr, nq, C.byref(a), C.byref(b), stream))
         return a.value, b.value
+
+    def count_probes_device(self, d_kmers_ptr, nq, stream=0):
+        """Total getLcp calls the reference's plQuery makes for these queries (SURVEY 8d's P x nq)."""
+        a = C.c_uint64(0)
+        self._ck(self._L.sapling_b200_count_probes_dev(self._h, d_kmers_ptr, nq, C.byref(a), stream))
+        return a.value
 
 
 def _host_ptr(a, itemsize):

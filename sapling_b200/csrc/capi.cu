@@ -36,6 +36,8 @@ int launch_sample(const IndexView& ix, uint64_t seed, uint64_t mut_seed, uint64_
                   uint64_t* d_kmers, cudaStream_t st);
 int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long* d_out, size_t nq,
                   unsigned long long* d_counters, cudaStream_t st);
+int launch_probe_count(const IndexView& ix, const uint64_t* d_kmers, size_t nq, unsigned long long* d_total,
+                       cudaStream_t st);
 int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps);
 int run_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm, int reps,
                       double* gacc_per_s);
@@ -1413,6 +1415,25 @@ int sapling_b200_verify_dev(sapling_b200_index* ix, const uint64_t* d_kmers, con
   SB_CUDA_CHECK(e);
   if (n_match) *n_match = h[0];
   if (n_minus1) *n_minus1 = h[1];
+  return 0;
+}
+
+int sapling_b200_count_probes_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, uint64_t* n_probes,
+                                  void* stream) {
+  if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  unsigned long long* d_c = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&d_c, 8));
+  SB_CUDA_CHECK(cudaMemsetAsync(d_c, 0, 8, st));
+  int rc = launch_probe_count(ix->view(), d_kmers, nq, d_c, st);
+  unsigned long long h = 0;
+  cudaError_t e = cudaMemcpyAsync(&h, d_c, 8, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_c);
+  if (rc) return rc;
+  SB_CUDA_CHECK(e);
+  if (n_probes) *n_probes = h;
   return 0;
 }
 

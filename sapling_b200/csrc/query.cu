@@ -713,6 +713,37 @@ __global__ void verify_kernel(const IndexView ix, const uint64_t* __restrict__ k
   }
 }
 
+// P of SURVEY 8d, counted on the device: the number of getLcp calls (sapling_api.h:115-120) the REFERENCE makes for each
+// query, i.e. the literal replay without the long-window shortcut; the final unverified rev[lo + 1] (:136,:247) is a
+// suffix-array read, not a getLcp call.  bench.py uses the mean as `probes_per_query` on every rank.
+__global__ void __launch_bounds__(kQueryThreads)
+probe_count_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, unsigned long long* __restrict__ total) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const unsigned lsh = 64u - 2u * (unsigned)ix.k;
+  const L2Policies pol = make_policies(ix.hints);
+  unsigned long long probes = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const uint64_t x = __ldg(kmers + i);
+    KmerQuery q;
+    q.q = x << lsh;
+    q.k = (uint32_t)ix.k;
+    uint64_t pred = predict_rank(ix, x, pol.model);
+    if (pred >= ix.n) pred = ix.n - 1;  // SURVEY H9, without bumping the out-of-range counter
+    Replay<false, false, KmerQuery, SaDirect, false, 0> rp;
+    rp.begin(pred);
+    SaDirect sa;
+    long long result;
+    for (;;) {
+      const bool final_read = rp.state == ST_FINAL;
+      const bool done = rp.step(ix, q, 0, pol, sa, &result);
+      if (!final_read) probes++;
+      if (done) break;
+    }
+  }
+  for (int o = 16; o; o >>= 1) probes += __shfl_xor_sync(0xffffffffu, probes, o);
+  if ((threadIdx.x & 31) == 0 && probes) atomicAdd(total, probes);
+}
+
 // random 32-byte-sector gather: each thread chases nothing, it just issues independent sector
 // reads at hashed addresses -- the "HBM random-sector roofline" denominator
 __global__ void __launch_bounds__(256)
@@ -1010,6 +1041,14 @@ int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long*
                   unsigned long long* d_counters, cudaStream_t st) {
   if (nq == 0) return 0;
   verify_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, d_out, nq, d_counters);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int launch_probe_count(const IndexView& ix, const uint64_t* d_kmers, size_t nq, unsigned long long* d_total,
+                       cudaStream_t st) {
+  if (nq == 0) return 0;
+  probe_count_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_total);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

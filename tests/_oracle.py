@@ -252,6 +252,11 @@ def ref_lib():
         L.ref_open.restype = C.c_void_p
         L.ref_open.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int]
         L.ref_close.argtypes = [C.c_void_p]
+        L.ref_from_parts.restype = C.c_void_p
+        L.ref_from_parts.argtypes = [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_int)]
+        L.ref_parts_genome.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_char_p]
+        L.ref_parts_rev.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, u32p, C.c_int]
+        L.ref_parts_model.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, i64p, i64p]
         L.ref_info.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                C.POINTER(C.c_int), C.POINTER(C.c_uint64)]
         for nm in ("ref_genome", "ref_xlist", "ref_ylist", "ref_rev", "ref_inv", "ref_lcp"):
@@ -285,16 +290,38 @@ def ref_lib():
 class Ref:
     """The unmodified reference `struct Sapling` (sapling_api.h:17) behind oracle/ref_harness.cpp."""
 
-    def __init__(self, fa, sa, sap, nb=-1, maxMem=-1, k=-1, err_fn=None, quiet=True):
+    def __init__(self, fa, sa, sap, nb=-1, maxMem=-1, k=-1, err_fn=None, quiet=True, _handle=None):
         self.L = ref_lib()
-        self.h = self.L.ref_open(_b(fa), _b(sa), _b(sap), nb, maxMem, k, _b(err_fn) if err_fn else None,
-                                 1 if quiet else 0)
+        self.h = _handle if _handle is not None else self.L.ref_open(
+            _b(fa), _b(sa), _b(sap), nb, maxMem, k, _b(err_fn) if err_fn else None, 1 if quiet else 0)
         n, kk, nbb, perfect = C.c_uint64(0), C.c_int(0), C.c_int(0), C.c_uint64(0)
         five = (C.c_int * 5)()
         self.L.ref_info(self.h, C.byref(n), C.byref(kk), C.byref(nbb), five, C.byref(perfect))
         self.n, self.k, self.nb = n.value, kk.value, nbb.value
         self.five = tuple(five)
         self.perfect = perfect.value
+
+    @classmethod
+    def from_parts(cls, genome: bytes, rev, k, nb, xlist, ylist, five, nthreads=4, chunk=1 << 26):
+        """`struct Sapling` filled member by member (oracle/ref_harness.cpp ref_from_parts): no constructor, no files.
+        `rev` is a uint32 array (rank -> position) or a callable rev(first, count) -> uint32 array, so that a 3.1 Gbp
+        suffix array can be streamed from the GPU index without a second 12 GB host copy."""
+        L = ref_lib()
+        n = len(genome)
+        f5 = (C.c_int * 5)(*[int(v) for v in five])
+        h = L.ref_from_parts(n, int(k), int(nb), f5)
+        if not h:
+            raise RuntimeError("ref_from_parts failed")
+        L.ref_parts_genome(h, 0, n, genome)
+        get = rev if callable(rev) else (lambda first, count: rev[first:first + count])
+        for first in range(0, n, chunk):
+            c = min(chunk, n - first)
+            L.ref_parts_rev(h, first, c, np.ascontiguousarray(get(first, c), dtype=np.uint32), nthreads)
+        xs = np.ascontiguousarray(xlist, dtype=np.int64)
+        ys = np.ascontiguousarray(ylist, dtype=np.int64)
+        assert len(xs) == (1 << nb) + 1 and len(ys) == len(xs)
+        L.ref_parts_model(h, 0, len(xs), xs, ys)
+        return cls(None, None, None, _handle=h)
 
     def close(self):
         if self.h:
@@ -378,11 +405,11 @@ def splitmix64_np(z):
 
 def kmers_at(genome: bytes, pos, k):
     """Packed k-mers (kmerize values) of genome[pos:pos+k] for an array of positions."""
-    g = _CODE[np.frombuffer(genome, dtype=np.uint8)]
+    g = np.frombuffer(genome, dtype=np.uint8)  # gathered first, coded second: no 8-bytes-per-base temporary
     pos = np.asarray(pos, dtype=np.int64)
     x = np.zeros(len(pos), dtype=np.uint64)
     for j in range(k):
-        x = (x << np.uint64(2)) | g[pos + j]
+        x = (x << np.uint64(2)) | _CODE[g[pos + j]]
     return x
 
 

@@ -100,3 +100,22 @@ def test_cuda_reproduces_reference_seed_loop(path):
     ix = S.Sapling.from_memory(d["genome"], None, k=int(d["k"]), flags=S.QUIET | S.KEEP_BUILD)
     _check_seeds(d, ix.seedBatch(d["read_list"], int(d["num_seeds"]), int(d["max_hits"])))
     ix.close()
+
+
+@pytest.mark.skipif(not O.ref_available(), reason="oracle/_ref not built (needs /root/reference at build time)")
+def test_reference_struct_filled_from_parts_equals_constructor(tmp_path):
+    """oracle/ref_harness.cpp ref_from_parts (the reference's struct filled member by member, used for the 3.1 Gbp
+    parity and CPU-baseline legs) answers exactly like the reference built through its own constructor and files."""
+    g = O.synth_genome(O.SEED_G + 3, 150000)
+    fa = str(tmp_path / "g.fa")
+    O.write_fasta(fa, g)
+    for k, nb in ((21, -1), (16, 9), (31, 12)):
+        ref = O.Ref(fa, fa + f".{k}.sa", fa + f".{k}.{nb}.sap", nb=nb, k=k)
+        parts = O.Ref.from_parts(ref.genome, ref.sa.astype(np.uint32), k, ref.nb, ref.xlist, ref.ylist, ref.five,
+                                 nthreads=2, chunk=40000)
+        km, _ = O.present_queries(g, k, 30000)
+        km = np.concatenate([km, O.mutate_queries(km, k)])
+        assert np.array_equal(parts.query_batch(km, nthreads=2), ref.query_batch(km, nthreads=2))
+        assert (parts.n, parts.k, parts.nb, parts.five) == (ref.n, ref.k, ref.nb, ref.five)
+        parts.close()
+        ref.close()

@@ -499,3 +499,18 @@ def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch)
     for v in ("PART", "PART_MIN", "PART_BITS", "LEAN", "LINE_SMEM", "PART_TILES", "ORDERED_PIPE", "PART_SCATTER",
               "PART_UNPERMUTE", "QV", "PACKED_SHIFT", "FLAT", "SLOT_IN_KMER", "PARK"):
         monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
+
+
+@pytest.mark.parametrize("name,k", [("rand200k", 21), ("gc1991", 16), ("tandem50", 16), ("repeat_tailA", 21)])
+def test_device_probe_count_matches_oracle(S, oracle_built, name, k):
+    """SURVEY 8d's P (getLcp calls per query of the reference algorithm) counted on the device == counted by the oracle."""
+    import torch
+    g = GENOMES[name]
+    port = O.Port.from_memory(g, k=k)
+    ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+    kmers = F.query_mix(g, k, 20000)
+    _, probes, _ = port.query_batch(kmers, nthreads=4, stats=True)
+    d = torch.from_numpy(kmers.astype(np.int64)).cuda()
+    assert ix.count_probes_device(d.data_ptr(), len(kmers)) == probes
+    ix.close()
+    port.close()
