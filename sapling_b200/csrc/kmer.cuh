@@ -1,0 +1,313 @@
+// kmer.cuh -- the k-mer query path: plQuery(unpack(kmer), kmer, k) (reference sapling_api.h:159-248) answered from the
+// rank lines in two separate phases, memory first, control flow second.
+//
+// Why this is the reference's answer.  For a k-mer (s.length() == length == k) every decision plQuery and binarySearch
+// (:133-153) take is a function of how the probed suffix compares with the query -- smaller ("suffix too small", :143,
+// :167: the first differing base, or the text ending first), equal on all k bases (:141, :164), or larger -- and the
+// suffix array is sorted.  So there are two ranks lb <= ub with
+//       rank r < lb  : smaller          lb <= r < ub : match          r >= ub : larger
+// and the whole probe sequence of the reference, including the ranks >= 2^31 arithmetic of :209,:225 and the
+// unverified rev[lo + 1] of :136, can be replayed in registers once lb and ub are known.  The carried LCPs (:140: getLcp
+// starts at min(loLcp, hiLcp) without re-checking earlier bases) never change an outcome for a k-mer: every LCP the
+// reference carries was computed from base 0 or from such a start, the suffixes at lo < mid < hi are sorted, hence
+// LCP(query, suffix[mid]) >= min(LCP(query, suffix[lo]), LCP(query, suffix[hi])) whichever side of them the query lies
+// on, so getLcp returns the true LCP and the comparison is the true one.  (Proved by the differential tests: the host
+// build of this file against the oracle on every fixture genome, and the GPU against the unmodified reference at 3.1 Gbp.)
+//
+// Phase 1 (memory): find lb and ub by SECTOR -- one 32-byte sector of a rank line classifies four ranks at once with
+// integer compares in delta space; the sector of the predicted rank settles most queries, its neighbour nearly all the
+// rest, a gallop + bisection over sectors the tail.  The reference's probe chain (2.3 dependent probes per query at 100 Mbp,
+// 4.3 at 3.1 Gbp where a third of the left-going queries walk ~31 binary-search steps) is not followed in memory at all.
+// Phase 2 (registers): the literal replay of :159-248 over {lb, ub}; long runs of binary-search steps that all go right are
+// jumped in closed form.  Phase 3: rev[answer rank] -- usually in a sector still in registers.
+#pragma once
+
+#include "common.cuh"
+
+namespace sb {
+
+#ifdef SB_HOST_SIM
+static unsigned long long g_sim_sector_loads = 0, g_sim_slow_entries = 0, g_sim_final_loads = 0;
+#define SB_SIM_ADD(x, v) ((x) += (v))
+#else
+#define SB_SIM_ADD(x, v) ((void)0)
+#endif
+
+// What a lane needs to classify sectors for one query.
+struct KmerKey {
+  uint64_t q;        // the k bases left-aligned (base 0 in the top two bits)
+  uint64_t qlo;      // smallest / largest line_bases-base integer whose first min(k, line_bases) bases are the query's
+  uint64_t qhi;
+};
+__device__ __forceinline__ KmerKey make_key(const IndexView& ix, uint64_t x) {
+  KmerKey key;
+  const int k = ix.k, b = ix.line_bases;
+  key.q = x << (64 - 2 * k);
+  if (k <= b) {
+    key.qlo = x << (2 * (b - k));
+    key.qhi = key.qlo | ((1ull << (2 * (b - k))) - 1ull);
+  } else {  // an entry holds fewer bases than the k-mer: equality on them is a tie the genome decides (see classify)
+    key.qlo = key.qhi = x >> (2 * (k - b));
+  }
+  return key;
+}
+
+// One classified sector: ranks 4s .. 4s+3.  c entries are smaller than the query, the next m match, the rest are larger
+// (ranks past the end of the suffix array count as larger).
+struct Sector {
+  uint32_t s;       // sector number; 0xFFFFFFFF: nothing held
+  uint32_t c, m;
+  uint32_t pos[4];  // rev[4s + j]
+};
+
+// Full compare of the query with the suffix at text position pos (escaped entries, ties): the rules of getLcp (:115-120)
+// and of the "suffix too small" test (:143,:167) -- the text ending inside the k-mer makes the suffix the smaller one.
+__device__ __forceinline__ void compare_with_genome(const IndexView& ix, const KmerKey& key, uint32_t pos, uint64_t pol,
+                                                    bool* small, bool* match) {
+  const uint32_t k = (uint32_t)ix.k;
+  const uint64_t g = load_bases_upto_pol(ix.genome, (uint64_t)pos, k, pol);
+  const uint64_t diff = key.q ^ g;
+  const uint32_t m = diff ? ((uint32_t)__clzll((long long)diff) >> 1) : 32u;
+  const uint64_t room = ix.n - (uint64_t)pos;
+  const uint32_t leff = room < (uint64_t)k ? (uint32_t)room : k;
+  const uint32_t lcp = m < leff ? m : leff;
+  *match = lcp == k;
+  *small = !*match && ((uint64_t)lcp == room || key.q > g);
+  SB_SIM_ADD(g_sim_slow_entries, 1);
+}
+
+// Classify sector s.  Fast path (no escaped entry, no tie): the entries are P0 + d_j with 21-bit deltas, so
+//   smaller  <=>  d_j < qlo - P0         match  <=>  qlo - P0 <= d_j <= qhi - P0
+// with both bounds clamped into the delta range: four 32-bit compares each.
+template <bool kTies>
+__device__ __forceinline__ void classify_sector(const IndexView& ix, const KmerKey& key, uint32_t s, const L2Policies& pol,
+                                                Sector* out) {
+  const U32x8 e = ld_u32x8_pol(ix.lines + (uint64_t)s * 8u, pol.sa);
+  SB_SIM_ADD(g_sim_sector_loads, 1);
+  const uint64_t P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
+  const uint32_t dlo = e.v[2], dhi = e.v[3];
+  const uint32_t d1 = dlo & kPackedEscape;
+  const uint32_t d2 = ((dlo >> 21) | (dhi << 11)) & kPackedEscape;
+  const uint32_t d3 = (dhi >> 10) & kPackedEscape;
+  const long long a = (long long)(key.qlo - P0), b = (long long)(key.qhi - P0);  // line_bases <= 31: no overflow
+  const int32_t a32 = a < 0 ? 0 : (a > (long long)kPackedEscape ? (int32_t)kPackedEscape : (int32_t)a);
+  const int32_t b32 = b < 0 ? -1 : (b > (long long)kPackedEscape ? (int32_t)kPackedEscape : (int32_t)b);
+  bool sm0 = 0 < a32, sm1 = (int32_t)d1 < a32, sm2 = (int32_t)d2 < a32, sm3 = (int32_t)d3 < a32;
+  bool ma0 = !sm0 && 0 <= b32, ma1 = !sm1 && (int32_t)d1 <= b32, ma2 = !sm2 && (int32_t)d2 <= b32,
+       ma3 = !sm3 && (int32_t)d3 <= b32;
+  // entries the deltas cannot decide: escapes (delta overflow, suffix within 32 bases of the end of the text, padding past
+  // the last rank) and, when the k-mer is longer than an entry's prefix, entries equal to the query on that prefix
+  const bool e0 = (dhi >> 31) != 0, e1 = d1 == kPackedEscape, e2 = d2 == kPackedEscape, e3 = d3 == kPackedEscape;
+  bool n0 = e0, n1 = e1, n2 = e2, n3 = e3;
+  if (kTies) { n0 |= ma0; n1 |= ma1; n2 |= ma2; n3 |= ma3; }
+  if (n0 | n1 | n2 | n3) {  // rare: decided by the packed genome, entry by entry
+    const uint64_t r0 = (uint64_t)s * 4u;
+    if (n0) { if (r0 < ix.n) compare_with_genome(ix, key, e.v[4], pol.genome, &sm0, &ma0); else sm0 = ma0 = false; }
+    if (n1) { if (r0 + 1 < ix.n) compare_with_genome(ix, key, e.v[5], pol.genome, &sm1, &ma1); else sm1 = ma1 = false; }
+    if (n2) { if (r0 + 2 < ix.n) compare_with_genome(ix, key, e.v[6], pol.genome, &sm2, &ma2); else sm2 = ma2 = false; }
+    if (n3) { if (r0 + 3 < ix.n) compare_with_genome(ix, key, e.v[7], pol.genome, &sm3, &ma3); else sm3 = ma3 = false; }
+  }
+  out->s = s;
+  out->c = (uint32_t)sm0 + (uint32_t)sm1 + (uint32_t)sm2 + (uint32_t)sm3;
+  out->m = (uint32_t)ma0 + (uint32_t)ma1 + (uint32_t)ma2 + (uint32_t)ma3;
+  out->pos[0] = e.v[4]; out->pos[1] = e.v[5]; out->pos[2] = e.v[6]; out->pos[3] = e.v[7];
+}
+
+struct Bounds {
+  uint32_t lb, ub;  // ranks [0, lb) smaller than the query, [lb, ub) match, [ub, n) larger
+};
+
+// Phase 1.  first = the classified sector of the predicted rank; on return *held is the sector that contains lb (or the last
+// one classified), kept for the final rev[] lookup next to `first`.
+template <bool kTies>
+__device__ __forceinline__ Bounds find_bounds(const IndexView& ix, const KmerKey& key, const L2Policies& pol,
+                                              const Sector& first, Sector* held) {
+  const uint32_t n32 = (uint32_t)ix.n;
+  const uint32_t last_s = (n32 - 1u) >> 2;
+  auto valid = [&](uint32_t s) -> uint32_t { return s == last_s ? n32 - 4u * s : 4u; };
+  // ---- lb: the first sector that is not entirely smaller (c < 4); it holds lb = 4 s + c ------------------------------------
+  // invariant: every sector <= full is entirely smaller (0xFFFFFFFF: none known), *held has c < 4
+  *held = first;
+  uint32_t full = 0xFFFFFFFFu;
+  bool found = false;
+  if (first.c == 4u) {  // look right: gallop until a sector is not full
+    full = first.s;
+    uint32_t step = 1;
+    for (;;) {
+      if (full == last_s) {  // every rank is smaller
+        Bounds b;
+        b.lb = b.ub = n32;
+        return b;
+      }
+      const uint32_t t = (last_s - full < step) ? last_s : full + step;
+      classify_sector<kTies>(ix, key, t, pol, held);
+      if (held->c == 4u) { full = t; step <<= 1; continue; }
+      found = held->c > 0u || t == full + 1u;
+      break;
+    }
+  } else if (first.c > 0u || first.s == 0u) {
+    found = true;
+  } else {  // c == 0: look left until a sector has a smaller entry
+    uint32_t step = 1;
+    for (;;) {
+      const uint32_t t = held->s > step ? held->s - step : 0u;
+      Sector x;
+      classify_sector<kTies>(ix, key, t, pol, &x);
+      if (x.c == 4u) { full = t; found = held->s == t + 1u; break; }
+      *held = x;
+      if (x.c > 0u || t == 0u) { found = true; break; }
+      step <<= 1;
+    }
+  }
+  while (!found) {  // bisection: full < sb <= held->s, sectors strictly between are unknown
+    if (held->s - full == 1u) break;
+    const uint32_t mid = full + ((held->s - full) >> 1);
+    Sector x;
+    classify_sector<kTies>(ix, key, mid, pol, &x);
+    if (x.c == 4u) { full = mid; continue; }
+    *held = x;
+    if (x.c > 0u) break;
+  }
+  Bounds b;
+  b.lb = 4u * held->s + held->c;
+  // ---- ub: matches run from lb; they end inside the held sector unless they reach its last valid entry -------------------
+  if (held->c + held->m < valid(held->s) || held->s == last_s) {
+    b.ub = b.lb + held->m;
+    return b;
+  }
+  // the run continues into the next sectors (repeated k-mers): first sector that is not all matches
+  uint32_t all = held->s;  // every valid entry of sectors (held->s, all] matches
+  uint32_t step = 1;
+  Sector x;
+  for (;;) {
+    if (all == last_s) { b.ub = n32; return b; }
+    const uint32_t t = (last_s - all < step) ? last_s : all + step;
+    classify_sector<kTies>(ix, key, t, pol, &x);
+    if (x.m == valid(t)) { all = t; step <<= 1; continue; }
+    break;
+  }
+  while (x.s - all > 1u) {
+    const uint32_t mid = all + ((x.s - all) >> 1);
+    Sector y;
+    classify_sector<kTies>(ix, key, mid, pol, &y);
+    if (y.m == valid(mid)) all = mid;
+    else x = y;
+  }
+  b.ub = 4u * x.s + x.m;
+  return b;
+}
+
+__device__ __forceinline__ uint32_t kmer_uhadd(uint32_t a, uint32_t b) {  // floor((a + b) / 2) without overflow
+#ifdef SB_HOST_SIM
+  return (uint32_t)(((uint64_t)a + b) >> 1);
+#else
+  return __uhadd(a, b);
+#endif
+}
+__device__ __forceinline__ uint32_t kmer_add_clamped(uint32_t a, uint32_t b, uint32_t top) {  // min(a + b, top), a <= top
+  const uint32_t t = a + b;
+  return (t < a || t > top) ? top : t;
+}
+__device__ __forceinline__ int kmer_flog2(uint32_t v) {  // floor(log2 v), v >= 1
+#ifdef SB_HOST_SIM
+  return 31 - __builtin_clz(v);
+#else
+  return 31 - __clz((int)v);
+#endif
+}
+
+// binarySearch (:133-153) over {lb, ub}; returns the rank it returns, or -1.
+__device__ __forceinline__ long long replay_binary_search(uint32_t lo, uint32_t hi, const Bounds& b) {
+  // A long search whose steps all go right (every mid below lb: the search from rank 0 that the (int)predicted arithmetic
+  // of :209,:225 causes for predicted ranks >= 2^31) is jumped in closed form: after j such steps
+  // lo = hi - ceil(D / 2^j), D = hi - lo.  Those mids are below lb (no match, "too small") as long as ceil(D / 2^j) >
+  // hi - lb, the base case hi == lo + 2 (:136) and the empty-interval exit (:142) need ceil(D / 2^(j-1)) >= 3; both hold
+  // for ceil(D / 2^j) >= G = max(hi - lb + 1, 2), and j = floor(log2(D - 1)) - floor(log2(G - 1)) - 1 guarantees that.
+  if (hi > lo && hi - lo > 32u) {
+    const uint32_t D = hi - lo;
+    const uint32_t T = b.lb > hi ? 0u : hi - b.lb;
+    const uint32_t G = T + 1u > 2u ? T + 1u : 2u;
+    const int j = kmer_flog2(D - 1u) - kmer_flog2(G - 1u) - 1;
+    if (j >= 1) lo = hi - (((D - 1u) >> j) + 1u);
+  }
+  for (;;) {
+    if (hi - lo == 2u) return (long long)(lo + 1u);               // :136 (unverified)
+    const uint32_t mid = kmer_uhadd(lo, hi);
+    if (mid >= b.lb && mid < b.ub) return (long long)mid;         // :141
+    if (lo + 1u >= hi) return -1;                                 // :142
+    if (mid < b.lb) lo = mid;                                     // :143-147
+    else hi = mid;                                                // :148-152
+  }
+}
+
+// Phase 2: plQuery (:159-248) for s.length() == length == k (no gallop loops) over {lb, ub}: the rank whose rev[] it
+// returns, or -1.  pred < n.
+__device__ __forceinline__ long long replay_plquery(const IndexView& ix, uint32_t pred, const Bounds& b) {
+  const uint32_t nm1 = (uint32_t)ix.n - 1u;
+  auto is_match = [&](uint32_t r) { return r >= b.lb && r < b.ub; };
+  if (is_match(pred)) return (long long)pred;  // :164
+  uint32_t lo, hi;
+  if (pred < b.lb) {  // suffix smaller than the query: look right (:167-204)
+    lo = pred;
+    hi = kmer_add_clamped(pred, (uint32_t)ix.mostOver, nm1);
+    if (is_match(hi)) return (long long)hi;  // :174
+    if (hi < b.lb) {                         // :175-183
+      lo = hi;
+      hi = kmer_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
+      if (is_match(hi)) return (long long)hi;
+    }
+  } else {  // look left (:206-243)
+    hi = pred;
+    if (ix.compat) {  // (int)predicted - mostUnder (:209): wraps negative for predicted >= 2^31
+      const int32_t v = (int32_t)(pred - (uint32_t)ix.mostUnder);
+      lo = (uint32_t)(v > 0 ? v : 0);
+    } else {
+      const uint32_t d = (uint32_t)ix.mostUnder;
+      lo = pred > d ? pred - d : 0u;
+    }
+    if (is_match(lo)) return (long long)lo;  // :213
+    if (!(lo < b.lb)) {                      // :220-228
+      hi = lo;
+      if (ix.compat) {
+        const int32_t v = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
+        lo = (uint32_t)(v > 0 ? v : 0);
+      } else {
+        const uint32_t d = (uint32_t)ix.maxUnder + 1u;
+        lo = pred > d ? pred - d : 0u;
+      }
+      if (is_match(lo)) return (long long)lo;
+    }
+  }
+  return replay_binary_search(lo, hi, b);  // :245
+}
+
+// rev[r] (the reference's suffix array, sapling_api.h:41) read from the rank lines
+__device__ __forceinline__ uint32_t rev_at(const IndexView& ix, uint64_t r, uint64_t pol) {
+  return ld_u32_pol(ix.lines + (r >> 2) * 8u + 4u + (r & 3u), pol);
+}
+
+// The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.
+template <bool kTies>
+__device__ __forceinline__ long long answer_kmer(const IndexView& ix, uint64_t x, uint32_t pred, const L2Policies& pol) {
+  const KmerKey key = make_key(ix, x);
+  Sector first, held;
+  classify_sector<kTies>(ix, key, pred >> 2, pol, &first);
+  const uint32_t j0 = pred & 3u;
+  if (j0 >= first.c && j0 < first.c + first.m) {  // rev[predicted] matches (:164): a third of all queries end here
+    const uint32_t a = (j0 & 1u) ? first.pos[1] : first.pos[0], c = (j0 & 1u) ? first.pos[3] : first.pos[2];
+    return (long long)((j0 & 2u) ? c : a);
+  }
+  const Bounds b = find_bounds<kTies>(ix, key, pol, first, &held);
+  const long long rank = replay_plquery(ix, pred, b);
+  if (rank < 0) return -1;  // :246
+  const uint32_t r = (uint32_t)rank, rs = r >> 2, j = r & 3u;
+  if (rs == held.s || rs == first.s) {
+    const Sector& h = rs == held.s ? held : first;
+    const uint32_t a = (j & 1u) ? h.pos[1] : h.pos[0], c = (j & 1u) ? h.pos[3] : h.pos[2];
+    return (long long)((j & 2u) ? c : a);
+  }
+  SB_SIM_ADD(g_sim_final_loads, 1);
+  return (long long)rev_at(ix, r, pol.sa);  // :247
+}
+
+}  // namespace sb
