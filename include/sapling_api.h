@@ -7,9 +7,12 @@
  * unchanged (they rely on `using namespace std` and on the <...> headers the reference header
  * pulls in, so this one provides both).  Additions: queryBatch().
  *
- * What is NOT here: any CPU implementation of the query.  Every query runs on the GPU; if the
- * library cannot create the index the constructor prints the error and exits (the reference
- * prints to cerr and continues into undefined behaviour, sapling_api.h:578-581).
+ * What is NOT here: any CPU implementation of the query.  Every query runs on the GPU.
+ * Errors follow the reference's convention -- print to cerr and carry on (sapling_api.h:578-581,:623-649) -- with
+ * defined results where the reference runs into undefined behaviour: a constructor that fails leaves an empty index
+ * (n = 0), and every query on it, like every failed call, prints the library's message and returns -1 / 0.
+ * Set SAPLING_B200_GPUS (a bit mask such as 0xff, or "all") to replicate the index onto several GPUs of the box at
+ * construction; queryBatch() then shards every batch over them.
  */
 #ifndef SAPLING_B200_DROPIN_SAPLING_API_H
 #define SAPLING_B200_DROPIN_SAPLING_API_H
@@ -48,7 +51,7 @@ struct Sapling
         host = make_shared<vector<uint32_t>>(owner->n);
         int rc = which == 0 ? sapling_b200_rev(owner->h.get(), 0, owner->n, host->data())
                             : sapling_b200_sa_rank(owner->h.get(), 0, owner->n, host->data());
-        if (rc != 0) { cerr << "sapling_b200: " << sapling_b200_last_error() << endl; exit(1); }
+        if (rc != 0) cerr << "sapling_b200: " << sapling_b200_last_error() << endl; /* zeros, like a failed read */
       }
       return (size_t)(*host)[i];
     }
@@ -81,23 +84,63 @@ struct Sapling
   size_t queryPiecewiseLinear(long long x)
   {
     uint64_t in = (uint64_t)x, out = 0;
-    check(sapling_b200_predict_batch(h.get(), &in, 1, &out));
+    if (!check(sapling_b200_predict_batch(h.get(), &in, 1, &out))) return 0;
     return (size_t)out;
   }
 
-  /* :159-248 -- one query per call (a kernel launch each: use queryBatch for throughput) */
+  /* :159-248 -- one query per call (a kernel launch each: use queryBatch / plQueryBatch for throughput).
+     A string with a byte other than A/C/G/T cannot occur in the cleaned genome (:520-548): the reference returns some
+     nearby position that its callers' verification rejects (align.cpp:283-285); here the answer is -1. */
   long long plQuery(string s, long kmer, size_t length)
   {
+    for (size_t i = 0; i < s.length(); i++)
+      if (bad(s[i])) return -1;
     long long r = sapling_b200_query_str(h.get(), s.data(), s.length(), (int64_t)kmer, length);
-    if (r == -2) { cerr << "sapling_b200: " << sapling_b200_last_error() << endl; exit(1); }
+    if (r == -2) { cerr << "sapling_b200: " << sapling_b200_last_error() << endl; return -1; }
     return r;
   }
 
-  /* addition: out[i] = plQuery(unpack(kmers[i]), kmers[i], k) for the whole batch */
+  /* addition: plQuery(queries[i], kmers[i], lengths[i]) for a whole batch of strings in one launch */
+  vector<long long> plQueryBatch(const vector<string> &queries, const vector<long long> &kmers, const vector<size_t> &lengths)
+  {
+    vector<long long> out(queries.size(), -1);
+    string blob;
+    vector<uint64_t> off;
+    vector<uint32_t> slens, lens;
+    vector<int64_t> km;
+    vector<size_t> which;
+    for (size_t i = 0; i < queries.size(); i++)
+    {
+      bool ok = true;
+      for (char c : queries[i]) ok = ok && !bad(c);
+      if (!ok) continue; /* -1, see plQuery */
+      which.push_back(i);
+      off.push_back(blob.size());
+      blob += queries[i];
+      slens.push_back((uint32_t)queries[i].length());
+      lens.push_back((uint32_t)lengths[i]);
+      km.push_back((int64_t)kmers[i]);
+    }
+    vector<int64_t> res(which.size(), -1);
+    if (!which.empty() && check(sapling_b200_query_str_batch(h.get(), blob.data(), off.data(), slens.data(), lens.data(),
+                                                             km.data(), which.size(), res.data())))
+      for (size_t j = 0; j < which.size(); j++) out[which[j]] = res[j];
+    return out;
+  }
+
+  /* addition: out[i] = plQuery(unpack(kmers[i]), kmers[i], k) for the whole batch (sharded over the GPUs of the index) */
   void queryBatch(const uint64_t *kmers, size_t nq, long long *out)
   {
     static_assert(sizeof(long long) == sizeof(int64_t), "");
-    check(sapling_b200_query_batch(h.get(), kmers, nq, reinterpret_cast<int64_t *>(out)));
+    if (!check(sapling_b200_query_batch(h.get(), kmers, nq, reinterpret_cast<int64_t *>(out))))
+      for (size_t i = 0; i < nq; i++) out[i] = -1;
+  }
+  /* the same in the narrow transfer format: kmer_bytes little-endian bytes per k-mer in, uint32 positions out
+     (0xFFFFFFFF = -1): 10 bytes per query over PCIe instead of 16 for k = 21 */
+  void queryBatchU32(const void *kmers, int kmer_bytes, size_t nq, uint32_t *out)
+  {
+    if (!check(sapling_b200_query_batch_u32(h.get(), kmers, kmer_bytes, nq, out)))
+      for (size_t i = 0; i < nq; i++) out[i] = 0xFFFFFFFFu;
   }
   vector<long long> queryBatch(const vector<long long> &kmers)
   {
@@ -119,7 +162,7 @@ struct Sapling
     for (size_t i = 0; i < reads.size(); i++) { blob += reads[i]; off[i + 1] = blob.size(); }
     SeedHits o;
     size_t m = reads.size() * 2 * numSeeds;
-    o.ref_pos.resize(m); o.sa_pos.resize(m); o.left.resize(m); o.right.resize(m);
+    o.ref_pos.assign(m, -1); o.sa_pos.assign(m, 0); o.left.assign(m, 0); o.right.assign(m, 0);
     check(sapling_b200_seed_batch(h.get(), blob.data(), off.data(), reads.size(), (uint32_t)numSeeds, (uint32_t)maxHits,
                                   reinterpret_cast<int64_t *>(o.ref_pos.data()), o.sa_pos.data(), o.left.data(),
                                   o.right.data()));
@@ -149,9 +192,17 @@ struct Sapling
     vals['A'] = 0; vals['C'] = 1; vals['G'] = 2; vals['T'] = 3;
     errorsFn = errorFn;
     if (myMaxMem != -1) maxMem = myMaxMem;
-    sapling_b200_index *p = sapling_b200_open(refFnString.c_str(), saFnString.c_str(), saplingFnString.c_str(),
-                                              numBuckets, myMaxMem, myK, errorFn.c_str(), SAPLING_B200_KEEP_BUILD);
-    if (!p) { cerr << "sapling_b200: " << sapling_b200_last_error() << endl; exit(1); }
+    if (myK != -1) k = myK;
+    uint64_t gpus = 0;
+    if (const char *e = getenv("SAPLING_B200_GPUS")) gpus = string(e) == "all" ? ~0ull : strtoull(e, nullptr, 0);
+    sapling_b200_index *p = sapling_b200_open_multi(refFnString.c_str(), saFnString.c_str(), saplingFnString.c_str(),
+                                                    numBuckets, myMaxMem, myK, errorFn.c_str(), SAPLING_B200_KEEP_BUILD, gpus);
+    if (!p)
+    { /* the reference prints and carries on (:578-581); so does this, with an empty index */
+      cerr << "sapling_b200: " << sapling_b200_last_error() << endl;
+      bind();
+      return;
+    }
     h = shared_ptr<sapling_b200_index>(p, sapling_b200_close);
     uint64_t nn = 0;
     sapling_b200_info(p, &nn, &k, &buckets, &maxOver, &maxUnder, &meanError, &mostOver, &mostUnder);
@@ -187,9 +238,10 @@ struct Sapling
 
 private:
   void bind() { sa.owner = this; sa.which = 1; rev.owner = this; rev.which = 0; }
-  void check(int rc)
+  bool check(int rc)
   {
-    if (rc != 0) { cerr << "sapling_b200: " << sapling_b200_last_error() << endl; exit(1); }
+    if (rc != 0) cerr << "sapling_b200: " << sapling_b200_last_error() << endl;
+    return rc == 0;
   }
 };
 

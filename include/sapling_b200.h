@@ -7,10 +7,13 @@
  * include/sapling_api.h wraps these into a `struct Sapling` with the reference's surface.
  *
  * Conventions: functions returning int give 0 on success, <0 on error (message in
- * sapling_b200_last_error()).  A handle owns all host and device memory of one index on ONE GPU
- * (the current CUDA device at creation).  Query calls do not mutate the index and may be issued
- * concurrently from several host threads on distinct streams.  There is no CPU fallback: every
- * call fails if no sm_100-class device is usable.
+ * sapling_b200_last_error()).  A handle owns all host and device memory of one index: it is built / ingested on ONE GPU
+ * (the current CUDA device at creation) and may then be replicated onto other GPUs of the box (sapling_b200_open_multi /
+ * sapling_b200_replicate); the host-pointer batch calls shard over all of them, the device-pointer calls address the
+ * handle's own GPU.  Query calls do not mutate the index and may be issued concurrently from several host threads on
+ * distinct streams.  There is no CPU fallback: every call fails if no sm_100-class device is usable.
+ * Resident per GPU: the 2-bit genome (n/4 bytes), the rank lines (8 n bytes: the suffix array together with the leading
+ * bases of every suffix) and the narrow model (8 bytes per bucket) -- 27.7 GB at 3.1 Gbp.
  */
 #ifndef SAPLING_B200_H
 #define SAPLING_B200_H
@@ -31,14 +34,6 @@ typedef struct sapling_b200_index sapling_b200_index;
                                         Identical results for genomes < 2^31 bp. */
 #define SAPLING_B200_KEEP_BUILD 4u   /* keep ISA / k-prefix runs on the device after construction
                                         (needed by count_hits / sa_rank) */
-
-#define SAPLING_B200_INLINE 8u       /* build the inline-prefix suffix array (16 B per base: rank -> {position, leading
-                                        bases}) whatever the genome size; default: only for genomes >= 400 Mbp */
-#define SAPLING_B200_NO_INLINE 16u   /* never build it */
-#define SAPLING_B200_PACKED 32u      /* build the rank lines (16 B per base: one 128-byte DRAM line holds the positions
-                                        and leading bases of the 16 ranks around a prediction) whatever the genome
-                                        size; default: for genomes >= 50 Mbp when HBM allows */
-#define SAPLING_B200_NO_PACKED 64u   /* never build them */
 
 /* ---- construction -------------------------------------------------------------------------- */
 
@@ -61,6 +56,16 @@ sapling_b200_index *sapling_b200_create(const char *genome, uint64_t n, const ui
 sapling_b200_index *sapling_b200_create_with_model(const char *genome, uint64_t n, const uint32_t *sa,
                                                    int k, int nb, const int64_t *xlist,
                                                    const int64_t *ylist, const int *five, unsigned flags);
+
+/* sapling_b200_open, then copies of the resident index on every other GPU whose bit is set in gpu_mask (bit d = CUDA
+ * device d; the handle's own device is implied).  The files are parsed and the index is built once; the copies travel
+ * device to device (cudaMemcpyPeer: NVLink / NVSwitch between peers).  SURVEY 8b / 8e. */
+sapling_b200_index *sapling_b200_open_multi(const char *ref_fn, const char *sa_fn, const char *sap_fn, int nb,
+                                            int maxMem, int k, const char *err_fn, unsigned flags, uint64_t gpu_mask);
+/* The same replication for an index created any other way.  Devices that already hold a copy are skipped. */
+int sapling_b200_replicate(sapling_b200_index *ix, uint64_t gpu_mask);
+/* Number of GPUs that hold the index (1 + replicas). */
+int sapling_b200_num_devices(const sapling_b200_index *ix);
 
 /* Private index cache (not a reference format): the 2-bit genome, the 32-bit suffix array, the model, the
  * error bounds and the chromosome table of an open index, written so that sapling_b200_open_cache restores the index
@@ -94,7 +99,8 @@ int sapling_b200_build_stats(const sapling_b200_index *ix, uint64_t *perfect, ui
                              uint64_t *n_under);
 /* Model checkpoints as the reference holds them (sapling_api.h:65): copies (1<<nb)+1 entries. */
 int sapling_b200_model(const sapling_b200_index *ix, int64_t *xlist, int64_t *ylist);
-/* Sapling::rev (sapling_api.h:41): copies count entries starting at rank `first` to the host. */
+/* Sapling::rev (sapling_api.h:41): copies count entries starting at rank `first` to the host (read out of the rank
+ * lines; the plain array is not kept resident). */
 int sapling_b200_rev(const sapling_b200_index *ix, uint64_t first, uint64_t count, uint32_t *out);
 /* Sapling::sa / lsa.inv (sapling_api.h:38; used by align.cpp:287): rank of text position pos.
  * Needs SAPLING_B200_KEEP_BUILD.  Copies count entries starting at position `first`. */
@@ -112,8 +118,8 @@ uint64_t sapling_b200_device_bytes(const sapling_b200_index *ix);
 /* Number of kernels launched for k-mer batches through this handle so far (both batch entry points; a partitioned batch
  * is eight launches). */
 uint64_t sapling_b200_launch_count(const sapling_b200_index *ix);
-/* Name of the CUDA kernel sapling_b200_query_batch(_dev) launches for this index (which layout it reads depends on
- * the genome size and the flags), and the resident blocks per SM it is compiled for. */
+/* Name of the CUDA kernel sapling_b200_query_batch(_dev) launches for a small batch on this index, and the resident
+ * blocks per SM it is compiled for. */
 const char *sapling_b200_query_kernel(const sapling_b200_index *ix, int *blocks_per_sm);
 /* The same for a batch of nq queries: a batch large enough to be partitioned (next entry) runs the in-order
  * kernel over the partitioned k-mers instead. */
@@ -143,13 +149,22 @@ int64_t sapling_b200_kmerize_adjusted(int k, int length, const char *s);
  * Host pointers; the library streams chunks through the GPU (pinned buffers are copied directly). */
 int sapling_b200_query_batch(sapling_b200_index *ix, const uint64_t *kmers, size_t nq, int64_t *out);
 
+/* The same answers in the narrow transfer format (the host path is bound by PCIe bytes: 16 per query above, 10 here for
+ * k = 21): kmers = nq little-endian integers of kmer_bytes bytes each (ceil(2k/8) <= kmer_bytes <= 8; 8 = the uint64
+ * array of sapling_b200_query_batch), out[i] = the position as uint32 (n < 2^32 always), 0xFFFFFFFF for -1. */
+int sapling_b200_query_batch_u32(sapling_b200_index *ix, const void *kmers, int kmer_bytes, size_t nq, uint32_t *out);
+
 /* Same on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream),
  * no copies, no synchronisation. */
 int sapling_b200_query_batch_dev(sapling_b200_index *ix, const uint64_t *d_kmers, size_t nq,
                                  int64_t *d_out, void *stream);
+int sapling_b200_query_batch_u32_dev(sapling_b200_index *ix, const uint64_t *d_kmers, size_t nq, uint32_t *d_out,
+                                     void *stream);
 
 /* long long plQuery(string s, long kmer, size_t length)   sapling_api.h:159.  s holds slen bases
- * (A/C/G/T), length <= slen is the reference's third argument. */
+ * (A/C/G/T), length <= slen is the reference's third argument.  A string with any other byte is REJECTED (-2 / error):
+ * the reference compares raw bytes (an 'N' never matches and sorts between 'G' and 'T'), which a 2-bit index cannot
+ * reproduce; its callers discard such seeds anyway (align.cpp:283-285). */
 int64_t sapling_b200_query_str(sapling_b200_index *ix, const char *s, size_t slen, int64_t kmer,
                                size_t length);
 /* Batch of strings: query i is s[offsets[i] .. offsets[i]+slens[i]) with kmers[i] and lengths[i]
@@ -172,13 +187,19 @@ int sapling_b200_count_hits(sapling_b200_index *ix, const uint32_t *sa_pos, size
  * plQuery(query, kmerize(query), k) returned AND whose k bases equal the seed (:279-285), else -1; for hits
  * sa_pos = Sapling::sa[ref_pos] (:287) and left/right = countHitsLeft/Right(sa_pos, max_hits) (:288-289), i.e. the
  * tuple the reference pushes at :291-297 (its first element is left+right+1).  Seeds with a non-ACGT byte and reads
- * shorter than k give -1.  Needs SAPLING_B200_KEEP_BUILD.  Host pointers / device pointers + stream. */
+ * shorter than k give -1.  Needs SAPLING_B200_KEEP_BUILD; max_hits <= 255. */
 int sapling_b200_seed_batch(sapling_b200_index *ix, const char *reads, const uint64_t *read_off, size_t n_reads,
                             uint32_t num_seeds, uint32_t max_hits, int64_t *ref_pos, uint32_t *sa_pos,
                             uint32_t *left, uint32_t *right);
+/* The same tuples in 10 bytes per seed instead of 20 (ref_pos as uint32 with 0xFFFFFFFF for "no hit", the two counts as
+ * bytes), blocks of reads pipelined through the GPU (upload, kernel and download of consecutive blocks overlap). */
+int sapling_b200_seed_batch_compact(sapling_b200_index *ix, const char *reads, const uint64_t *read_off, size_t n_reads,
+                                    uint32_t num_seeds, uint32_t max_hits, uint32_t *ref_pos, uint32_t *sa_pos,
+                                    uint8_t *left, uint8_t *right);
+/* Device pointers + stream, compact types, no copies, no synchronisation. */
 int sapling_b200_seed_batch_dev(sapling_b200_index *ix, const char *d_reads, const uint64_t *d_read_off,
-                                size_t n_reads, uint32_t num_seeds, uint32_t max_hits, int64_t *d_ref_pos,
-                                uint32_t *d_sa_pos, uint32_t *d_left, uint32_t *d_right, void *stream);
+                                size_t n_reads, uint32_t num_seeds, uint32_t max_hits, uint32_t *d_ref_pos,
+                                uint32_t *d_sa_pos, uint8_t *d_left, uint8_t *d_right, void *stream);
 
 /* Number of queries so far whose predicted rank was >= n (reference: out-of-bounds read). */
 uint64_t sapling_b200_oob_count(sapling_b200_index *ix);

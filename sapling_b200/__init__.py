@@ -11,7 +11,3 @@ from .api import (Sapling, SaplingError, kmerize, kmerize_adjusted, lib, lib_pat
 QUIET = 1
 NO_COMPAT = 2
 KEEP_BUILD = 4
-INLINE = 8
-NO_INLINE = 16
-PACKED = 32
-NO_PACKED = 64

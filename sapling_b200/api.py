@@ -20,6 +20,7 @@ _u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 _i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
 _u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
 _i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
 
 # name -> (restype, argtypes): every symbol include/sapling_b200.h declares
 SYMBOLS = {
@@ -27,6 +28,10 @@ SYMBOLS = {
     "sapling_b200_create": (C.c_void_p, [C.c_char_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint]),
     "sapling_b200_create_with_model": (C.c_void_p, [C.c_char_p, C.c_uint64, C.c_void_p, C.c_int, C.c_int, _i64p, _i64p, _i32p, C.c_uint]),
     "sapling_b200_create_synthetic": (C.c_void_p, [C.c_uint64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint]),
+    "sapling_b200_open_multi": (C.c_void_p, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_uint,
+                                             C.c_uint64]),
+    "sapling_b200_replicate": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "sapling_b200_num_devices": (C.c_int, [C.c_void_p]),
     "sapling_b200_close": (None, [C.c_void_p]),
     "sapling_b200_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64)] + [C.POINTER(C.c_int)] * 7),
     "sapling_b200_genome": (C.c_void_p, [C.c_void_p]),
@@ -51,11 +56,14 @@ SYMBOLS = {
     "sapling_b200_kmerize_adjusted": (C.c_int64, [C.c_int, C.c_int, C.c_char_p]),
     "sapling_b200_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sapling_b200_query_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "sapling_b200_query_batch_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "sapling_b200_query_batch_u32_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "sapling_b200_query_str": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int64, C.c_size_t]),
     "sapling_b200_query_str_batch": (C.c_int, [C.c_void_p, C.c_char_p, _u64p, _u32p, C.c_void_p, _i64p, C.c_size_t, _i64p]),
     "sapling_b200_predict_batch": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p]),
     "sapling_b200_count_hits": (C.c_int, [C.c_void_p, _u32p, C.c_size_t, C.c_uint32, _u32p, _u32p]),
     "sapling_b200_seed_batch": (C.c_int, [C.c_void_p, C.c_char_p, _u64p, C.c_size_t, C.c_uint32, C.c_uint32, _i64p, _u32p, _u32p, _u32p]),
+    "sapling_b200_seed_batch_compact": (C.c_int, [C.c_void_p, C.c_char_p, _u64p, C.c_size_t, C.c_uint32, C.c_uint32, _u32p, _u32p, _u8p, _u8p]),
     "sapling_b200_seed_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_uint32, C.c_uint32,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sapling_b200_oob_count": (C.c_uint64, [C.c_void_p]),
@@ -169,6 +177,13 @@ class Sapling:
         L = lib()
         return cls(_handle=L.sapling_b200_create_synthetic(seed, n, numBuckets, maxMem, k,
                                                            1 if keep_host_genome else 0, flags) or 0)
+
+    @classmethod
+    def open_multi(cls, refFn, saFn, sapFn, numBuckets=-1, maxMem=-1, k=-1, errorFn="", flags=1, gpu_mask=0):
+        """The reference constructor, then replicas on the GPUs of gpu_mask (include/sapling_b200.h)."""
+        L = lib()
+        return cls(_handle=L.sapling_b200_open_multi(_b(refFn), _b(saFn), _b(sapFn), numBuckets, maxMem, k,
+                                                     _b(errorFn or ""), flags, gpu_mask) or 0)
 
     @classmethod
     def from_cache(cls, path, flags=1):
@@ -321,6 +336,31 @@ class Sapling:
         self._ck(self._L.sapling_b200_query_batch(self._h, ptr_in, nq, ptr_out))
         return out
 
+    def queryBatchU32(self, kmers, kmer_bytes=8, out=None, nq=None):
+        """The narrow transfer format of the host path: `kmers` holds nq little-endian integers of kmer_bytes bytes each
+        (a uint64 array for 8, a uint8 array of nq * kmer_bytes otherwise; numpy or pinned torch), the answers come
+        back as uint32 positions with 0xFFFFFFFF for -1."""
+        ptr_in, count = _host_ptr(kmers, 8 if kmer_bytes == 8 else 1)
+        if nq is None:
+            nq = count if kmer_bytes == 8 else count // kmer_bytes
+        if out is None:
+            out = np.empty(nq, dtype=np.uint32)
+        ptr_out, nq2 = _host_ptr(out, 4)
+        assert nq2 >= nq
+        self._ck(self._L.sapling_b200_query_batch_u32(self._h, ptr_in, kmer_bytes, nq, ptr_out))
+        return out
+
+    def queryBatchU32Device(self, d_kmers_ptr, nq, d_out_ptr, stream=0):
+        self._ck(self._L.sapling_b200_query_batch_u32_dev(self._h, d_kmers_ptr, nq, d_out_ptr, stream))
+
+    def replicate(self, gpu_mask):
+        """Copies of the index on every other GPU whose bit is set (device to device); host batches then shard over them."""
+        self._ck(self._L.sapling_b200_replicate(self._h, gpu_mask))
+        return self.num_devices()
+
+    def num_devices(self):
+        return int(self._L.sapling_b200_num_devices(self._h))
+
     def queryBatchDevice(self, d_kmers_ptr, nq, d_out_ptr, stream=0):
         """Device-resident batch: raw device pointers (e.g. torch .data_ptr()), enqueued on `stream`."""
         self._ck(self._L.sapling_b200_query_batch_dev(self._h, d_kmers_ptr, nq, d_out_ptr, stream))
@@ -342,6 +382,19 @@ class Sapling:
         rp, sp = np.empty(m, np.int64), np.empty(m, np.uint32)
         lf, rt = np.empty(m, np.uint32), np.empty(m, np.uint32)
         self._ck(self._L.sapling_b200_seed_batch(self._h, blob, off, len(reads), num_seeds, max_hits, rp, sp, lf, rt))
+        shp = (len(reads), 2, num_seeds)
+        return rp.reshape(shp), sp.reshape(shp), lf.reshape(shp), rt.reshape(shp)
+
+    def seedBatchCompact(self, reads, num_seeds=7, max_hits=32):
+        """seedBatch in the 10-bytes-per-seed transfer format: ref_pos uint32 (0xFFFFFFFF = no verified hit), sa_pos uint32,
+        left / right uint8; blocks of reads are pipelined through the GPU."""
+        off = np.zeros(len(reads) + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(r) for r in reads])
+        blob = b"".join(reads)
+        m = len(reads) * 2 * num_seeds
+        rp, sp = np.empty(m, np.uint32), np.empty(m, np.uint32)
+        lf, rt = np.empty(m, np.uint8), np.empty(m, np.uint8)
+        self._ck(self._L.sapling_b200_seed_batch_compact(self._h, blob, off, len(reads), num_seeds, max_hits, rp, sp, lf, rt))
         shp = (len(reads), 2, num_seeds)
         return rp.reshape(shp), sp.reshape(shp), lf.reshape(shp), rt.reshape(shp)
 
@@ -380,7 +433,7 @@ class Sapling:
 
 
 def _host_ptr(a, itemsize):
-    """(void*, element count) of a numpy array or a CPU torch tensor of 8-byte elements."""
+    """(void*, element count) of a numpy array or a CPU torch tensor of `itemsize`-byte elements."""
     if isinstance(a, np.ndarray):
         assert a.flags["C_CONTIGUOUS"] and a.dtype.itemsize == itemsize
         return C.c_void_p(a.ctypes.data), a.size

@@ -16,16 +16,11 @@ int synth_genome_packed(uint64_t seed, uint64_t n, uint64_t* d_packed, cudaStrea
 int unpack_genome(const uint64_t* d_packed, uint64_t n, char* d_ascii, cudaStream_t st);
 
 // ---- suffix array (sa_build.cu) ----
-// d_ext (optional, n entries): also filled, from the sort keys (27 leading bases per suffix) -- no extra gather
 int build_suffix_array(const uint64_t* d_genome, uint64_t n, uint32_t* d_sa, uint32_t* d_isa, cudaStream_t st,
-                       int* rounds_out, ExtEntry* d_ext = nullptr);
-constexpr int kExtBasesFromSort = 27;
-// ext[r] = {sa[r], 32 leading bases of that suffix} by a gather over the packed genome (for suffix arrays that were
-// loaded rather than built here)
-int build_ext_by_gather(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, ExtEntry* d_ext, cudaStream_t st);
-// rank lines (common.cuh IndexView): d_packed must hold packed_sectors(n, shift) * 32 bytes
-int build_rank_lines(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, int bases, int shift,
-                     uint32_t* d_packed, cudaStream_t st);
+                       int* rounds_out);
+// rank lines (common.cuh): d_lines must hold line_sectors(n) * 32 bytes
+int build_rank_lines(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, int bases, uint32_t* d_lines,
+                     cudaStream_t st);
 int invert_permutation(const uint32_t* d_src, uint64_t n, uint32_t* d_dst, cudaStream_t st);
 // sufcheck-style validation: counts adjacent pairs that are out of order / undecided within
 // max_chars, and positions where isa[sa[r]] != r.
@@ -53,6 +48,9 @@ int build_model(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, cons
 
 // narrow device layout of the model (model.cu)
 int build_narrow_model(const ModelEntry* d_model, int nb, int shift, uint2* d_narrow, int* ok, cudaStream_t st);
+// checkpoints first .. first+count-1 (of (1<<nb)+1) rebuilt from the narrow table into two int64 device arrays
+int widen_model(const uint2* d_narrow, int nb, int shift, long long last_x, long long last_y, uint64_t first,
+                uint64_t count, long long* d_xs, long long* d_ys, cudaStream_t st);
 
 // countHitsLeft/Right (sapling_api.h:254-263, 283-289) over kflag
 int count_hits(const uint8_t* d_kflag, uint64_t n, int k, const uint32_t* d_sa_pos, size_t count,

@@ -9,9 +9,11 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sapling_b200.h"
@@ -22,22 +24,21 @@
 namespace sb {
 
 // launchers in query.cu
-int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, cudaStream_t st,
-                      const char** name_out = nullptr, const uint16_t* d_slot = nullptr,
-                      unsigned long long* d_tiles = nullptr);
 int launch_string_query(const IndexView& ix, const uint64_t* d_words, const uint64_t* d_word_off,
                         const uint32_t* d_slens, const uint32_t* d_lengths, const long long* d_kmers, size_t nq,
                         long long* d_out, cudaStream_t st);
 int launch_predict(const IndexView& ix, const uint64_t* d_kmers, size_t nq, uint64_t* d_out, cudaStream_t st);
 int launch_seeds(const IndexView& ix, const uint32_t* d_isa, const uint8_t* d_kflag, const char* d_reads,
-                 const uint64_t* d_off, size_t n_reads, uint32_t num_seeds, uint32_t maxHits, long long* d_ref_pos,
-                 uint32_t* d_sa_pos, uint32_t* d_left, uint32_t* d_right, cudaStream_t st);
+                 const uint64_t* d_off, size_t n_reads, uint32_t num_seeds, uint32_t maxHits, uint32_t* d_ref_pos,
+                 uint32_t* d_sa_pos, uint8_t* d_left, uint8_t* d_right, cudaStream_t st);
+int launch_rev_extract(const IndexView& ix, uint64_t first, uint64_t count, uint32_t* d_out, cudaStream_t st);
 int launch_sample(const IndexView& ix, uint64_t seed, uint64_t mut_seed, uint64_t first, size_t nq,
                   uint64_t* d_kmers, cudaStream_t st);
 int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long* d_out, size_t nq,
                   unsigned long long* d_counters, cudaStream_t st);
 int launch_probe_count(const IndexView& ix, const uint64_t* d_kmers, size_t nq, unsigned long long* d_total,
                        cudaStream_t st);
+int launch_unpack_kmers(const void* d_packed, int kmer_bytes, size_t nq, uint64_t* d_kmers, cudaStream_t st);
 int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps);
 int run_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm, int reps,
                       double* gacc_per_s);
@@ -52,6 +53,46 @@ void set_error(const char* fmt, ...) {
 }
 const char* last_error() { return g_err; }
 
+// Experiment settings, read ONCE when an index is created from SAPLING_B200_TUNE="key=value,key=value" (measurement
+// scripts and tests only; nothing on the launch path reads the environment).  Defaults are the measured choices.
+struct Tuning {
+  int partition = 1;                  // part=0: never partition a batch
+  size_t partition_min = (size_t)1 << 22;  // part_min=N: smallest batch that is partitioned
+  int partition_bits = -1;            // part_bits=B: force the slice count (2^B)
+  int occupancy = 0;                  // occ=3..6: resident blocks per SM of the query kernels (0 = their defaults)
+  int hints = -1;                     // hints=<HINT_* bits>
+  int line_bases = 0;                 // line_bases=b: leading bases per rank-line entry (tests: forces escapes / ties)
+  int chunk_log2 = 0;                 // chunk_log2=l: chunk size of the host-pointer batch path
+  int narrow = 1;                     // narrow=0: keep the wide model table
+  static Tuning from_env() {
+    Tuning t;
+    const char* e = getenv("SAPLING_B200_TUNE");
+    if (!e) return t;
+    std::string s(e);
+    size_t p = 0;
+    while (p < s.size()) {
+      size_t q = s.find(',', p);
+      if (q == std::string::npos) q = s.size();
+      const std::string kv = s.substr(p, q - p);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos) {
+        const std::string key = kv.substr(0, eq);
+        const long long v = atoll(kv.c_str() + eq + 1);
+        if (key == "part") t.partition = (int)v;
+        else if (key == "part_min") t.partition_min = (size_t)v;
+        else if (key == "part_bits") t.partition_bits = (int)v;
+        else if (key == "occ") t.occupancy = (int)v;
+        else if (key == "hints") t.hints = (int)v;
+        else if (key == "line_bases") t.line_bases = (int)v;
+        else if (key == "chunk_log2") t.chunk_log2 = (int)v;
+        else if (key == "narrow") t.narrow = (int)v;
+      }
+      p = q + 1;
+    }
+    return t;
+  }
+};
+
 }  // namespace sb
 
 using namespace sb;
@@ -59,6 +100,7 @@ using namespace sb;
 struct sapling_b200_index {
   int device = 0;
   unsigned flags = 0;
+  Tuning tune;
   uint64_t n = 0;
   int k = 21, nb = 18, maxMem = 10;  // sapling_api.h:26,29,32
   ModelStats stats{};
@@ -66,26 +108,28 @@ struct sapling_b200_index {
   std::vector<std::pair<uint64_t, std::string>> chr_ends;  // Sapling::chrEnds, ascending
 
   uint64_t* d_genome = nullptr;
-  uint32_t* d_sa = nullptr;
-  ExtEntry* d_ext = nullptr;   // inline-prefix suffix array (see want_ext)
-  int ext_bases = 0;
-  uint32_t* d_packed = nullptr;  // rank lines (common.cuh IndexView; see want_packed)
-  int packed_bases = 0, packed_shift = 3;
+  uint32_t* d_lines = nullptr;  // rank lines (common.cuh): the resident form of the suffix array
+  int line_bases = 0;
+  uint32_t* d_sa = nullptr;    // plain rank -> position array: build time, and kept with KEEP_BUILD
   uint32_t* d_isa = nullptr;   // only with KEEP_BUILD
   uint8_t* d_kflag = nullptr;  // only with KEEP_BUILD
-  ModelEntry* d_model = nullptr;
-  uint2* d_narrow = nullptr;  // 8-byte-per-bucket layout used by the query kernels (model.cu)
+  ModelEntry* d_model = nullptr;  // wide checkpoints: build time; resident only when the narrow form cannot hold them
+  uint2* d_narrow = nullptr;      // 8-byte-per-bucket layout used by the query kernels (model.cu)
   long long last_x = 0, last_y = 0;
   unsigned hints = 0;
   unsigned long long* d_oob = nullptr;
   uint64_t device_bytes = 0;
   int sa_rounds = 0;
 
+  // replicas of this index on other GPUs (sapling_b200_replicate): the host-pointer batch calls shard over
+  // {this, replicas...}; a replica owns its device arrays, shares nothing mutable with the primary
+  std::vector<sapling_b200_index*> replicas;
+  bool is_replica = false;
+
   // staging for the host-pointer batch API
   std::mutex mu;
   // Chunks flow through three streams (upload, kernel, download) chained by events, kSlots chunks in flight, so
-  // that both copy engines and the SMs stay busy at once: the host-fed rate is then set by PCIe (measured on the
-  // bench box: 50 GB/s per direction with both directions active -> 6.2 G queries/s at 8 B in + 8 B out).
+  // that both copy engines and the SMs stay busy at once: the host-fed rate is then set by PCIe.
   // Chunk size: the first upload and the last download are not overlapped with anything (favours small chunks), but
   // every chunk costs ~40 us of copy-engine / cross-stream latency (favours large ones).  Measured on B200 (c2, 50 M
   // queries): 4 Mi queries per chunk 5.4 G q/s, 2 Mi 5.3, 0.8 Mi 4.5 (profiles/r1u_*); the optimum grows like sqrt(nq).
@@ -94,10 +138,11 @@ struct sapling_b200_index {
   std::atomic<uint64_t> launches{0};  // query kernels launched through this handle (sapling_b200_launch_count)
   cudaStream_t streams[3] = {nullptr, nullptr, nullptr};  // 0 upload, 1 kernel, 2 download
   cudaEvent_t ev_up[kSlots] = {}, ev_k[kSlots] = {}, ev_down[kSlots] = {};
-  uint64_t* d_in[kSlots] = {};
-  long long* d_out[kSlots] = {};
-  uint64_t* h_in[kSlots] = {};
-  long long* h_out[kSlots] = {};
+  uint64_t* d_in[kSlots] = {};    // unpacked k-mers (8 bytes each)
+  void* d_raw[kSlots] = {};       // uploaded bytes of the packed-k-mer entry point
+  long long* d_out[kSlots] = {};  // answers (8 bytes each, or 4 in the u32 entry point)
+  void* h_in[kSlots] = {};
+  void* h_out[kSlots] = {};
 
   // scratch of the partitioned batch path (partition.cu), one block per stream it was used on, grown on demand
   struct PartWs {
@@ -114,7 +159,7 @@ struct sapling_b200_index {
     cudaEvent_t ev[5];
     bool partitioned;
   };
-  std::vector<ProfCall> prof_calls;
+  std::deque<ProfCall> prof_calls;
 
   // single-query path (plQuery drop-in): one mapped pinned block, no per-call allocation
   std::mutex mu1;
@@ -125,13 +170,12 @@ struct sapling_b200_index {
   IndexView view() const {
     IndexView v;
     v.genome = d_genome;
-    v.sa = d_sa;
-    v.ext = d_ext;
-    v.ext_bases = ext_bases;
-    v.packed = d_packed;
-    v.packed_bases = packed_bases;
-    v.packed_shift = packed_shift;
+    v.lines = d_lines;
+    v.line_bases = line_bases;
     v.model = d_model;
+    v.narrow = d_narrow;
+    v.last_x = last_x;
+    v.last_y = last_y;
     v.n = n;
     v.k = k;
     v.nb = nb;
@@ -142,14 +186,12 @@ struct sapling_b200_index {
     v.mostUnder = stats.mostUnder;
     v.oob_counter = d_oob;
     v.compat = (flags & SAPLING_B200_NO_COMPAT) ? 0 : 1;
-    v.narrow = d_narrow;
-    v.last_x = last_x;
-    v.last_y = last_y;
     v.hints = hints;
     return v;
   }
 
   ~sapling_b200_index() {
+    for (auto* r : replicas) delete r;
     cudaSetDevice(device);
     for (auto& kv : part_ws) cudaFree(kv.second.p);
     for (auto& c : prof_calls)
@@ -161,6 +203,7 @@ struct sapling_b200_index {
       if (ev_k[i]) cudaEventDestroy(ev_k[i]);
       if (ev_down[i]) cudaEventDestroy(ev_down[i]);
       cudaFree(d_in[i]);
+      cudaFree(d_raw[i]);
       cudaFree(d_out[i]);
       if (h_in[i]) cudaFreeHost(h_in[i]);
       if (h_out[i]) cudaFreeHost(h_out[i]);
@@ -168,9 +211,8 @@ struct sapling_b200_index {
     if (s1) cudaStreamDestroy(s1);
     if (m1) cudaFreeHost(m1);
     cudaFree(d_genome);
+    cudaFree(d_lines);
     cudaFree(d_sa);
-    cudaFree(d_ext);
-    cudaFree(d_packed);
     cudaFree(d_isa);
     cudaFree(d_kflag);
     cudaFree(d_model);
@@ -194,17 +236,11 @@ struct Say {
   }
 };
 
-int require_device(int* dev_out) {
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) {
-    set_error("no usable CUDA device: %s (libsapling_b200 has no CPU fallback)", cudaGetErrorString(e));
-    return -1;
-  }
+int check_device(int dev) {
   cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
+  cudaError_t e = cudaGetDeviceProperties(&prop, dev);
   if (e != cudaSuccess) {
-    set_error("cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    set_error("cudaGetDeviceProperties(%d): %s", dev, cudaGetErrorString(e));
     return -1;
   }
   if (prop.major < 10) {
@@ -212,6 +248,17 @@ int require_device(int* dev_out) {
               dev, prop.name, prop.major, prop.minor);
     return -1;
   }
+  return 0;
+}
+
+int require_device(int* dev_out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    set_error("no usable CUDA device: %s (libsapling_b200 has no CPU fallback)", cudaGetErrorString(e));
+    return -1;
+  }
+  if (check_device(dev)) return -1;
   *dev_out = dev;
   return 0;
 }
@@ -227,13 +274,12 @@ int dev_alloc(sapling_b200_index* ix, T** p, uint64_t count) {
   ix->device_bytes += bytes;
   return 0;
 }
-
-// suffix array: whole 64-byte lines, tail zeroed (the query kernel fetches the aligned line around a rank)
-int alloc_sa(sapling_b200_index* ix, uint64_t n) {
-  const uint64_t m = sa_alloc_entries(n);
-  if (dev_alloc(ix, &ix->d_sa, m)) return -1;
-  if (m > n) SB_CUDA_CHECK(cudaMemset(ix->d_sa + n, 0, (m - n) * 4));
-  return 0;
+template <typename T>
+void dev_free(sapling_b200_index* ix, T** p, uint64_t count) {
+  if (!*p) return;
+  cudaFree(*p);
+  *p = nullptr;
+  ix->device_bytes -= (count ? count : 1) * sizeof(T);
 }
 
 // FASTA cleaning rule of sapling_api.h:520-548 / util.h:17-20
@@ -291,7 +337,29 @@ int upload_genome(sapling_b200_index* ix, const char* genome, uint64_t n) {
   return 0;
 }
 
-// [u64 n][u64 inv[n]][u64 m][u64 lcp[m]]   (sapling_api.h:565-577): only inv is needed
+// Pinned double buffer for streaming a file through the GPU: the read of piece i+1 overlaps the copy of piece i.
+struct PinnedPair {
+  void* h[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  size_t bytes = 0;
+  int init(size_t b) {
+    bytes = b;
+    for (int i = 0; i < 2; i++) {
+      SB_CUDA_CHECK(cudaMallocHost(&h[i], b));
+      SB_CUDA_CHECK(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    return 0;
+  }
+  ~PinnedPair() {
+    for (int i = 0; i < 2; i++) {
+      if (h[i]) cudaFreeHost(h[i]);
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    }
+  }
+};
+
+// [u64 n][u64 inv[n]][u64 m][u64 lcp[m]]   (sapling_api.h:565-577): only inv is needed.  The 8-byte entries are narrowed
+// on the host into a pinned buffer whose upload overlaps the next read.
 int read_sa_file(sapling_b200_index* ix, const char* path) {
   FILE* f = fopen(path, "rb");
   if (!f) { set_error("cannot open %s", path); return -1; }
@@ -305,30 +373,59 @@ int read_sa_file(sapling_b200_index* ix, const char* path) {
   if (dev_alloc(ix, &ix->d_isa, sz)) { fclose(f); return -1; }
   const size_t CH = 1u << 22;
   std::vector<uint64_t> buf(CH);
-  std::vector<uint32_t> buf32(CH);
-  for (uint64_t o = 0; o < sz; o += CH) {
+  PinnedPair pp;
+  if (pp.init(CH * 4)) { fclose(f); return -1; }
+  int slot = 0;
+  for (uint64_t o = 0; o < sz; o += CH, slot ^= 1) {
     const size_t c = (size_t)std::min<uint64_t>(CH, sz - o);
     if (fread(buf.data(), 8, c, f) != c) { fclose(f); set_error("Error reading suffix array from file"); return -1; }
-    for (size_t i = 0; i < c; i++) buf32[i] = (uint32_t)buf[i];
-    cudaError_t e = cudaMemcpy(ix->d_isa + o, buf32.data(), c * 4, cudaMemcpyHostToDevice);
+    cudaEventSynchronize(pp.ev[slot]);  // the copy that last used this buffer
+    uint32_t* h32 = static_cast<uint32_t*>(pp.h[slot]);
+    for (size_t i = 0; i < c; i++) h32[i] = (uint32_t)buf[i];
+    cudaError_t e = cudaMemcpyAsync(ix->d_isa + o, h32, c * 4, cudaMemcpyHostToDevice, 0);
     if (e != cudaSuccess) { fclose(f); SB_CUDA_CHECK(e); }
+    cudaEventRecord(pp.ev[slot], 0);
   }
   fclose(f);
-  if (alloc_sa(ix, sz)) return -1;
+  if (dev_alloc(ix, &ix->d_sa, sz)) return -1;
   // rev[inv[i]] = i  (sapling_api.h:609-611)
   if (invert_permutation(ix->d_isa, sz, ix->d_sa, 0)) return -1;
   SB_CUDA_CHECK(cudaDeviceSynchronize());
   return 0;
 }
 
+// The plain rank -> position array of an index whose resident form is the rank lines: ix->d_sa if it is still there,
+// else a scratch copy extracted from the lines (freed by the guard).
+struct SaGuard {
+  const uint32_t* sa = nullptr;
+  uint32_t* scratch = nullptr;
+  ~SaGuard() { if (scratch) cudaFree(scratch); }
+  int get(const sapling_b200_index* ix) {
+    if (ix->d_sa) { sa = ix->d_sa; return 0; }
+    SB_CUDA_CHECK(cudaMalloc(&scratch, (ix->n ? ix->n : 1) * 4));
+    if (launch_rev_extract(ix->view(), 0, ix->n, scratch, 0)) return -1;
+    SB_CUDA_CHECK(cudaDeviceSynchronize());
+    sa = scratch;
+    return 0;
+  }
+};
+
 int write_sa_file(const sapling_b200_index* ix, const char* path) {
-  if (!ix->d_isa) { set_error("write_sa: ISA not resident (open with SAPLING_B200_KEEP_BUILD)"); return -1; }
-  FILE* f = fopen(path, "wb");
-  if (!f) { set_error("cannot write %s", path); return -1; }
   const uint64_t n = ix->n;
+  SaGuard sg;
+  if (sg.get(ix)) return -1;
+  uint32_t* d_isa_tmp = nullptr;
+  const uint32_t* d_isa = ix->d_isa;
+  if (!d_isa) {
+    SB_CUDA_CHECK(cudaMalloc(&d_isa_tmp, (n ? n : 1) * 4));
+    if (invert_permutation(sg.sa, n, d_isa_tmp, 0)) { cudaFree(d_isa_tmp); return -1; }
+    d_isa = d_isa_tmp;
+  }
+  FILE* f = fopen(path, "wb");
+  if (!f) { cudaFree(d_isa_tmp); set_error("cannot write %s", path); return -1; }
   uint32_t* d_lcp = nullptr;
-  SB_CUDA_CHECK(cudaMalloc(&d_lcp, (n ? n : 1) * 4));
-  if (compute_lcp(ix->d_genome, n, ix->d_sa, d_lcp, 0)) { cudaFree(d_lcp); fclose(f); return -1; }
+  if (cudaMalloc(&d_lcp, (n ? n : 1) * 4) != cudaSuccess) { cudaGetLastError(); cudaFree(d_isa_tmp); fclose(f); set_error("write_sa: allocation failed"); return -1; }
+  if (compute_lcp(ix->d_genome, n, sg.sa, d_lcp, 0)) { cudaFree(d_lcp); cudaFree(d_isa_tmp); fclose(f); return -1; }
   const size_t CH = 1u << 22;
   std::vector<uint64_t> buf(CH);
   std::vector<uint32_t> buf32(CH);
@@ -342,9 +439,10 @@ int write_sa_file(const sapling_b200_index* ix, const char* path) {
     }
     return 0;
   };
-  int rc = dump(ix->d_isa, n);
+  int rc = dump(d_isa, n);
   if (!rc) rc = dump(d_lcp, n - 1);
   cudaFree(d_lcp);
+  cudaFree(d_isa_tmp);
   fclose(f);
   if (rc) set_error("error writing %s", path);
   return rc;
@@ -398,7 +496,8 @@ int validate_params(sapling_b200_index* ix) {
   return 0;
 }
 
-int finish_model_checks(sapling_b200_index* ix) {
+// after the model is on the device (wide form): bounds, narrow table, L2 policy
+int finish_model(sapling_b200_index* ix) {
   if (ix->nb < 1 || ix->nb > 31 || ix->nb > 2 * ix->k) {
     set_error("nb=%d out of range for k=%d (need 1 <= nb <= min(2k,31))", ix->nb, ix->k);
     return -1;
@@ -412,113 +511,41 @@ int finish_model_checks(sapling_b200_index* ix) {
     if (dev_alloc(ix, &ix->d_oob, 1)) return -1;
     SB_CUDA_CHECK(cudaMemset(ix->d_oob, 0, 8));
   }
-  // query-side layout + L2 residency policy (experiment knobs: SAPLING_B200_NARROW=0, SAPLING_B200_HINTS=<bits>)
-  const char* e_narrow = getenv("SAPLING_B200_NARROW");
-  const char* e_hints = getenv("SAPLING_B200_HINTS");
-  // measured (gpurun r2d / r2e): with the batch partitioned the suffix-array slice is what L2 should hold -- evict_last on
-  // it makes the c3 kernel time stable at 10.0-10.1 ms per 250 M queries where the other policies flip between 10 and 16
-  ix->hints = e_hints ? (unsigned)atoi(e_hints) : (HINT_GENOME_KEEP | HINT_MODEL_KEEP | HINT_SA_KEEP | HINT_IO_STREAM);
-  if (const char* e_persist = getenv("SAPLING_B200_L2_PERSIST_MB")) {
-    // optional: widen the L2 set-aside that evict_last ("persisting") lines may occupy
-    cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)atoi(e_persist) << 20);
-    cudaGetLastError();
-  }
-  if (const char* e_fetch = getenv("SAPLING_B200_L2_FETCH")) {
-    // optional: DRAM -> L2 fetch granularity hint (32/64/128 bytes)
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e_fetch));
-    cudaGetLastError();
-  }
+  // measured (gpurun r2d / r2e): with the batch partitioned the rank-line slice is what L2 should hold -- evict_last on it
+  // makes the c3 kernel time stable where the other policies flip between two regimes
+  ix->hints = ix->tune.hints >= 0 ? (unsigned)ix->tune.hints
+                                  : (HINT_GENOME_KEEP | HINT_MODEL_KEEP | HINT_SA_KEEP | HINT_IO_STREAM);
   const uint64_t B = 1ull << ix->nb;
   ModelEntry last;
   SB_CUDA_CHECK(cudaMemcpy(&last, ix->d_model + B, sizeof(last), cudaMemcpyDeviceToHost));
   ix->last_x = last.x;
   ix->last_y = last.y;
-  if (!ix->d_narrow && !(e_narrow && atoi(e_narrow) == 0)) {
-    const int shift = 2 * ix->k - ix->nb;
-    if (shift >= 0 && shift <= 31) {
-      if (dev_alloc(ix, &ix->d_narrow, B)) return -1;
-      int ok = 0;
-      if (build_narrow_model(ix->d_model, ix->nb, shift, ix->d_narrow, &ok, 0)) return -1;
-      if (!ok) {
-        cudaFree(ix->d_narrow);
-        ix->d_narrow = nullptr;
-        ix->device_bytes -= B * sizeof(uint2);
-      }
-    }
+  const int shift = 2 * ix->k - ix->nb;
+  if (!ix->d_narrow && ix->tune.narrow && shift >= 0 && shift <= 31) {
+    if (dev_alloc(ix, &ix->d_narrow, B)) return -1;
+    int ok = 0;
+    if (build_narrow_model(ix->d_model, ix->nb, shift, ix->d_narrow, &ok, 0)) return -1;
+    if (!ok) dev_free(ix, &ix->d_narrow, B);
   }
+  // the narrow table reconstructs xlist / ylist exactly (model.cu widen_model): the 16-byte-per-bucket table goes
+  if (ix->d_narrow) dev_free(ix, &ix->d_model, B + 1);
   return 0;
 }
 
-// Inline-prefix suffix array: trades 16 bytes of HBM per base for one DRAM line per probe instead of two.  It pays
-// once the packed genome no longer lives in L2 (measured: c3, 3.1 Gbp); below that the plain layout is as fast and
-// four times smaller.  SAPLING_B200_INLINE / _NO_INLINE (flags) or SAPLING_B200_INLINE=0|1 (environment) override.
-// Rank lines (common.cuh IndexView): 16 bytes of HBM per base (8 with SAPLING_B200_PACKED_SHIFT=4) so that one
-// 128-byte DRAM line answers a whole query.  Pays as soon as the index no longer lives in L2.
-// SAPLING_B200_PACKED / _NO_PACKED (flags) or SAPLING_B200_PACKED=0|1 (environment) override the default.
-constexpr uint64_t kPackedMinGenome = 50000000ull;
-int packed_shift_setting() {
-  const char* e = getenv("SAPLING_B200_PACKED_SHIFT");
-  // measured (gpurun r2c / r2e, tools/part_sweep.py): tiling lines (shift 4) answer a partitioned batch faster than the
-  // overlapping ones at half the memory (c3: 10.1 against 12.9 ms per 250 M queries); shift 3 stays selectable
-  return (e && atoi(e) == 3) ? 3 : 4;
-}
-bool want_packed(const sapling_b200_index* ix) {
-  if (ix->flags & SAPLING_B200_NO_PACKED) return false;
-  if (const char* e = getenv("SAPLING_B200_PACKED")) return atoi(e) != 0;
-  if (ix->flags & SAPLING_B200_PACKED) return true;
-  if (ix->flags & SAPLING_B200_INLINE) return false;  // the caller asked for the other layout
-  if (ix->n < kPackedMinGenome) return false;
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
-  // the lines are allocated after the suffix-array builder has released its transients (~34 bytes per base); the
-  // model builder then needs ~14 more next to them
-  return (double)free_b > (14.0 + 9.0 + (packed_shift_setting() == 3 ? 16.0 : 8.0)) * (double)ix->n + 2e9 &&
-         (double)free_b > 40.0 * (double)ix->n + 2e9;
-}
-
-int build_packed(sapling_b200_index* ix) {
-  if (ix->d_packed || !want_packed(ix)) return 0;
-  ix->packed_shift = packed_shift_setting();
-  ix->packed_bases = packed_bases_for(ix->n);
-  if (const char* e = getenv("SAPLING_B200_PACKED_BASES")) {  // test knob: force escapes / the long-query fallback
-    const int b = atoi(e);
-    if (b >= 4 && b <= 32) ix->packed_bases = b;
-  }
-  if (dev_alloc(ix, &ix->d_packed, packed_sectors(ix->n, ix->packed_shift) * 8)) return -1;
-  return build_rank_lines(ix->d_genome, ix->n, ix->d_sa, ix->packed_bases, ix->packed_shift, ix->d_packed, 0);
-}
-
-bool want_ext(const sapling_b200_index* ix) {
-  if (ix->flags & SAPLING_B200_NO_INLINE) return false;
-  if (const char* e = getenv("SAPLING_B200_INLINE")) return atoi(e) != 0;
-  if (ix->flags & SAPLING_B200_INLINE) return true;
-  if (want_packed(ix)) return false;  // the rank lines supersede it
-  if (ix->n < 400000000ull) return false;
-  size_t free_b = 0, total_b = 0;
-  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return false; }
-  // the entries themselves + the transient peak of the GPU suffix-array and model builders (~34 bytes per base)
-  return (double)free_b > 50.0 * (double)ix->n + 2e9;
-}
-
-// builds whatever is missing: SA (+ISA), kflags, model.  model_given: d_model & stats already set.
+// builds whatever is missing: SA (+ISA), rank lines, kflags, model.  model_given: d_model & stats already set.
 int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, const Say& say) {
   const uint64_t n = ix->n;
   const bool keep = (ix->flags & SAPLING_B200_KEEP_BUILD) != 0;
   if (!ix->d_sa) {
     say("Building suffix array\n");
-    if (alloc_sa(ix, n) || dev_alloc(ix, &ix->d_isa, n)) return -1;
-    if (want_ext(ix)) {
-      if (dev_alloc(ix, &ix->d_ext, n)) return -1;
-      ix->ext_bases = kExtBasesFromSort;
-    }
-    if (build_suffix_array(ix->d_genome, n, ix->d_sa, ix->d_isa, 0, &ix->sa_rounds, ix->d_ext)) return -1;
+    if (dev_alloc(ix, &ix->d_sa, n) || dev_alloc(ix, &ix->d_isa, n)) return -1;
+    if (build_suffix_array(ix->d_genome, n, ix->d_sa, ix->d_isa, 0, &ix->sa_rounds)) return -1;
     say("Built suffix array of size %llu\n", (unsigned long long)n);
-  } else if (!ix->d_ext && want_ext(ix)) {
-    if (dev_alloc(ix, &ix->d_ext, n)) return -1;
-    ix->ext_bases = 32;
-    if (build_ext_by_gather(ix->d_genome, n, ix->d_sa, ix->d_ext, 0)) return -1;
   }
-  if (build_packed(ix)) return -1;
+  ix->line_bases = line_bases_for(n);
+  if (ix->tune.line_bases >= 4 && ix->tune.line_bases <= kLineMaxBases) ix->line_bases = ix->tune.line_bases;
+  if (dev_alloc(ix, &ix->d_lines, line_sectors(n) * 8)) return -1;
+  if (build_rank_lines(ix->d_genome, n, ix->d_sa, ix->line_bases, ix->d_lines, 0)) return -1;
   const bool need_build_arrays = !model_given || keep;
   if (need_build_arrays) {
     if (!ix->d_isa) {
@@ -572,12 +599,19 @@ int build_missing(sapling_b200_index* ix, bool model_given, const char* err_fn, 
       }
     }
   }
-  if (!keep) {
-    if (ix->d_isa) { cudaFree(ix->d_isa); ix->d_isa = nullptr; ix->device_bytes -= n * 4; }
-    if (ix->d_kflag) { cudaFree(ix->d_kflag); ix->d_kflag = nullptr; ix->device_bytes -= n; }
-  }
   SB_CUDA_CHECK(cudaDeviceSynchronize());
-  return finish_model_checks(ix);
+  return finish_model(ix);
+}
+
+// what stays resident after construction: the rank lines replace the plain suffix array; the inverse suffix array and
+// the lcp >= k flags stay only with KEEP_BUILD (count_hits / sa_rank / seed_batch)
+void drop_build_arrays(sapling_b200_index* ix) {
+  const bool keep = (ix->flags & SAPLING_B200_KEEP_BUILD) != 0;
+  if (!keep) {
+    dev_free(ix, &ix->d_sa, ix->n);
+    dev_free(ix, &ix->d_isa, ix->n);
+    dev_free(ix, &ix->d_kflag, ix->n);
+  }
 }
 
 int ensure_staging(sapling_b200_index* ix) {
@@ -588,6 +622,7 @@ int ensure_staging(sapling_b200_index* ix) {
     SB_CUDA_CHECK(cudaEventCreateWithFlags(&ix->ev_k[i], cudaEventDisableTiming));
     SB_CUDA_CHECK(cudaEventCreateWithFlags(&ix->ev_down[i], cudaEventDisableTiming));
     SB_CUDA_CHECK(cudaMalloc(&ix->d_in[i], sapling_b200_index::kChunk * 8));
+    SB_CUDA_CHECK(cudaMalloc(&ix->d_raw[i], sapling_b200_index::kChunk * 8));
     SB_CUDA_CHECK(cudaMalloc(&ix->d_out[i], sapling_b200_index::kChunk * 8));
   }
   return 0;
@@ -608,13 +643,30 @@ bool is_pinned(const void* p) {
   return a.type == cudaMemoryTypeHost;
 }
 
+// 2-bit pack of a query string the way the kernels read it (32 bases per word, base 0 in the top two bits).  Returns
+// false when the string holds a byte other than A/C/G/T: the reference compares raw bytes (getLcp :118, :143), a 2-bit
+// code cannot reproduce that ordering, so such queries are rejected rather than answered differently.
+bool pack_query_string(const char* q, size_t slen, uint64_t* w) {
+  bool ok = true;
+  for (size_t j = 0; j < slen; j++) {
+    const char c = q[j];
+    uint64_t v = 0;
+    if (c == 'C') v = 1;
+    else if (c == 'G') v = 2;
+    else if (c == 'T') v = 3;
+    else if (c != 'A') ok = false;
+    w[j >> 5] |= v << (62 - 2 * (j & 31));
+  }
+  return ok;
+}
+
 }  // namespace
 
 // =============================================================================================
 extern "C" {
 
 const char* sapling_b200_last_error(void) { return last_error(); }
-const char* sapling_b200_version(void) { return "sapling_b200 0.1 (sm_100a)"; }
+const char* sapling_b200_version(void) { return "sapling_b200 0.2 (sm_100a)"; }
 
 int64_t sapling_b200_kmerize(int k, const char* s) {
   // sapling_api.h:73-78 with vals[] of :494-498 (non-ACGT bytes hash as 0)
@@ -641,6 +693,7 @@ static sapling_b200_index* new_index(unsigned flags, int nb, int maxMem, int k) 
   sapling_b200_index* ix = new sapling_b200_index();
   ix->device = dev;
   ix->flags = flags;
+  ix->tune = Tuning::from_env();
   ix->nb = nb;                          // sapling_api.h:500
   if (k != -1) ix->k = k;               // :503-506
   if (maxMem != -1) ix->maxMem = maxMem;  // :507-510
@@ -685,8 +738,6 @@ sapling_b200_index* sapling_b200_open(const char* ref_fn, const char* sa_fn, con
 
   const bool have_sa = file_exists(sa_fn);
   const bool have_sap = file_exists(sap_fn);
-  const unsigned user_flags = ix->flags;
-  if (!have_sa) ix->flags |= SAPLING_B200_KEEP_BUILD;  // ISA needed to write the .sa file
   if (have_sa) {
     say("Reading suffix array from file\n");
     if (read_sa_file(ix, sa_fn)) return fail();
@@ -709,20 +760,16 @@ sapling_b200_index* sapling_b200_open(const char* ref_fn, const char* sa_fn, con
     say("Writing Sapling to file\n");
     if (sapling_b200_write_sap(ix, sap_fn)) return fail();
   }
-  if (!(user_flags & SAPLING_B200_KEEP_BUILD)) {
-    ix->flags = user_flags;
-    if (ix->d_isa) { cudaFree(ix->d_isa); ix->d_isa = nullptr; ix->device_bytes -= ix->n * 4; }
-    if (ix->d_kflag) { cudaFree(ix->d_kflag); ix->d_kflag = nullptr; ix->device_bytes -= ix->n; }
-  }
   if (use_cache && sapling_b200_save_cache(ix, cache_fn.c_str())) say("%s\n", last_error());  // not fatal
+  drop_build_arrays(ix);
   return ix;
 }
 
 // ---- private index cache ---------------------------------------------------------------------------------
 // The reference's files are what they are -- a .sa file is 16 bytes per base (50 GB at 3.1 Gbp) and has to be inverted,
-// the FASTA has to be cleaned and packed.  The cache holds the three arrays the device needs in the form it needs them
+// the FASTA has to be cleaned and packed.  The cache holds the arrays the device needs in the form it needs them
 // (2-bit genome, 32-bit suffix array, {x, y} model: 5.6 bytes per base at c3 instead of 17 + FASTA) plus the scalars, so
-// a later open is three sequential reads.  Native endianness, like the reference's own files.
+// a later open is three sequential reads through pinned double buffers.  Native endianness, like the reference's files.
 namespace {
 constexpr char kCacheMagic[8] = {'S', 'B', '2', '0', '0', 'I', 'D', 'X'};
 constexpr uint32_t kCacheVersion = 1;
@@ -733,31 +780,83 @@ struct CacheHeader {
   uint32_t n_chr;
   uint64_t n, perfect, n_over, n_under, genome_words, model_entries;
 };
+constexpr size_t kIoPiece = (size_t)64 << 20;
 int write_dev(FILE* f, const void* d, size_t bytes) {
-  std::vector<char> buf(std::min<size_t>(bytes, (size_t)64 << 20));
-  for (size_t o = 0; o < bytes; o += buf.size()) {
-    const size_t m = std::min(buf.size(), bytes - o);
-    SB_CUDA_CHECK(cudaMemcpy(buf.data(), static_cast<const char*>(d) + o, m, cudaMemcpyDeviceToHost));
-    if (fwrite(buf.data(), 1, m, f) != m) { set_error("index cache: short write"); return -1; }
+  PinnedPair pp;
+  if (pp.init(std::min(bytes ? bytes : 1, kIoPiece))) return -1;
+  // download of piece i+1 overlaps the fwrite of piece i
+  size_t o = 0;
+  int slot = 0;
+  size_t m = std::min(pp.bytes, bytes);
+  if (m) {
+    SB_CUDA_CHECK(cudaMemcpyAsync(pp.h[0], d, m, cudaMemcpyDeviceToHost, 0));
+    cudaEventRecord(pp.ev[0], 0);
+  }
+  while (o < bytes) {
+    const size_t next_o = o + m;
+    const size_t next_m = next_o < bytes ? std::min(pp.bytes, bytes - next_o) : 0;
+    if (next_m) {
+      SB_CUDA_CHECK(cudaMemcpyAsync(pp.h[slot ^ 1], static_cast<const char*>(d) + next_o, next_m, cudaMemcpyDeviceToHost, 0));
+      cudaEventRecord(pp.ev[slot ^ 1], 0);
+    }
+    SB_CUDA_CHECK(cudaEventSynchronize(pp.ev[slot]));
+    if (fwrite(pp.h[slot], 1, m, f) != m) { set_error("index cache: short write"); return -1; }
+    o = next_o;
+    m = next_m;
+    slot ^= 1;
   }
   return 0;
 }
 int read_dev(FILE* f, void* d, size_t bytes) {
-  std::vector<char> buf(std::min<size_t>(bytes, (size_t)64 << 20));
-  for (size_t o = 0; o < bytes; o += buf.size()) {
-    const size_t m = std::min(buf.size(), bytes - o);
-    if (fread(buf.data(), 1, m, f) != m) { set_error("index cache: file is truncated"); return -1; }
-    SB_CUDA_CHECK(cudaMemcpy(static_cast<char*>(d) + o, buf.data(), m, cudaMemcpyHostToDevice));
+  PinnedPair pp;
+  if (pp.init(std::min(bytes ? bytes : 1, kIoPiece))) return -1;
+  int slot = 0;
+  for (size_t o = 0; o < bytes; o += pp.bytes, slot ^= 1) {
+    const size_t m = std::min(pp.bytes, bytes - o);
+    cudaEventSynchronize(pp.ev[slot]);  // the upload that last used this buffer
+    if (fread(pp.h[slot], 1, m, f) != m) { set_error("index cache: file is truncated"); return -1; }
+    SB_CUDA_CHECK(cudaMemcpyAsync(static_cast<char*>(d) + o, pp.h[slot], m, cudaMemcpyHostToDevice, 0));
+    cudaEventRecord(pp.ev[slot], 0);
   }
+  SB_CUDA_CHECK(cudaDeviceSynchronize());
   return 0;
+}
+// xlist / ylist as the wide table, from whichever form is resident, into a scratch device array
+int wide_model_scratch(const sapling_b200_index* ix, ModelEntry** out) {
+  const uint64_t count = (1ull << ix->nb) + 1;
+  SB_CUDA_CHECK(cudaMalloc(out, count * sizeof(ModelEntry)));
+  if (ix->d_model) {
+    SB_CUDA_CHECK(cudaMemcpy(*out, ix->d_model, count * sizeof(ModelEntry), cudaMemcpyDeviceToDevice));
+    return 0;
+  }
+  // widen into two int64 arrays, then interleave on the host side of nothing: do it in pieces through x / y scratch
+  long long *dx = nullptr, *dy = nullptr;
+  const uint64_t P = 1ull << 24;
+  SB_CUDA_CHECK(cudaMalloc(&dx, std::min(P, count) * 8));
+  if (cudaMalloc(&dy, std::min(P, count) * 8) != cudaSuccess) { cudaFree(dx); set_error("model scratch allocation failed"); return -1; }
+  int rc = 0;
+  for (uint64_t o = 0; o < count && !rc; o += P) {
+    const uint64_t c = std::min(P, count - o);
+    rc = widen_model(ix->d_narrow, ix->nb, 2 * ix->k - ix->nb, ix->last_x, ix->last_y, o, c, dx, dy, 0);
+    if (!rc && cudaMemcpy2D(reinterpret_cast<char*>(*out + o), 16, dx, 8, 8, c, cudaMemcpyDeviceToDevice) != cudaSuccess) rc = -1;
+    if (!rc && cudaMemcpy2D(reinterpret_cast<char*>(*out + o) + 8, 16, dy, 8, 8, c, cudaMemcpyDeviceToDevice) != cudaSuccess) rc = -1;
+  }
+  cudaFree(dx);
+  cudaFree(dy);
+  if (rc) { cudaFree(*out); *out = nullptr; set_error("model reconstruction failed"); }
+  return rc;
 }
 }  // namespace
 
 int sapling_b200_save_cache(const sapling_b200_index* ix, const char* path) {
   if (!ix || !path || !path[0]) { set_error("save_cache: null index or empty path"); return -1; }
   cudaSetDevice(ix->device);
+  SaGuard sg;
+  if (sg.get(ix)) return -1;
+  ModelEntry* d_wide = nullptr;
+  if (wide_model_scratch(ix, &d_wide)) return -1;
   FILE* f = fopen(path, "wb");
-  if (!f) { set_error("cannot write index cache %s", path); return -1; }
+  if (!f) { cudaFree(d_wide); set_error("cannot write index cache %s", path); return -1; }
   CacheHeader h{};
   memcpy(h.magic, kCacheMagic, 8);
   h.version = kCacheVersion;
@@ -775,10 +874,11 @@ int sapling_b200_save_cache(const sapling_b200_index* ix, const char* path) {
   }
   if (rc) set_error("index cache: short write");
   if (!rc) rc = write_dev(f, ix->d_genome, h.genome_words * 8);
-  if (!rc) rc = write_dev(f, ix->d_sa, ix->n * 4);
-  if (!rc) rc = write_dev(f, ix->d_model, h.model_entries * sizeof(ModelEntry));
+  if (!rc) rc = write_dev(f, sg.sa, ix->n * 4);
+  if (!rc) rc = write_dev(f, d_wide, h.model_entries * sizeof(ModelEntry));
   if (!rc && fwrite(kCacheMagic, 8, 1, f) != 1) { set_error("index cache: short write"); rc = -1; }
   if (fclose(f) != 0 && !rc) { set_error("index cache: close failed"); rc = -1; }
+  cudaFree(d_wide);
   if (rc) remove(path);
   return rc;
 }
@@ -815,7 +915,7 @@ sapling_b200_index* sapling_b200_open_cache(const char* path, unsigned flags) {
   }
   say("Reading index cache\n");
   if (dev_alloc(ix, &ix->d_genome, h.genome_words) || read_dev(f, ix->d_genome, h.genome_words * 8)) return fail();
-  if (alloc_sa(ix, h.n) || read_dev(f, ix->d_sa, h.n * 4)) return fail();
+  if (dev_alloc(ix, &ix->d_sa, h.n) || read_dev(f, ix->d_sa, h.n * 4)) return fail();
   if (dev_alloc(ix, &ix->d_model, h.model_entries) || read_dev(f, ix->d_model, h.model_entries * sizeof(ModelEntry))) return fail();
   char tail[8];
   if (fread(tail, 8, 1, f) != 1 || memcmp(tail, kCacheMagic, 8) != 0) { set_error("index cache %s: file is truncated", path); return fail(); }
@@ -829,6 +929,7 @@ sapling_b200_index* sapling_b200_open_cache(const char* path, unsigned flags) {
     if (rc) { set_error("index cache: genome download failed"); return fail(); }
   }
   if (build_missing(ix, true, nullptr, say)) return fail();
+  drop_build_arrays(ix);
   fclose(f);
   return ix;
 }
@@ -845,7 +946,7 @@ static sapling_b200_index* create_common(const char* genome, uint64_t n, const u
   if (validate_params(ix)) return fail();
   if (upload_genome(ix, genome, n)) return fail();
   if (sa) {
-    if (alloc_sa(ix, n)) return fail();
+    if (dev_alloc(ix, &ix->d_sa, n)) return fail();
     if (cudaMemcpy(ix->d_sa, sa, n * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
       set_error("suffix array upload failed");
       return fail();
@@ -860,6 +961,7 @@ static sapling_b200_index* create_common(const char* genome, uint64_t n, const u
     model_given = true;
   }
   if (build_missing(ix, model_given, nullptr, say)) return fail();
+  drop_build_arrays(ix);
   return ix;
 }
 
@@ -895,8 +997,76 @@ sapling_b200_index* sapling_b200_create_synthetic(uint64_t seed, uint64_t n, int
   }
   ix->chr_ends.push_back({n, "chr1"});
   if (build_missing(ix, false, nullptr, say)) return fail();
+  drop_build_arrays(ix);
   return ix;
 }
+
+// ---- replicas on other GPUs ---------------------------------------------------------------------------------
+// The index is ingested / built ONCE, on the handle's own GPU; every other GPU named in gpu_mask then receives a copy of the
+// resident arrays by cudaMemcpyPeer (NVLink / NVSwitch when the GPUs are peers, through the host otherwise).  There is no
+// collective on the query path: the host-pointer batch calls cut a batch into contiguous slices, one per GPU.
+int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (ix->is_replica) { set_error("replicate: handle is itself a replica"); return -1; }
+  int ndev = 0;
+  SB_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  std::lock_guard<std::mutex> lock(ix->mu);
+  const uint64_t B = 1ull << ix->nb;
+  for (int dev = 0; dev < ndev && dev < 64; dev++) {
+    if (!((gpu_mask >> dev) & 1ull) || dev == ix->device) continue;
+    bool have = false;
+    for (auto* r : ix->replicas) have |= r->device == dev;
+    if (have) continue;
+    if (check_device(dev)) return -1;
+    sapling_b200_index* r = new sapling_b200_index();
+    r->device = dev;
+    r->is_replica = true;
+    r->flags = ix->flags;
+    r->tune = ix->tune;
+    r->n = ix->n; r->k = ix->k; r->nb = ix->nb; r->maxMem = ix->maxMem;
+    r->stats = ix->stats;
+    r->line_bases = ix->line_bases;
+    r->last_x = ix->last_x; r->last_y = ix->last_y;
+    r->hints = ix->hints;
+    auto fail = [&](const char* what) {
+      set_error("replicate to device %d: %s: %s", dev, what, cudaGetErrorString(cudaGetLastError()));
+      delete r;
+      cudaSetDevice(ix->device);
+      return -1;
+    };
+    if (cudaSetDevice(dev) != cudaSuccess) return fail("cudaSetDevice");
+    int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, dev, ix->device) == cudaSuccess && can) {
+      cudaDeviceEnablePeerAccess(ix->device, 0);  // direct NVLink copies; already-enabled is fine
+      cudaGetLastError();
+    }
+    auto copy = [&](auto** dst, const auto* src, uint64_t count) -> bool {
+      if (!src) return true;
+      if (dev_alloc(r, dst, count)) return false;
+      return cudaMemcpyPeer(*dst, dev, src, ix->device, count * sizeof(**dst)) == cudaSuccess;
+    };
+    if (!copy(&r->d_genome, ix->d_genome, packed_words(ix->n))) return fail("genome");
+    if (!copy(&r->d_lines, ix->d_lines, line_sectors(ix->n) * 8)) return fail("rank lines");
+    if (!copy(&r->d_narrow, ix->d_narrow, B)) return fail("model");
+    if (!copy(&r->d_model, ix->d_model, B + 1)) return fail("wide model");
+    if (!copy(&r->d_isa, ix->d_isa, ix->n)) return fail("inverse suffix array");
+    if (!copy(&r->d_kflag, ix->d_kflag, ix->n)) return fail("k flags");
+    if (dev_alloc(r, &r->d_oob, 1) || cudaMemset(r->d_oob, 0, 8) != cudaSuccess) return fail("counter");
+    if (cudaDeviceSynchronize() != cudaSuccess) return fail("synchronize");
+    ix->replicas.push_back(r);
+  }
+  cudaSetDevice(ix->device);
+  return 0;
+}
+
+sapling_b200_index* sapling_b200_open_multi(const char* ref_fn, const char* sa_fn, const char* sap_fn, int nb, int maxMem,
+                                            int k, const char* err_fn, unsigned flags, uint64_t gpu_mask) {
+  sapling_b200_index* ix = sapling_b200_open(ref_fn, sa_fn, sap_fn, nb, maxMem, k, err_fn, flags);
+  if (ix && sapling_b200_replicate(ix, gpu_mask)) { delete ix; return nullptr; }
+  return ix;
+}
+
+int sapling_b200_num_devices(const sapling_b200_index* ix) { return ix ? 1 + (int)ix->replicas.size() : 0; }
 
 void sapling_b200_close(sapling_b200_index* ix) { delete ix; }
 
@@ -935,21 +1105,53 @@ int sapling_b200_build_stats(const sapling_b200_index* ix, uint64_t* perfect, ui
 int sapling_b200_model(const sapling_b200_index* ix, int64_t* xlist, int64_t* ylist) {
   if (!ix) { set_error("null index"); return -1; }
   const uint64_t count = (1ull << ix->nb) + 1;
-  std::vector<ModelEntry> m(count);
   cudaSetDevice(ix->device);
-  SB_CUDA_CHECK(cudaMemcpy(m.data(), ix->d_model, count * sizeof(ModelEntry), cudaMemcpyDeviceToHost));
-  for (uint64_t i = 0; i < count; i++) {
-    if (xlist) xlist[i] = m[i].x;
-    if (ylist) ylist[i] = m[i].y;
+  if (ix->d_model) {
+    std::vector<ModelEntry> m(count);
+    SB_CUDA_CHECK(cudaMemcpy(m.data(), ix->d_model, count * sizeof(ModelEntry), cudaMemcpyDeviceToHost));
+    for (uint64_t i = 0; i < count; i++) {
+      if (xlist) xlist[i] = m[i].x;
+      if (ylist) ylist[i] = m[i].y;
+    }
+    return 0;
   }
-  return 0;
+  // rebuilt from the narrow table, piece by piece
+  const uint64_t P = std::min<uint64_t>(count, 1ull << 24);
+  long long *dx = nullptr, *dy = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&dx, P * 8));
+  if (cudaMalloc(&dy, P * 8) != cudaSuccess) { cudaFree(dx); set_error("model: scratch allocation failed"); return -1; }
+  int rc = 0;
+  for (uint64_t o = 0; o < count && !rc; o += P) {
+    const uint64_t c = std::min(P, count - o);
+    rc = widen_model(ix->d_narrow, ix->nb, 2 * ix->k - ix->nb, ix->last_x, ix->last_y, o, c, dx, dy, 0);
+    if (!rc && xlist && cudaMemcpy(xlist + o, dx, c * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+    if (!rc && ylist && cudaMemcpy(ylist + o, dy, c * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = -1;
+  }
+  cudaFree(dx);
+  cudaFree(dy);
+  if (rc) set_error("model: reconstruction from the narrow table failed");
+  return rc;
 }
 
 int sapling_b200_rev(const sapling_b200_index* ix, uint64_t first, uint64_t count, uint32_t* out) {
   if (!ix || first + count > ix->n) { set_error("rev: range out of bounds"); return -1; }
+  if (count == 0) return 0;
   cudaSetDevice(ix->device);
-  SB_CUDA_CHECK(cudaMemcpy(out, ix->d_sa + first, count * 4, cudaMemcpyDeviceToHost));
-  return 0;
+  if (ix->d_sa) {
+    SB_CUDA_CHECK(cudaMemcpy(out, ix->d_sa + first, count * 4, cudaMemcpyDeviceToHost));
+    return 0;
+  }
+  const uint64_t P = std::min<uint64_t>(count, 1ull << 26);
+  uint32_t* d = nullptr;
+  SB_CUDA_CHECK(cudaMalloc(&d, P * 4));
+  int rc = 0;
+  for (uint64_t o = 0; o < count && !rc; o += P) {
+    const uint64_t c = std::min(P, count - o);
+    rc = launch_rev_extract(ix->view(), first + o, c, d, 0);
+    if (!rc && cudaMemcpy(out + o, d, c * 4, cudaMemcpyDeviceToHost) != cudaSuccess) { set_error("rev: download failed"); rc = -1; }
+  }
+  cudaFree(d);
+  return rc;
 }
 
 int sapling_b200_sa_rank(const sapling_b200_index* ix, uint64_t first, uint64_t count, uint32_t* out) {
@@ -990,46 +1192,37 @@ int sapling_b200_check_sa(const sapling_b200_index* ix, uint32_t max_chars, uint
                           uint64_t* bad_perm) {
   if (!ix) { set_error("null index"); return -1; }
   cudaSetDevice(ix->device);
-  return check_suffix_array(ix->d_genome, ix->n, ix->d_sa, ix->d_isa, max_chars, bad_order, undecided, bad_perm, 0);
+  SaGuard sg;
+  if (sg.get(ix)) return -1;
+  return check_suffix_array(ix->d_genome, ix->n, sg.sa, ix->d_isa, max_chars, bad_order, undecided, bad_perm, 0);
 }
 
 uint64_t sapling_b200_device_bytes(const sapling_b200_index* ix) { return ix ? ix->device_bytes : 0; }
 
 uint64_t sapling_b200_launch_count(const sapling_b200_index* ix) {
-  return ix ? ix->launches.load(std::memory_order_relaxed) : 0;
-}
-
-const char* sapling_b200_query_kernel(const sapling_b200_index* ix, int* blocks_per_sm) {
-  if (!ix) return "";
-  const char* name = "";
-  const int qv = launch_kmer_query(ix->view(), nullptr, 0, nullptr, nullptr, &name);
-  if (blocks_per_sm) *blocks_per_sm = qv;
-  return name;
+  if (!ix) return 0;
+  uint64_t v = ix->launches.load(std::memory_order_relaxed);
+  for (auto* r : ix->replicas) v += r->launches.load(std::memory_order_relaxed);
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------
 
 // How many top k-mer bits to partition a batch of nq queries by; 0 = answer it in the caller's order.
-// The slice of the index one bin maps to (suffix array or rank lines + model, both monotone in the k-mer) should fit
-// the part of L2 that data shared by all SMs gets (~48 MB, profiles/r1_experiments.md section 1) with room for the
-// genome and the streams; each bin should still receive enough queries to amortise its line fills.
-// SAPLING_B200_PART=0 disables, SAPLING_B200_PART_BITS forces a bin count, SAPLING_B200_PART_MIN sets the smallest batch.
+// The slice of the index one bin maps to (rank lines + model, both monotone in the k-mer) should fit the part of L2 that
+// data shared by all SMs gets (~48 MB, profiles/r1_experiments.md section 1) with room for the genome and the streams;
+// each bin should still receive enough queries to amortise its line fills.
 static int partition_bits(const sapling_b200_index* ix, size_t nq) {
-  if (const char* e = getenv("SAPLING_B200_PART")) {
-    if (atoi(e) == 0) return 0;
-  }
-  size_t min_nq = (size_t)1 << 22;
-  if (const char* e = getenv("SAPLING_B200_PART_MIN")) min_nq = (size_t)atoll(e);
-  if (nq < min_nq || nq >= (1ull << 32)) return 0;
+  const Tuning& t = ix->tune;
+  if (!t.partition || !ix->d_narrow) return 0;
+  if (nq < t.partition_min || nq >= (1ull << 32)) return 0;
   const int kbits = 2 * ix->k;
   int bits;
-  if (const char* e = getenv("SAPLING_B200_PART_BITS")) {
-    bits = atoi(e);
+  if (t.partition_bits >= 0) {
+    bits = t.partition_bits;
   } else {
-    const double sa_bytes = ix->d_packed ? (double)packed_sectors(ix->n, ix->packed_shift) * 32.0
-                            : ix->d_ext  ? 16.0 * (double)ix->n
-                                         : 4.0 * (double)ix->n;
-    const double model_bytes = (ix->d_narrow ? 8.0 : 16.0) * (double)(1ull << ix->nb);
+    const double sa_bytes = (double)line_sectors(ix->n) * 32.0;
+    const double model_bytes = 8.0 * (double)(1ull << ix->nb);
     const double slice = 32e6;  // measured (gpurun r2f): c3 10 bits (26 MB slices) 15.0 ms per step, 11 bits 15.9, 9 bits bistable
     bits = 1;
     while (bits < kPartMaxBits && (sa_bytes + model_bytes) / (double)(1ull << bits) > slice) bits++;
@@ -1041,26 +1234,29 @@ static int partition_bits(const sapling_b200_index* ix, size_t nq) {
   return bits < 1 ? 0 : bits;
 }
 
-// One batch of k-mers already on the device -> answers, enqueued on st.
+// One batch of k-mers already on the device -> answers (long long, or uint32_t when d_out32 != nullptr), enqueued on st.
 static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint64_t* d_kmers, size_t nq, long long* d_out,
-                          cudaStream_t st) {
+                          uint32_t* d_out32, cudaStream_t st) {
   if (nq == 0) return 0;
   const int bits = partition_bits(ix, nq);
+  cudaEvent_t evs[5];
   cudaEvent_t* ev = nullptr;
   {
     std::lock_guard<std::mutex> lock(ix->mu_prof);
     if (ix->profiling) {
       sapling_b200_index::ProfCall c;
-      for (int i = 0; i < 5; i++) SB_CUDA_CHECK(cudaEventCreate(&c.ev[i]));
+      for (int i = 0; i < 5; i++) {
+        if (cudaEventCreate(&c.ev[i]) != cudaSuccess) {
+          for (int j = 0; j < i; j++) cudaEventDestroy(c.ev[j]);
+          set_error("cudaEventCreate failed: %s", cudaGetErrorString(cudaGetLastError()));
+          return -1;
+        }
+        evs[i] = c.ev[i];  // copied while the list is locked
+      }
       c.partitioned = bits != 0;
       ix->prof_calls.push_back(c);
-      ev = ix->prof_calls.back().ev;  // stays valid: the vector is only touched under mu_prof and read after a sync
+      ev = evs;
     }
-  }
-  cudaEvent_t evs[5];
-  if (ev) {
-    for (int i = 0; i < 5; i++) evs[i] = ev[i];
-    ev = evs;
   }
   auto plain = [&]() -> int {
     ix->launches.fetch_add(1, std::memory_order_relaxed);
@@ -1069,7 +1265,7 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
       cudaEventRecord(ev[1], st);
       cudaEventRecord(ev[2], st);
     }
-    const int rc = launch_kmer_query(v, d_kmers, nq, d_out, st);
+    const int rc = launch_kmer_query(v, d_kmers, nq, d_out, d_out32, ix->tune.occupancy, st);
     if (ev) {
       cudaEventRecord(ev[3], st);
       cudaEventRecord(ev[4], st);
@@ -1098,7 +1294,7 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
   }
   if (!ws) return plain();
   ix->launches.fetch_add(8, std::memory_order_relaxed);  // histogram, three column-scan passes, bin scan, scatter, query, un-permute
-  return launch_partitioned_query(v, d_kmers, nq, d_out, ws, bits, st, ev);
+  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, ix->tune.occupancy, st, ev);
 }
 
 int sapling_b200_profile(sapling_b200_index* ix, int on) {
@@ -1110,6 +1306,7 @@ int sapling_b200_profile(sapling_b200_index* ix, int on) {
 
 int sapling_b200_stage_ms(sapling_b200_index* ix, double ms[4]) {
   if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
   std::lock_guard<std::mutex> lock(ix->mu_prof);
   for (int i = 0; i < 4; i++) ms[i] = 0.0;
   int calls = 0;
@@ -1134,74 +1331,124 @@ int sapling_b200_query_partition_bits(const sapling_b200_index* ix, size_t nq) {
 
 const char* sapling_b200_query_kernel_for(const sapling_b200_index* ix, size_t nq, int* blocks_per_sm) {
   if (!ix) return "";
-  if (partition_bits(ix, nq) == 0) return sapling_b200_query_kernel(ix, blocks_per_sm);
-  const char* te = getenv("SAPLING_B200_PART_TILES");
-  const bool in_order = !(te && atoi(te) == 0);
-  // non-null dummies: "this batch arrives partitioned, with an in-order tile counter" (nothing is launched)
-  static const uint16_t slot_tag = 0;
-  static unsigned long long tile_tag = 0;
-  const char* name = "";
-  const int qv = launch_kmer_query(ix->view(), nullptr, 0, nullptr, nullptr, &name, &slot_tag, in_order ? &tile_tag : nullptr);
-  if (blocks_per_sm) *blocks_per_sm = qv;
-  return name;
+  const bool ordered = partition_bits(ix, nq) != 0;
+  if (blocks_per_sm) *blocks_per_sm = kmer_query_blocks_per_sm(ordered, ix->tune.occupancy);
+  return kmer_query_kernel_name(ordered);
+}
+const char* sapling_b200_query_kernel(const sapling_b200_index* ix, int* blocks_per_sm) {
+  return sapling_b200_query_kernel_for(ix, 1, blocks_per_sm);
 }
 
 int sapling_b200_query_batch_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, int64_t* d_out,
                                  void* stream) {
   if (!ix) { set_error("null index"); return -1; }
-  return run_kmer_batch(ix, ix->view(), d_kmers, nq, reinterpret_cast<long long*>(d_out),
+  cudaSetDevice(ix->device);
+  return run_kmer_batch(ix, ix->view(), d_kmers, nq, reinterpret_cast<long long*>(d_out), nullptr,
                         static_cast<cudaStream_t>(stream));
 }
 
-int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size_t nq, int64_t* out) {
+int sapling_b200_query_batch_u32_dev(sapling_b200_index* ix, const uint64_t* d_kmers, size_t nq, uint32_t* d_out,
+                                     void* stream) {
   if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
+  return run_kmer_batch(ix, ix->view(), d_kmers, nq, nullptr, d_out, static_cast<cudaStream_t>(stream));
+}
+
+// The chunk pipeline of the host-pointer entry points on ONE device.  kmers: nq integers of kmer_bytes (5..8) little-endian
+// bytes each; out: nq answers of out_bytes (8: long long, 4: uint32_t with 0xFFFFFFFF for -1).
+static int host_batch_one(sapling_b200_index* ix, const char* kmers, int kmer_bytes, size_t nq, char* out, int out_bytes) {
   if (nq == 0) return 0;
   std::lock_guard<std::mutex> lock(ix->mu);
-  cudaSetDevice(ix->device);
+  if (cudaSetDevice(ix->device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", ix->device); return -1; }
   if (ensure_staging(ix)) return -1;
   const bool pin_in = is_pinned(kmers), pin_out = is_pinned(out);
   if ((!pin_in || !pin_out) && ensure_pinned(ix)) return -1;
   const IndexView v = ix->view();
   size_t CH = 1u << 18;  // ~sqrt(2 * nq * 1e5) rounded to a power of two, within [256 Ki, 4 Mi]
   while (CH < sapling_b200_index::kChunk && (double)(2 * CH) * (double)(2 * CH) <= 8.0 * (double)nq * 1e5) CH *= 2;
-  if (const char* e = getenv("SAPLING_B200_CHUNK_LOG2")) {  // experiment knob
-    const int l = atoi(e);
-    if (l >= 12 && (1ull << l) <= sapling_b200_index::kChunk) CH = 1ull << l;
-  }
+  if (ix->tune.chunk_log2 >= 12 && (1ull << ix->tune.chunk_log2) <= sapling_b200_index::kChunk) CH = 1ull << ix->tune.chunk_log2;
   const int NS = sapling_b200_index::kSlots;
   const size_t nchunks = (nq + CH - 1) / CH;
   cudaStream_t s_up = ix->streams[0], s_k = ix->streams[1], s_down = ix->streams[2];
+  int rc = 0;
   // chunk c lives in slot c % NS: upload -> kernel -> download, each on its own stream, ordered by events
-  for (size_t c = 0; c < nchunks + (size_t)NS; c++) {
+  for (size_t c = 0; c < nchunks + (size_t)NS && !rc; c++) {
     if (c >= (size_t)NS) {  // retire chunk c-NS: its slot is about to be reused
       const size_t r = c - (size_t)NS;
       const int s = (int)(r % (size_t)NS);
-      SB_CUDA_CHECK(cudaEventSynchronize(ix->ev_down[s]));
+      if (cudaEventSynchronize(ix->ev_down[s]) != cudaSuccess) { rc = -1; break; }
       if (!pin_out) {
         const size_t o = r * CH, m = std::min(CH, nq - o);
-        memcpy(out + o, ix->h_out[s], m * 8);
+        memcpy(out + o * out_bytes, ix->h_out[s], m * out_bytes);
       }
     }
     if (c < nchunks) {
       const int s = (int)(c % (size_t)NS);
       const size_t o = c * CH, m = std::min(CH, nq - o);
-      const uint64_t* src = kmers + o;
+      const char* src = kmers + o * kmer_bytes;
       if (!pin_in) {
-        memcpy(ix->h_in[s], kmers + o, m * 8);
-        src = ix->h_in[s];
+        memcpy(ix->h_in[s], src, m * kmer_bytes);
+        src = static_cast<const char*>(ix->h_in[s]);
       }
-      SB_CUDA_CHECK(cudaMemcpyAsync(ix->d_in[s], src, m * 8, cudaMemcpyHostToDevice, s_up));
-      SB_CUDA_CHECK(cudaEventRecord(ix->ev_up[s], s_up));
-      SB_CUDA_CHECK(cudaStreamWaitEvent(s_k, ix->ev_up[s], 0));
-      if (run_kmer_batch(ix, v, ix->d_in[s], m, ix->d_out[s], s_k)) return -1;
-      SB_CUDA_CHECK(cudaEventRecord(ix->ev_k[s], s_k));
-      SB_CUDA_CHECK(cudaStreamWaitEvent(s_down, ix->ev_k[s], 0));
-      void* dst = pin_out ? (void*)(out + o) : (void*)ix->h_out[s];
-      SB_CUDA_CHECK(cudaMemcpyAsync(dst, ix->d_out[s], m * 8, cudaMemcpyDeviceToHost, s_down));
-      SB_CUDA_CHECK(cudaEventRecord(ix->ev_down[s], s_down));
+      void* d_up = kmer_bytes == 8 ? (void*)ix->d_in[s] : ix->d_raw[s];
+      if (cudaMemcpyAsync(d_up, src, m * kmer_bytes, cudaMemcpyHostToDevice, s_up) != cudaSuccess) { rc = -1; break; }
+      cudaEventRecord(ix->ev_up[s], s_up);
+      cudaStreamWaitEvent(s_k, ix->ev_up[s], 0);
+      if (kmer_bytes != 8 && launch_unpack_kmers(ix->d_raw[s], kmer_bytes, m, ix->d_in[s], s_k)) { rc = -1; break; }
+      if (run_kmer_batch(ix, v, ix->d_in[s], m, out_bytes == 8 ? ix->d_out[s] : nullptr,
+                         out_bytes == 8 ? nullptr : reinterpret_cast<uint32_t*>(ix->d_out[s]), s_k)) { rc = -2; break; }
+      cudaEventRecord(ix->ev_k[s], s_k);
+      cudaStreamWaitEvent(s_down, ix->ev_k[s], 0);
+      void* dst = pin_out ? (void*)(out + o * out_bytes) : ix->h_out[s];
+      if (cudaMemcpyAsync(dst, ix->d_out[s], m * out_bytes, cudaMemcpyDeviceToHost, s_down) != cudaSuccess) { rc = -1; break; }
+      cudaEventRecord(ix->ev_down[s], s_down);
     }
   }
+  if (rc) {
+    // leave nothing in flight behind an error: copies may still be writing into the caller's buffer or the staging slots
+    for (int i = 0; i < 3; i++) cudaStreamSynchronize(ix->streams[i]);
+    if (rc == -1) set_error("query_batch: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
   return 0;  // every chunk was retired (event-synchronised) inside the loop
+}
+
+// Host-pointer batch over the handle's GPU and its replicas: contiguous slices, one host thread per device.
+static int host_batch(sapling_b200_index* ix, const void* kmers, int kmer_bytes, size_t nq, void* out, int out_bytes) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (nq == 0) return 0;
+  const char* in = static_cast<const char*>(kmers);
+  char* o = static_cast<char*>(out);
+  const size_t G = 1 + ix->replicas.size();
+  if (G == 1 || nq < 2 * G * 65536) return host_batch_one(ix, in, kmer_bytes, nq, o, out_bytes);
+  std::vector<int> rcs(G, 0);
+  std::vector<std::string> errs(G);
+  std::vector<std::thread> th;
+  for (size_t g = 0; g < G; g++) {
+    const size_t lo = nq * g / G, hi = nq * (g + 1) / G;
+    sapling_b200_index* dev_ix = g == 0 ? ix : ix->replicas[g - 1];
+    th.emplace_back([=, &rcs, &errs]() {
+      rcs[g] = host_batch_one(dev_ix, in + lo * kmer_bytes, kmer_bytes, hi - lo, o + lo * out_bytes, out_bytes);
+      if (rcs[g]) errs[g] = last_error();  // the error text is thread-local
+    });
+  }
+  for (auto& t : th) t.join();
+  cudaSetDevice(ix->device);
+  for (size_t g = 0; g < G; g++)
+    if (rcs[g]) { set_error("%s", errs[g].c_str()); return -1; }
+  return 0;
+}
+
+int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size_t nq, int64_t* out) {
+  return host_batch(ix, kmers, 8, nq, out, 8);
+}
+
+int sapling_b200_query_batch_u32(sapling_b200_index* ix, const void* kmers, int kmer_bytes, size_t nq, uint32_t* out) {
+  if (ix && (kmer_bytes < 1 || kmer_bytes > 8 || 8 * kmer_bytes < 2 * ix->k)) {
+    set_error("query_batch_u32: kmer_bytes=%d cannot hold a %d-mer (need ceil(2k/8) .. 8)", kmer_bytes, ix->k);
+    return -1;
+  }
+  return host_batch(ix, kmers, kmer_bytes, nq, out, 4);
 }
 
 int sapling_b200_query_str_batch(sapling_b200_index* ix, const char* s, const uint64_t* offsets, const uint32_t* slens,
@@ -1219,12 +1466,10 @@ int sapling_b200_query_str_batch(sapling_b200_index* ix, const char* s, const ui
   }
   std::vector<uint64_t> words(total, 0);
   for (size_t i = 0; i < nq; i++) {
-    const char* q = s + offsets[i];
-    uint64_t* w = words.data() + word_off[i];
-    for (uint32_t j = 0; j < slens[i]; j++) {
-      const char c = q[j];
-      const uint64_t v = c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0;
-      w[j >> 5] |= v << (62 - 2 * (j & 31));
+    if (!pack_query_string(s + offsets[i], slens[i], words.data() + word_off[i])) {
+      set_error("query %zu holds a byte other than A/C/G/T: the reference compares raw bytes there, which the 2-bit index "
+                "cannot reproduce (rejected, not answered differently)", i);
+      return -1;
     }
   }
   uint64_t *d_words = nullptr, *d_off = nullptr;
@@ -1267,10 +1512,10 @@ int64_t sapling_b200_query_str(sapling_b200_index* ix, const char* s, size_t sle
     uint64_t* m = ix->m1;
     const size_t nw = (slen + 31) / 32 + 1;
     for (size_t i = 0; i < nw; i++) m[i] = 0;
-    for (size_t j = 0; j < slen; j++) {
-      const char c = s[j];
-      const uint64_t v = c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 0;
-      m[j >> 5] |= v << (62 - 2 * (j & 31));
+    if (!pack_query_string(s, slen, m)) {
+      set_error("plQuery: the query holds a byte other than A/C/G/T: the reference compares raw bytes there, which the "
+                "2-bit index cannot reproduce (rejected, not answered differently)");
+      return -2;
     }
     m[66] = 0;
     m[67] = (uint64_t)kmer;
@@ -1331,77 +1576,145 @@ int sapling_b200_count_hits(sapling_b200_index* ix, const uint32_t* sa_pos, size
   return 0;
 }
 
+static int seed_args_ok(sapling_b200_index* ix, uint32_t num_seeds, uint32_t max_hits) {
+  if (!ix) { set_error("null index"); return -1; }
+  if (!ix->d_kflag || !ix->d_isa) {
+    set_error("seed_batch: inverse suffix array / k-prefix flags not resident (open with SAPLING_B200_KEEP_BUILD)");
+    return -1;
+  }
+  if (num_seeds == 0) { set_error("seed_batch: num_seeds must be >= 1"); return -1; }
+  if (max_hits > 255) { set_error("seed_batch: max_hits must be <= 255 (hit counts travel as bytes)"); return -1; }
+  return 0;
+}
+
+// Blocks of reads flow through the same three-stream pipeline as the k-mer batches: the upload of block i+1 and the
+// download of block i-1 overlap the seed kernel of block i.  Per seed 10 bytes come back (ref_pos 4, sa_pos 4, left 1,
+// right 1).
+int sapling_b200_seed_batch_compact(sapling_b200_index* ix, const char* reads, const uint64_t* read_off, size_t n_reads,
+                                    uint32_t num_seeds, uint32_t max_hits, uint32_t* ref_pos, uint32_t* sa_pos,
+                                    uint8_t* left, uint8_t* right) {
+  if (seed_args_ok(ix, num_seeds, max_hits)) return -1;
+  if (n_reads == 0) return 0;
+  std::lock_guard<std::mutex> lock(ix->mu);
+  cudaSetDevice(ix->device);
+  if (ensure_staging(ix)) return -1;
+  const size_t per_read = 2 * (size_t)num_seeds;
+  const size_t RB = std::max<size_t>(1, std::min<size_t>(n_reads, ((size_t)1 << 20) / per_read));  // reads per block
+  constexpr int NS = 3;
+  struct Slot {
+    char* d_reads = nullptr; size_t reads_cap = 0;
+    uint64_t* d_off = nullptr;
+    uint32_t *d_rp = nullptr, *d_sp = nullptr;
+    uint8_t *d_l = nullptr, *d_r = nullptr;
+    std::vector<uint64_t> off;
+  } slot[NS];
+  int rc = 0;
+  auto cleanup = [&]() {
+    for (auto& s : slot) { cudaFree(s.d_reads); cudaFree(s.d_off); cudaFree(s.d_rp); cudaFree(s.d_sp); cudaFree(s.d_l); cudaFree(s.d_r); }
+  };
+  for (auto& s : slot) {
+    if (cudaMalloc(&s.d_off, (RB + 1) * 8) || cudaMalloc(&s.d_rp, RB * per_read * 4) || cudaMalloc(&s.d_sp, RB * per_read * 4) ||
+        cudaMalloc(&s.d_l, RB * per_read) || cudaMalloc(&s.d_r, RB * per_read)) {
+      cudaGetLastError();
+      cleanup();
+      set_error("seed_batch: device allocation failed");
+      return -1;
+    }
+    s.off.resize(RB + 1);
+  }
+  cudaStream_t s_up = ix->streams[0], s_k = ix->streams[1], s_down = ix->streams[2];
+  const IndexView v = ix->view();
+  const size_t nblocks = (n_reads + RB - 1) / RB;
+  for (size_t b = 0; b < nblocks + NS && !rc; b++) {
+    if (b >= (size_t)NS && cudaEventSynchronize(ix->ev_down[(b - NS) % NS]) != cudaSuccess) { rc = -1; break; }
+    if (b < nblocks) {
+      Slot& s = slot[b % NS];
+      const int e = (int)(b % NS);
+      const size_t r0 = b * RB, m = std::min(RB, n_reads - r0);
+      const uint64_t base = read_off[r0], nbytes = read_off[r0 + m] - base;
+      if (nbytes > s.reads_cap) {
+        cudaFree(s.d_reads);
+        s.reads_cap = 0;
+        if (cudaMalloc(&s.d_reads, nbytes + (nbytes >> 2) + 64) != cudaSuccess) { rc = -1; break; }
+        s.reads_cap = nbytes + (nbytes >> 2) + 64;
+      }
+      for (size_t i = 0; i <= m; i++) s.off[i] = read_off[r0 + i] - base;
+      if (cudaMemcpyAsync(s.d_reads, reads + base, nbytes, cudaMemcpyHostToDevice, s_up) != cudaSuccess ||
+          cudaMemcpyAsync(s.d_off, s.off.data(), (m + 1) * 8, cudaMemcpyHostToDevice, s_up) != cudaSuccess) { rc = -1; break; }
+      cudaEventRecord(ix->ev_up[e], s_up);
+      cudaStreamWaitEvent(s_k, ix->ev_up[e], 0);
+      if (launch_seeds(v, ix->d_isa, ix->d_kflag, s.d_reads, s.d_off, m, num_seeds, max_hits, s.d_rp, s.d_sp, s.d_l, s.d_r, s_k)) { rc = -2; break; }
+      cudaEventRecord(ix->ev_k[e], s_k);
+      cudaStreamWaitEvent(s_down, ix->ev_k[e], 0);
+      const size_t t0 = r0 * per_read, tm = m * per_read;
+      cudaMemcpyAsync(ref_pos + t0, s.d_rp, tm * 4, cudaMemcpyDeviceToHost, s_down);
+      cudaMemcpyAsync(sa_pos + t0, s.d_sp, tm * 4, cudaMemcpyDeviceToHost, s_down);
+      cudaMemcpyAsync(left + t0, s.d_l, tm, cudaMemcpyDeviceToHost, s_down);
+      if (cudaMemcpyAsync(right + t0, s.d_r, tm, cudaMemcpyDeviceToHost, s_down) != cudaSuccess) { rc = -1; break; }
+      cudaEventRecord(ix->ev_down[e], s_down);
+      // the offsets of this slot are reused NS blocks later: the upload must have consumed them (s_up is in order, and the
+      // ev_down wait above retires the block that used the slot before)
+    }
+  }
+  for (int i = 0; i < 3; i++) cudaStreamSynchronize(ix->streams[i]);
+  cleanup();
+  if (rc == -1) set_error("seed_batch: %s", cudaGetErrorString(cudaGetLastError()));
+  return rc ? -1 : 0;
+}
+
+// The same tuples in the reference-shaped types (int64 positions with -1, 32-bit counts).
 int sapling_b200_seed_batch(sapling_b200_index* ix, const char* reads, const uint64_t* read_off, size_t n_reads,
                             uint32_t num_seeds, uint32_t max_hits, int64_t* ref_pos, uint32_t* sa_pos, uint32_t* left,
                             uint32_t* right) {
-  if (!ix) { set_error("null index"); return -1; }
-  if (!ix->d_kflag || !ix->d_isa) {
-    set_error("seed_batch: inverse suffix array / k-prefix flags not resident (open with SAPLING_B200_KEEP_BUILD)");
-    return -1;
-  }
-  if (num_seeds == 0) { set_error("seed_batch: num_seeds must be >= 1"); return -1; }
-  if (n_reads == 0) return 0;
-  cudaSetDevice(ix->device);
+  if (seed_args_ok(ix, num_seeds, max_hits)) return -1;
   const size_t total = n_reads * 2 * (size_t)num_seeds;
-  const uint64_t nbytes = read_off[n_reads];
-  char* d_reads = nullptr;
-  uint64_t* d_off = nullptr;
-  long long* d_rp = nullptr;
-  uint32_t *d_sp = nullptr, *d_l = nullptr, *d_r = nullptr;
-  int rc = -1;
-  do {
-    if (cudaMalloc(&d_reads, nbytes ? nbytes : 1) || cudaMalloc(&d_off, (n_reads + 1) * 8) || cudaMalloc(&d_rp, total * 8) ||
-        cudaMalloc(&d_sp, total * 4) || cudaMalloc(&d_l, total * 4) || cudaMalloc(&d_r, total * 4)) {
-      set_error("seed_batch: device allocation failed");
-      break;
-    }
-    cudaMemcpy(d_reads, reads, nbytes, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_off, read_off, (n_reads + 1) * 8, cudaMemcpyHostToDevice);
-    if (launch_seeds(ix->view(), ix->d_isa, ix->d_kflag, d_reads, d_off, n_reads, num_seeds, max_hits, d_rp, d_sp, d_l,
-                     d_r, 0))
-      break;
-    cudaMemcpy(ref_pos, d_rp, total * 8, cudaMemcpyDeviceToHost);
-    cudaMemcpy(sa_pos, d_sp, total * 4, cudaMemcpyDeviceToHost);
-    cudaMemcpy(left, d_l, total * 4, cudaMemcpyDeviceToHost);
-    cudaError_t e = cudaMemcpy(right, d_r, total * 4, cudaMemcpyDeviceToHost);
-    if (e != cudaSuccess) { set_error("seed_batch: %s", cudaGetErrorString(e)); break; }
-    rc = 0;
-  } while (0);
-  cudaFree(d_reads); cudaFree(d_off); cudaFree(d_rp); cudaFree(d_sp); cudaFree(d_l); cudaFree(d_r);
-  return rc;
+  std::vector<uint32_t> rp(total);
+  std::vector<uint8_t> l(total), r(total);
+  if (sapling_b200_seed_batch_compact(ix, reads, read_off, n_reads, num_seeds, max_hits, rp.data(), sa_pos, l.data(), r.data()))
+    return -1;
+  for (size_t i = 0; i < total; i++) {
+    ref_pos[i] = rp[i] == 0xFFFFFFFFu ? -1 : (int64_t)rp[i];
+    left[i] = l[i];
+    right[i] = r[i];
+  }
+  return 0;
 }
 
 int sapling_b200_seed_batch_dev(sapling_b200_index* ix, const char* d_reads, const uint64_t* d_read_off, size_t n_reads,
-                                uint32_t num_seeds, uint32_t max_hits, int64_t* d_ref_pos, uint32_t* d_sa_pos,
-                                uint32_t* d_left, uint32_t* d_right, void* stream) {
-  if (!ix) { set_error("null index"); return -1; }
-  if (!ix->d_kflag || !ix->d_isa) {
-    set_error("seed_batch: inverse suffix array / k-prefix flags not resident (open with SAPLING_B200_KEEP_BUILD)");
-    return -1;
-  }
-  if (num_seeds == 0) { set_error("seed_batch: num_seeds must be >= 1"); return -1; }
-  return launch_seeds(ix->view(), ix->d_isa, ix->d_kflag, d_reads, d_read_off, n_reads, num_seeds, max_hits,
-                      reinterpret_cast<long long*>(d_ref_pos), d_sa_pos, d_left, d_right,
-                      static_cast<cudaStream_t>(stream));
+                                uint32_t num_seeds, uint32_t max_hits, uint32_t* d_ref_pos, uint32_t* d_sa_pos,
+                                uint8_t* d_left, uint8_t* d_right, void* stream) {
+  if (seed_args_ok(ix, num_seeds, max_hits)) return -1;
+  cudaSetDevice(ix->device);
+  return launch_seeds(ix->view(), ix->d_isa, ix->d_kflag, d_reads, d_read_off, n_reads, num_seeds, max_hits, d_ref_pos,
+                      d_sa_pos, d_left, d_right, static_cast<cudaStream_t>(stream));
 }
 
 uint64_t sapling_b200_oob_count(sapling_b200_index* ix) {
   if (!ix || !ix->d_oob) return 0;
-  unsigned long long v = 0;
+  unsigned long long total = 0;
+  auto one = [&](sapling_b200_index* d) {
+    unsigned long long v = 0;
+    cudaSetDevice(d->device);
+    cudaMemcpy(&v, d->d_oob, 8, cudaMemcpyDeviceToHost);
+    total += v;
+  };
+  one(ix);
+  for (auto* r : ix->replicas) one(r);
   cudaSetDevice(ix->device);
-  cudaMemcpy(&v, ix->d_oob, 8, cudaMemcpyDeviceToHost);
-  return v;
+  return total;
 }
 
 int sapling_b200_sample_queries_dev(sapling_b200_index* ix, uint64_t seed, uint64_t mut_seed, uint64_t first,
                                     size_t nq, uint64_t* d_kmers, void* stream) {
   if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
   return launch_sample(ix->view(), seed, mut_seed, first, nq, d_kmers, static_cast<cudaStream_t>(stream));
 }
 
 int sapling_b200_verify_dev(sapling_b200_index* ix, const uint64_t* d_kmers, const int64_t* d_out, size_t nq,
                             uint64_t* n_match, uint64_t* n_minus1, void* stream) {
   if (!ix) { set_error("null index"); return -1; }
+  cudaSetDevice(ix->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   unsigned long long* d_c = nullptr;
   SB_CUDA_CHECK(cudaMalloc(&d_c, 16));

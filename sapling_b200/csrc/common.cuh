@@ -5,9 +5,10 @@
 //            of word i/32 ("big-endian in word": integer order of a word == lexicographic order
 //            of its 32 bases).  A=0 C=1 G=2 T=3 (the vals[] table of the reference,
 //            sapling_api.h:494-498).  Padded with GENOME_PAD_WORDS zero words.
-//   sa     : uint32_t[n], rank -> text position (the reference's `rev`, sapling_api.h:41).
-//   model  : ModelEntry[(1<<nb)+1] = {x, y} checkpoints (xlist/ylist, sapling_api.h:65) interleaved
-//            so that the two checkpoints a query needs are 32 contiguous bytes.
+//   lines  : rank lines -- the reference's `rev` (sapling_api.h:41) together with the leading bases of every suffix,
+//            16 ranks per 128-byte line (below).  The ONLY resident copy of the suffix array.
+//   narrow : uint2[1<<nb] = {xoff, y}: the checkpoints xlist/ylist (sapling_api.h:65) in 8 bytes per bucket (model.cu);
+//            model : ModelEntry[(1<<nb)+1] = {x, y}, resident only when the narrow form cannot represent the table.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -16,50 +17,34 @@
 namespace sb {
 
 constexpr int GENOME_PAD_WORDS = 4;
-// The suffix array is allocated in whole 64-byte lines (16 ranks) so that the query kernel may fetch the
-// aligned line around any rank (query.cuh SaLine).
-inline uint64_t sa_alloc_entries(uint64_t n) { return (n + 15ull) & ~15ull; }
 
 struct __align__(16) ModelEntry {
   long long x;
   long long y;
 };
 
-// Everything the query kernels read; passed by value as a kernel argument (lives in the
-// constant bank, so the scalars cost no memory traffic).
-// Inline-prefix suffix array ("ext"): rank -> {text position, the first ext_bases bases of that suffix}.  One 16-byte
-// entry answers a whole probe (rev[r] AND the suffix compare) from a single DRAM line, where the plain layout needs the
-// suffix-array line and then a dependent packed-genome line.  Used for genomes too large for L2.
-struct __align__(16) ExtEntry {
-  uint32_t pos;
-  uint32_t reserved;
-  uint64_t prefix;  // bases left-aligned, zero padded (same convention as load_bases32)
-};
-
-// Rank lines ("packed" suffix array): the layout built around the one fact that decides this kernel on B200 -- an L2
-// miss fills a whole 128-byte DRAM line whatever the width of the load (profiles/r1_gather_dram_granularity.txt), so
-// the cost of a query is the number of distinct LINES it touches.  A rank line holds 16 consecutive ranks as four
-// self-contained 32-byte sectors; a sector answers four whole probes (rev[r] AND the suffix compare) on its own:
-//   v[0..1]  P0  = the first `packed_bases` bases of the suffix at the sector's first rank, as a 2*packed_bases-bit integer
+// Rank lines: the layout built around the one fact that decides this path on B200 -- an L2 miss fills a whole 128-byte
+// DRAM line whatever the width of the load (profiles/r1_gather_dram_granularity.txt), so the cost of a query is the number
+// of distinct LINES it touches.  A rank line holds 16 consecutive ranks as four self-contained 32-byte sectors; sector s
+// holds ranks 4s .. 4s+3 and classifies all four against a query on its own (kmer.cuh):
+//   v[0..1]  P0  = the first `line_bases` bases of the suffix at the sector's first rank, as a 2*line_bases-bit integer
 //   v[2..3]  D   = three 21-bit deltas d1,d2,d3 (bits 0-20, 21-41, 42-62): P_j = P0 + d_j   (suffixes are sorted, so d_j >= 0)
 //                  d_j == kPackedEscape, or bit 63 for entry 0: "compare this entry against the packed genome instead"
-//                  (delta overflow, or a suffix that ends within 32 bases of the end of the text)
+//                  (delta overflow, a suffix that ends within 32 bases of the end of the text, padding past the last rank)
 //   v[4..7]  the four text positions (the reference's rev[r])
-// Line L starts at rank L << packed_shift.  packed_shift == 4: lines tile the ranks.  packed_shift == 3: consecutive
-// lines overlap by half, so that the window [predicted - mostUnder, predicted + mostOver] of a typical query lies inside
-// ONE line (the "anchor" line) instead of straddling two with probability 1/4.
 constexpr uint32_t kPackedEscape = 0x1FFFFFu;
 constexpr int kPackedDeltaBits = 21;
+constexpr int kLineMaxBases = 31;  // 2 * bases <= 62 bits: differences of prefixes fit a signed 64-bit integer
 
+// Everything the query kernels read; passed by value as a kernel argument (lives in the constant bank, so the scalars
+// cost no memory traffic).
 struct IndexView {
   const uint64_t* genome;
-  const uint32_t* sa;
-  const ExtEntry* ext;  // nullptr: not built
-  int ext_bases;        // how many leading bases ext[].prefix holds (27 from the GPU builder's sort keys, 32 from a gather)
-  const uint32_t* packed;  // rank lines (see above); nullptr: not built
-  int packed_bases;        // leading bases per entry (<= 32)
-  int packed_shift;        // 3 or 4
-  const ModelEntry* model;
+  const uint32_t* lines;   // rank lines (see above)
+  int line_bases;          // leading bases per entry (<= kLineMaxBases)
+  const ModelEntry* model; // wide checkpoints; nullptr when `narrow` represents the table
+  const uint2* narrow;     // 8 bytes per bucket (model.cu); nullptr -> use the wide `model` table
+  long long last_x, last_y;  // checkpoint (1<<nb): the largest k-mer of the genome
   uint64_t n;
   int k;
   int nb;
@@ -67,19 +52,15 @@ struct IndexView {
   int maxOver, maxUnder, mostOver, mostUnder;
   int compat;  // 1: the reference's (int)predicted window arithmetic (sapling_api.h:209,225)
   unsigned long long* oob_counter;  // incremented when predicted >= n (reference: UB)
-  // Narrow model (8 bytes per bucket, see model.cu); nullptr -> use the wide `model` table.
-  const uint2* narrow;
-  long long last_x, last_y;  // checkpoint (1<<nb): the largest k-mer of the genome
-  // L2 residency hints (HINT_* bits)
-  unsigned hints;
+  unsigned hints;  // L2 residency hints (HINT_* bits)
 };
 
 enum : unsigned {
   HINT_GENOME_KEEP = 1u,   // packed genome loads: L2 evict_last
   HINT_MODEL_KEEP = 2u,    // model loads: L2 evict_last
-  HINT_SA_STREAM = 4u,     // suffix-array loads: L2 evict_first
+  HINT_SA_STREAM = 4u,     // rank-line loads: L2 evict_first
   HINT_IO_STREAM = 8u,     // k-mer reads / result writes: ld.cs / st.cs
-  HINT_SA_KEEP = 16u       // suffix-array / rank-line loads: L2 evict_last (wins over HINT_SA_STREAM)
+  HINT_SA_KEEP = 16u       // rank-line loads: L2 evict_last (wins over HINT_SA_STREAM)
 };
 
 #define SB_CUDA_CHECK(expr)                                                          \
@@ -220,15 +201,15 @@ __device__ __forceinline__ void pack_rank_sector(const uint64_t* __restrict__ ge
   out[2] = (uint32_t)D;
   out[3] = (uint32_t)(D >> 32);
 }
-// sectors in a rank-line array over n ranks (one extra line so that the last anchor line is whole)
-inline uint64_t packed_sectors(uint64_t n, int shift) { return (((n + (1ull << shift) - 1) >> shift) + 2) * 4; }
+// sectors in a rank-line array over n ranks (whole lines, one spare)
+inline uint64_t line_sectors(uint64_t n) { return (((n + 15ull) >> 4) + 1ull) * 4ull; }
 // how many leading bases a 21-bit delta can carry: the mean gap between consecutive distinct prefixes, 4^bases / n,
 // must stay well (16x) below 2^21 or escapes stop being rare
-inline int packed_bases_for(uint64_t n) {
+inline int line_bases_for(uint64_t n) {
   int lg = 0;
   while ((1ull << (lg + 1)) <= n) lg++;
   int b = (lg + 17) / 2;
-  return b < 8 ? 8 : (b > 32 ? 32 : b);
+  return b < 8 ? 8 : (b > kLineMaxBases ? kLineMaxBases : b);
 }
 
 // Same, but only `need` (<=32) leading bases are required: skips the second word when the first

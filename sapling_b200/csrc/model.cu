@@ -39,7 +39,36 @@ __global__ void narrow_kernel(const ModelEntry* __restrict__ model, uint64_t B, 
   }
 }
 
+// the inverse: checkpoints first .. first+count-1 of xlist / ylist (sapling_api.h:65) rebuilt from the narrow table
+__global__ void widen_kernel(const uint2* __restrict__ narrow, uint64_t B, int shift, long long last_x, long long last_y,
+                             uint64_t first, uint64_t count, long long* __restrict__ xs, long long* __restrict__ ys) {
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    const uint64_t b = first + i;
+    long long x = last_x, y = last_y;
+    if (b < B) {
+      const uint2 e = narrow[b];
+      const uint64_t src = (e.x & kNarrowFill) ? b - (e.x & ~kNarrowFill) : b;
+      const uint32_t xoff = (e.x & kNarrowFill) ? narrow[src].x : e.x;
+      x = (long long)((src << shift) + xoff);
+      y = (long long)e.y;
+    }
+    xs[i] = x;
+    ys[i] = y;
+  }
+}
+
 }  // namespace
+
+int widen_model(const uint2* d_narrow, int nb, int shift, long long last_x, long long last_y, uint64_t first,
+                uint64_t count, long long* d_xs, long long* d_ys, cudaStream_t st) {
+  if (count == 0) return 0;
+  uint64_t g = (count + 255) / 256;
+  if (g > 148ull * 16) g = 148ull * 16;
+  widen_kernel<<<(int)g, 256, 0, st>>>(d_narrow, 1ull << nb, shift, last_x, last_y, first, count, d_xs, d_ys);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
 
 // Returns 0 and sets *ok = 1 when every checkpoint is representable (always true for a model built by
 // buildPiecewiseLinear; a hand-edited .sap file may not be, then the wide table is used).

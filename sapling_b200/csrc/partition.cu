@@ -14,13 +14,12 @@
 //   A  part_hist_kernel     chunk c (kPartChunk queries) x bin -> count            cnt[c][bin]  (chunk-major: every
 //                           pass reads or writes whole rows; a bin-major table cost 1024 strided sectors per chunk)
 //   S  part_col*_kernel     exclusive scan down every column (over chunks), then over bins     off[c][bin], bin_start[bin]
-//   B  part_scatter_kernel  k-mer -> part_kmer[bin_start + off + local rank], its index inside the chunk -> part_slot
+//   B  part_scatter_staged_kernel  k-mer -> part_kmer[bin_start + off + local rank], its index inside the chunk (slot) with it
 //   Q  query kernel (query.cu) over part_kmer in order; result word = slot << 48 | answer
 //   U  part_unpermute_kernel  chunk c gathers its answers bin by bin into shared memory, writes out[] coalesced
 #include "partition.cuh"
 
-#include <stdlib.h>
-#include <string.h>
+#include <mutex>
 
 namespace sb {
 
@@ -113,26 +112,6 @@ part_scan_bins_kernel(const uint32_t* __restrict__ cnt, size_t nchunks, uint32_t
   if (threadIdx.x == 0) bin_start[nbins] = a[nbins - 1];
 }
 
-// B: scatter.  The order of a chunk's queries inside one bin is whatever the shared-memory atomics make it: the slot
-// travels with the query, so the un-permute pass does not care.
-__global__ void __launch_bounds__(kHistThreads)
-part_scatter_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
-                    const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
-                    uint64_t* __restrict__ part_kmer, uint16_t* __restrict__ part_slot) {
-  extern __shared__ uint32_t cur[];
-  const size_t c = blockIdx.x;
-  for (uint32_t b = threadIdx.x; b < nbins; b += kHistThreads) cur[b] = bin_start[b] + off[c * nbins + b];
-  __syncthreads();
-  const size_t base = c * kPartChunk;
-  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t i = threadIdx.x; i < m; i += kHistThreads) {
-    const uint64_t x = __ldcs(kmers + base + i);
-    const uint32_t pos = atomicAdd(&cur[bin_of(x, pshift, nbins)], 1u);
-    part_kmer[pos] = x;
-    part_slot[pos] = (uint16_t)i;
-  }
-}
-
 // Block-wide exclusive scan of 2048 counters in shared memory; thread t owns the kPer = 2048 / kThreads consecutive
 // counters from t * kPer.  On return a[b] = sum of the counts before b; own[j] holds the thread's own exclusive starts.
 template <int kThreads>
@@ -173,10 +152,11 @@ __device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t 
   }
 }
 
-// B': the same scatter staged through shared memory.  The direct scatter above sends every warp store to 32 different
-// lines (measured: 1.0 ms per 50 M queries, 40 % of the query kernel's own time).  Here a block first sorts its chunk
-// by bin inside shared memory and then writes the sorted chunk out in order: consecutive threads store consecutive
-// addresses for as long as the bin lasts (chunk / bins queries on average).
+// B: the scatter, staged through shared memory.  A direct scatter sends every warp store to 32 different lines (measured:
+// 1.0 ms per 50 M queries).  Here a block first sorts its chunk by bin inside shared memory and then writes the sorted
+// chunk out in order: consecutive threads store consecutive addresses for as long as the bin lasts (chunk / bins queries
+// on average).  The order of a chunk's queries inside one bin is whatever the shared-memory atomics make it: the slot
+// travels with the query, so the un-permute pass does not care.
 // The (chunk, bin) counts are already known -- pass A wrote them, the scan turned them into offsets -- so the block
 // does not count again: it requests its column of the offset table together with its k-mers (each thread keeps 16 of
 // them in registers), scans the run lengths into run starts, and then ONE shared-memory atomic per k-mer hands out the
@@ -256,9 +236,21 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
 }
 
 // U: chunk c collects its answers.  Warp w walks bins w, w+32, ...; the run (bin, c) is read coalesced by the lanes.
+// Out = long long (the reference's return type, -1 for "not found") or uint32_t (0xFFFFFFFF for -1: the host path's
+// download format).
+template <typename Out>
+__device__ __forceinline__ void store_answer(Out* p, uint32_t v);
+template <>
+__device__ __forceinline__ void store_answer<long long>(long long* p, uint32_t v) {
+  __stcs(p, v == 0xFFFFFFFFu ? -1ll : (long long)v);
+}
+template <>
+__device__ __forceinline__ void store_answer<uint32_t>(uint32_t* p, uint32_t v) { __stcs(p, v); }
+
+template <typename Out>
 __global__ void __launch_bounds__(kUnpermThreads, 2)
 part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
-                      const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start, long long* __restrict__ out) {
+                      const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start, Out* __restrict__ out) {
   // answers staged as 32 bits (a position < n <= 2^32 - 16, or 0xFFFFFFFF for -1): 64 KB per chunk, so that two blocks
   // share an SM and one block's loads overlap the other's stores
   extern __shared__ uint32_t buf32[];
@@ -291,74 +283,18 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
   __syncthreads();
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) {
-    const uint32_t v = buf32[i];
-    __stcs(out + base + i, v == 0xFFFFFFFFu ? -1ll : (long long)v);
-  }
+  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) store_answer<Out>(out + base + i, buf32[i]);
 }
 
-// U': the same un-permute with the work split by ELEMENT instead of by bin.  Above, a warp walks whole (bin, chunk) runs,
-// which leaves most lanes idle once runs are shorter than a warp (2048 bins: 8 queries per run, 4.3 ms per 250 M
-// queries against 1.2 ms at 256 bins).  Here the block first scans the chunk's run lengths, then thread i of the chunk's
-// sorted order finds its run by binary search over the scanned starts in shared memory: neighbouring threads read
-// neighbouring answers whatever the run length.
-constexpr int kFlatThreads = kPartChunk / 16;
-__global__ void __launch_bounds__(kFlatThreads)
-part_unpermute_flat_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
-                           const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
-                           long long* __restrict__ out) {
-  extern __shared__ long long buf[];                                   // [kPartChunk] answers in the caller's order
-  uint32_t* lstart = reinterpret_cast<uint32_t*>(buf + kPartChunk);    // [2048] first sorted index of the bin's run
-  uint32_t* gdelta = lstart + 2048;                                    // [2048] position in res - sorted index
-  __shared__ uint32_t wsum[32];
-  const size_t c = blockIdx.x;
-  const size_t base = c * kPartChunk;
-  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  constexpr int kPer = 2048 / kFlatThreads;
-  uint32_t gpos[kPer];
-#pragma unroll
-  for (int j = 0; j < kPer; j++) {
-    const uint32_t b = (uint32_t)kPer * threadIdx.x + j;
-    uint32_t len = 0;
-    gpos[j] = 0;
-    if (b < nbins) {
-      const uint32_t* row = off + c * nbins + b;
-      const uint32_t r0 = row[0];
-      len = row[nbins] - r0;
-      gpos[j] = bin_start[b] + r0;
-    }
-    lstart[b] = len;
-  }
-  __syncthreads();
-  {
-    uint32_t own[kPer];
-    scan_2048<kFlatThreads>(lstart, wsum, own);
-#pragma unroll
-    for (int j = 0; j < kPer; j++) gdelta[(uint32_t)kPer * threadIdx.x + j] = gpos[j] - own[j];
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < m; i += kFlatThreads) {
-    uint32_t b = 0;  // last bin whose run starts at or before i (empty runs share their start with the next one)
-#pragma unroll
-    for (uint32_t step = 1024; step; step >>= 1)
-      if (lstart[b + step] <= i) b += step;
-    const unsigned long long v = (unsigned long long)__ldcs(res + gdelta[b] + i);
-    buf[v >> 48] = (long long)(v << 16) >> 16;
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < m; i += kFlatThreads) __stcs(out + base + i, buf[i]);
-}
-
-// U'': lane GROUPS per run.  The flat kernel above pays an 11-step binary search in shared memory per element (ncu r2d:
-// 3 warp instructions per answer, a third of the issue slots, 1.95 ms per 250 M answers where the bytes alone take 0.7).
-// Here kGroup lanes (a power of two near half the mean run length) own a run: they read its bounds once and then
+// U': lane GROUPS per run.  Above, a warp walks whole (bin, chunk) runs, which leaves most lanes idle once runs are shorter
+// than a warp (2048 bins: 8 queries per run).  Here kGroup lanes (a power of two near half the mean run length) own a run: they read its bounds once and then
 // kGroup consecutive answers per step -- no scan, no search, and neighbouring lanes still read neighbouring addresses.
 // The bounds of kBatch runs are requested before the first answer is, so the two dependent loads overlap across runs.
-template <int kGroup>
+template <int kGroup, typename Out>
 __global__ void __launch_bounds__(kUnpermThreads, 2)
 part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
                             const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
-                            long long* __restrict__ out) {
+                            Out* __restrict__ out) {
   extern __shared__ uint32_t buf32[];  // [kPartChunk] answers in the caller's order, 32 bits each (see part_unpermute_kernel)
   constexpr uint32_t kGroups = kUnpermThreads / kGroup;
   constexpr int kBatch = 4;  // 8 was measured slower (spills at the 32-register cap of two 1024-thread blocks per SM)
@@ -388,16 +324,13 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
   __syncthreads();
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) {
-    const uint32_t v = buf32[i];
-    __stcs(out + base + i, v == 0xFFFFFFFFu ? -1ll : (long long)v);
-  }
+  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) store_answer<Out>(out + base + i, buf32[i]);
 }
 
 }  // namespace
 
-constexpr size_t kUnpermFlatSmem = (size_t)kPartChunk * sizeof(long long) + 2 * 2048 * 4;
 constexpr size_t kScatterSmem = (size_t)kPartChunk * 10 + 2 * 2048 * 4;
+constexpr size_t kUnpermSmem = (size_t)kPartChunk * sizeof(uint32_t);
 
 size_t partition_workspace_bytes(size_t nq, int pbits) {
   const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
@@ -407,37 +340,58 @@ size_t partition_workspace_bytes(size_t nq, int pbits) {
          up((size_t)kScanSegs * nbins * 4);
 }
 
-int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, void* ws,
-                             int pbits, cudaStream_t st, cudaEvent_t* ev) {
+// Opt-in to the large dynamic shared memory of the scatter and un-permute kernels.  Function attributes belong to the
+// device (context) they were set on, and one process may hold indexes on several GPUs: once per device.
+static int set_kernel_attributes() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+#define SB_SMEM(kernel, bytes)                                                                              \
+  SB_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));   \
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+  SB_SMEM(part_scatter_staged_kernel<false>, kScatterSmem);
+  SB_SMEM(part_scatter_staged_kernel<true>, kScatterSmem);
+  SB_SMEM(part_unpermute_kernel<long long>, kUnpermSmem);
+  SB_SMEM(part_unpermute_kernel<uint32_t>, kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<4, long long>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<8, long long>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<16, long long>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<4, uint32_t>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<8, uint32_t>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<16, uint32_t>), kUnpermSmem);
+#undef SB_SMEM
+  cudaGetLastError();
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+}
+
+template <typename Out>
+static void launch_unpermute(const long long* res, size_t nq, uint32_t nbins, size_t nchunks, const uint32_t* cnt,
+                             const uint32_t* bin_start, Out* out, int pbits, cudaStream_t st) {
+  // lane groups per run, the group about half the mean run length; a whole warp per run from 64 answers per run
+  const uint32_t mean_run = kPartChunk >> pbits;
+  const unsigned g = (unsigned)nchunks;
+  if (mean_run >= 64)
+    part_unpermute_kernel<Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+  else if (mean_run >= 32)
+    part_unpermute_group_kernel<16, Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+  else if (mean_run >= 16)
+    part_unpermute_group_kernel<8, Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+  else
+    part_unpermute_group_kernel<4, Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+}
+
+int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
+                             void* ws, int pbits, int occupancy, cudaStream_t st, cudaEvent_t* ev) {
   if (nq == 0) return 0;
   if (pbits < 1 || pbits > kPartMaxBits || pbits > 2 * ix.k || nq >= (1ull << 32)) {
     set_error("launch_partitioned_query: pbits=%d nq=%zu out of range", pbits, nq);
     return -1;
   }
-  static bool attr_set = false;  // benign race: the attribute is idempotent
-  if (!attr_set) {
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(uint32_t))));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_flat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kUnpermFlatSmem));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kScatterSmem));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_scatter_staged_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)kScatterSmem));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(uint32_t))));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(uint32_t))));
-    SB_CUDA_CHECK(cudaFuncSetAttribute(part_unpermute_group_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(kPartChunk * sizeof(uint32_t))));
-    // two 64 KB un-permute blocks per SM need the large shared-memory carve-out
-    cudaFuncSetAttribute(part_unpermute_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(part_unpermute_group_kernel<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(part_unpermute_group_kernel<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaFuncSetAttribute(part_unpermute_group_kernel<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    cudaGetLastError();
-    attr_set = true;
-  }
+  if (set_kernel_attributes()) return -1;
   const size_t nchunks = (nq + kPartChunk - 1) / kPartChunk;
   const uint32_t nbins = 1u << pbits;
   const int pshift = 2 * ix.k - pbits;
@@ -450,8 +404,6 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   uint32_t* bin_start = reinterpret_cast<uint32_t*>(p); p += up((size_t)(nbins + 1) * 4);
   unsigned long long* tiles = reinterpret_cast<unsigned long long*>(p); p += 256;
   uint32_t* segsum = reinterpret_cast<uint32_t*>(p);
-  const char* te = getenv("SAPLING_B200_PART_TILES");  // 0 = static grid-stride schedule (kept for A/B measurements)
-  const bool in_order = !(te && atoi(te) == 0);
 
   if (ev) cudaEventRecord(ev[0], st);
   part_hist_kernel<<<(unsigned)nchunks, kHistThreads, nbins * 4, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt);
@@ -465,51 +417,22 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   }
   part_scan_bins_kernel<<<1, 1024, 0, st>>>(cnt, nchunks, nbins, bin_start, tiles);
   if (ev) cudaEventRecord(ev[1], st);
-  const char* se = getenv("SAPLING_B200_PART_SCATTER");  // 0 = the direct scatter (kept for A/B measurements)
-  // slots inside the k-mer words: only the in-order pipelined kernel reads that format (query.cu), k <= 25
-  const char* ke = getenv("SAPLING_B200_SLOT_IN_KMER");  // 0 = separate slot array (A/B measurements)
-  const char* oe = getenv("SAPLING_B200_ORDERED_PIPE");
-  bool slot_in_kmer = 2 * ix.k + 14 <= 64 && in_order && ix.narrow != nullptr && !(oe && atoi(oe) == 0) &&
-                      !(se && atoi(se) == 0) && !(ke && atoi(ke) == 0);
-  if (slot_in_kmer) {  // ask the launcher which kernel this batch would get: only the in-order pipelined one reads the format
-    const char* name = "";
-    launch_kmer_query(ix, nullptr, 0, nullptr, st, &name, slot_in_kmer_tag(), tiles);
-    slot_in_kmer = strcmp(name, "kmer_query_ordered_kernel") == 0;
-  }
-  if (slot_in_kmer) {
+  // the slot of a query rides in bits 50-63 of its k-mer word when the k-mer leaves room (k <= 25): one store and one
+  // load per query instead of two of each
+  const bool slot_in_kmer = 2 * ix.k + 14 <= 64;
+  if (slot_in_kmer)
     part_scatter_staged_kernel<true><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
-  } else if (se && atoi(se) == 0) {
-    part_scatter_kernel<<<(unsigned)nchunks, kHistThreads, nbins * 4, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt,
-                                                                            bin_start, part_kmer, part_slot);
-  } else {
+  else
     part_scatter_staged_kernel<false><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
-  }
   SB_CUDA_CHECK(cudaGetLastError());
   if (ev) cudaEventRecord(ev[2], st);
-  if (launch_kmer_query(ix, part_kmer, nq, res, st, nullptr, slot_in_kmer ? slot_in_kmer_tag() : part_slot,
-                        in_order ? tiles : nullptr))
+  if (launch_kmer_query_ordered(ix, part_kmer, nq, res, slot_in_kmer ? slot_in_kmer_tag() : part_slot, tiles, occupancy, st))
     return -1;
   if (ev) cudaEventRecord(ev[3], st);
-  // 0 = the run-per-warp un-permute, 1 = the flat one (both kept for A/B measurements); default: lane groups per run,
-  // the group about half the mean run length (a whole warp from 64 answers per run: that is the run-per-warp kernel)
-  const char* ue = getenv("SAPLING_B200_PART_UNPERMUTE");
-  const uint32_t mean_run = kPartChunk >> pbits;
-  const size_t ubytes = kPartChunk * sizeof(uint32_t);
-  if ((ue && atoi(ue) == 0) || (!ue && mean_run >= 64)) {
-    part_unpermute_kernel<<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
-  } else if (!ue || atoi(ue) != 1) {
-    if (mean_run >= 32)
-      part_unpermute_group_kernel<16><<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
-    else if (mean_run >= 16)
-      part_unpermute_group_kernel<8><<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
-    else
-      part_unpermute_group_kernel<4><<<(unsigned)nchunks, kUnpermThreads, ubytes, st>>>(res, nq, nbins, nchunks, cnt, bin_start, d_out);
-  } else {
-    part_unpermute_flat_kernel<<<(unsigned)nchunks, kFlatThreads, kUnpermFlatSmem, st>>>(res, nq, nbins, nchunks, cnt,
-                                                                                          bin_start, d_out);
-  }
+  if (d_out32) launch_unpermute<uint32_t>(res, nq, nbins, nchunks, cnt, bin_start, d_out32, pbits, st);
+  else launch_unpermute<long long>(res, nq, nbins, nchunks, cnt, bin_start, d_out, pbits, st);
   if (ev) cudaEventRecord(ev[4], st);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;

@@ -90,41 +90,6 @@ __global__ void sa_scatter_back(const uint32_t* __restrict__ slot, const uint32_
   for (uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; t < m; t += stride) sa[slot[t]] = pos[t];
 }
 
-// ext[r].prefix from the sorted base-5 keys: digit j (0 = past the end, 1..4 = A..T) -> 2-bit base, end padded with 0
-__global__ void ext_prefix_from_keys(const uint64_t* __restrict__ keys, uint64_t n, ExtEntry* __restrict__ ext) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-    uint64_t key = keys[r], pre = 0;
-#pragma unroll
-    for (int j = kKeyChars - 1; j >= 0; j--) {
-      const uint64_t d = key % 5ull;
-      key /= 5ull;
-      pre |= (d ? d - 1ull : 0ull) << (62 - 2 * j);
-    }
-    ext[r].prefix = pre;
-    ext[r].reserved = 0;
-  }
-}
-__global__ void ext_pos_from_sa(const uint32_t* __restrict__ sa, uint64_t n, ExtEntry* __restrict__ ext) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) ext[r].pos = sa[r];
-}
-__global__ void ext_gather(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ sa, uint64_t n,
-                           ExtEntry* __restrict__ ext) {
-  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += stride) {
-    const uint32_t p = sa[r];
-    const uint64_t room = n - p;
-    uint64_t g = load_bases32(genome, p);
-    if (room < 32) g &= ~0ull << (64 - 2 * room);  // nothing but zeros past the end of the text
-    ExtEntry e;
-    e.pos = p;
-    e.reserved = 0;
-    e.prefix = g;
-    ext[r] = e;
-  }
-}
-
 __global__ void sa_invert(const uint32_t* __restrict__ src, uint64_t n, uint32_t* __restrict__ dst) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[src[i]] = (uint32_t)i;
@@ -132,10 +97,10 @@ __global__ void sa_invert(const uint32_t* __restrict__ src, uint64_t n, uint32_t
 
 // rank lines (common.cuh IndexView): one thread per 32-byte sector
 __global__ void rank_lines_kernel(const uint64_t* __restrict__ genome, const uint32_t* __restrict__ sa, uint64_t n,
-                                  int bases, int shift, uint64_t sectors, uint32_t* __restrict__ out) {
+                                  int bases, uint64_t sectors, uint32_t* __restrict__ out) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < sectors; s += stride) {
-    const uint64_t r0 = ((s >> 2) << shift) + ((s & 3u) << 2);
+    const uint64_t r0 = s * 4;
     uint32_t v[8];
     pack_rank_sector(genome, sa, n, bases, r0, v);
     uint4* dst = reinterpret_cast<uint4*>(out + s * 8);
@@ -170,23 +135,17 @@ int invert_permutation(const uint32_t* d_src, uint64_t n, uint32_t* d_dst, cudaS
   return 0;
 }
 
+int build_rank_lines(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, int bases, uint32_t* d_lines,
+                     cudaStream_t st) {
+  const uint64_t sectors = line_sectors(n);
+  rank_lines_kernel<<<grid_for(sectors), 256, 0, st>>>(d_genome, d_sa, n, bases, sectors, d_lines);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
 // d_sa (out): rank -> position.  d_isa (out): position -> rank.  Both uint32[n], caller-allocated.
-int build_ext_by_gather(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, ExtEntry* d_ext, cudaStream_t st) {
-  ext_gather<<<grid_for(n), 256, 0, st>>>(d_genome, d_sa, n, d_ext);
-  SB_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
-int build_rank_lines(const uint64_t* d_genome, uint64_t n, const uint32_t* d_sa, int bases, int shift,
-                     uint32_t* d_packed, cudaStream_t st) {
-  const uint64_t sectors = packed_sectors(n, shift);
-  rank_lines_kernel<<<grid_for(sectors), 256, 0, st>>>(d_genome, d_sa, n, bases, shift, sectors, d_packed);
-  SB_CUDA_CHECK(cudaGetLastError());
-  return 0;
-}
-
 int build_suffix_array(const uint64_t* d_genome, uint64_t n, uint32_t* d_sa, uint32_t* d_isa, cudaStream_t st,
-                       int* rounds_out, ExtEntry* d_ext) {
+                       int* rounds_out) {
   if (n == 0 || n >= 0xFFFFFF00ull) {
     set_error("build_suffix_array: n=%llu unsupported (need 0 < n < 2^32-256)", (unsigned long long)n);
     return -1;
@@ -222,10 +181,6 @@ int build_suffix_array(const uint64_t* d_genome, uint64_t n, uint32_t* d_sa, uin
     SB_CUDA_CHECK(cudaMemcpyAsync(d_sa, dv.Current(), n * 4, cudaMemcpyDeviceToDevice, st));
   uint64_t* keys_sorted = dk.Current();
   uint64_t* keys_other = dk.Alternate();
-
-  // the sorted keys ARE the leading bases of the suffixes in rank order (members of a tied group share them, so later
-  // rounds, which only permute positions inside groups, leave them valid)
-  if (d_ext) ext_prefix_from_keys<<<grid_for(n), 256, 0, st>>>(keys_sorted, n, d_ext);
 
   // group structure after the first sort
   sa_mark_heads<<<grid_for(n), 256, 0, st>>>(keys_sorted, n, head.as<uint8_t>());
@@ -302,7 +257,6 @@ int build_suffix_array(const uint64_t* d_genome, uint64_t n, uint32_t* d_sa, uin
     }
   }
   if (rounds_out) *rounds_out = rounds;
-  if (d_ext) ext_pos_from_sa<<<grid_for(n), 256, 0, st>>>(d_sa, n, d_ext);
   SB_CUDA_CHECK(cudaGetLastError());
   SB_CUDA_CHECK(cudaStreamSynchronize(st));
   return 0;

@@ -1,8 +1,8 @@
 // sim_query.cpp -- TEST INFRASTRUCTURE ONLY.
-// Compiles the *device* query code (sapling_b200/csrc/query.cuh, common.cuh) for the host with g++
-// by supplying host stand-ins for the handful of CUDA intrinsics it uses, so that the control-flow
-// replay can be differential-tested against the oracle on a machine without a GPU.  It is never
-// linked into libsapling_b200.so and never used by the product.
+// Compiles the *device* query code (sapling_b200/csrc/kmer.cuh, query.cuh, common.cuh) for the host with g++
+// by supplying host stand-ins for the handful of CUDA intrinsics it uses, so that the query path can be
+// differential-tested against the oracle on a machine without a GPU.  It is never linked into libsapling_b200.so
+// and never used by the product.
 #define SB_HOST_SIM 1
 #include <cstdint>
 #include <cstring>
@@ -19,9 +19,41 @@ static inline unsigned long long atomicAdd(unsigned long long* p, unsigned long 
   unsigned long long o = *p; *p += v; return o;
 }
 
+#include "../../sapling_b200/csrc/kmer.cuh"
 #include "../../sapling_b200/csrc/query.cuh"
 
 namespace sb { void set_error(const char*, ...) {} const char* last_error() { return ""; } }
+
+namespace {
+// rank lines built by the same pack_rank_sector the build kernel runs
+uint32_t* build_lines(const uint64_t* genome, const uint32_t* sa, uint64_t n, int bases, unsigned long long* n_escapes) {
+  const uint64_t sectors = sb::line_sectors(n);
+  uint32_t* lines = new uint32_t[sectors * 8];
+  unsigned long long esc = 0;
+  for (uint64_t s = 0; s < sectors; s++) {
+    sb::pack_rank_sector(genome, sa, n, bases, s * 4, lines + s * 8);
+    const uint64_t D = ((uint64_t)lines[s * 8 + 3] << 32) | lines[s * 8 + 2];
+    if (s * 4 < n) {
+      esc += (D >> 63);
+      for (int j = 1; j < 4; j++) esc += ((D >> (21 * (j - 1))) & 0x1FFFFFu) == 0x1FFFFFu && s * 4 + j < n;
+    }
+  }
+  if (n_escapes) *n_escapes = esc;
+  return lines;
+}
+sb::IndexView make_view(const uint64_t* genome, const uint32_t* lines, int bases, const int64_t* model_xy, uint64_t n, int k,
+                        int nb, const int* five, int compat, unsigned long long* oob, const uint2* narrow,
+                        const int64_t* last_xy) {
+  sb::IndexView ix;
+  ix.genome = genome; ix.lines = lines; ix.line_bases = bases;
+  ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
+  ix.narrow = narrow; ix.last_x = last_xy ? last_xy[0] : 0; ix.last_y = last_xy ? last_xy[1] : 0;
+  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
+  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
+  ix.compat = compat; ix.oob_counter = oob; ix.hints = 0;
+  return ix;
+}
+}  // namespace
 
 extern "C" {
 
@@ -29,157 +61,146 @@ void sim_skip_counters(unsigned long long* tried, unsigned long long* ok) {
   *tried = sb::g_sim_skip_tried;
   *ok = sb::g_sim_skip_ok;
 }
+// sector loads / genome-decided entries / extra rev[] loads of the k-mer path so far
+void sim_kmer_counters(unsigned long long* sectors, unsigned long long* slow, unsigned long long* finals) {
+  *sectors = sb::g_sim_sector_loads;
+  *slow = sb::g_sim_slow_entries;
+  *finals = sb::g_sim_final_loads;
+}
 
-// genome: packed words (with pad), sa: n entries, model: interleaved {x,y} x ((1<<nb)+1)
+// The batch k-mer path (kmer.cuh answer_kmer) exactly as the kernels call it.
+// genome: packed words (with pad), sa: n entries, model: interleaved {x,y} x ((1<<nb)+1); bases: leading bases per
+// rank-line entry (0 = the library's choice for n).  out_lines may be NULL; otherwise it receives line_sectors(n) * 8
+// words (to compare with the GPU's).
+void sim_kmer_answer(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
+                     const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
+                     unsigned long long* oob, const uint2* narrow, const int64_t* last_xy, int bases,
+                     uint32_t* out_lines, unsigned long long* n_escapes) {
+  if (bases <= 0) bases = sb::line_bases_for(n);
+  uint32_t* lines = build_lines(genome, sa, n, bases, n_escapes);
+  if (out_lines) memcpy(out_lines, lines, sb::line_sectors(n) * 32);
+  const sb::IndexView ix = make_view(genome, lines, bases, model_xy, n, k, nb, five, compat, oob, narrow, last_xy);
+  const sb::L2Policies pol = sb::make_policies(0);
+  const uint64_t kmask = k >= 32 ? ~0ull : ((1ull << (2 * k)) - 1ull);
+  for (size_t i = 0; i < nq; i++) {
+    const uint64_t x = kmers[i] & kmask;
+    const uint32_t pred = (uint32_t)sb::clamp_prediction(ix, sb::predict_rank(ix, x, pol.model));
+    out[i] = k > bases ? sb::answer_kmer<true>(ix, x, pred, pol) : sb::answer_kmer<false>(ix, x, pred, pol);
+  }
+  delete[] lines;
+}
+
+// The literal replay (query.cuh Replay) for k-mers: what the string kernel and the probe counter run.
+// probes != NULL: receives the total number of getLcp calls (kSkip off), as bench.py's device counter does.
 void sim_kmer_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                     const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
-                    unsigned long long* oob, const uint2* narrow, const int64_t* last_xy) {
-  sb::IndexView ix;
-  ix.genome = genome; ix.sa = sa; ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
-  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
-  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
-  ix.compat = compat; ix.oob_counter = oob;
-  ix.narrow = narrow; ix.last_x = last_xy[0]; ix.last_y = last_xy[1]; ix.hints = 0;
+                    unsigned long long* oob, const uint2* narrow, const int64_t* last_xy, unsigned long long* probes) {
+  const int bases = sb::line_bases_for(n);
+  uint32_t* lines = build_lines(genome, sa, n, bases, nullptr);
+  const sb::IndexView ix = make_view(genome, lines, bases, model_xy, n, k, nb, five, compat, oob, narrow, last_xy);
+  const sb::L2Policies pol = sb::make_policies(0);
+  unsigned long long np = 0;
   for (size_t i = 0; i < nq; i++) {
     sb::KmerQuery q; q.q = kmers[i] << (64 - 2 * k); q.k = (uint32_t)k;
-    out[i] = sb::pl_query<false>(ix, q, kmers[i]);
-  }
-}
-
-// rank lines (common.cuh IndexView) built by the same pack_rank_sector the build kernel runs, then the packed-mode
-// replay.  out_packed may be NULL; otherwise it receives packed_sectors(n, shift) * 8 words (to compare with the GPU's).
-void sim_kmer_batch_packed(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
-                           const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
-                           unsigned long long* oob, int bases, int shift, uint32_t* out_packed,
-                           unsigned long long* n_escapes) {
-  const uint64_t sectors = sb::packed_sectors(n, shift);
-  uint32_t* packed = out_packed ? out_packed : new uint32_t[sectors * 8];
-  unsigned long long esc = 0;
-  for (uint64_t s = 0; s < sectors; s++) {
-    const uint64_t r0 = ((s >> 2) << shift) + ((s & 3u) << 2);
-    sb::pack_rank_sector(genome, sa, n, bases, r0, packed + s * 8);
-    const uint64_t D = ((uint64_t)packed[s * 8 + 3] << 32) | packed[s * 8 + 2];
-    if (r0 < n) {
-      esc += (D >> 63);
-      for (int j = 1; j < 4; j++) esc += ((D >> (21 * (j - 1))) & 0x1FFFFFu) == 0x1FFFFFu && r0 + j < n;
-    }
-  }
-  if (n_escapes) *n_escapes = esc;
-  sb::IndexView ix;
-  ix.genome = genome; ix.sa = sa; ix.ext = nullptr; ix.ext_bases = 0;
-  ix.packed = packed; ix.packed_bases = bases; ix.packed_shift = shift;
-  ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
-  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
-  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
-  ix.compat = compat; ix.oob_counter = oob;
-  ix.narrow = nullptr; ix.last_x = 0; ix.last_y = 0; ix.hints = 0;
-  const sb::L2Policies pol = sb::make_policies(0);
-  for (size_t i = 0; i < nq; i++) {
-    sb::KmerQuery q; q.q = kmers[i] << (64 - 2 * k); q.k = (uint32_t)k;
-    const uint64_t pred = sb::clamp_prediction(ix, sb::predict_rank(ix, kmers[i], pol.model));
-    sb::SaPacked sp;
-    sp.anchor(ix, pred);
-    out[i] = sb::pl_query_from<false, false, sb::KmerQuery, sb::SaPacked, true, 2>(ix, q, pred, 0, pol, sp);
-  }
-  if (!out_packed) delete[] packed;
-}
-
-// The lean 32-bit k-mer replay (query.cuh kmer_replay32) on the three layouts.  mode 0: suffix-array sector + packed
-// genome; 1: inline-prefix entries (ext_bases leading bases, k <= ext_bases); 2: rank lines (bases, shift).
-int sim_kmer_batch_lean(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
-                        const int* five, int compat, const uint64_t* kmers, size_t nq, int64_t* out,
-                        unsigned long long* oob, int mode, int bases, int shift) {
-  sb::IndexView ix;
-  ix.genome = genome; ix.sa = sa; ix.ext = nullptr; ix.ext_bases = 0;
-  ix.packed = nullptr; ix.packed_bases = bases; ix.packed_shift = shift;
-  ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
-  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
-  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
-  ix.compat = compat; ix.oob_counter = oob;
-  ix.narrow = nullptr; ix.last_x = 0; ix.last_y = 0; ix.hints = 0;
-  if (!sb::lean_eligible(ix)) return -1;
-  uint32_t* packed = nullptr;
-  sb::ExtEntry* ext = nullptr;
-  // the device arrays are padded to whole lines; sectors are read whole
-  uint32_t* sa_pad = new uint32_t[sb::sa_alloc_entries(n) + 16]();
-  memcpy(sa_pad, sa, n * sizeof(uint32_t));
-  ix.sa = sa_pad;
-  if (mode == 4 && shift != 4) return -2;  // the flat replay reads tiling lines only
-  if (mode == 2 || mode == 3 || mode == 4 || mode == 5) {
-    const uint64_t sectors = sb::packed_sectors(n, shift);
-    packed = new uint32_t[sectors * 8];
-    for (uint64_t s = 0; s < sectors; s++) {
-      const uint64_t r0 = ((s >> 2) << shift) + ((s & 3u) << 2);
-      sb::pack_rank_sector(genome, sa, n, bases, r0, packed + s * 8);
-    }
-    ix.packed = packed;
-  } else if (mode == 1) {
-    ext = new sb::ExtEntry[n];
-    for (uint64_t r = 0; r < n; r++) {
-      ext[r].pos = sa[r];
-      ext[r].reserved = 0;
-      const uint64_t w = sb::load_bases32(genome, sa[r]);
-      ext[r].prefix = bases >= 32 ? w : (w >> (64 - 2 * bases)) << (64 - 2 * bases);
-    }
-    ix.ext = ext;
-    ix.ext_bases = bases;
-  }
-  const sb::L2Policies pol = sb::make_policies(0);
-  for (size_t i = 0; i < nq; i++) {
-    const uint64_t q = kmers[i] << (64 - 2 * k);
-    const uint32_t pred = (uint32_t)sb::clamp_prediction(ix, sb::predict_rank(ix, kmers[i], pol.model));
-    if (mode == 4) {
-      out[i] = sb::kmer_replay_flat<true>(ix, q, pred, pol);
-    } else if (mode == 5) {  // the replay cut in two (parked tails): three probes, then binarySearch resumed cold
-      sb::SaPacked32 sp;
-      sp.anchor(ix, pred);
-      sb::Lean32 st;
-      long long r = 0;
-      if (!sb::kmer_replay32_head<2, true>(ix, q, pred, pol, sp, st, &r)) {
-        sb::SaPacked32 cold;
-        cold.abase = 0xFFFFFFF0u;
-        cold.cur = 0xFFFFFFFFu;
-        r = sb::kmer_replay32_tail<2, true>(ix, q, pol, cold, st);
-      }
-      out[i] = r;
-    } else if (mode == 2) {
-      sb::SaPacked32 sp;
-      sp.anchor(ix, pred);
-      out[i] = sb::kmer_replay32<2, true>(ix, q, pred, pol, sp);
-    } else if (mode == 3) {  // anchor line staged in the thread's shared-memory slot
-      uint4 slot[sb::kLineSlotU4];
-      sb::SaLine32 sl;
-      sl.sm = slot;
-      sl.anchor(ix, pred, pol.sa);
-      out[i] = sb::kmer_replay32<2, true>(ix, q, pred, pol, sl);
-    } else if (mode == 1) {
-      sb::SaNone32 none;
-      out[i] = sb::kmer_replay32<1, true>(ix, q, pred, pol, none);
+    if (!probes) {
+      out[i] = sb::pl_query<false>(ix, q, kmers[i]);
     } else {
-      sb::SaSector32 ss;
-      ss.fill(ix, pred, pol.sa);
-      out[i] = sb::kmer_replay32<0, true>(ix, q, pred, pol, ss);
+      uint64_t pred = sb::predict_rank(ix, kmers[i], pol.model);
+      if (pred >= n) pred = n - 1;
+      sb::Replay<false, sb::KmerQuery, false> rp;
+      rp.begin(pred);
+      long long result;
+      for (;;) {
+        const bool final_read = rp.state == sb::ST_FINAL;
+        const bool done = rp.step(ix, q, pol, &result);
+        if (!final_read) np++;
+        if (done) break;
+      }
+      out[i] = result;
     }
   }
-  delete[] packed;
-  delete[] ext;
-  delete[] sa_pad;
-  return 0;
+  if (probes) *probes = np;
+  delete[] lines;
 }
 
 void sim_string_batch(const uint64_t* genome, const uint32_t* sa, const int64_t* model_xy, uint64_t n, int k, int nb,
                       const int* five, int compat, const uint64_t* words, const uint64_t* word_off,
                       const uint32_t* slens, const uint32_t* lengths, const int64_t* kmers, size_t nq, int64_t* out,
                       unsigned long long* oob, const uint2* narrow, const int64_t* last_xy) {
-  sb::IndexView ix;
-  ix.genome = genome; ix.sa = sa; ix.model = reinterpret_cast<const sb::ModelEntry*>(model_xy);
-  ix.n = n; ix.k = k; ix.nb = nb; ix.shift = 2 * k - nb;
-  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
-  ix.compat = compat; ix.oob_counter = oob;
-  ix.narrow = narrow; ix.last_x = last_xy[0]; ix.last_y = last_xy[1]; ix.hints = 0;
+  const int bases = sb::line_bases_for(n);
+  uint32_t* lines = build_lines(genome, sa, n, bases, nullptr);
+  const sb::IndexView ix = make_view(genome, lines, bases, model_xy, n, k, nb, five, compat, oob, narrow, last_xy);
   for (size_t i = 0; i < nq; i++) {
     sb::StringQuery q; q.w = words + word_off[i]; q.slen_ = slens[i]; q.length_ = lengths[i];
     out[i] = sb::pl_query<true>(ix, q, (uint64_t)kmers[i]);
   }
+  delete[] lines;
+}
+
+// Phase 2 of the k-mer path on its own (kmer.cuh replay_plquery: the reference's control flow over {lb, ub}) against a
+// direct transcription of the reference's plQuery / binarySearch (sapling_api.h:133-248) with the same abstract
+// comparator -- size_t arithmetic, the (int) casts of :209 and :225, recursion unrolled, nothing jumped.  No genome is
+// needed, so ranks >= 2^31 and windows of any size are testable on the CPU.  Returns the number of cases in
+// which the two disagree; *first_bad receives the index of the first one.
+static long long literal_plquery(uint64_t n, uint64_t pred, uint64_t lb, uint64_t ub, const int* five, int compat) {
+  const long long maxOver = five[0], maxUnder = five[1], mostOver = five[3], mostUnder = five[4];
+  auto small = [&](uint64_t r) { return r < lb; };
+  auto match = [&](uint64_t r) { return r >= lb && r < ub; };
+  if (match(pred)) return (long long)pred;                                   // :164
+  uint64_t lo, hi;
+  if (small(pred)) {                                                          // :167
+    lo = pred;
+    hi = pred + (uint64_t)mostOver < n - 1 ? pred + (uint64_t)mostOver : n - 1;  // :171
+    if (match(hi)) return (long long)hi;                                      // :174
+    if (small(hi)) {                                                          // :175
+      lo = hi;
+      hi = pred + (uint64_t)maxOver + 1 < n - 1 ? pred + (uint64_t)maxOver + 1 : n - 1;  // :180
+      if (match(hi)) return (long long)hi;                                    // :183
+    }
+  } else {
+    if (compat) {
+      const int v = (int)(unsigned)pred - (int)mostUnder;                     // :209  (int)predicted-mostUnder
+      lo = (uint64_t)(v > 0 ? v : 0);
+    } else {
+      lo = pred > (uint64_t)mostUnder ? pred - (uint64_t)mostUnder : 0;
+    }
+    hi = pred;
+    if (match(lo)) return (long long)lo;                                      // :213
+    if (!small(lo)) {                                                         // :220
+      hi = lo;
+      if (compat) {
+        const int v = (int)((unsigned)pred - (unsigned)maxUnder - 1u);        // :225 (two's complement wrap, as compiled)
+        lo = (uint64_t)(v > 0 ? v : 0);
+      } else {
+        lo = pred > (uint64_t)maxUnder + 1 ? pred - (uint64_t)maxUnder - 1 : 0;
+      }
+      if (match(lo)) return (long long)lo;                                    // :228
+    }
+  }
+  for (;;) {                                                                  // binarySearch :133-153
+    if (hi == lo + 2) return (long long)(lo + 1);
+    const uint64_t mid = (lo + hi) >> 1;
+    if (match(mid)) return (long long)mid;
+    if (lo + 1 >= hi) return -1;
+    if (small(mid)) lo = mid; else hi = mid;
+  }
+}
+uint64_t sim_replay_abstract(uint64_t n, const uint64_t* pred, const uint64_t* lb, const uint64_t* ub, size_t count,
+                             const int* five, int compat, uint64_t* first_bad) {
+  sb::IndexView ix;
+  memset(&ix, 0, sizeof(ix));
+  ix.n = n; ix.k = 21;
+  ix.maxOver = five[0]; ix.maxUnder = five[1]; ix.mostOver = five[3]; ix.mostUnder = five[4];
+  ix.compat = compat;
+  uint64_t bad = 0;
+  for (size_t i = 0; i < count; i++) {
+    sb::Bounds b;
+    b.lb = (uint32_t)lb[i];
+    b.ub = (uint32_t)ub[i];
+    const long long got = sb::replay_plquery(ix, (uint32_t)pred[i], b);
+    const long long exp = literal_plquery(n, pred[i], lb[i], ub[i], five, compat);
+    if (got != exp && bad++ == 0 && first_bad) *first_bad = i;
+  }
+  return bad;
 }
 }

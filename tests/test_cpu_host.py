@@ -81,7 +81,7 @@ def _sim():
         return _SIM
     so = os.path.join(ROOT, "build", "libsim_query.so")
     src = os.path.join(ROOT, "tests", "sim", "sim_query.cpp")
-    deps = [src] + [os.path.join(ROOT, "sapling_b200", "csrc", f) for f in ("query.cuh", "common.cuh")]
+    deps = [src] + [os.path.join(ROOT, "sapling_b200", "csrc", f) for f in ("kmer.cuh", "query.cuh", "common.cuh")]
     os.makedirs(os.path.dirname(so), exist_ok=True)
     if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(d) for d in deps):
         tmp = f"{so}.{os.getpid()}.tmp"
@@ -90,81 +90,35 @@ def _sim():
         os.replace(tmp, so)
     L = C.CDLL(so)
     i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    u64c = C.POINTER(C.c_uint64)
+    L.sim_kmer_answer.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
+                                  C.c_size_t, O.i64p, u64c, C.c_void_p, O.i64p, C.c_int, C.c_void_p, u64c]
     L.sim_kmer_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
-                                 C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_void_p, O.i64p]
+                                 C.c_size_t, O.i64p, u64c, C.c_void_p, O.i64p, u64c]
     L.sim_string_batch.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
-                                   O.u64p, O.u32p, O.u32p, O.i64p, C.c_size_t, O.i64p, C.POINTER(C.c_uint64),
-                                   C.c_void_p, O.i64p]
-    L.sim_kmer_batch_packed.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
-                                        C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_void_p,
-                                        C.POINTER(C.c_uint64)]
-    L.sim_kmer_batch_lean.restype = C.c_int
-    L.sim_kmer_batch_lean.argtypes = [O.u64p, O.u32p, O.i64p, C.c_uint64, C.c_int, C.c_int, i32p, C.c_int, O.u64p,
-                                      C.c_size_t, O.i64p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_int]
+                                   O.u64p, O.u32p, O.u32p, O.i64p, C.c_size_t, O.i64p, u64c, C.c_void_p, O.i64p]
+    L.sim_replay_abstract.restype = C.c_uint64
+    L.sim_replay_abstract.argtypes = [C.c_uint64, O.u64p, O.u64p, O.u64p, C.c_size_t, i32p, C.c_int, u64c]
     _SIM = L
     return L
 
 
-@pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])
-def test_lean_kmer_replay_on_host_matches_oracle(oracle_built, name):
-    """query.cuh kmer_replay32 (32-bit ranks, the nine cases of the replay folded into one update; what the batch
-    kernels run) compiled for the host == oracle, on all three layouts: suffix-array sector + packed genome, inline
-    prefixes, rank lines (overlapping / tiling, prefixes shorter than k, escapes); the model's own error bounds, bounds
-    that collapse the left window to rank 0 (long-window shortcut), tiny bounds; compat and 64-bit-safe
-    window arithmetic."""
-    L = _sim()
-    g = F.small_genomes()[name]
-    n = len(g)
-    for k, nb in ((21, -1), (11, 4), (31, 10), (16, -1), (32, 12)):
-        if n < 4 * k:
-            continue
-        if k == 32:
-            continue  # oracle-undefined (SURVEY F4)
-        base = O.Port.from_memory(g, nb=nb, k=k)
-        packed, sa = F.pack_genome(g), base.sa
-        model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
-        kmers = F.query_mix(g, k, 3000)
-        tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(max(0, n - 40), n)], dtype=np.uint64)
-        kmers = np.concatenate([kmers, tail])
-        f0 = list(base.five)
-        for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30], [2, 2, 1, 1, 1],
-                       [1, 40, 1, 9, 30]):
-            port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
-            five = np.array(five_t, dtype=np.int32)
-            exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
-            cases = [(0, 0, 3), (2, 6, 3), (2, 12, 4), (2, 21, 3), (2, 32, 4), (2, 16, 4),
-                     (3, 6, 4), (3, 12, 3), (3, 21, 4), (3, 32, 3), (3, 16, 3),
-                     (4, 6, 4), (4, 12, 4), (4, 21, 4), (4, 32, 4), (4, 16, 4), (4, 24, 4),
-                     (5, 6, 4), (5, 12, 3), (5, 21, 4), (5, 32, 3), (5, 24, 4)]
-            cases += [(1, b, 3) for b in (27, 32) if k <= b]
-            for mode, bases, shift in cases:
-                out = np.empty(len(kmers), dtype=np.int64)
-                c = C.c_uint64(0)
-                rc = L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c),
-                                           mode, bases, shift)
-                assert rc == 0
-                bad = np.nonzero(out != exp)[0]
-                assert len(bad) == 0 and c.value == oob, (name, k, nb, five_t, mode, bases, shift, bad[:5], out[bad[:5]],
-                                                          exp[bad[:5]])
-            # 64-bit-safe window arithmetic (SAPLING_B200_NO_COMPAT) has no oracle: lean replay == general replay
-            gen = np.empty(len(kmers), dtype=np.int64)
-            last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
-            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), gen, C.byref(c), None, last)
-            for mode, bases, shift in cases[:3] + [(4, 12, 4), (4, 21, 4)]:
-                out = np.empty(len(kmers), dtype=np.int64)
-                assert L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), out,
-                                             C.byref(c), mode, bases, shift) == 0
-                assert np.array_equal(out, gen), (name, k, nb, five_t, mode, "no-compat")
-            port.close()
-        base.close()
+def _answer(L, packed, sa, model, n, k, nb, five, compat, kmers, nptr, last, bases):
+    out = np.empty(len(kmers), dtype=np.int64)
+    oob, esc = C.c_uint64(0), C.c_uint64(0)
+    L.sim_kmer_answer(packed, sa, model, n, k, nb, five, compat, kmers, len(kmers), out, C.byref(oob), nptr, last, bases,
+                      None, C.byref(esc))
+    return out, oob.value, esc.value
 
 
 @pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])
-def test_rank_line_query_code_on_host_matches_oracle(oracle_built, name):
-    """The rank-line layout (common.cuh pack_rank_sector + query.cuh SaPacked, the default for genomes >= 50 Mbp)
-    compiled for the host == oracle: overlapping and tiling lines, prefixes shorter than / as long as / longer than k
-    (genome fallback on ties), prefixes wide enough that 21-bit deltas overflow (escapes), suffixes at the end of the
-    text, and the collapsed left window of SURVEY F5."""
+def test_kmer_path_on_host_matches_oracle(oracle_built, name):
+    """kmer.cuh (what the batch kernels run: sector classification, bounds, the reference's control flow replayed in
+    registers) compiled for the host == oracle: rank-line prefixes shorter than / as long as / longer than k (ties decided
+    by the genome), prefixes wide enough that 21-bit deltas overflow (escapes), suffixes at the end of the text; the
+    model's own error bounds, bounds that collapse the left window to rank 0 (the closed-form jump), tiny
+    bounds (the reference's wrong answers must be reproduced too); wide and narrow model; compat and 64-bit-safe window
+    arithmetic."""
     L = _sim()
     g = F.small_genomes()[name]
     n = len(g)
@@ -175,31 +129,41 @@ def test_rank_line_query_code_on_host_matches_oracle(oracle_built, name):
         base = O.Port.from_memory(g, nb=nb, k=k)
         packed, sa = F.pack_genome(g), base.sa
         model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
+        last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
+        narrow, nok = F.narrow_model(base.xlist, base.ylist, k, base.nb)
+        layouts = [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else [])
         kmers = F.query_mix(g, k, 3000)
         # every suffix of the last 40 positions as a query too (short suffixes are escaped entries)
         tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(max(0, n - 40), n)], dtype=np.uint64)
         kmers = np.concatenate([kmers, tail])
         f0 = list(base.five)
-        for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30]):
+        for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30], [2, 2, 1, 1, 1],
+                       [1, 40, 1, 9, 30], [0, 0, 0, 0, 0]):
             port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
             five = np.array(five_t, dtype=np.int32)
             exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
-            for bases in (6, 12, 16, 21, 32):
-                for shift in (3, 4):
-                    out = np.empty(len(kmers), dtype=np.int64)
-                    c, e = C.c_uint64(0), C.c_uint64(0)
-                    L.sim_kmer_batch_packed(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c),
-                                            bases, shift, None, C.byref(e))
-                    assert np.array_equal(out, exp) and c.value == oob, (name, k, nb, five_t, bases, shift)
-                    escapes += e.value
             port.close()
+            for bases in (0, 6, 12, 16, 21, 31):
+                for nptr in layouts:
+                    out, c, e = _answer(L, packed, sa, model, n, k, base.nb, five, 1, kmers, nptr, last, bases)
+                    bad = np.nonzero(out != exp)[0]
+                    assert len(bad) == 0 and c == oob, (name, k, nb, five_t, bases, bad[:5], out[bad[:5]], exp[bad[:5]])
+                    escapes += e
+            # 64-bit-safe window arithmetic (SAPLING_B200_NO_COMPAT) has no oracle: k-mer path == literal replay
+            gen = np.empty(len(kmers), dtype=np.int64)
+            c = C.c_uint64(0)
+            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 0, kmers, len(kmers), gen, C.byref(c), None, last, None)
+            for bases in (0, 12):
+                out, _, _ = _answer(L, packed, sa, model, n, k, base.nb, five, 0, kmers, layouts[-1], last, bases)
+                assert np.array_equal(out, gen), (name, k, nb, five_t, bases, "no-compat")
         base.close()
     assert escapes > 0  # at least the short suffixes at the end of the text
 
 
 @pytest.mark.parametrize("name", ["rand20k", "gc1991", "gc0110", "polyC", "tandem_CT", "tandem50", "repeat_tailA"])
-def test_device_query_code_on_host_matches_oracle(oracle_built, name):
-    """query.cuh (the device replay of plQuery) compiled for the host == oracle, k-mers and strings."""
+def test_literal_replay_on_host_matches_oracle(oracle_built, name):
+    """query.cuh (the literal replay of plQuery: what the string-query kernel and the probe counter run) compiled for the
+    host == oracle, k-mers and strings; the probe count equals the oracle's count of getLcp calls."""
     L = _sim()
     g = F.small_genomes()[name]
     n = len(g)
@@ -224,12 +188,17 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
         for five_t in (f0, [f0[0], f0[1], f0[2], f0[3], 1 << 30], [f0[0], 2, f0[2], 1, 1 << 30]):
             port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
             five = np.array(five_t, dtype=np.int32)
-            exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
+            exp, probes, oob = port.query_batch(kmers, nthreads=2, stats=True)
             for nptr in layouts:  # wide table, then the narrow 8-byte layout
                 out = np.empty(len(kmers), dtype=np.int64)
                 c = C.c_uint64(0)
-                L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last)
+                L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last,
+                                 None)
                 assert np.array_equal(out, exp) and c.value == oob, (name, k, nb, five_t)
+            np_ = C.c_uint64(0)
+            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), layouts[-1],
+                             last, C.byref(np_))
+            assert np.array_equal(out, exp) and np_.value == probes, (name, k, nb, five_t, np_.value, probes)
             exp2 = np.array([port.query_str(s, x) for s, x in zip(strs, km)], dtype=np.int64)
             out2 = np.empty(len(strs), dtype=np.int64)
             L.sim_string_batch(packed, sa, model, n, k, base.nb, five, 1, words, offs, slens, slens, km, len(strs), out2,
@@ -240,15 +209,14 @@ def test_device_query_code_on_host_matches_oracle(oracle_built, name):
     tried, ok = C.c_uint64(0), C.c_uint64(0)
     L.sim_skip_counters(C.byref(tried), C.byref(ok))
     assert tried.value > 1000 and ok.value > 1000, (tried.value, ok.value)  # the shortcut was exercised (cumulative)
-    print(f"long-window shortcut: tried {tried.value}, accepted {ok.value}")
 
 
 @pytest.mark.parametrize("seed", range(40))
-def test_randomised_replay_against_oracle(oracle_built, seed):
-    """Randomised differential test of the device replay code (host simulation) against the oracle: random genome
+def test_randomised_kmer_path_against_oracle(oracle_built, seed):
+    """Randomised differential test of the device query code (host simulation) against the oracle: random genome
     recipes (uniform, skewed, short tandem units, planted repeats), random k, bucket count and error bounds (bounds
-    smaller than the model's true errors included: the replay must reproduce the reference's wrong answers too), every
-    replay variant and layout the batch kernels can run."""
+    smaller than the model's true errors included: the reference's wrong answers must be reproduced), random rank-line
+    prefix lengths, both model layouts; the literal replay as well."""
     L = _sim()
     rng = np.random.default_rng(9000 + seed)
     n = int(rng.integers(400, 6000))
@@ -272,33 +240,61 @@ def test_randomised_replay_against_oracle(oracle_built, seed):
     model = np.ascontiguousarray(np.stack([base.xlist, base.ylist], axis=1).reshape(-1))
     last = np.array([base.xlist[-1], base.ylist[-1]], dtype=np.int64)
     narrow, nok = F.narrow_model(base.xlist, base.ylist, k, base.nb)
+    layouts = [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else [])
     kmers = F.query_mix(g, k, 1500, seed=seed)
     f0 = list(base.five)
     bounds = [f0, [int(rng.integers(0, 6)), int(rng.integers(0, 6)), 1, int(rng.integers(0, 4)), int(rng.integers(0, 4))],
-              [f0[0], f0[1], f0[2], f0[3], 1 << 30]]
+              [f0[0], f0[1], f0[2], f0[3], 1 << 30],
+              [int(rng.integers(0, 300)), int(rng.integers(0, 300)), 1, int(rng.integers(0, 40)), int(rng.integers(0, 40))]]
     for five_t in bounds:
         port = O.Port.from_parts(g, sa, k, base.nb, base.xlist, base.ylist, five_t)
         five = np.array(five_t, dtype=np.int32)
         exp, _, oob = port.query_batch(kmers, nthreads=2, stats=True)
         port.close()
-        for nptr in [None] + ([narrow.ctypes.data_as(C.c_void_p)] if nok else []):
+        for nptr in layouts:
             out = np.empty(len(kmers), dtype=np.int64)
             c = C.c_uint64(0)
-            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last)
-            assert np.array_equal(out, exp) and c.value == oob, (seed, n, k, nb, five_t, "general", nptr is not None)
-        pb = int(rng.integers(4, 33))
-        cases = [(0, 0, 3), (2, pb, 3), (2, pb, 4), (3, pb, 3), (3, pb, 4), (4, pb, 4), (5, pb, 4), (5, pb, 3)]
-        cases += [(1, b, 3) for b in (27, 32) if k <= b]
-        for mode, bases, shift in cases:
-            out = np.empty(len(kmers), dtype=np.int64)
-            c = C.c_uint64(0)
-            rc = L.sim_kmer_batch_lean(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c),
-                                       mode, bases, shift)
-            assert rc == 0
+            L.sim_kmer_batch(packed, sa, model, n, k, base.nb, five, 1, kmers, len(kmers), out, C.byref(c), nptr, last, None)
+            assert np.array_equal(out, exp) and c.value == oob, (seed, n, k, nb, five_t, "literal", nptr is not None)
+        for bases in (0, int(rng.integers(4, 32)), int(rng.integers(4, 32))):
+            out, c, _ = _answer(L, packed, sa, model, n, k, base.nb, five, 1, kmers, layouts[-1], last, bases)
             bad = np.nonzero(out != exp)[0]
-            assert len(bad) == 0 and c.value == oob, (seed, n, k, nb, five_t, mode, bases, shift, bad[:5], out[bad[:5]],
-                                                      exp[bad[:5]])
+            assert len(bad) == 0 and c == oob, (seed, n, k, nb, five_t, bases, bad[:5], out[bad[:5]], exp[bad[:5]])
     base.close()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_register_replay_against_literal_control_flow(seed):
+    """Phase 2 of the k-mer path (kmer.cuh replay_plquery: plQuery's control flow over the match range [lb, ub), with the
+    closed-form jump over binary-search steps that all go right) against a direct transcription of sapling_api.h:133-248
+    driven by the same abstract comparator.  No genome is involved, so suffix arrays of > 2^31 ranks -- where the
+    reference's (int)predicted casts (:209, :225) turn a bounded search into one from rank 0 -- are covered on
+    the CPU: predictions on both sides of 2^31, match ranges near and far from the prediction, empty ranges (absent
+    k-mers), windows from 0 to thousands of ranks, both window arithmetics."""
+    L = _sim()
+    rng = np.random.default_rng(77 + seed)
+    count = 200000
+    for n in (3_100_000_000, (1 << 31) + 5, (1 << 32) - 300, 5000, 37):
+        for five_t in ([25, 12, 1, 4, 3], [4231, 4498, 11, 29, 28], [2, 2, 1, 1, 1], [0, 0, 0, 0, 0],
+                       [int(rng.integers(0, 5000)), int(rng.integers(0, 5000)), 1, int(rng.integers(0, 60)),
+                        int(rng.integers(0, 60))]):
+            pred = rng.integers(0, n, size=count, dtype=np.uint64)
+            # some predictions right at the edges and around 2^31
+            pred[:2000] = rng.integers(0, min(n, 200), size=2000, dtype=np.uint64)
+            pred[2000:4000] = np.uint64(n - 1) - rng.integers(0, min(n, 200), size=2000, dtype=np.uint64)
+            if n > (1 << 31) + 200:
+                pred[4000:8000] = np.uint64((1 << 31) - 100) + rng.integers(0, 200, size=4000, dtype=np.uint64)
+            spread = rng.choice([3, 8, 40, 6000, n], size=count, p=[0.45, 0.25, 0.15, 0.1, 0.05]).astype(np.int64)
+            off = (rng.random(count) * 2 - 1) * spread
+            lb = np.clip(pred.astype(np.int64) + off.astype(np.int64), 0, n).astype(np.uint64)
+            run = rng.choice([0, 1, 2, 5, 300], size=count, p=[0.3, 0.5, 0.1, 0.07, 0.03]).astype(np.uint64)
+            ub = np.minimum(lb + run, np.uint64(n))
+            five = np.array(five_t, dtype=np.int32)
+            for compat in (1, 0):
+                first = C.c_uint64(0)
+                bad = L.sim_replay_abstract(n, pred, lb, ub, count, five, compat, C.byref(first))
+                i = first.value
+                assert bad == 0, (n, five_t, compat, bad, int(pred[i]), int(lb[i]), int(ub[i]))
 
 
 @pytest.mark.parametrize("seed", range(10))

@@ -183,31 +183,28 @@ def test_no_compat_equals_compat_below_2g(S, oracle_built):
 
 
 def test_layout_and_hint_variants_agree(S, oracle_built, monkeypatch):
-    """The narrow (8 B/bucket) model layout and every L2-hint combination return the oracle's answers; genomes with
-    many empty buckets exercise the forward-fill encoding."""
+    """The narrow (8 B/bucket) and wide model layouts, every L2-hint combination and every compiled occupancy return the
+    oracle's answers; genomes with many empty buckets exercise the forward-fill encoding.  (SAPLING_B200_TUNE is read
+    once, when an index is created.)"""
     for name, k, nb in (("gc0110", 16, 10), ("gc1991", 21, -1), ("rand200k", 21, -1), ("tandem50", 21, 8)):
         g = GENOMES[name]
         port = O.Port.from_memory(g, nb=nb, k=k)
         kmers = F.query_mix(g, k, 8000, seed=11)
         exp = port.query_batch(kmers, nthreads=4)
-        for narrow, hints in ((0, 0), (1, 0), (1, 15), (0, 15), (1, 5)):
-            monkeypatch.setenv("SAPLING_B200_NARROW", str(narrow))
-            monkeypatch.setenv("SAPLING_B200_HINTS", str(hints))
+        for narrow, hints, occ in ((0, 0, 0), (1, 0, 3), (1, 15, 4), (0, 15, 5), (1, 5, 6), (1, 27, 0)):
+            monkeypatch.setenv("SAPLING_B200_TUNE", f"narrow={narrow},hints={hints},occ={occ}")
             ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
-            for sector, line, pipe, qv in (("1", "0", "0", "4"), ("1", "0", "0", "3"), ("1", "0", "0", "5"),
-                                           ("1", "0", "0", "6"), ("0", "1", "1", "4"), ("0", "1", "1", "3"),
-                                           ("0", "1", "0", "4"), ("0", "1", "0", "8"), ("0", "0", "1", "4"),
-                                           ("0", "0", "1", "5"), ("0", "0", "0", "4"), ("0", "0", "0", "6"),
-                                           ("0", "0", "0", "8")):
-                monkeypatch.setenv("SAPLING_B200_SECTOR", sector)
-                monkeypatch.setenv("SAPLING_B200_LINE", line)
-                monkeypatch.setenv("SAPLING_B200_PIPELINE", pipe)
-                monkeypatch.setenv("SAPLING_B200_QV", qv)
-                assert np.array_equal(ix.queryBatch(kmers), exp), (name, narrow, hints, sector, line, pipe, qv)
+            assert np.array_equal(ix.queryBatch(kmers), exp), (name, narrow, hints, occ)
+            got32 = ix.queryBatchU32(kmers)
+            assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, "u32")
             pred = ix.queryPiecewiseLinear(kmers[:500])
             assert [int(p) for p in pred] == [port.predict(int(x)) for x in kmers[:500]]
+            x, y = ix.model()  # rebuilt from the narrow table when that is the resident form
+            assert np.array_equal(x, port.xlist) and np.array_equal(y, port.ylist)
+            assert np.array_equal(ix.rev(), port.sa)  # read back out of the rank lines
             ix.close()
         port.close()
+    monkeypatch.delenv("SAPLING_B200_TUNE")
 
 
 def test_k32_cross_checked_by_equal_range(S, oracle_built):
@@ -245,7 +242,7 @@ def test_seed_batch_matches_align_seed_loop(S, oracle_built, name, k):
     reads += [b"ACGT", g[100:100 + k], g[7:7 + k + 1], b"N" * 60, g[5:155].lower(), g[-150:], g[:150]]
     port = O.Port.from_memory(g, k=k)
     ix = S.Sapling.from_memory(g, None, k=k, flags=S.QUIET | S.KEEP_BUILD)
-    for num_seeds, max_hits in ((7, 32), (1, 4), (3, 1000)):
+    for num_seeds, max_hits in ((7, 32), (1, 4), (3, 255)):
         exp = port.seed_batch(reads, num_seeds, max_hits)
         got = ix.seedBatch(reads, num_seeds, max_hits)
         for a, b, what in zip(got, exp, ("ref_pos", "sa_pos", "left", "right")):
@@ -255,105 +252,73 @@ def test_seed_batch_matches_align_seed_loop(S, oracle_built, name, k):
     port.close()
 
 
-@pytest.mark.parametrize("name", ["rand200k", "gc1991", "tandem50", "repeat_tailA", "polyC"])
-def test_inline_prefix_suffix_array(S, oracle_built, name):
-    """The inline-prefix suffix array (rank -> {position, leading bases}; default for genomes >= 400 Mbp) returns the
-    oracle's answers on both build paths: from the GPU suffix-array builder's sort keys (27 bases) and by gather for a
-    suffix array that was supplied (32 bases)."""
-    g = GENOMES[name]
-    for k, nb in ((21, -1), (16, 8), (11, -1), (27, 10), (31, 12)):
-        if len(g) < 4 * k:
-            continue
-        port = O.Port.from_memory(g, nb=nb, k=k)
-        kmers = F.query_mix(g, k, 6000, seed=3)
-        exp = port.query_batch(kmers, nthreads=4)
-        a = S.Sapling.from_memory(g, None, numBuckets=nb, k=k, flags=S.QUIET | S.INLINE)        # sort-key prefixes
-        b = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k, flags=S.QUIET | S.INLINE)     # gathered prefixes
-        c = S.Sapling.from_memory(g, None, numBuckets=nb, k=k, flags=S.QUIET | S.NO_INLINE)
-        assert a.device_bytes() >= c.device_bytes() + 16 * len(g)
-        for ix in (a, b, c):
-            assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb)
-            ix.close()
-        port.close()
-
-
 @pytest.mark.parametrize("name", ["rand200k", "gc1991", "gc0110", "tandem50", "repeat_tailA", "polyC"])
 def test_rank_line_layout(S, oracle_built, name, monkeypatch):
-    """The rank-line layout (one 32-byte sector = four {position, prefix} entries; default for genomes >= 50 Mbp)
-    returns the oracle's answers: overlapping (shift 3) and tiling (shift 4) lines, prefixes shorter than / equal to /
-    longer than k (the first falls back to the packed genome on ties, the last overflows the 21-bit deltas and
-    escapes), every resident-blocks variant of the kernel, and suffixes at the very end of the text."""
+    """The rank lines (the resident form of the suffix array) built on the GPU are byte-identical to the host build of the
+    same packing code, and the k-mer path returns the oracle's answers for entry prefixes shorter than / as long as /
+    longer than k (ties decided by the genome) and wide enough that 21-bit deltas overflow (escaped entries)."""
+    import ctypes as C
+    import test_cpu_host as T
+    L = T._sim()
     g = GENOMES[name]
-    for k, nb in ((21, -1), (16, 8), (11, -1), (31, 12)):
-        if len(g) < 4 * k:
+    n = len(g)
+    for k, nb in ((21, -1), (16, 8), (11, 4), (31, 10)):
+        if n < 4 * k:
             continue
         port = O.Port.from_memory(g, nb=nb, k=k)
-        kmers = F.query_mix(g, k, 6000, seed=7)
-        tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(len(g) - 40, len(g))], dtype=np.uint64)
+        kmers = F.query_mix(g, k, 6000, seed=5)
+        tail = np.array([O.kmerize(k, g[i:i + k] + b"A" * k) for i in range(max(0, n - 40), n)], dtype=np.uint64)
         kmers = np.concatenate([kmers, tail])
-        exp = port.query_batch(kmers, nthreads=4)
-        plain = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k, flags=S.QUIET | S.NO_PACKED | S.NO_INLINE)
-        assert plain.query_kernel()[0] == "kmer_query_sector_kernel"
-        for shift in ("3", "4"):
-            for bases in ("0", "8", "14", "32"):   # 0 = the default for this genome size
-                monkeypatch.setenv("SAPLING_B200_PACKED_SHIFT", shift)
-                monkeypatch.setenv("SAPLING_B200_PACKED_BASES", bases)
-                ix = S.Sapling.from_memory(g, port.sa if bases != "8" else None, numBuckets=nb, k=k,
-                                           flags=S.QUIET | S.PACKED)
-                assert ix.device_bytes() >= plain.device_bytes() + (16 if shift == "3" else 8) * len(g)
-                for refill, kernel in (("1", "kmer_query_packed_refill_kernel"), ("0", "kmer_query_packed_kernel")):
-                    monkeypatch.setenv("SAPLING_B200_REFILL", refill)
-                    # the refill kernel reads the narrow model layout, which needs 2k - nb <= 31
-                    assert ix.query_kernel()[0] == (kernel if 2 * k - port.nb <= 31 else "kmer_query_packed_kernel")
-                    for qv in ("2", "3", "4", "5", "6"):
-                        monkeypatch.setenv("SAPLING_B200_QV", qv)
-                        assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb, shift, bases, refill, qv)
-                        # ragged batch sizes: fewer queries than lanes, than warps, one over a block boundary
-                        for m in (1, 31, 33, 257, 4097):
-                            assert np.array_equal(ix.queryBatch(kmers[:m]), exp[:m]), (name, k, m, refill, qv)
-                    monkeypatch.delenv("SAPLING_B200_QV")
-                monkeypatch.delenv("SAPLING_B200_REFILL")
-                ix.close()
-        plain.close()
+        exp, _, oob = port.query_batch(kmers, nthreads=4, stats=True)
+        packed = F.pack_genome(g)
+        model = np.ascontiguousarray(np.stack([port.xlist, port.ylist], axis=1).reshape(-1))
+        last = np.array([port.xlist[-1], port.ylist[-1]], dtype=np.int64)
+        five = np.array(port.five, dtype=np.int32)
+        for bases in (0, 6, 12, 21, 31):
+            monkeypatch.setenv("SAPLING_B200_TUNE", f"line_bases={bases}")
+            ix = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k)
+            assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb, bases)
+            assert ix.oob_count() == oob
+            # host build of the same lines == what the simulation answers from
+            out, c, _ = T._answer(L, packed, port.sa, model, n, k, port.nb, five, 1, kmers, None, last, bases)
+            assert np.array_equal(out, exp)
+            ix.close()
         port.close()
+    monkeypatch.delenv("SAPLING_B200_TUNE")
 
 
 @pytest.mark.parametrize("name", ["rand200k", "gc0110", "tandem50", "repeat_tailA", "polyC"])
 def test_partitioned_batch(S, oracle_built, name, monkeypatch):
-    """The partitioned batch path (partition.cu: bucket the batch by the top bits of the k-mer, answer it slice by
-    slice, put the answers back in the caller's order) returns exactly what the oracle returns for the caller's order:
-    every layout, bin counts from 2 to 2048 (more bins than buckets included), batches smaller than one partition
-    chunk, ragged last chunks, several chunks, k-mers that all fall into one bin."""
+    """The partitioned batch path (histogram, scans, staged scatter, in-order query kernel, un-permute) returns the answers
+    of the unpartitioned kernel and of the oracle for every slice count, both slot formats (inside the k-mer word for
+    k <= 25, side array above), ragged last chunks and 64-bit / 32-bit outputs."""
     g = GENOMES[name]
-    for k, nb in ((21, -1), (16, 8), (11, 4), (31, 12)):
+    for k, nb in ((21, -1), (16, 6), (31, 10), (11, 4)):
         if len(g) < 4 * k:
             continue
         port = O.Port.from_memory(g, nb=nb, k=k)
-        base = F.query_mix(g, k, 6000, seed=11)
-        kmers = np.concatenate([base, base[::-1], np.sort(base), np.full(3000, base[0], dtype=np.uint64)] * 2)  # 42000 > 2 chunks
+        kmers = F.query_mix(g, k, 40000, seed=9)[:37777]  # ragged last chunk (16384 per chunk)
         exp = port.query_batch(kmers, nthreads=4)
-        for flags in (S.NO_PACKED | S.NO_INLINE, S.PACKED, S.INLINE | S.NO_PACKED):
-            ix = S.Sapling.from_memory(g, port.sa, numBuckets=nb, k=k, flags=S.QUIET | flags)
-            monkeypatch.setenv("SAPLING_B200_PART", "0")
-            assert ix.partition_bits(len(kmers)) == 0
-            plain = ix.queryBatch(kmers)
-            assert np.array_equal(plain, exp)
-            monkeypatch.setenv("SAPLING_B200_PART", "1")
-            monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
-            for bits in (1, 3, 8, 9, 10, 11):  # un-permute: run-per-warp up to 8, then lane groups of 16, 8, 4
-                monkeypatch.setenv("SAPLING_B200_PART_BITS", str(bits))
-                assert ix.partition_bits(len(kmers)) == min(bits, 2 * k)
-                for m in (len(kmers), 8192, 8193, 16384, 16385, 32767, 1, 33, 5000):
-                    assert np.array_equal(ix.queryBatch(kmers[:m]), exp[:m]), (name, k, nb, flags, bits, m)
-            monkeypatch.delenv("SAPLING_B200_PART_BITS")
-            assert ix.oob_count() >= 0
+        for bits in (1, 3, 5, 8, 11):
+            if bits > 2 * k:
+                continue
+            monkeypatch.setenv("SAPLING_B200_TUNE", f"part_min=1,part_bits={bits},chunk_log2=22")
+            ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+            assert ix.partition_bits(len(kmers)) == bits
+            assert ix.query_kernel(len(kmers))[0] == "kmer_query_ordered_kernel"
+            assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, nb, bits)
+            got32 = ix.queryBatchU32(kmers)
+            assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, k, bits, "u32")
             ix.close()
+        monkeypatch.setenv("SAPLING_B200_TUNE", "part=0")
+        ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+        assert ix.partition_bits(len(kmers)) == 0 and ix.query_kernel(len(kmers))[0] == "kmer_query_kernel"
+        assert np.array_equal(ix.queryBatch(kmers), exp)
+        ix.close()
         port.close()
-    monkeypatch.delenv("SAPLING_B200_PART_MIN", raising=False)
-    monkeypatch.delenv("SAPLING_B200_PART", raising=False)
+    monkeypatch.delenv("SAPLING_B200_TUNE")
 
 
-@pytest.mark.gpu
 def test_index_cache_round_trip(S, oracle_built, tmp_path, monkeypatch):
     """an index opened from the reference's files (two-record FASTA; .sa and .sap built and written on the
     way), saved as a private cache and restored from it is the same index: scalars, chromosome table, genome, suffix
@@ -411,94 +376,81 @@ def test_index_cache_round_trip(S, oracle_built, tmp_path, monkeypatch):
             S.Sapling.from_cache(str(tmp_path / "bad.b200"), flags=S.QUIET)
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("name,k", [("rand200k", 21), ("tandem50", 16), ("gc0110", 31)])
 def test_partitioned_large_batch(S, oracle_built, name, k, monkeypatch):
-    """A batch of many partition chunks (2.1 M queries = 129 chunks: the column scan of the offset table works in 64 row
-    segments of more than one row, the last chunk is ragged) answered through the partitioned path, with the slot inside
-    the k-mer word (k <= 25) and in the side array (k = 31), equals the same batch answered in the caller's order, and
-    its first 40 000 answers equal the oracle's."""
+    """A batch of several hundred chunks through the default partitioning rule (>= 2^22 queries) and through forced slice
+    counts, packed 6-byte k-mers in and 32-bit answers out (the narrow host format), against the oracle."""
     g = GENOMES[name]
     port = O.Port.from_memory(g, k=k)
-    rng = np.random.default_rng(17)
-    q0 = F.query_mix(g, k, 40000, seed=23)
-    kmers = np.concatenate([q0, rng.choice(q0, size=2_100_000 - len(q0) + 777)])
-    exp_head = port.query_batch(q0, nthreads=4)
-    for flags in (S.PACKED, S.NO_PACKED | S.NO_INLINE):
-        ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, list(port.five), flags=S.QUIET | flags)
-        monkeypatch.setenv("SAPLING_B200_PART", "0")
-        plain = ix.queryBatch(kmers)
-        assert np.array_equal(plain[:len(q0)], exp_head)
-        monkeypatch.setenv("SAPLING_B200_PART", "1")
-        monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
-        monkeypatch.setenv("SAPLING_B200_CHUNK_LOG2", "22")  # the host entry point hands the whole batch to one call
-        for bits in (5, 10):
-            monkeypatch.setenv("SAPLING_B200_PART_BITS", str(bits))
-            assert ix.partition_bits(len(kmers)) == bits
-            got = ix.queryBatch(kmers)
-            assert np.array_equal(got, plain), (name, k, flags, bits, int((got != plain).sum()))
+    base = F.query_mix(g, k, 300000, seed=21)
+    kmers = np.tile(base, 15)[:(1 << 22) + 12345]
+    exp = port.query_batch(base, nthreads=4)
+    exp = np.tile(exp, 15)[:len(kmers)]
+    for tune in ("", "part_bits=7", "part_bits=11,occ=4", "part=0"):
+        if tune:
+            monkeypatch.setenv("SAPLING_B200_TUNE", tune)
+        ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+        assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, tune)
+        kb = (2 * k + 7) // 8
+        raw = np.ascontiguousarray(kmers.view(np.uint8).reshape(-1, 8)[:, :kb]).reshape(-1)
+        got32 = ix.queryBatchU32(raw, kmer_bytes=kb, nq=len(kmers))
+        assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, k, tune, "packed")
         ix.close()
+    monkeypatch.delenv("SAPLING_B200_TUNE", raising=False)
     port.close()
-    for v in ("PART", "PART_MIN", "PART_BITS", "CHUNK_LOG2"):
-        monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("name", ["rand200k", "gc0110", "tandem50"])
-def test_replay_and_partition_variants_agree(S, oracle_built, name, monkeypatch):
-    """Every selectable variant of the batch path returns the oracle's answers: the lean 32-bit replay against the
-    general one, the anchor line staged in shared memory against sector-by-sector fetches, the in-order tile schedule
-    with and without the software pipeline against the static grid-stride schedule, the staged against the direct
-    scatter, the flat and the lane-group against the run-per-warp un-permute, the flat replay against the lean one -- on all three index layouts, collapsed left windows
-     included."""
-    g = GENOMES[name]
-    for k, nb, five_fn in ((21, -1, None), (16, 8, lambda f: [f[0], f[1], f[2], f[3], 1 << 30]), (31, 12, None)):
-        if len(g) < 4 * k:
-            continue
-        base = O.Port.from_memory(g, nb=nb, k=k)
-        five = list(base.five) if five_fn is None else five_fn(list(base.five))
-        port = O.Port.from_parts(g, base.sa, k, base.nb, base.xlist, base.ylist, five)
-        q0 = F.query_mix(g, k, 6000, seed=5)
-        kmers = np.concatenate([q0, np.sort(q0), q0[::-1]] * 2)  # 36000: several partition chunks
-        exp = port.query_batch(kmers, nthreads=4)
-        for flags in (S.NO_PACKED | S.NO_INLINE, S.PACKED, S.INLINE | S.NO_PACKED):
-            for shift in (("3", "4") if flags == S.PACKED else ("3",)):
-                monkeypatch.setenv("SAPLING_B200_PACKED_SHIFT", shift)
-                ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, five, flags=S.QUIET | flags)
-                for part in ("0", "1"):
-                    monkeypatch.setenv("SAPLING_B200_PART", part)
-                    monkeypatch.setenv("SAPLING_B200_PART_MIN", "1")
-                    monkeypatch.setenv("SAPLING_B200_PART_BITS", "5")
-                    for lean, line_smem in (("1", "1"), ("1", "0"), ("0", "0")):
-                        monkeypatch.setenv("SAPLING_B200_LEAN", lean)
-                        monkeypatch.setenv("SAPLING_B200_LINE_SMEM", line_smem)
-                        # last two: SLOT_IN_KMER (slot inside the partitioned k-mer word, k <= 25), PARK (unfinished
-                        # queries parked after three probes; needs the former)
-                        combos = ((("1", "1", "1", "1", "1", "1", "1"), ("1", "0", "1", "2", "1", "1", "1"),
-                                   ("0", "1", "0", "0", "1", "1", "1"), ("0", "1", "1", "0", "0", "1", "1"),
-                                   ("1", "1", "1", "2", "0", "1", "0"), ("1", "1", "1", "2", "0", "0", "1"),
-                                   ("1", "1", "1", "1", "0", "1", "1"))
-                                  if part == "1" else (("1", "1", "1", "1", "1", "1", "1"), ("1", "1", "1", "1", "0", "1", "1")))
-                        for tiles, pipe, scat, unp, flat, sik, park in combos:
-                            monkeypatch.setenv("SAPLING_B200_SLOT_IN_KMER", sik)
-                            monkeypatch.setenv("SAPLING_B200_PARK", park)
-                            monkeypatch.setenv("SAPLING_B200_FLAT", flat)  # kmer_replay_flat / kmer_replay32 (tiling lines)
-                            monkeypatch.setenv("SAPLING_B200_PART_TILES", tiles)
-                            monkeypatch.setenv("SAPLING_B200_ORDERED_PIPE", pipe)
-                            monkeypatch.setenv("SAPLING_B200_PART_SCATTER", scat)
-                            monkeypatch.setenv("SAPLING_B200_PART_UNPERMUTE", unp)
-                            for qv in ("3", "4", "5"):
-                                monkeypatch.setenv("SAPLING_B200_QV", qv)
-                                got = ix.queryBatch(kmers)
-                                assert np.array_equal(got, exp), (name, k, flags, shift, part, lean, line_smem, tiles,
-                                                                  pipe, scat, unp, flat, sik, park, qv)
-                            assert np.array_equal(ix.queryBatch(kmers[:8191]), exp[:8191])
-                ix.close()
-        port.close()
-        base.close()
-    for v in ("PART", "PART_MIN", "PART_BITS", "LEAN", "LINE_SMEM", "PART_TILES", "ORDERED_PIPE", "PART_SCATTER",
-              "PART_UNPERMUTE", "QV", "PACKED_SHIFT", "FLAT", "SLOT_IN_KMER", "PARK"):
-        monkeypatch.delenv("SAPLING_B200_" + v, raising=False)
+def test_stray_high_bits_are_ignored(S, oracle_built, monkeypatch):
+    """Bits above 2k are not part of a k-mer: a word that carries them (a sign-extended or wider hash) is answered like the
+    masked k-mer on every path, never used to index the model (which would read out of bounds)."""
+    g = GENOMES["rand200k"]
+    k = 21
+    port = O.Port.from_memory(g, k=k)
+    kmers = F.query_mix(g, k, 50000, seed=2)
+    exp = port.query_batch(kmers, nthreads=4)
+    dirty = kmers | (np.uint64(0xABCDE) << np.uint64(42)) | (np.uint64(1) << np.uint64(63))
+    for tune in ("part=0", "part_min=1,part_bits=5,chunk_log2=22"):
+        monkeypatch.setenv("SAPLING_B200_TUNE", tune)
+        ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+        assert np.array_equal(ix.queryBatch(dirty), exp), tune
+        assert ix.oob_count() == 0
+        ix.close()
+    monkeypatch.delenv("SAPLING_B200_TUNE")
+    port.close()
+
+
+def test_strings_with_other_bytes_are_rejected(S, oracle_built):
+    """A query string holding a byte other than A/C/G/T is refused: the reference compares raw bytes (an N never matches
+    and sorts between G and T), which a 2-bit index cannot reproduce -- better an error than a different answer."""
+    g = GENOMES["rand200k"]
+    ix = S.Sapling.from_memory(g, None, k=21)
+    s = bytearray(g[500:540])
+    s[7] = ord("N")
+    with pytest.raises(S.SaplingError):
+        ix.plQuery(bytes(s), S.kmerize(21, bytes(s)), 21)
+    with pytest.raises(S.SaplingError):
+        ix.plQueryBatch([g[100:140], bytes(s)], [S.kmerize(21, g[100:140]), S.kmerize(21, bytes(s))])
+    assert ix.plQuery(g[100:140], S.kmerize(21, g[100:140]), 21) >= 0
+    ix.close()
+
+
+def test_replicas_answer_like_the_primary(S, oracle_built):
+    """sapling_b200_replicate: the index copied device to device onto every other GPU of the box; a host batch sharded over
+    all of them returns exactly the single-GPU answers (needs >= 2 GPUs)."""
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    g = GENOMES["rand200k"]
+    k = 21
+    ix = S.Sapling.from_memory(g, None, k=k, flags=S.QUIET | S.KEEP_BUILD)
+    kmers = np.tile(F.query_mix(g, k, 200000, seed=4), 8)
+    one = ix.queryBatch(kmers)
+    assert ix.replicate((1 << ngpu) - 1) == ngpu
+    assert np.array_equal(ix.queryBatch(kmers), one)
+    got32 = ix.queryBatchU32(kmers)
+    assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), one)
+    ix.close()
 
 
 @pytest.mark.parametrize("name,k", [("rand200k", 21), ("gc1991", 16), ("tandem50", 16), ("repeat_tailA", 21)])
