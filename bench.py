@@ -319,7 +319,7 @@ def run_reference_arm(args):
     return 0
 
 
-def single_thread_drivers(genome, k, log):
+def single_thread_drivers(ix, genome, k, log):
     """the reference's own drivers as shipped (oracle/_ref/sapling_example,
     oracle/_ref/binarysearch), single thread, their own stdout timers (sapling_example.cpp:134-141,
     binarysearch.cpp:249-257).  They build through the reference's constructor, so only for genomes <= 100 Mbp."""
@@ -333,6 +333,7 @@ def single_thread_drivers(genome, k, log):
     try:
         fa = os.path.join(tmp, "g.fa")
         open(fa, "wb").write(fasta_bytes(genome))
+        ix.write_sa(fa + ".sa")  # the drivers' default saFn: otherwise the reference builds the suffix array itself (sa.h DC3)
         nq = 5_000_000
         t0 = time.time()
         r = subprocess.run([exe, fa, f"k={k}", f"maxMem={MAXMEM}", f"nq={nq}", f"qLen={k}"], cwd=tmp, capture_output=True,
@@ -392,7 +393,7 @@ def cpu_baseline_and_parity(ix, d_batch, args, sample, stream, log):
         finally:
             subprocess.run(["rm", "-rf", tmp])
         if args.workload in ("c1", "c2"):
-            cpu["single_thread_drivers"] = single_thread_drivers(genome, k, log)
+            cpu["single_thread_drivers"] = single_thread_drivers(ix, genome, k, log)
     return cpu, parity
 
 

@@ -1214,7 +1214,7 @@ uint64_t sapling_b200_launch_count(const sapling_b200_index* ix) {
 // each bin should still receive enough queries to amortise its line fills.
 static int partition_bits(const sapling_b200_index* ix, size_t nq) {
   const Tuning& t = ix->tune;
-  if (!t.partition || !ix->d_narrow) return 0;
+  if (!t.partition) return 0;
   if (nq < t.partition_min || nq >= (1ull << 32)) return 0;
   const int kbits = 2 * ix->k;
   int bits;
@@ -1222,7 +1222,7 @@ static int partition_bits(const sapling_b200_index* ix, size_t nq) {
     bits = t.partition_bits;
   } else {
     const double sa_bytes = (double)line_sectors(ix->n) * 32.0;
-    const double model_bytes = 8.0 * (double)(1ull << ix->nb);
+    const double model_bytes = (ix->d_narrow ? 8.0 : 16.0) * (double)(1ull << ix->nb);
     const double slice = 32e6;  // measured (gpurun r2f): c3 10 bits (26 MB slices) 15.0 ms per step, 11 bits 15.9, 9 bits bistable
     bits = 1;
     while (bits < kPartMaxBits && (sa_bytes + model_bytes) / (double)(1ull << bits) > slice) bits++;

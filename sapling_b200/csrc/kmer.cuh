@@ -55,9 +55,8 @@ __device__ __forceinline__ KmerKey make_key(const IndexView& ix, uint64_t x) {
 // One classified sector: ranks 4s .. 4s+3.  c entries are smaller than the query, the next m match, the rest are larger
 // (ranks past the end of the suffix array count as larger).
 struct Sector {
-  uint32_t s;       // sector number; 0xFFFFFFFF: nothing held
+  uint32_t s;  // sector number
   uint32_t c, m;
-  uint32_t pos[4];  // rev[4s + j]
 };
 
 // Full compare of the query with the suffix at text position pos (escaped entries, ties): the rules of getLcp (:115-120)
@@ -76,12 +75,13 @@ __device__ __forceinline__ void compare_with_genome(const IndexView& ix, const K
   SB_SIM_ADD(g_sim_slow_entries, 1);
 }
 
-// Classify sector s.  Fast path (no escaped entry, no tie): the entries are P0 + d_j with 21-bit deltas, so
+// Classify sector s; pos[] receives its four text positions.  Fast path (no escaped entry, no tie): the entries are
+// P0 + d_j with 21-bit deltas, so
 //   smaller  <=>  d_j < qlo - P0         match  <=>  qlo - P0 <= d_j <= qhi - P0
 // with both bounds clamped into the delta range: four 32-bit compares each.
 template <bool kTies>
-__device__ __forceinline__ void classify_sector(const IndexView& ix, const KmerKey& key, uint32_t s, const L2Policies& pol,
-                                                Sector* out) {
+__device__ __forceinline__ Sector classify_sector(const IndexView& ix, const KmerKey& key, uint32_t s, const L2Policies& pol,
+                                                  uint32_t pos[4]) {
   const U32x8 e = ld_u32x8_pol(ix.lines + (uint64_t)s * 8u, pol.sa);
   SB_SIM_ADD(g_sim_sector_loads, 1);
   const uint64_t P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
@@ -107,94 +107,118 @@ __device__ __forceinline__ void classify_sector(const IndexView& ix, const KmerK
     if (n2) { if (r0 + 2 < ix.n) compare_with_genome(ix, key, e.v[6], pol.genome, &sm2, &ma2); else sm2 = ma2 = false; }
     if (n3) { if (r0 + 3 < ix.n) compare_with_genome(ix, key, e.v[7], pol.genome, &sm3, &ma3); else sm3 = ma3 = false; }
   }
-  out->s = s;
-  out->c = (uint32_t)sm0 + (uint32_t)sm1 + (uint32_t)sm2 + (uint32_t)sm3;
-  out->m = (uint32_t)ma0 + (uint32_t)ma1 + (uint32_t)ma2 + (uint32_t)ma3;
-  out->pos[0] = e.v[4]; out->pos[1] = e.v[5]; out->pos[2] = e.v[6]; out->pos[3] = e.v[7];
+  Sector out;
+  out.s = s;
+  out.c = (uint32_t)sm0 + (uint32_t)sm1 + (uint32_t)sm2 + (uint32_t)sm3;
+  out.m = (uint32_t)ma0 + (uint32_t)ma1 + (uint32_t)ma2 + (uint32_t)ma3;
+  pos[0] = e.v[4]; pos[1] = e.v[5]; pos[2] = e.v[6]; pos[3] = e.v[7];
+  return out;
 }
 
 struct Bounds {
   uint32_t lb, ub;  // ranks [0, lb) smaller than the query, [lb, ub) match, [ub, n) larger
 };
 
-// Phase 1.  first = the classified sector of the predicted rank; on return *held is the sector that contains lb (or the last
-// one classified), kept for the final rev[] lookup next to `first`.
-template <bool kTies>
-__device__ __forceinline__ Bounds find_bounds(const IndexView& ix, const KmerKey& key, const L2Policies& pol,
-                                              const Sector& first, Sector* held) {
-  const uint32_t n32 = (uint32_t)ix.n;
-  const uint32_t last_s = (n32 - 1u) >> 2;
-  auto valid = [&](uint32_t s) -> uint32_t { return s == last_s ? n32 - 4u * s : 4u; };
-  // ---- lb: the first sector that is not entirely smaller (c < 4); it holds lb = 4 s + c ------------------------------------
-  // invariant: every sector <= full is entirely smaller (0xFFFFFFFF: none known), *held has c < 4
-  *held = first;
-  uint32_t full = 0xFFFFFFFFu;
-  bool found = false;
-  if (first.c == 4u) {  // look right: gallop until a sector is not full
-    full = first.s;
-    uint32_t step = 1;
-    for (;;) {
-      if (full == last_s) {  // every rank is smaller
-        Bounds b;
-        b.lb = b.ub = n32;
-        return b;
+// Phase 1: lb and ub by sector.  Both are the same search over sectors for the boundary of a monotone property --
+//   mode 0: "every entry of the sector is smaller than the query"   (true for sectors left of lb's, false from it on)
+//   mode 1: "every valid entry of the sector matches"               (true from lb's sector to the one before ub's)
+// -- written as a state that is FED one classified sector at a time and answers with the next sector it wants, so that
+// there is one classification site whatever a lane is doing (looking left or right, galloping or bisecting, extending the
+// match run), and so that the kernels can re-pack the unfinished queries of a block between two sector loads.
+// State: `yes` = the last sector known to have the property (-1: the virtual sector before the array), `no` = the first
+// sector known not to have it (sector last_s + 1 with nothing in it: the virtual sector after the array).  While one of the
+// two is virtual the search gallops away from the other (1, 2, 4 ... sectors), then it bisects.  The sector of the
+// predicted rank (`first`) is remembered: the run of matches often ends in it.
+struct Search {
+  int32_t yes;
+  uint32_t no_s, no_c, no_m;
+  uint32_t first_c, first_m;  // the sector pred >> 2 (fed first)
+  uint32_t step_log2;
+  uint32_t mode;
+  uint32_t lb;
+  uint32_t t;  // the sector to classify next
+
+  __device__ __forceinline__ void begin(const IndexView& ix, uint32_t pred) {
+    yes = -1;
+    no_s = (((uint32_t)ix.n - 1u) >> 2) + 1u;
+    no_c = no_m = first_c = first_m = 0;
+    step_log2 = 0;
+    mode = 0;
+    lb = 0;
+    t = pred >> 2;
+  }
+  // x = the classification of sector t.  true: *out is final.  false: classify sector t (updated) and feed again.
+  __device__ __forceinline__ bool feed(const IndexView& ix, uint32_t pred, const Sector& x, bool is_first, Bounds* out) {
+    const uint32_t n32 = (uint32_t)ix.n;
+    const int32_t last_s = (int32_t)((n32 - 1u) >> 2);
+    const uint32_t last_valid = n32 - 4u * (uint32_t)last_s;
+    const uint32_t valid = (int32_t)x.s == last_s ? last_valid : 4u;
+    if (is_first) { first_c = x.c; first_m = x.m; }
+    const bool has = mode ? (x.m == valid) : (x.c == 4u);
+    if (has) yes = (int32_t)x.s;
+    else { no_s = x.s; no_c = x.c; no_m = x.m; }
+    if (mode == 0 && (yes + 1 == (int32_t)no_s || ((int32_t)no_s <= last_s && no_c > 0u))) {
+      // lb lies in sector no_s (or is n: nothing but smaller suffixes)
+      const uint32_t raw = 4u * no_s + no_c;
+      lb = raw < n32 ? raw : n32;
+      const uint32_t nv = (int32_t)no_s == last_s ? last_valid : 4u;
+      if ((int32_t)no_s >= last_s || no_m == 0u || no_c + no_m < nv) {  // the match run ends inside this sector
+        out->lb = lb;
+        out->ub = lb + no_m;
+        return true;
       }
-      const uint32_t t = (last_s - full < step) ? last_s : full + step;
-      classify_sector<kTies>(ix, key, t, pol, held);
-      if (held->c == 4u) { full = t; step <<= 1; continue; }
-      found = held->c > 0u || t == full + 1u;
-      break;
+      // the run reaches the end of the sector: search for the first sector that is not all matches
+      mode = 1;
+      yes = (int32_t)no_s;
+      step_log2 = 0;
+      no_s = (uint32_t)(last_s + 1); no_c = 0; no_m = 0;
+      const int32_t fs = (int32_t)(pred >> 2);
+      if (fs > yes) {  // the first sector lies to the right and is already classified: use it
+        const uint32_t fv = fs == last_s ? last_valid : 4u;
+        if (first_m == fv) yes = fs;
+        else { no_s = (uint32_t)fs; no_c = first_c; no_m = first_m; }
+      }
     }
-  } else if (first.c > 0u || first.s == 0u) {
-    found = true;
-  } else {  // c == 0: look left until a sector has a smaller entry
-    uint32_t step = 1;
-    for (;;) {
-      const uint32_t t = held->s > step ? held->s - step : 0u;
-      Sector x;
-      classify_sector<kTies>(ix, key, t, pol, &x);
-      if (x.c == 4u) { full = t; found = held->s == t + 1u; break; }
-      *held = x;
-      if (x.c > 0u || t == 0u) { found = true; break; }
-      step <<= 1;
+    if (mode == 1 && yes + 1 == (int32_t)no_s) {
+      const uint32_t raw = 4u * no_s + no_m;
+      out->lb = lb;
+      out->ub = raw < n32 ? raw : n32;
+      return true;
     }
+    // next sector to classify
+    if ((int32_t)no_s > last_s) {  // nothing known to the right yet: gallop right
+      const uint32_t cand = (uint32_t)yes + (1u << step_log2);
+      t = cand < (uint32_t)last_s ? cand : (uint32_t)last_s;
+      step_log2++;
+    } else if (yes < 0) {          // nothing known to the left yet: gallop left
+      const uint32_t step = 1u << step_log2;
+      t = no_s > step ? no_s - step : 0u;
+      step_log2++;
+    } else {
+      t = (uint32_t)yes + ((no_s - (uint32_t)yes) >> 1);
+    }
+    return false;
   }
-  while (!found) {  // bisection: full < sb <= held->s, sectors strictly between are unknown
-    if (held->s - full == 1u) break;
-    const uint32_t mid = full + ((held->s - full) >> 1);
-    Sector x;
-    classify_sector<kTies>(ix, key, mid, pol, &x);
-    if (x.c == 4u) { full = mid; continue; }
-    *held = x;
-    if (x.c > 0u) break;
+  // the part of the state that is not recomputable, in four words (for the kernels' shared-memory queues)
+  __device__ __forceinline__ uint4 pack() const {
+    const uint32_t bits = no_c | (no_m << 3) | (first_c << 6) | (first_m << 9) | (step_log2 << 12) | (mode << 18);
+    return make_uint4((uint32_t)yes, no_s, lb, bits);
   }
-  Bounds b;
-  b.lb = 4u * held->s + held->c;
-  // ---- ub: matches run from lb; they end inside the held sector unless they reach its last valid entry -------------------
-  if (held->c + held->m < valid(held->s) || held->s == last_s) {
-    b.ub = b.lb + held->m;
-    return b;
+  __device__ __forceinline__ void unpack(const uint4& w, uint32_t next_t) {
+    yes = (int32_t)w.x; no_s = w.y; lb = w.z;
+    no_c = w.w & 7u; no_m = (w.w >> 3) & 7u; first_c = (w.w >> 6) & 7u; first_m = (w.w >> 9) & 7u;
+    step_log2 = (w.w >> 12) & 63u; mode = (w.w >> 18) & 1u;
+    t = next_t;
   }
-  // the run continues into the next sectors (repeated k-mers): first sector that is not all matches
-  uint32_t all = held->s;  // every valid entry of sectors (held->s, all] matches
-  uint32_t step = 1;
-  Sector x;
-  for (;;) {
-    if (all == last_s) { b.ub = n32; return b; }
-    const uint32_t t = (last_s - all < step) ? last_s : all + step;
-    classify_sector<kTies>(ix, key, t, pol, &x);
-    if (x.m == valid(t)) { all = t; step <<= 1; continue; }
-    break;
-  }
-  while (x.s - all > 1u) {
-    const uint32_t mid = all + ((x.s - all) >> 1);
-    Sector y;
-    classify_sector<kTies>(ix, key, mid, pol, &y);
-    if (y.m == valid(mid)) all = mid;
-    else x = y;
-  }
-  b.ub = 4u * x.s + x.m;
-  return b;
+};
+
+// rev[predicted] when it matches the query (:164), from the classification of its own sector
+__device__ __forceinline__ bool direct_match(uint32_t pred, const Sector& x, const uint32_t pos[4], uint32_t* idx) {
+  const uint32_t j0 = pred & 3u;
+  if (j0 < x.c || j0 >= x.c + x.m) return false;
+  const uint32_t a = (j0 & 1u) ? pos[1] : pos[0], c = (j0 & 1u) ? pos[3] : pos[2];
+  *idx = (j0 & 2u) ? c : a;
+  return true;
 }
 
 __device__ __forceinline__ uint32_t kmer_uhadd(uint32_t a, uint32_t b) {  // floor((a + b) / 2) without overflow
@@ -286,28 +310,31 @@ __device__ __forceinline__ uint32_t rev_at(const IndexView& ix, uint64_t r, uint
   return ld_u32_pol(ix.lines + (r >> 2) * 8u + 4u + (r & 3u), pol);
 }
 
+// The answer once the bounds are known: phase 2, then rev[rank] -- in a line this lane has just read.
+__device__ __forceinline__ long long finish_kmer(const IndexView& ix, uint32_t pred, const Bounds& b, const L2Policies& pol) {
+  const long long rank = replay_plquery(ix, pred, b);
+  if (rank < 0) return -1;  // :246
+  SB_SIM_ADD(g_sim_final_loads, 1);
+  return (long long)rev_at(ix, (uint32_t)rank, pol.sa);  // :247
+}
+
 // The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.
 template <bool kTies>
 __device__ __forceinline__ long long answer_kmer(const IndexView& ix, uint64_t x, uint32_t pred, const L2Policies& pol) {
   const KmerKey key = make_key(ix, x);
-  Sector first, held;
-  classify_sector<kTies>(ix, key, pred >> 2, pol, &first);
-  const uint32_t j0 = pred & 3u;
-  if (j0 >= first.c && j0 < first.c + first.m) {  // rev[predicted] matches (:164): a third of all queries end here
-    const uint32_t a = (j0 & 1u) ? first.pos[1] : first.pos[0], c = (j0 & 1u) ? first.pos[3] : first.pos[2];
-    return (long long)((j0 & 2u) ? c : a);
+  Search se;
+  se.begin(ix, pred);
+  Bounds b;
+  bool is_first = true;
+  for (;;) {
+    uint32_t pos[4];
+    const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+    uint32_t idx;
+    if (is_first && direct_match(pred, sc, pos, &idx)) return (long long)idx;  // :164: a third of all queries
+    if (se.feed(ix, pred, sc, is_first, &b)) break;
+    is_first = false;
   }
-  const Bounds b = find_bounds<kTies>(ix, key, pol, first, &held);
-  const long long rank = replay_plquery(ix, pred, b);
-  if (rank < 0) return -1;  // :246
-  const uint32_t r = (uint32_t)rank, rs = r >> 2, j = r & 3u;
-  if (rs == held.s || rs == first.s) {
-    const Sector& h = rs == held.s ? held : first;
-    const uint32_t a = (j & 1u) ? h.pos[1] : h.pos[0], c = (j & 1u) ? h.pos[3] : h.pos[2];
-    return (long long)((j & 2u) ? c : a);
-  }
-  SB_SIM_ADD(g_sim_final_loads, 1);
-  return (long long)rev_at(ix, r, pol.sa);  // :247
+  return finish_kmer(ix, pred, b, pol);
 }
 
 }  // namespace sb

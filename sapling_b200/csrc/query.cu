@@ -38,6 +38,30 @@ kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t
   }
 }
 
+// The two checkpoints of a k-mer's bucket, in either model layout, requested one tile ahead of their use.
+template <bool kNarrow>
+struct ModelPair;
+template <>
+struct ModelPair<true> {
+  NarrowPair p;
+  __device__ __forceinline__ void load(const IndexView& ix, uint64_t x, uint64_t pol) { p = narrow_load(ix, x, pol); }
+  __device__ __forceinline__ uint64_t predict(const IndexView& ix, uint64_t x, uint64_t pol) const {
+    return narrow_finish(ix, x, p, pol);
+  }
+};
+template <>
+struct ModelPair<false> {
+  longlong2 lo, hi;
+  __device__ __forceinline__ void load(const IndexView& ix, uint64_t x, uint64_t pol) {
+    const uint64_t b = x >> ix.shift;
+    lo = ld_s64x2_pol(reinterpret_cast<const longlong2*>(ix.model + b), pol);
+    hi = ld_s64x2_pol(reinterpret_cast<const longlong2*>(ix.model + b + 1), pol);
+  }
+  __device__ __forceinline__ uint64_t predict(const IndexView&, uint64_t x, uint64_t) const {
+    return interpolate((long long)x, lo.x, lo.y, hi.x, hi.y);
+  }
+};
+
 // In-order, software-pipelined kernel of the partitioned batch path (partition.cu).  The batch arrives bucketed by the top
 // bits of the k-mer and must be WALKED IN ORDER for that to pay: warps claim tiles of 32 consecutive queries from a global
 // counter (four tiles per atomic), so the ~190 k queries in flight on the GPU always fall into one or two slices of the
@@ -45,11 +69,29 @@ kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t
 // answers query t of its warp's tile sequence the k-mers of tile t+2 and the model checkpoints of tile t+1 are already
 // requested, so the two dependent round trips that head every query (k-mer -> checkpoints -> first sector) overlap with
 // the previous tile.  The slot of a query rides in bits 50-63 of its k-mer word (k <= 25) or comes from a side array.
-template <int kMinBlocks, bool kTies>
+//
+// Lane occupancy.  A third of the queries are answered by the sector of their predicted rank, nearly all the others by
+// one neighbouring sector; one in eight needs a third sector or more (errors beyond the 95 % bounds, match runs crossing a
+// sector end, absent k-mers far from their prediction).  A warp that loops until its slowest lane is done spends most of
+// its instructions with 2-4 lanes alive (ncu, profiles/s2_*: 13.7 of 32 lanes active per instruction).  So a tile gets
+// exactly TWO classification rounds in place; what is still unresolved is pushed -- its search state is 36 bytes -- onto
+// the warp's own stack in shared memory, and whenever 32 have piled up the warp pops them and runs one more round with
+// every lane busy.  No block-wide barrier: the warps stay independent.
+constexpr int kWarpsPerBlock = kQueryThreads / 32;
+constexpr int kStackCap = 64;  // at most 31 left over + 32 pushed by a tile (or pushed back by a drain)
+struct TailStacks {
+  uint32_t x_lo[kWarpsPerBlock][kStackCap], x_hi[kWarpsPerBlock][kStackCap];
+  uint32_t pred[kWarpsPerBlock][kStackCap], idx[kWarpsPerBlock][kStackCap], t[kWarpsPerBlock][kStackCap];
+  uint4 st[kWarpsPerBlock][kStackCap];
+};
+
+template <int kMinBlocks, bool kTies, bool kNarrow>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
-  const unsigned lane = threadIdx.x & 31u;
+  __shared__ TailStacks stacks;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const unsigned lt_mask = (1u << lane) - 1u;
   const L2Policies pol = make_policies(ix.hints);
   // a partitioned batch has fewer than 2^32 queries (launch_partitioned_query): indices are 32-bit
   const uint32_t nq32 = (uint32_t)nq, last = nq32 - 1u;
@@ -76,21 +118,91 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   const bool in_kmer = slot == slot_in_kmer_tag();
   // bits above 2k are not part of a k-mer (and bits 50-63 may carry the slot): never indexed with
   const uint64_t kmask = ix.k >= 32 ? ~0ull : ((1ull << (2 * ix.k)) - 1ull);
+  auto store = [&](uint32_t i, uint64_t xw, long long r) {
+    const unsigned long long sl = in_kmer ? (unsigned long long)(xw >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
+    __stcs(out + i, slot_word(sl, r));
+  };
+  unsigned stacked = 0;  // warp-uniform: entries on this warp's stack
+  // push the lanes with `pending` set; everything a later round needs travels in the record
+  auto push = [&](bool pending, uint64_t xw, uint32_t pred, uint32_t i, const Search& se) {
+    const unsigned m = __ballot_sync(0xffffffffu, pending);
+    if (pending) {
+      const unsigned e = stacked + (unsigned)__popc(m & lt_mask);
+      stacks.x_lo[warp][e] = (uint32_t)xw;
+      stacks.x_hi[warp][e] = (uint32_t)(xw >> 32);
+      stacks.pred[warp][e] = pred;
+      stacks.idx[warp][e] = i;
+      stacks.t[warp][e] = se.t;
+      stacks.st[warp][e] = se.pack();
+    }
+    stacked += (unsigned)__popc(m);
+    __syncwarp();
+  };
+  // pop the top `m` (<= 32) entries: one more classification round with every lane busy
+  auto drain = [&](unsigned m) {
+    stacked -= m;
+    const bool have = lane < m;
+    const unsigned e = stacked + lane;
+    uint64_t xw = 0;
+    uint32_t pred = 0, i = 0;
+    Search se;
+    se.begin(ix, 0);
+    if (have) {
+      xw = ((uint64_t)stacks.x_hi[warp][e] << 32) | stacks.x_lo[warp][e];
+      pred = stacks.pred[warp][e];
+      i = stacks.idx[warp][e];
+      se.unpack(stacks.st[warp][e], stacks.t[warp][e]);
+    }
+    __syncwarp();  // every record is in registers before any slot is written again
+    bool pending = false;
+    if (have) {
+      const KmerKey key = make_key(ix, xw & kmask);
+      uint32_t pos[4];
+      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+      Bounds b;
+      if (se.feed(ix, pred, sc, false, &b)) store(i, xw, finish_kmer(ix, pred, b, pol));
+      else pending = true;
+    }
+    push(pending, xw, pred, i, se);
+  };
+
   uint32_t t0 = claim(), t1 = claim(), t2 = claim();
   if (t0 >= nq32) return;
   uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1);
-  NarrowPair m0 = narrow_load(ix, x0 & kmask, pol.model);
+  ModelPair<kNarrow> m0;
+  m0.load(ix, x0 & kmask, pol.model);
   while (t0 < nq32) {
     const uint64_t x2 = kmer_at(t2);
-    const NarrowPair m1 = narrow_load(ix, x1 & kmask, pol.model);
+    ModelPair<kNarrow> m1;
+    m1.load(ix, x1 & kmask, pol.model);
     const uint32_t i = t0 + lane;
+    bool pending = false;
+    uint32_t pred = 0;
+    Search se;
+    se.begin(ix, 0);
     if (i < nq32) {
-      const unsigned long long sl = in_kmer ? (unsigned long long)(x0 >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
       const uint64_t x = x0 & kmask;
-      const uint32_t pred = (uint32_t)clamp_prediction(ix, narrow_finish(ix, x, m0, pol.model));
-      const long long r = answer_kmer<kTies>(ix, x, pred, pol);
-      __stcs(out + i, slot_word(sl, r));
+      pred = (uint32_t)clamp_prediction(ix, m0.predict(ix, x, pol.model));
+      const KmerKey key = make_key(ix, x);
+      se.begin(ix, pred);
+      Bounds b;
+      uint32_t pos[4], idx;
+      // round 1: the sector of the predicted rank
+      Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+      if (direct_match(pred, sc, pos, &idx)) {  // :164
+        store(i, x0, (long long)idx);
+      } else {
+        bool resolved = se.feed(ix, pred, sc, true, &b);
+        if (!resolved) {  // round 2: the neighbour the search asks for
+          sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+          resolved = se.feed(ix, pred, sc, false, &b);
+        }
+        if (resolved) store(i, x0, finish_kmer(ix, pred, b, pol));
+        else pending = true;
+      }
     }
+    push(pending, x0, pred, i, se);
+    if (stacked >= 32u) drain(32u);
     x0 = x1;
     x1 = x2;
     m0 = m1;
@@ -98,6 +210,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     t1 = t2;
     t2 = claim();
   }
+  while (stacked) drain(stacked < 32u ? stacked : 32u);
 }
 
 // plQuery(s, kmer, length) for strings of any length (sapling_api.h:159): the literal replay with the gallop loops.
@@ -380,18 +493,21 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 }
 
 // A partitioned batch (partition.cu): d_tiles is the zeroed in-order tile counter, d_slot the slot array or
-// slot_in_kmer_tag(); results are slot words (see slot_word).  Needs the narrow model.
+// slot_in_kmer_tag(); results are slot words (see slot_word).
 int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
                               const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st) {
   if (nq == 0) return 0;
-  if (!ix.narrow) { set_error("the in-order query kernel needs the narrow model layout"); return -1; }
   const int bps = kmer_query_blocks_per_sm(true, occupancy);
   const int grid = query_grid(nq, bps);
-  const bool ties = has_ties(ix);
-#define SB_LAUNCH(B)                                                                                                     \
-  do {                                                                                                                   \
-    if (ties) kmer_query_ordered_kernel<B, true><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
-    else kmer_query_ordered_kernel<B, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles);     \
+  const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
+#define SB_LAUNCH_N(B, T, N) \
+  kmer_query_ordered_kernel<B, T, N><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
+#define SB_LAUNCH(B)                                       \
+  do {                                                     \
+    if (ties && narrow) SB_LAUNCH_N(B, true, true);        \
+    else if (ties) SB_LAUNCH_N(B, true, false);            \
+    else if (narrow) SB_LAUNCH_N(B, false, true);          \
+    else SB_LAUNCH_N(B, false, false);                     \
   } while (0)
   switch (bps) {
     case 3: SB_LAUNCH(3); break;
@@ -400,6 +516,7 @@ int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers,
     default: SB_LAUNCH(5); break;
   }
 #undef SB_LAUNCH
+#undef SB_LAUNCH_N
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
