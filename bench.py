@@ -521,25 +521,39 @@ def main():
     probes_per_q = ix.count_probes_device(d_kmers[0].data_ptr(), psample, stream) / psample
 
     # ---- end-to-end through the host C ABI ---------------------------------------------------
+    # The host path is bound by PCIe bytes, so the headline goes through the narrow transfer format of the C ABI
+    # (sapling_b200_query_batch_u32: ceil(2k/8)-byte k-mers up, 32-bit positions down -- 10 bytes per query at k = 21);
+    # the reference-shaped int64 entry point (16 bytes per query) is timed beside it.
+    import numpy as np
     e2e_steps = args.e2e_steps or min(args.steps, 5)
+    kb = (2 * k + 7) // 8
+    dev_answers = device_answers_host(ix, d_kmers[0], nq, stream)
     h_kmers = torch.empty(nq, dtype=torch.int64).pin_memory()
-    h_out = torch.empty(nq, dtype=torch.int64).pin_memory()
     h_kmers.copy_(d_kmers[0])
     torch.cuda.synchronize()
-    ix.queryBatch(h_kmers, out=h_out)  # warm-up (allocates staging)
-    ix.queryBatch(h_kmers, out=h_out)
-    barrier()
-    launches0 = ix.launch_count()
-    t0 = time.perf_counter()
-    for s in range(e2e_steps):
-        ix.queryBatch(h_kmers, out=h_out)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_s = max_over_ranks(e2e_s, dist, "cuda")
-    e2e_value = world * nq * e2e_steps / e2e_s
-    e2e_launches = ix.launch_count() - launches0
-    e2e_equal = bool(torch.equal(h_out, device_answers_host(ix, d_kmers[0], nq, stream)))
-    del h_kmers, h_out
+    h_packed = torch.empty(nq * kb, dtype=torch.uint8).pin_memory()
+    h_packed.copy_(torch.from_numpy(np.ascontiguousarray(h_kmers.numpy().view(np.uint8).reshape(-1, 8)[:, :kb]).reshape(-1)))
+    h_out32 = torch.empty(nq, dtype=torch.int32).pin_memory()
+    h_out = torch.empty(nq, dtype=torch.int64).pin_memory()
+
+    def timed(fn):
+        fn()  # warm-up (allocates staging)
+        fn()
+        barrier()
+        l0 = ix.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0, dist, "cuda")
+        return world * nq * e2e_steps / dt, ix.launch_count() - l0
+
+    e2e_value, e2e_launches = timed(lambda: ix.queryBatchU32(h_packed, kmer_bytes=kb, out=h_out32, nq=nq))
+    e2e64_value, _ = timed(lambda: ix.queryBatch(h_kmers, out=h_out))
+    got32 = h_out32.to(torch.int64) & 0xFFFFFFFF
+    e2e_equal = bool(torch.equal(torch.where(got32 == 0xFFFFFFFF, torch.full_like(got32, -1), got32), dev_answers)
+                     and torch.equal(h_out, dev_answers))
+    del h_kmers, h_out, h_packed, h_out32, dev_answers, got32
 
     if rank != 0:
         if dist is not None:
@@ -619,8 +633,11 @@ def main():
                      "random_sector_gather_gbs": gather},
         "sustained": sustained,
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8,
-                "steps": e2e_steps, "api": "sapling_b200_query_batch (pinned host buffers)", "numa_node": numa_node,
+        "e2e": {"value": e2e_value, "unit": "queries/s", "h2d_bytes_per_step": nq * kb, "d2h_bytes_per_step": nq * 4,
+                "steps": e2e_steps, "api": f"sapling_b200_query_batch_u32 (pinned host buffers: {kb}-byte k-mers up, uint32 "
+                                           f"positions down)", "numa_node": numa_node,
+                "int64_api": {"value": e2e64_value, "api": "sapling_b200_query_batch (uint64 k-mers up, int64 answers down)",
+                              "h2d_bytes_per_step": nq * 8, "d2h_bytes_per_step": nq * 8},
                 "answers_equal_device_path": e2e_equal},
         "gpu_launches": args.steps * launches_per_step, "e2e_gpu_launches": e2e_launches,
         "clocks": clocks, "self_check": {"matching": int(n_match), "minus1": int(n_m1), "of": nq},

@@ -148,56 +148,63 @@ struct Search {
     t = pred >> 2;
   }
   // x = the classification of sector t.  true: *out is final.  false: classify sector t (updated) and feed again.
+  // Single exit and select-style updates on purpose: the lanes of a warp are in different cases here (looking left, right,
+  // bisecting, extending a run), and a branch per case would keep them apart -- through the NEXT round's classification
+  // as well, because the branches only reconverge where the paths that are done rejoin (ncu s3: the second round ran twice
+  // per tile with 7 lanes each).
   __device__ __forceinline__ bool feed(const IndexView& ix, uint32_t pred, const Sector& x, bool is_first, Bounds* out) {
     const uint32_t n32 = (uint32_t)ix.n;
     const int32_t last_s = (int32_t)((n32 - 1u) >> 2);
     const uint32_t last_valid = n32 - 4u * (uint32_t)last_s;
     const uint32_t valid = (int32_t)x.s == last_s ? last_valid : 4u;
-    if (is_first) { first_c = x.c; first_m = x.m; }
+    first_c = is_first ? x.c : first_c;
+    first_m = is_first ? x.m : first_m;
     const bool has = mode ? (x.m == valid) : (x.c == 4u);
-    if (has) yes = (int32_t)x.s;
-    else { no_s = x.s; no_c = x.c; no_m = x.m; }
-    if (mode == 0 && (yes + 1 == (int32_t)no_s || ((int32_t)no_s <= last_s && no_c > 0u))) {
-      // lb lies in sector no_s (or is n: nothing but smaller suffixes)
+    yes = has ? (int32_t)x.s : yes;
+    no_s = has ? no_s : x.s;
+    no_c = has ? no_c : x.c;
+    no_m = has ? no_m : x.m;
+    bool done = false;
+    // mode 0 ends when the boundary sector is known: lb lies in sector no_s (or is n: nothing but smaller suffixes)
+    const bool lb_known = mode == 0 && (yes + 1 == (int32_t)no_s || ((int32_t)no_s <= last_s && no_c > 0u));
+    if (lb_known) {
       const uint32_t raw = 4u * no_s + no_c;
       lb = raw < n32 ? raw : n32;
       const uint32_t nv = (int32_t)no_s == last_s ? last_valid : 4u;
-      if ((int32_t)no_s >= last_s || no_m == 0u || no_c + no_m < nv) {  // the match run ends inside this sector
-        out->lb = lb;
-        out->ub = lb + no_m;
-        return true;
-      }
-      // the run reaches the end of the sector: search for the first sector that is not all matches
-      mode = 1;
-      yes = (int32_t)no_s;
-      step_log2 = 0;
-      no_s = (uint32_t)(last_s + 1); no_c = 0; no_m = 0;
+      const bool ends_inside = (int32_t)no_s >= last_s || no_m == 0u || no_c + no_m < nv;
+      out->lb = lb;
+      out->ub = lb + no_m;
+      done = ends_inside;
+      // otherwise the run of matches reaches the end of the sector: search on for the first sector that is not all
+      // matches (mode 1); the first sector, if it lies to the right, is already classified
       const int32_t fs = (int32_t)(pred >> 2);
-      if (fs > yes) {  // the first sector lies to the right and is already classified: use it
-        const uint32_t fv = fs == last_s ? last_valid : 4u;
-        if (first_m == fv) yes = fs;
-        else { no_s = (uint32_t)fs; no_c = first_c; no_m = first_m; }
-      }
+      const uint32_t fv = fs == last_s ? last_valid : 4u;
+      const bool use_first = fs > (int32_t)no_s;
+      const bool first_all = first_m == fv;
+      mode = ends_inside ? 0u : 1u;
+      yes = (use_first && first_all) ? fs : (int32_t)no_s;
+      step_log2 = 0;
+      const bool first_is_no = use_first && !first_all;
+      no_s = first_is_no ? (uint32_t)fs : (uint32_t)(last_s + 1);
+      no_c = first_is_no ? first_c : 0u;
+      no_m = first_is_no ? first_m : 0u;
     }
-    if (mode == 1 && yes + 1 == (int32_t)no_s) {
+    if (!done && mode == 1u && yes + 1 == (int32_t)no_s) {
       const uint32_t raw = 4u * no_s + no_m;
       out->lb = lb;
       out->ub = raw < n32 ? raw : n32;
-      return true;
+      done = true;
     }
-    // next sector to classify
-    if ((int32_t)no_s > last_s) {  // nothing known to the right yet: gallop right
-      const uint32_t cand = (uint32_t)yes + (1u << step_log2);
-      t = cand < (uint32_t)last_s ? cand : (uint32_t)last_s;
-      step_log2++;
-    } else if (yes < 0) {          // nothing known to the left yet: gallop left
-      const uint32_t step = 1u << step_log2;
-      t = no_s > step ? no_s - step : 0u;
-      step_log2++;
-    } else {
-      t = (uint32_t)yes + ((no_s - (uint32_t)yes) >> 1);
-    }
-    return false;
+    // the next sector to classify (computed for every lane; meaningless once done)
+    const bool go_right = (int32_t)no_s > last_s;  // nothing known to the right yet: gallop right
+    const bool go_left = !go_right && yes < 0;     // nothing known to the left yet: gallop left
+    const uint32_t step = 1u << step_log2;
+    const uint32_t cand_r = (uint32_t)yes + step < (uint32_t)last_s ? (uint32_t)yes + step : (uint32_t)last_s;
+    const uint32_t cand_l = no_s > step ? no_s - step : 0u;
+    const uint32_t cand_b = (uint32_t)yes + ((no_s - (uint32_t)yes) >> 1);
+    t = go_right ? cand_r : (go_left ? cand_l : cand_b);
+    step_log2 += (go_right || go_left) ? 1u : 0u;
+    return done;
   }
   // the part of the state that is not recomputable, in four words (for the kernels' shared-memory queues)
   __device__ __forceinline__ uint4 pack() const {

@@ -176,33 +176,40 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     ModelPair<kNarrow> m1;
     m1.load(ix, x1 & kmask, pol.model);
     const uint32_t i = t0 + lane;
-    bool pending = false;
+    // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
+    const bool active = i < nq32;
+    bool done = false, resolved = false;
+    long long r = -1;
     uint32_t pred = 0;
+    KmerKey key;
+    key.q = key.qlo = key.qhi = 0;
+    Bounds b;
+    b.lb = b.ub = 0;
     Search se;
     se.begin(ix, 0);
-    if (i < nq32) {
+    if (active) {  // round 1: the sector of the predicted rank
       const uint64_t x = x0 & kmask;
       pred = (uint32_t)clamp_prediction(ix, m0.predict(ix, x, pol.model));
-      const KmerKey key = make_key(ix, x);
+      key = make_key(ix, x);
       se.begin(ix, pred);
-      Bounds b;
-      uint32_t pos[4], idx;
-      // round 1: the sector of the predicted rank
-      Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
-      if (direct_match(pred, sc, pos, &idx)) {  // :164
-        store(i, x0, (long long)idx);
-      } else {
-        bool resolved = se.feed(ix, pred, sc, true, &b);
-        if (!resolved) {  // round 2: the neighbour the search asks for
-          sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
-          resolved = se.feed(ix, pred, sc, false, &b);
-        }
-        if (resolved) store(i, x0, finish_kmer(ix, pred, b, pol));
-        else pending = true;
-      }
+      uint32_t pos[4], idx = 0;
+      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+      done = direct_match(pred, sc, pos, &idx);  // :164
+      r = (long long)idx;
+      resolved = se.feed(ix, pred, sc, true, &b);
     }
-    push(pending, x0, pred, i, se);
-    if (stacked >= 32u) drain(32u);
+    if (active && !done && !resolved) {  // round 2: the neighbour the search asks for
+      uint32_t pos[4];
+      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+      resolved = se.feed(ix, pred, sc, false, &b);
+    }
+    if (active && !done && resolved) {  // phase 2 + rev[rank]
+      r = finish_kmer(ix, pred, b, pol);
+      done = true;
+    }
+    if (active && done) store(i, x0, r);
+    push(active && !done, x0, pred, i, se);
+    while (stacked >= 32u) drain(32u);
     x0 = x1;
     x1 = x2;
     m0 = m1;
