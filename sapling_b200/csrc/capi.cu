@@ -522,10 +522,10 @@ int finish_model(sapling_b200_index* ix) {
   ix->last_y = last.y;
   const int shift = 2 * ix->k - ix->nb;
   if (!ix->d_narrow && ix->tune.narrow && shift >= 0 && shift <= 31) {
-    if (dev_alloc(ix, &ix->d_narrow, B)) return -1;
+    if (dev_alloc(ix, &ix->d_narrow, B + 1)) return -1;  // + the pad entry (model.cu)
     int ok = 0;
     if (build_narrow_model(ix->d_model, ix->nb, shift, ix->d_narrow, &ok, 0)) return -1;
-    if (!ok) dev_free(ix, &ix->d_narrow, B);
+    if (!ok) dev_free(ix, &ix->d_narrow, B + 1);
   }
   // the narrow table reconstructs xlist / ylist exactly (model.cu widen_model): the 16-byte-per-bucket table goes
   if (ix->d_narrow) dev_free(ix, &ix->d_model, B + 1);
@@ -1047,7 +1047,7 @@ int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
     };
     if (!copy(&r->d_genome, ix->d_genome, packed_words(ix->n))) return fail("genome");
     if (!copy(&r->d_lines, ix->d_lines, line_sectors(ix->n) * 8)) return fail("rank lines");
-    if (!copy(&r->d_narrow, ix->d_narrow, B)) return fail("model");
+    if (!copy(&r->d_narrow, ix->d_narrow, B + 1)) return fail("model");
     if (!copy(&r->d_model, ix->d_model, B + 1)) return fail("wide model");
     if (!copy(&r->d_isa, ix->d_isa, ix->n)) return fail("inverse suffix array");
     if (!copy(&r->d_kflag, ix->d_kflag, ix->n)) return fail("k flags");

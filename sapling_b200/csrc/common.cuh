@@ -269,17 +269,19 @@ __device__ __forceinline__ uint64_t interpolate(long long x, long long xlo, long
 // b - (xoff & 0x7fffffff) (the reference's forward fill, sapling_api.h:437-449).
 constexpr uint32_t kNarrowFill = 0x80000000u;
 
-// The two narrow entries of x's bucket (the second one is clamped at the table end and ignored there).
+// The two narrow entries of x's bucket.
 struct NarrowPair {
   uint2 e0, e1;
 };
 __device__ __forceinline__ NarrowPair narrow_load(const IndexView& ix, uint64_t x, uint64_t pol) {
   const uint32_t b = (uint32_t)(x >> ix.shift);  // nb <= 31 (capi.cu): bucket numbers are 32-bit
-  const uint32_t last = (uint32_t)((1ull << ix.nb) - 1ull);
-  NarrowPair p;
-  p.e0 = ld_u32x2_pol(ix.narrow + b, pol);
-  p.e1 = ld_u32x2_pol(ix.narrow + (b < last ? b + 1u : b), pol);
-  return p;
+  // the table has one entry more than buckets (flagged "filled"), so bucket b + 1 is always readable: two adjacent 8-byte
+  // loads from one address
+  const uint2* p = ix.narrow + b;
+  NarrowPair r;
+  r.e0 = ld_u32x2_pol(p, pol);
+  r.e1 = ld_u32x2_pol(p + 1, pol);
+  return r;
 }
 __device__ __forceinline__ uint64_t narrow_finish(const IndexView& ix, uint64_t x, const NarrowPair& p, uint64_t pol) {
   const uint64_t b = (uint32_t)(x >> ix.shift);  // nb <= 31: fits 32 bits (the 64-bit type only serves the rare paths below)
@@ -287,7 +289,8 @@ __device__ __forceinline__ uint64_t narrow_finish(const IndexView& ix, uint64_t 
   // Common case -- both buckets hold a k-mer and b is not the last bucket: the three differences the interpolation needs
   // fit 32 bits (the narrow layout implies shift <= 31: xoff < 2^31, ranks < 2^32), so they are formed from the entries'
   // offsets without rebuilding the 64-bit checkpoints.  Same real values, hence the same doubles as interpolate() below.
-  if (!((p.e0.x | p.e1.x) & kNarrowFill) && (uint32_t)b != (uint32_t)(B - 1)) {
+  // (for the last bucket the "next" entry is the table's pad, whose flag is set: it takes the general path below)
+  if (!((p.e0.x | p.e1.x) & kNarrowFill)) {
     const uint32_t xl = (uint32_t)x & ((1u << ix.shift) - 1u);          // x - (b << shift)
     const int32_t dx = (int32_t)xl - (int32_t)p.e0.x;                    // x - xlo
     const uint32_t den = (1u << ix.shift) + p.e1.x - p.e0.x;             // xhi - xlo in [1, 2^32)

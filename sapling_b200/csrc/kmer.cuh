@@ -272,43 +272,39 @@ __device__ __forceinline__ long long replay_binary_search(uint32_t lo, uint32_t 
 }
 
 // Phase 2: plQuery (:159-248) for s.length() == length == k (no gallop loops) over {lb, ub}: the rank whose rev[] it
-// returns, or -1.  pred < n.
+// returns, or -1.  pred < n.  Both sides' windows are computed for every lane and selected (the lanes of a warp go left
+// and right in equal numbers); only binarySearch is a loop.
 __device__ __forceinline__ long long replay_plquery(const IndexView& ix, uint32_t pred, const Bounds& b) {
   const uint32_t nm1 = (uint32_t)ix.n - 1u;
   auto is_match = [&](uint32_t r) { return r >= b.lb && r < b.ub; };
-  if (is_match(pred)) return (long long)pred;  // :164
-  uint32_t lo, hi;
-  if (pred < b.lb) {  // suffix smaller than the query: look right (:167-204)
-    lo = pred;
-    hi = kmer_add_clamped(pred, (uint32_t)ix.mostOver, nm1);
-    if (is_match(hi)) return (long long)hi;  // :174
-    if (hi < b.lb) {                         // :175-183
-      lo = hi;
-      hi = kmer_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
-      if (is_match(hi)) return (long long)hi;
-    }
-  } else {  // look left (:206-243)
-    hi = pred;
-    if (ix.compat) {  // (int)predicted - mostUnder (:209): wraps negative for predicted >= 2^31
-      const int32_t v = (int32_t)(pred - (uint32_t)ix.mostUnder);
-      lo = (uint32_t)(v > 0 ? v : 0);
-    } else {
-      const uint32_t d = (uint32_t)ix.mostUnder;
-      lo = pred > d ? pred - d : 0u;
-    }
-    if (is_match(lo)) return (long long)lo;  // :213
-    if (!(lo < b.lb)) {                      // :220-228
-      hi = lo;
-      if (ix.compat) {
-        const int32_t v = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
-        lo = (uint32_t)(v > 0 ? v : 0);
-      } else {
-        const uint32_t d = (uint32_t)ix.maxUnder + 1u;
-        lo = pred > d ? pred - d : 0u;
-      }
-      if (is_match(lo)) return (long long)lo;
-    }
+  // look right (:167-204): hi = min(n-1, predicted + mostOver), then min(n-1, predicted + maxOver + 1)
+  const uint32_t hi1 = kmer_add_clamped(pred, (uint32_t)ix.mostOver, nm1);
+  const uint32_t hi2 = kmer_add_clamped(pred, (uint32_t)ix.maxOver + 1u, nm1);
+  // look left (:206-243): lo = max(0, (int)predicted - mostUnder), then max(0, (int)predicted - maxUnder - 1); the (int)
+  // cast wraps negative for predicted >= 2^31, which compat mode keeps
+  uint32_t lo1, lo2;
+  if (ix.compat) {
+    const int32_t v1 = (int32_t)(pred - (uint32_t)ix.mostUnder);
+    const int32_t v2 = (int32_t)(pred - (uint32_t)ix.maxUnder - 1u);
+    lo1 = (uint32_t)(v1 > 0 ? v1 : 0);
+    lo2 = (uint32_t)(v2 > 0 ? v2 : 0);
+  } else {
+    const uint32_t d1 = (uint32_t)ix.mostUnder, d2 = (uint32_t)ix.maxUnder + 1u;
+    lo1 = pred > d1 ? pred - d1 : 0u;
+    lo2 = pred > d2 ? pred - d2 : 0u;
   }
+  const bool right = pred < b.lb;          // suffix smaller than the query (:167)
+  const uint32_t p1 = right ? hi1 : lo1;   // the first bound probed (:171 / :209)
+  const uint32_t p2 = right ? hi2 : lo2;   // the second one (:180 / :225)
+  // the second bound is probed when the first is still on the same side of the query as the prediction (:175 / :220)
+  const bool second = right ? (p1 < b.lb) : !(p1 < b.lb);
+  long long rank = -2;                                        // -2: not decided before binarySearch
+  if (is_match(pred)) rank = (long long)pred;                 // :164
+  else if (is_match(p1)) rank = (long long)p1;                // :174 / :213
+  else if (second && is_match(p2)) rank = (long long)p2;      // :183 / :228
+  if (rank != -2) return rank;
+  const uint32_t lo = right ? (second ? hi1 : pred) : (second ? lo2 : lo1);
+  const uint32_t hi = right ? (second ? hi2 : hi1) : (second ? lo1 : pred);
   return replay_binary_search(lo, hi, b);  // :245
 }
 

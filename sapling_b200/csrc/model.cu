@@ -17,7 +17,11 @@ namespace {
 __global__ void narrow_kernel(const ModelEntry* __restrict__ model, uint64_t B, int shift, uint2* __restrict__ out,
                               int* __restrict__ bad) {
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += stride) {
+  for (uint64_t b = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; b <= B; b += stride) {
+    if (b == B) {  // pad entry: lets the query kernels read bucket b + 1 unconditionally; flagged, so never interpolated with
+      out[b] = make_uint2(kNarrowFill, 0u);
+      continue;
+    }
     const long long x = model[b].x, y = model[b].y;
     const long long base = (long long)(b << shift);
     uint2 e;
@@ -70,6 +74,7 @@ int widen_model(const uint2* d_narrow, int nb, int shift, long long last_x, long
   return 0;
 }
 
+// d_narrow holds (1 << nb) + 1 entries (the last one is a pad).
 // Returns 0 and sets *ok = 1 when every checkpoint is representable (always true for a model built by
 // buildPiecewiseLinear; a hand-edited .sap file may not be, then the wide table is used).
 int build_narrow_model(const ModelEntry* d_model, int nb, int shift, uint2* d_narrow, int* ok, cudaStream_t st) {

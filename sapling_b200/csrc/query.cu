@@ -166,15 +166,34 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     push(pending, xw, pred, i, se);
   };
 
-  uint32_t t0 = claim(), t1 = claim(), t2 = claim();
+  // Pipeline, in tiles ahead of the one being answered: k-mers 3, model checkpoints 2, prediction 1 -- and with the
+  // prediction an L2 prefetch of its sector: the first read of a query is the one that goes to DRAM (the later ones stay in
+  // the same 128-byte line), and it is now on its way a whole tile before the lane asks for it.
+  auto predict = [&](uint64_t xw, const ModelPair<kNarrow>& m, bool real) -> uint32_t {
+    uint64_t p = m.predict(ix, xw & kmask, pol.model);
+    if (real) p = clamp_prediction(ix, p);  // counts predictions past the last rank: real queries only
+    else if (p >= ix.n) p = ix.n - 1;
+#ifndef SB_HOST_SIM
+    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ix.lines + (p >> 2) * 8u));
+#endif
+    return (uint32_t)p;
+  };
+  uint32_t t0 = claim(), t1 = claim(), t2 = claim(), t3 = claim();
   if (t0 >= nq32) return;
-  uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1);
-  ModelPair<kNarrow> m0;
-  m0.load(ix, x0 & kmask, pol.model);
-  while (t0 < nq32) {
-    const uint64_t x2 = kmer_at(t2);
-    ModelPair<kNarrow> m1;
+  uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1), x2 = kmer_at(t2);
+  ModelPair<kNarrow> m1;
+  uint32_t pred0;
+  {
+    ModelPair<kNarrow> m0;
+    m0.load(ix, x0 & kmask, pol.model);
     m1.load(ix, x1 & kmask, pol.model);
+    pred0 = predict(x0, m0, t0 + lane < nq32);
+  }
+  while (t0 < nq32) {
+    const uint64_t x3 = kmer_at(t3);
+    ModelPair<kNarrow> m2;
+    m2.load(ix, x2 & kmask, pol.model);
+    const uint32_t pred1 = predict(x1, m1, t1 + lane < nq32);
     const uint32_t i = t0 + lane;
     // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
     const bool active = i < nq32;
@@ -189,7 +208,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     se.begin(ix, 0);
     if (active) {  // round 1: the sector of the predicted rank
       const uint64_t x = x0 & kmask;
-      pred = (uint32_t)clamp_prediction(ix, m0.predict(ix, x, pol.model));
+      pred = pred0;
       key = make_key(ix, x);
       se.begin(ix, pred);
       uint32_t pos[4], idx = 0;
@@ -212,10 +231,13 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     while (stacked >= 32u) drain(32u);
     x0 = x1;
     x1 = x2;
-    m0 = m1;
+    x2 = x3;
+    m1 = m2;
+    pred0 = pred1;
     t0 = t1;
     t1 = t2;
-    t2 = claim();
+    t2 = t3;
+    t3 = claim();
   }
   while (stacked) drain(stacked < 32u ? stacked : 32u);
 }

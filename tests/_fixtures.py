@@ -106,4 +106,6 @@ def narrow_model(xlist, ylist, k, nb):
     ok = bool(((x >= 0) & (y >= 0) & (y <= 0xFFFFFFFF)).all() and (x[src] == x).all() and (y[src] == y).all()
               and (inside | (x < base)).all())
     xoff = np.where(inside, x - base, 0x80000000 | (np.arange(B) - src)).astype(np.uint32)
-    return np.ascontiguousarray(np.stack([xoff, y.astype(np.uint32)], axis=1)), ok
+    table = np.stack([xoff, y.astype(np.uint32)], axis=1)
+    pad = np.array([[0x80000000, 0]], dtype=np.uint32)  # entry B: flagged, lets the kernels read bucket b + 1 unconditionally
+    return np.ascontiguousarray(np.concatenate([table, pad])), ok
