@@ -207,6 +207,21 @@ def host_ram_available():
     return avail
 
 
+class stdout_to_stderr:
+    """The reference's constructor prints its progress lines to stdout (C++ cout and printf): keep them off this program's
+    stdout, which carries exactly one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def have_cuda():
     try:
         import torch
@@ -384,7 +399,8 @@ def cpu_baseline_and_parity(ix, d_batch, args, sample, stream, log):
         try:
             open(fa, "wb").write(fasta_bytes(genome))
             ix.write_sa(sa_fn)
-            ref = O.Ref(fa, sa_fn, sap_fn, nb=args.nb, maxMem=MAXMEM, k=k)
+            with stdout_to_stderr():
+                ref = O.Ref(fa, sa_fn, sap_fn, nb=args.nb, maxMem=MAXMEM, k=k)
             ix.write_sap(gpu_sap)
             parity["sap_bytes_identical_to_reference"] = open(gpu_sap, "rb").read() == open(sap_fn, "rb").read()
             ref.close()

@@ -490,7 +490,9 @@ const char* kmer_query_kernel_name(bool ordered) { return ordered ? "kmer_query_
 // `occupancy` (Tuning, capi.cu) overrides for A/B runs.
 int kmer_query_blocks_per_sm(bool ordered, int occupancy) {
   if (occupancy == 3 || occupancy == 4 || occupancy == 5 || occupancy == 6) return occupancy;
-  return ordered ? 5 : 4;
+  // measured (gpurun s5, c3): the in-order kernel at 4 blocks per SM (64 registers, nothing spilled) 6.43 ms per 250 M
+  // queries, at 5 (48 registers, 52 bytes spilled) 7.48, at 6 11.7
+  return 4;
 }
 
 // A batch in the caller's order.  d_out32 != nullptr: 32-bit answers (0xFFFFFFFF = -1) instead of long long.

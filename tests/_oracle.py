@@ -384,6 +384,62 @@ class Ref:
 
 
 # ----------------------------------------------------------------------------------------------
+# The reference's libdivsufsort submodule (oracle/_ref/libdivsuf_ref.so, oracle/ref_divsuf_harness.c): divsufsort() and the
+# independent match-range oracle sa_search() (suffixarray/libdivsufsort/lib/utils.c:259-326).
+DIVSUF_SO = os.path.join(ROOT, "oracle", "_ref", "libdivsuf_ref.so")
+_divsuf = None
+i64c = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def divsuf_available():
+    return os.path.exists(DIVSUF_SO)
+
+
+def divsuf_lib():
+    global _divsuf
+    if _divsuf is None:
+        L = C.CDLL(DIVSUF_SO)
+        L.ref_sa_search_batch.argtypes = [u8p, C.c_int64, u8p, C.c_int64, C.c_int64, i64c, i64c, i64c]
+        L.ref_divsufsort.restype = C.c_int
+        L.ref_divsufsort.argtypes = [u8p, i64c, C.c_int64]
+        L.ref_sufcheck.restype = C.c_int
+        L.ref_sufcheck.argtypes = [u8p, i64c, C.c_int64]
+        _divsuf = L
+    return _divsuf
+
+
+def sa_search_batch(genome: bytes, sa, kmers, k):
+    """(left, count) of libdivsufsort's sa_search for each packed k-mer: the ranks [left, left + count) are exactly the
+    suffixes that start with it."""
+    T = np.frombuffer(genome, dtype=np.uint8)
+    SA = np.ascontiguousarray(sa, dtype=np.int64)
+    kmers = np.asarray(kmers, dtype=np.uint64)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)
+    pat = np.empty((len(kmers), k), dtype=np.uint8)
+    for j in range(k):
+        pat[:, j] = letters[((kmers >> np.uint64(2 * (k - 1 - j))) & np.uint64(3)).astype(np.int64)]
+    left = np.empty(len(kmers), dtype=np.int64)
+    cnt = np.empty(len(kmers), dtype=np.int64)
+    divsuf_lib().ref_sa_search_batch(np.ascontiguousarray(T), len(T), np.ascontiguousarray(pat).reshape(-1), k, len(kmers), SA,
+                                     left, cnt)
+    return left, cnt
+
+
+def divsufsort(genome: bytes):
+    T = np.ascontiguousarray(np.frombuffer(genome, dtype=np.uint8))
+    SA = np.empty(len(T), dtype=np.int64)
+    rc = divsuf_lib().ref_divsufsort(T, SA, len(T))
+    assert rc == 0
+    return SA
+
+
+def sufcheck(genome: bytes, sa):
+    T = np.ascontiguousarray(np.frombuffer(genome, dtype=np.uint8))
+    return int(divsuf_lib().ref_sufcheck(T, np.ascontiguousarray(sa, dtype=np.int64), len(T)))
+
+
+# ----------------------------------------------------------------------------------------------
 # Shared input generators (seeded, identical everywhere)
 
 SEED_G = 0x5A91_1C0D_E5EE_D001

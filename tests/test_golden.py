@@ -11,7 +11,8 @@ import pytest
 import _oracle as O
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("seeds."))
+FIXTURES = sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+                  if not os.path.basename(p).startswith(("seeds.", "chr3_")))
 SEED_FIXTURES = sorted(glob.glob(os.path.join(HERE, "golden", "seeds.*.npz")))
 SEED_IDS = [os.path.basename(p)[:-4] for p in SEED_FIXTURES]
 IDS = [os.path.basename(p)[:-4] for p in FIXTURES]
@@ -119,3 +120,75 @@ def test_reference_struct_filled_from_parts_equals_constructor(tmp_path):
         assert (parts.n, parts.k, parts.nb, parts.five) == (ref.n, ref.k, ref.nb, ref.five)
         parts.close()
         ref.close()
+
+
+@pytest.mark.skipif(not O.divsuf_available(), reason="oracle/_ref/libdivsuf_ref.so not built (needs /root/reference at build time)")
+def test_port_suffix_array_and_equal_range_pinned_to_libdivsufsort():
+    """The reference's own cross-checks: the oracle port's suffix array == divsufsort()'s (and passes its
+    sufcheck), and the port's match-range helper so_equal_range == sa_search (lib/utils.c:259-326) for present and absent
+    patterns of every k the tests use, 32 included (where the reference's Sapling itself is undefined)."""
+    import _fixtures as F
+    for name in ("rand20k", "gc1991", "tandem50", "repeat_tailA", "polyC"):
+        g = F.small_genomes()[name]
+        port = O.Port.from_memory(g, k=min(21, len(g) // 8))
+        sa = port.sa
+        assert np.array_equal(O.divsufsort(g), sa.astype(np.int64)), name
+        assert O.sufcheck(g, sa) == 0
+        for k in (11, 16, 21, 31, 32):
+            if len(g) < 4 * k:
+                continue
+            km, _ = O.present_queries(g, k, 600)
+            km = np.concatenate([km, O.mutate_queries(km, k, every=1)])
+            left, cnt = O.sa_search_batch(g, sa, km, k)
+            for i in range(len(km)):
+                lb, ub = port.equal_range(O.unpack_kmer(int(km[i]), k))
+                assert ub - lb == cnt[i] and (cnt[i] == 0 or lb == left[i]), (name, k, i)
+            assert (cnt[:600] > 0).all()
+        port.close()
+
+
+CHR3 = os.path.join(HERE, "golden", "chr3_10M.npz")
+
+
+def load_chr3():
+    """The real-genome fixture (tests/golden/make_golden_chr3.py): genome bytes, expected stats, queries, the reference's
+    answers."""
+    sys_path = os.path.join(HERE, "golden")
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden_chr3", os.path.join(sys_path, "make_golden_chr3.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    z = np.load(CHR3)
+    n, k = int(z["n"]), int(z["k"])
+    g = mod.unpack2(z["packed"], n)
+    present, _ = O.present_queries(g, k, mod.NQ)
+    kmers = np.concatenate([present, O.mutate_queries(present, k, every=1)])
+    return g, k, int(z["nb"]), tuple(int(v) for v in z["five"]), int(z["perfect"]), kmers, z["answers"].astype(np.int64)
+
+
+def test_port_reproduces_reference_on_real_chr3():
+    """human chr3 10 Mbp (the SSW demo data shipped with the reference) -- n = 9,850,001, nb = 19,
+    maxOver = 4231, maxUnder = 4498, mostOver = 29, mostUnder = 28, meanError = 11, perfect = 1,635,411 -- and the
+    reference's answers to 200 000 present / mutated 21-mers, reproduced by the oracle port from the genome alone."""
+    g, k, nb, five, perfect, kmers, answers = load_chr3()
+    assert (len(g), nb, five, perfect) == (9_850_001, 19, (4231, 4498, 11, 29, 28), 1_635_411)
+    port = O.Port.from_memory(g, k=k)
+    assert (port.nb, port.five, port.perfect) == (nb, five, perfect)
+    assert np.array_equal(port.query_batch(kmers, nthreads=4), answers)
+    port.close()
+
+
+@pytest.mark.gpu
+def test_cuda_reproduces_reference_on_real_chr3(monkeypatch):
+    """The same fixture through the CUDA path: suffix array + model built on the GPU give the reference's statistics, and
+    the partitioned and unpartitioned kernels give the reference's answers (real sequence: error bounds in the thousands,
+    repeated 21-mers, escaped rank-line entries)."""
+    import sapling_b200 as S
+    g, k, nb, five, perfect, kmers, answers = load_chr3()
+    for tune in ("part=0", "part_min=1,part_bits=6,chunk_log2=22"):
+        monkeypatch.setenv("SAPLING_B200_TUNE", tune)
+        ix = S.Sapling.from_memory(g, None, k=k)
+        assert (ix.n, ix.buckets, ix.five, ix.perfectPredictions) == (len(g), nb, five, perfect)
+        assert np.array_equal(ix.queryBatch(kmers), answers), tune
+        ix.close()
+    monkeypatch.delenv("SAPLING_B200_TUNE")
