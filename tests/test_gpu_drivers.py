@@ -27,15 +27,25 @@ def _run(binary, fa, cwd, *args):
 def test_unmodified_sapling_example_runs_on_the_shim(tmp_path):
     g = O.synth_genome(O.SEED_G + 21, 300_000)
     outs = {}
-    for tag, binary in (("ref", "sapling_example"), ("b200", "sapling_example_b200")):
+    batched = os.path.join(O.ROOT, "sapling_b200", "bin", "sapling_example_batched")
+    for tag, binary in (("ref", os.path.join(REFDIR, "sapling_example")), ("b200", os.path.join(REFDIR, "sapling_example_b200")),
+                        ("batched", batched)):
+        if not os.path.exists(binary):
+            continue
         d = tmp_path / tag
         d.mkdir()
         fa = str(d / "g.fa")
         O.write_fasta(fa, g)
-        outs[tag] = _run(os.path.join(REFDIR, binary), fa, str(d), "k=21", "nq=20000")
+        outs[tag] = _run(binary, fa, str(d), "k=21", "nq=20000")
     pat = re.compile(r"Piecewise linear correctness: (\d+) out of (\d+)")
     a, b = pat.findall(outs["ref"]), pat.findall(outs["b200"])
     assert len(a) == 6 and a == b, (a, b)   # six query lengths k-10..k+80, same counts
+    if "batched" in outs:  # sapling_b200/host/sapling_example_batched.cpp: one batched call per experiment, same report
+        assert pat.findall(outs["batched"]) == a
+        assert open(tmp_path / "ref" / "queries.out").read() == open(tmp_path / "batched" / "queries.out").read()
+        t = [float(x) for x in re.findall(r"Piecewise linear time: ([0-9.eE+-]+)", outs["batched"])]
+        tr = [float(x) for x in re.findall(r"Piecewise linear time: ([0-9.eE+-]+)", outs["ref"])]
+        print("sapling_example timers, reference vs batched:", list(zip(tr, t)))
     # both wrote the same index files
     for ext in (".sa", ".sap"):
         fa_ref, fa_b = str(tmp_path / "ref" / "g.fa") + ext, str(tmp_path / "b200" / "g.fa") + ext

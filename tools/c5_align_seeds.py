@@ -58,8 +58,9 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     d_reads = torch.from_numpy(reads.reshape(-1)).cuda()
     d_off = torch.from_numpy(off.view(np.int64)).cuda()
-    d_rp = torch.empty(total, dtype=torch.int64, device="cuda")
-    d_sp, d_l, d_r = (torch.empty(total, dtype=torch.int32, device="cuda") for _ in range(3))
+    d_rp = torch.empty(total, dtype=torch.int32, device="cuda")   # compact tuples: 4 + 4 + 1 + 1 bytes per seed
+    d_sp = torch.empty(total, dtype=torch.int32, device="cuda")
+    d_l, d_r = (torch.empty(total, dtype=torch.uint8, device="cuda") for _ in range(2))
     args = (d_reads.data_ptr(), d_off.data_ptr(), n_reads, NUM_SEEDS, MAX_HITS, d_rp.data_ptr(), d_sp.data_ptr(),
             d_l.data_ptr(), d_r.data_ptr(), st)
     for _ in range(3):
@@ -76,17 +77,20 @@ def main():
     # end to end through the host C ABI (reads on the host, tuples back on the host)
     read_list = None
     blob = reads.tobytes()
-    rp, sp = np.empty(total, np.int64), np.empty(total, np.uint32)
-    lf, rt = np.empty(total, np.uint32), np.empty(total, np.uint32)
+    rp32, sp = np.empty(total, np.uint32), np.empty(total, np.uint32)
+    lf8, rt8 = np.empty(total, np.uint8), np.empty(total, np.uint8)
     L = S.lib()
-    L.sapling_b200_seed_batch(ix._h, blob, off, n_reads, NUM_SEEDS, MAX_HITS, rp, sp, lf, rt)
+    L.sapling_b200_seed_batch_compact(ix._h, blob, off, n_reads, NUM_SEEDS, MAX_HITS, rp32, sp, lf8, rt8)
     t0 = time.perf_counter()
     for _ in range(3):
-        assert L.sapling_b200_seed_batch(ix._h, blob, off, n_reads, NUM_SEEDS, MAX_HITS, rp, sp, lf, rt) == 0
+        assert L.sapling_b200_seed_batch_compact(ix._h, blob, off, n_reads, NUM_SEEDS, MAX_HITS, rp32, sp, lf8, rt8) == 0
     dt = (time.perf_counter() - t0) / 3
     res["e2e"] = {"ms": round(dt * 1e3, 2), "Gseeds_per_s": round(total / dt / 1e9, 3), "Mreads_per_s": round(n_reads / dt / 1e6, 2),
-                  "h2d_bytes": len(blob) + off.nbytes, "d2h_bytes": total * 20}
-    assert np.array_equal(rp, d_rp.cpu().numpy())
+                  "h2d_bytes": len(blob) + off.nbytes, "d2h_bytes": total * 10,
+                  "api": "sapling_b200_seed_batch_compact (blocks of reads pipelined, 10 bytes per seed back)"}
+    assert np.array_equal(rp32, d_rp.cpu().numpy().view(np.uint32))
+    rp = np.where(rp32 == 0xFFFFFFFF, -1, rp32.astype(np.int64))
+    lf, rt = lf8.astype(np.uint32), rt8.astype(np.uint32)
     hits = rp.reshape(n_reads, 2, NUM_SEEDS) >= 0
     res["reads_with_a_hit"] = int(hits.any(axis=(1, 2)).sum())
     res["seed_hits"] = int(hits.sum())
