@@ -549,8 +549,11 @@ def main():
     h_kmers = torch.empty(nq, dtype=torch.int64).pin_memory()
     h_kmers.copy_(d_kmers[0])
     torch.cuda.synchronize()
-    h_packed = torch.empty(nq * kb, dtype=torch.uint8).pin_memory()
-    h_packed.copy_(torch.from_numpy(np.ascontiguousarray(h_kmers.numpy().view(np.uint8).reshape(-1, 8)[:, :kb]).reshape(-1)))
+    if kb == 8:
+        h_packed = h_kmers
+    else:
+        h_packed = torch.empty(nq * kb, dtype=torch.uint8).pin_memory()
+        h_packed.copy_(torch.from_numpy(np.ascontiguousarray(h_kmers.numpy().view(np.uint8).reshape(-1, 8)[:, :kb]).reshape(-1)))
     h_out32 = torch.empty(nq, dtype=torch.int32).pin_memory()
     h_out = torch.empty(nq, dtype=torch.int64).pin_memory()
 

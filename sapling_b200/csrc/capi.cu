@@ -64,6 +64,7 @@ struct Tuning {
   int line_bases = 0;                 // line_bases=b: leading bases per rank-line entry (tests: forces escapes / ties)
   int chunk_log2 = 0;                 // chunk_log2=l: chunk size of the host-pointer batch path
   int narrow = 1;                     // narrow=0: keep the wide model table
+  int query_variant = -1;             // qv=0..5: what the in-order kernel carries a tile ahead / keeps (query.cu)
   static Tuning from_env() {
     Tuning t;
     const char* e = getenv("SAPLING_B200_TUNE");
@@ -86,6 +87,7 @@ struct Tuning {
         else if (key == "line_bases") t.line_bases = (int)v;
         else if (key == "chunk_log2") t.chunk_log2 = (int)v;
         else if (key == "narrow") t.narrow = (int)v;
+        else if (key == "qv") t.query_variant = (int)v;
       }
       p = q + 1;
     }
@@ -143,6 +145,30 @@ struct sapling_b200_index {
   long long* d_out[kSlots] = {};  // answers (8 bytes each, or 4 in the u32 entry point)
   void* h_in[kSlots] = {};
   void* h_out[kSlots] = {};
+
+  // staging of the seed-batch path: three blocks of reads in flight (upload / kernel / download), buffers kept between
+  // calls and grown on demand; pinned host mirrors for callers whose own buffers are pageable
+  struct SeedSlot {
+    char *d_reads = nullptr, *h_reads = nullptr;
+    size_t reads_cap = 0;
+    uint64_t *d_off = nullptr, *h_off = nullptr;
+    size_t off_cap = 0;
+    uint32_t *d_rp = nullptr, *d_sp = nullptr, *h_rp = nullptr, *h_sp = nullptr;
+    uint8_t *d_l = nullptr, *d_r = nullptr, *h_l = nullptr, *h_r = nullptr;
+    size_t seeds_cap = 0;
+    void release() {
+      cudaFree(d_reads); cudaFree(d_off); cudaFree(d_rp); cudaFree(d_sp); cudaFree(d_l); cudaFree(d_r);
+      if (h_reads) cudaFreeHost(h_reads);
+      if (h_off) cudaFreeHost(h_off);
+      if (h_rp) cudaFreeHost(h_rp);
+      if (h_sp) cudaFreeHost(h_sp);
+      if (h_l) cudaFreeHost(h_l);
+      if (h_r) cudaFreeHost(h_r);
+      *this = SeedSlot();
+    }
+  };
+  static constexpr int kSeedSlots = 3;
+  SeedSlot seed_slots[kSeedSlots];
 
   // scratch of the partitioned batch path (partition.cu), one block per stream it was used on, grown on demand
   struct PartWs {
@@ -210,6 +236,7 @@ struct sapling_b200_index {
     }
     if (s1) cudaStreamDestroy(s1);
     if (m1) cudaFreeHost(m1);
+    for (auto& ss : seed_slots) ss.release();
     cudaFree(d_genome);
     cudaFree(d_lines);
     cudaFree(d_sa);
@@ -1294,7 +1321,7 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
   }
   if (!ws) return plain();
   ix->launches.fetch_add(8, std::memory_order_relaxed);  // histogram, three column-scan passes, bin scan, scatter, query, un-permute
-  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, ix->tune.occupancy, st, ev);
+  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, ix->tune.occupancy, ix->tune.query_variant, st, ev);
 }
 
 int sapling_b200_profile(sapling_b200_index* ix, int on) {
@@ -1598,68 +1625,95 @@ int sapling_b200_seed_batch_compact(sapling_b200_index* ix, const char* reads, c
   std::lock_guard<std::mutex> lock(ix->mu);
   cudaSetDevice(ix->device);
   if (ensure_staging(ix)) return -1;
+  using Slot = sapling_b200_index::SeedSlot;
+  constexpr int NS = sapling_b200_index::kSeedSlots;
   const size_t per_read = 2 * (size_t)num_seeds;
   const size_t RB = std::max<size_t>(1, std::min<size_t>(n_reads, ((size_t)1 << 20) / per_read));  // reads per block
-  constexpr int NS = 3;
-  struct Slot {
-    char* d_reads = nullptr; size_t reads_cap = 0;
-    uint64_t* d_off = nullptr;
-    uint32_t *d_rp = nullptr, *d_sp = nullptr;
-    uint8_t *d_l = nullptr, *d_r = nullptr;
-    std::vector<uint64_t> off;
-  } slot[NS];
-  int rc = 0;
-  auto cleanup = [&]() {
-    for (auto& s : slot) { cudaFree(s.d_reads); cudaFree(s.d_off); cudaFree(s.d_rp); cudaFree(s.d_sp); cudaFree(s.d_l); cudaFree(s.d_r); }
-  };
-  for (auto& s : slot) {
-    if (cudaMalloc(&s.d_off, (RB + 1) * 8) || cudaMalloc(&s.d_rp, RB * per_read * 4) || cudaMalloc(&s.d_sp, RB * per_read * 4) ||
-        cudaMalloc(&s.d_l, RB * per_read) || cudaMalloc(&s.d_r, RB * per_read)) {
-      cudaGetLastError();
-      cleanup();
-      set_error("seed_batch: device allocation failed");
-      return -1;
+  const size_t nblocks = (n_reads + RB - 1) / RB;
+  // pinned caller buffers are copied from / to directly; pageable ones go through the slots' pinned mirrors
+  const bool pin_in = is_pinned(reads);
+  const bool pin_out = is_pinned(ref_pos) && is_pinned(sa_pos) && is_pinned(left) && is_pinned(right);
+  auto grow = [&](Slot& s, size_t read_bytes, size_t seeds) -> int {
+    if (s.off_cap < RB + 1) {
+      cudaFree(s.d_off);
+      if (s.h_off) cudaFreeHost(s.h_off);
+      s.d_off = nullptr; s.h_off = nullptr; s.off_cap = 0;
+      if (cudaMalloc(&s.d_off, (RB + 1) * 8) != cudaSuccess || cudaMallocHost(&s.h_off, (RB + 1) * 8) != cudaSuccess) return -1;
+      s.off_cap = RB + 1;
     }
-    s.off.resize(RB + 1);
-  }
+    if (s.reads_cap < read_bytes) {
+      const size_t cap = read_bytes + (read_bytes >> 2) + 64;
+      cudaFree(s.d_reads);
+      if (s.h_reads) cudaFreeHost(s.h_reads);
+      s.d_reads = nullptr; s.h_reads = nullptr; s.reads_cap = 0;
+      if (cudaMalloc(&s.d_reads, cap) != cudaSuccess || cudaMallocHost(&s.h_reads, cap) != cudaSuccess) return -1;
+      s.reads_cap = cap;
+    }
+    if (s.seeds_cap < seeds) {
+      cudaFree(s.d_rp); cudaFree(s.d_sp); cudaFree(s.d_l); cudaFree(s.d_r);
+      if (s.h_rp) cudaFreeHost(s.h_rp);
+      if (s.h_sp) cudaFreeHost(s.h_sp);
+      if (s.h_l) cudaFreeHost(s.h_l);
+      if (s.h_r) cudaFreeHost(s.h_r);
+      s.d_rp = s.d_sp = s.h_rp = s.h_sp = nullptr; s.d_l = s.d_r = s.h_l = s.h_r = nullptr; s.seeds_cap = 0;
+      if (cudaMalloc(&s.d_rp, seeds * 4) != cudaSuccess || cudaMalloc(&s.d_sp, seeds * 4) != cudaSuccess ||
+          cudaMalloc(&s.d_l, seeds) != cudaSuccess || cudaMalloc(&s.d_r, seeds) != cudaSuccess ||
+          cudaMallocHost(&s.h_rp, seeds * 4) != cudaSuccess || cudaMallocHost(&s.h_sp, seeds * 4) != cudaSuccess ||
+          cudaMallocHost(&s.h_l, seeds) != cudaSuccess || cudaMallocHost(&s.h_r, seeds) != cudaSuccess)
+        return -1;
+      s.seeds_cap = seeds;
+    }
+    return 0;
+  };
   cudaStream_t s_up = ix->streams[0], s_k = ix->streams[1], s_down = ix->streams[2];
   const IndexView v = ix->view();
-  const size_t nblocks = (n_reads + RB - 1) / RB;
+  int rc = 0;
   for (size_t b = 0; b < nblocks + NS && !rc; b++) {
-    if (b >= (size_t)NS && cudaEventSynchronize(ix->ev_down[(b - NS) % NS]) != cudaSuccess) { rc = -1; break; }
+    if (b >= (size_t)NS) {  // retire block b - NS: its slot is about to be reused
+      const size_t rb = b - NS;
+      Slot& s = ix->seed_slots[rb % NS];
+      if (cudaEventSynchronize(ix->ev_down[rb % NS]) != cudaSuccess) { rc = -1; break; }
+      if (!pin_out) {
+        const size_t r0 = rb * RB, m = std::min(RB, n_reads - r0), t0 = r0 * per_read, tm = m * per_read;
+        memcpy(ref_pos + t0, s.h_rp, tm * 4);
+        memcpy(sa_pos + t0, s.h_sp, tm * 4);
+        memcpy(left + t0, s.h_l, tm);
+        memcpy(right + t0, s.h_r, tm);
+      }
+    }
     if (b < nblocks) {
-      Slot& s = slot[b % NS];
+      Slot& s = ix->seed_slots[b % NS];
       const int e = (int)(b % NS);
       const size_t r0 = b * RB, m = std::min(RB, n_reads - r0);
       const uint64_t base = read_off[r0], nbytes = read_off[r0 + m] - base;
-      if (nbytes > s.reads_cap) {
-        cudaFree(s.d_reads);
-        s.reads_cap = 0;
-        if (cudaMalloc(&s.d_reads, nbytes + (nbytes >> 2) + 64) != cudaSuccess) { rc = -1; break; }
-        s.reads_cap = nbytes + (nbytes >> 2) + 64;
+      if (grow(s, (size_t)nbytes, RB * per_read)) { cudaGetLastError(); set_error("seed_batch: allocation failed"); rc = -2; break; }
+      for (size_t i = 0; i <= m; i++) s.h_off[i] = read_off[r0 + i] - base;
+      const char* src = reads + base;
+      if (!pin_in) {
+        memcpy(s.h_reads, src, (size_t)nbytes);
+        src = s.h_reads;
       }
-      for (size_t i = 0; i <= m; i++) s.off[i] = read_off[r0 + i] - base;
-      if (cudaMemcpyAsync(s.d_reads, reads + base, nbytes, cudaMemcpyHostToDevice, s_up) != cudaSuccess ||
-          cudaMemcpyAsync(s.d_off, s.off.data(), (m + 1) * 8, cudaMemcpyHostToDevice, s_up) != cudaSuccess) { rc = -1; break; }
+      if (cudaMemcpyAsync(s.d_reads, src, nbytes, cudaMemcpyHostToDevice, s_up) != cudaSuccess ||
+          cudaMemcpyAsync(s.d_off, s.h_off, (m + 1) * 8, cudaMemcpyHostToDevice, s_up) != cudaSuccess) { rc = -1; break; }
       cudaEventRecord(ix->ev_up[e], s_up);
       cudaStreamWaitEvent(s_k, ix->ev_up[e], 0);
       if (launch_seeds(v, ix->d_isa, ix->d_kflag, s.d_reads, s.d_off, m, num_seeds, max_hits, s.d_rp, s.d_sp, s.d_l, s.d_r, s_k)) { rc = -2; break; }
       cudaEventRecord(ix->ev_k[e], s_k);
       cudaStreamWaitEvent(s_down, ix->ev_k[e], 0);
       const size_t t0 = r0 * per_read, tm = m * per_read;
-      cudaMemcpyAsync(ref_pos + t0, s.d_rp, tm * 4, cudaMemcpyDeviceToHost, s_down);
-      cudaMemcpyAsync(sa_pos + t0, s.d_sp, tm * 4, cudaMemcpyDeviceToHost, s_down);
-      cudaMemcpyAsync(left + t0, s.d_l, tm, cudaMemcpyDeviceToHost, s_down);
-      if (cudaMemcpyAsync(right + t0, s.d_r, tm, cudaMemcpyDeviceToHost, s_down) != cudaSuccess) { rc = -1; break; }
+      cudaMemcpyAsync(pin_out ? ref_pos + t0 : s.h_rp, s.d_rp, tm * 4, cudaMemcpyDeviceToHost, s_down);
+      cudaMemcpyAsync(pin_out ? sa_pos + t0 : s.h_sp, s.d_sp, tm * 4, cudaMemcpyDeviceToHost, s_down);
+      cudaMemcpyAsync(pin_out ? left + t0 : s.h_l, s.d_l, tm, cudaMemcpyDeviceToHost, s_down);
+      if (cudaMemcpyAsync(pin_out ? right + t0 : s.h_r, s.d_r, tm, cudaMemcpyDeviceToHost, s_down) != cudaSuccess) { rc = -1; break; }
       cudaEventRecord(ix->ev_down[e], s_down);
-      // the offsets of this slot are reused NS blocks later: the upload must have consumed them (s_up is in order, and the
-      // ev_down wait above retires the block that used the slot before)
     }
   }
-  for (int i = 0; i < 3; i++) cudaStreamSynchronize(ix->streams[i]);
-  cleanup();
-  if (rc == -1) set_error("seed_batch: %s", cudaGetErrorString(cudaGetLastError()));
-  return rc ? -1 : 0;
+  if (rc) {
+    for (int i = 0; i < 3; i++) cudaStreamSynchronize(ix->streams[i]);  // nothing in flight behind an error
+    if (rc == -1) set_error("seed_batch: %s", cudaGetErrorString(cudaGetLastError()));
+    return -1;
+  }
+  return 0;  // every block was retired (event-synchronised) inside the loop
 }
 
 // The same tuples in the reference-shaped types (int64 positions with -1, 32-bit counts).

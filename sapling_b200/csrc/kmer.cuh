@@ -75,15 +75,13 @@ __device__ __forceinline__ void compare_with_genome(const IndexView& ix, const K
   SB_SIM_ADD(g_sim_slow_entries, 1);
 }
 
-// Classify sector s; pos[] receives its four text positions.  Fast path (no escaped entry, no tie): the entries are
-// P0 + d_j with 21-bit deltas, so
+// Classify sector s (its 32 bytes in e); pos[] receives its four text positions.  Fast path (no escaped entry, no tie): the
+// entries are P0 + d_j with 21-bit deltas, so
 //   smaller  <=>  d_j < qlo - P0         match  <=>  qlo - P0 <= d_j <= qhi - P0
 // with both bounds clamped into the delta range: four 32-bit compares each.
 template <bool kTies>
-__device__ __forceinline__ Sector classify_sector(const IndexView& ix, const KmerKey& key, uint32_t s, const L2Policies& pol,
-                                                  uint32_t pos[4]) {
-  const U32x8 e = ld_u32x8_pol(ix.lines + (uint64_t)s * 8u, pol.sa);
-  SB_SIM_ADD(g_sim_sector_loads, 1);
+__device__ __forceinline__ Sector classify_loaded(const IndexView& ix, const KmerKey& key, uint32_t s, const U32x8& e,
+                                                  const L2Policies& pol, uint32_t pos[4]) {
   const uint64_t P0 = ((uint64_t)e.v[1] << 32) | e.v[0];
   const uint32_t dlo = e.v[2], dhi = e.v[3];
   const uint32_t d1 = dlo & kPackedEscape;
@@ -113,6 +111,15 @@ __device__ __forceinline__ Sector classify_sector(const IndexView& ix, const Kme
   out.m = (uint32_t)ma0 + (uint32_t)ma1 + (uint32_t)ma2 + (uint32_t)ma3;
   pos[0] = e.v[4]; pos[1] = e.v[5]; pos[2] = e.v[6]; pos[3] = e.v[7];
   return out;
+}
+__device__ __forceinline__ U32x8 load_sector(const IndexView& ix, uint32_t s, const L2Policies& pol) {
+  SB_SIM_ADD(g_sim_sector_loads, 1);
+  return ld_u32x8_pol(ix.lines + (uint64_t)s * 8u, pol.sa);
+}
+template <bool kTies>
+__device__ __forceinline__ Sector classify_sector(const IndexView& ix, const KmerKey& key, uint32_t s, const L2Policies& pol,
+                                                  uint32_t pos[4]) {
+  return classify_loaded<kTies>(ix, key, s, load_sector(ix, s, pol), pol, pos);
 }
 
 struct Bounds {
@@ -319,6 +326,24 @@ __device__ __forceinline__ long long finish_kmer(const IndexView& ix, uint32_t p
   if (rank < 0) return -1;  // :246
   SB_SIM_ADD(g_sim_final_loads, 1);
   return (long long)rev_at(ix, (uint32_t)rank, pol.sa);  // :247
+}
+// The same with the positions of the (up to) two sectors the lane classified still in registers: the answer rank nearly
+// always lies in one of them, and the dependent rev[] load (and its sector request) is skipped.
+__device__ __forceinline__ long long finish_kmer_pos(const IndexView& ix, uint32_t pred, const Bounds& b, const L2Policies& pol,
+                                                     uint32_t sec_a, const uint32_t pos_a[4], uint32_t sec_b,
+                                                     const uint32_t pos_b[4]) {
+  const long long rank = replay_plquery(ix, pred, b);
+  if (rank < 0) return -1;  // :246
+  const uint32_t r = (uint32_t)rank, rs = r >> 2, j = r & 3u;
+  if (rs == sec_a || rs == sec_b) {
+    const bool use_b = rs == sec_b;
+    const uint32_t p0 = use_b ? pos_b[0] : pos_a[0], p1 = use_b ? pos_b[1] : pos_a[1];
+    const uint32_t p2 = use_b ? pos_b[2] : pos_a[2], p3 = use_b ? pos_b[3] : pos_a[3];
+    const uint32_t lo = (j & 1u) ? p1 : p0, hi = (j & 1u) ? p3 : p2;
+    return (long long)((j & 2u) ? hi : lo);
+  }
+  SB_SIM_ADD(g_sim_final_loads, 1);
+  return (long long)rev_at(ix, r, pol.sa);  // :247
 }
 
 // The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.

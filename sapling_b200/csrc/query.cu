@@ -85,7 +85,10 @@ struct TailStacks {
   uint4 st[kWarpsPerBlock][kStackCap];
 };
 
-template <int kMinBlocks, bool kTies, bool kNarrow>
+// kAhead: what travels one tile ahead with the prediction -- 0 nothing, 1 an L2 prefetch of its sector, 2 the sector itself
+// (the first classification then never waits for memory; eight more registers).  kKeepPos: the text positions of the
+// sectors classified in place stay in registers for the final rev[] lookup.
+template <int kMinBlocks, bool kTies, bool kNarrow, int kAhead, bool kKeepPos>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -167,14 +170,15 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   };
 
   // Pipeline, in tiles ahead of the one being answered: k-mers 3, model checkpoints 2, prediction 1 -- and with the
-  // prediction an L2 prefetch of its sector: the first read of a query is the one that goes to DRAM (the later ones stay in
-  // the same 128-byte line), and it is now on its way a whole tile before the lane asks for it.
-  auto predict = [&](uint64_t xw, const ModelPair<kNarrow>& m, bool real) -> uint32_t {
+  // prediction its sector (kAhead): the first read of a query is the one that goes to DRAM (the later ones stay in the same
+  // 128-byte line), and it is on its way a whole tile before the lane needs it.
+  auto predict = [&](uint64_t xw, const ModelPair<kNarrow>& m, bool real, U32x8* sector) -> uint32_t {
     uint64_t p = m.predict(ix, xw & kmask, pol.model);
     if (real) p = clamp_prediction(ix, p);  // counts predictions past the last rank: real queries only
     else if (p >= ix.n) p = ix.n - 1;
+    if (kAhead == 2) *sector = load_sector(ix, (uint32_t)(p >> 2), pol);
 #ifndef SB_HOST_SIM
-    asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ix.lines + (p >> 2) * 8u));
+    if (kAhead == 1) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ix.lines + (p >> 2) * 8u));
 #endif
     return (uint32_t)p;
   };
@@ -183,17 +187,23 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1), x2 = kmer_at(t2);
   ModelPair<kNarrow> m1;
   uint32_t pred0;
+  U32x8 sec0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) sec0.v[j] = 0;
   {
     ModelPair<kNarrow> m0;
     m0.load(ix, x0 & kmask, pol.model);
     m1.load(ix, x1 & kmask, pol.model);
-    pred0 = predict(x0, m0, t0 + lane < nq32);
+    pred0 = predict(x0, m0, t0 + lane < nq32, &sec0);
   }
   while (t0 < nq32) {
     const uint64_t x3 = kmer_at(t3);
     ModelPair<kNarrow> m2;
     m2.load(ix, x2 & kmask, pol.model);
-    const uint32_t pred1 = predict(x1, m1, t1 + lane < nq32);
+    U32x8 sec1;
+#pragma unroll
+    for (int j = 0; j < 8; j++) sec1.v[j] = 0;
+    const uint32_t pred1 = predict(x1, m1, t1 + lane < nq32, &sec1);
     const uint32_t i = t0 + lane;
     // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
     const bool active = i < nq32;
@@ -206,24 +216,28 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     b.lb = b.ub = 0;
     Search se;
     se.begin(ix, 0);
+    uint32_t pos_a[4] = {0, 0, 0, 0}, pos_b[4] = {0, 0, 0, 0};
+    uint32_t sec_a = 0xFFFFFFFFu, sec_b = 0xFFFFFFFFu;
     if (active) {  // round 1: the sector of the predicted rank
       const uint64_t x = x0 & kmask;
       pred = pred0;
       key = make_key(ix, x);
       se.begin(ix, pred);
-      uint32_t pos[4], idx = 0;
-      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
-      done = direct_match(pred, sc, pos, &idx);  // :164
+      uint32_t idx = 0;
+      sec_a = se.t;
+      const Sector sc = kAhead == 2 ? classify_loaded<kTies>(ix, key, se.t, sec0, pol, pos_a)
+                                    : classify_sector<kTies>(ix, key, se.t, pol, pos_a);
+      done = direct_match(pred, sc, pos_a, &idx);  // :164
       r = (long long)idx;
       resolved = se.feed(ix, pred, sc, true, &b);
     }
     if (active && !done && !resolved) {  // round 2: the neighbour the search asks for
-      uint32_t pos[4];
-      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
+      sec_b = se.t;
+      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos_b);
       resolved = se.feed(ix, pred, sc, false, &b);
     }
     if (active && !done && resolved) {  // phase 2 + rev[rank]
-      r = finish_kmer(ix, pred, b, pol);
+      r = kKeepPos ? finish_kmer_pos(ix, pred, b, pol, sec_a, pos_a, sec_b, pos_b) : finish_kmer(ix, pred, b, pol);
       done = true;
     }
     if (active && done) store(i, x0, r);
@@ -234,6 +248,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     x2 = x3;
     m1 = m2;
     pred0 = pred1;
+    if (kAhead == 2) sec0 = sec1;
     t0 = t1;
     t1 = t2;
     t2 = t3;
@@ -486,10 +501,12 @@ static inline bool has_ties(const IndexView& ix) { return ix.k > ix.line_bases; 
 
 const char* kmer_query_kernel_name(bool ordered) { return ordered ? "kmer_query_ordered_kernel" : "kmer_query_kernel"; }
 
+constexpr int kOrderedDefaultVariant = 2;  // kAhead 1, positions not kept (measured: see launch_kmer_query_ordered)
+
 // Resident blocks per SM the kernels are compiled for (register cap = 65536 / (256 * blocks)).  Measured defaults;
 // `occupancy` (Tuning, capi.cu) overrides for A/B runs.
 int kmer_query_blocks_per_sm(bool ordered, int occupancy) {
-  if (occupancy == 3 || occupancy == 4 || occupancy == 5 || occupancy == 6) return occupancy;
+  if (occupancy == 3 || occupancy == 4 || occupancy == 5 || (occupancy == 6 && !ordered)) return occupancy;
   // measured (gpurun s5, c3): the in-order kernel at 4 blocks per SM (64 registers, nothing spilled) 6.43 ms per 250 M
   // queries, at 5 (48 registers, 52 bytes spilled) 7.48, at 6 11.7
   return 4;
@@ -524,15 +541,29 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 }
 
 // A partitioned batch (partition.cu): d_tiles is the zeroed in-order tile counter, d_slot the slot array or
-// slot_in_kmer_tag(); results are slot words (see slot_word).
+// slot_in_kmer_tag(); results are slot words (see slot_word).  variant: kAhead * 2 + kKeepPos (Tuning `qv`), < 0 = default.
 int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
-                              const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st) {
+                              const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, int variant,
+                              cudaStream_t st) {
   if (nq == 0) return 0;
   const int bps = kmer_query_blocks_per_sm(true, occupancy);
   const int grid = query_grid(nq, bps);
   const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
-#define SB_LAUNCH_N(B, T, N) \
-  kmer_query_ordered_kernel<B, T, N><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
+  if (variant < 0 || variant > 5) variant = kOrderedDefaultVariant;
+#define SB_LAUNCH_V(B, T, N, A, P) \
+  kmer_query_ordered_kernel<B, T, N, A, P><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
+#define SB_LAUNCH_N(B, T, N)                                                     \
+  do {                                                                           \
+    if (!(!T && N)) { SB_LAUNCH_V(B, T, N, 1, false); break; } /* experiments: the common instantiation only */ \
+    switch (variant) {                                                           \
+      case 0: SB_LAUNCH_V(B, T, N, 0, false); break;                             \
+      case 1: SB_LAUNCH_V(B, T, N, 0, true); break;                              \
+      case 2: SB_LAUNCH_V(B, T, N, 1, false); break;                             \
+      case 3: SB_LAUNCH_V(B, T, N, 1, true); break;                              \
+      case 4: SB_LAUNCH_V(B, T, N, 2, false); break;                             \
+      default: SB_LAUNCH_V(B, T, N, 2, true); break;                             \
+    }                                                                            \
+  } while (0)
 #define SB_LAUNCH(B)                                       \
   do {                                                     \
     if (ties && narrow) SB_LAUNCH_N(B, true, true);        \
@@ -542,12 +573,12 @@ int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers,
   } while (0)
   switch (bps) {
     case 3: SB_LAUNCH(3); break;
-    case 4: SB_LAUNCH(4); break;
-    case 6: SB_LAUNCH(6); break;
-    default: SB_LAUNCH(5); break;
+    case 5: SB_LAUNCH(5); break;
+    default: SB_LAUNCH(4); break;
   }
 #undef SB_LAUNCH
 #undef SB_LAUNCH_N
+#undef SB_LAUNCH_V
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
