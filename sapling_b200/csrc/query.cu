@@ -501,8 +501,6 @@ static inline bool has_ties(const IndexView& ix) { return ix.k > ix.line_bases; 
 
 const char* kmer_query_kernel_name(bool ordered) { return ordered ? "kmer_query_ordered_kernel" : "kmer_query_kernel"; }
 
-constexpr int kOrderedDefaultVariant = 2;  // kAhead 1, positions not kept (measured: see launch_kmer_query_ordered)
-
 // Resident blocks per SM the kernels are compiled for (register cap = 65536 / (256 * blocks)).  Measured defaults;
 // `occupancy` (Tuning, capi.cu) overrides for A/B runs.
 int kmer_query_blocks_per_sm(bool ordered, int occupancy) {
@@ -549,21 +547,12 @@ int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers,
   const int bps = kmer_query_blocks_per_sm(true, occupancy);
   const int grid = query_grid(nq, bps);
   const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
-  if (variant < 0 || variant > 5) variant = kOrderedDefaultVariant;
-#define SB_LAUNCH_V(B, T, N, A, P) \
-  kmer_query_ordered_kernel<B, T, N, A, P><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
-#define SB_LAUNCH_N(B, T, N)                                                     \
-  do {                                                                           \
-    if (!(!T && N)) { SB_LAUNCH_V(B, T, N, 1, false); break; } /* experiments: the common instantiation only */ \
-    switch (variant) {                                                           \
-      case 0: SB_LAUNCH_V(B, T, N, 0, false); break;                             \
-      case 1: SB_LAUNCH_V(B, T, N, 0, true); break;                              \
-      case 2: SB_LAUNCH_V(B, T, N, 1, false); break;                             \
-      case 3: SB_LAUNCH_V(B, T, N, 1, true); break;                              \
-      case 4: SB_LAUNCH_V(B, T, N, 2, false); break;                             \
-      default: SB_LAUNCH_V(B, T, N, 2, true); break;                             \
-    }                                                                            \
-  } while (0)
+  // Measured (gpurun s7, c3, 4 blocks per SM, ms per 250 M queries): nothing ahead 6.70, L2 prefetch of the sector 6.43,
+  // the sector itself a tile ahead 6.59; keeping the classified sectors' positions for the final rev[] lookup costs more
+  // registers than the load it saves (6.94 / 6.68 / 6.55).  The prefetch variant is the one instantiated.
+  (void)variant;
+#define SB_LAUNCH_N(B, T, N) \
+  kmer_query_ordered_kernel<B, T, N, 1, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
 #define SB_LAUNCH(B)                                       \
   do {                                                     \
     if (ties && narrow) SB_LAUNCH_N(B, true, true);        \
@@ -578,7 +567,6 @@ int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers,
   }
 #undef SB_LAUNCH
 #undef SB_LAUNCH_N
-#undef SB_LAUNCH_V
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
