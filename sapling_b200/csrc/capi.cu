@@ -1061,10 +1061,16 @@ int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
       cudaSetDevice(ix->device);
       return -1;
     };
-    if (cudaSetDevice(dev) != cudaSuccess) return fail("cudaSetDevice");
+    // direct NVLink / NVSwitch copies need peer access enabled on both ends; "already enabled" is fine
     int can = 0;
+    if (cudaDeviceCanAccessPeer(&can, ix->device, dev) == cudaSuccess && can) {
+      cudaSetDevice(ix->device);
+      cudaDeviceEnablePeerAccess(dev, 0);
+      cudaGetLastError();
+    }
+    if (cudaSetDevice(dev) != cudaSuccess) return fail("cudaSetDevice");
     if (cudaDeviceCanAccessPeer(&can, dev, ix->device) == cudaSuccess && can) {
-      cudaDeviceEnablePeerAccess(ix->device, 0);  // direct NVLink copies; already-enabled is fine
+      cudaDeviceEnablePeerAccess(ix->device, 0);
       cudaGetLastError();
     }
     auto copy = [&](auto** dst, const auto* src, uint64_t count) -> bool {
