@@ -1039,13 +1039,27 @@ int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
   SB_CUDA_CHECK(cudaGetDeviceCount(&ndev));
   std::lock_guard<std::mutex> lock(ix->mu);
   const uint64_t B = 1ull << ix->nb;
+  std::vector<sapling_b200_index*> fresh;
+  auto abandon = [&](int dev, const char* what) {
+    set_error("replicate to device %d: %s: %s", dev, what, cudaGetErrorString(cudaGetLastError()));
+    for (auto* r : fresh) {
+      cudaSetDevice(r->device);
+      cudaDeviceSynchronize();
+      delete r;
+    }
+    cudaSetDevice(ix->device);
+    return -1;
+  };
+  // pass 1: allocate on every new GPU and start its copies (asynchronous, one stream per destination: the copies to
+  // different GPUs run side by side through the switch)
   for (int dev = 0; dev < ndev && dev < 64; dev++) {
     if (!((gpu_mask >> dev) & 1ull) || dev == ix->device) continue;
     bool have = false;
     for (auto* r : ix->replicas) have |= r->device == dev;
     if (have) continue;
-    if (check_device(dev)) return -1;
+    if (check_device(dev)) return abandon(dev, "device check");
     sapling_b200_index* r = new sapling_b200_index();
+    fresh.push_back(r);
     r->device = dev;
     r->is_replica = true;
     r->flags = ix->flags;
@@ -1055,12 +1069,6 @@ int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
     r->line_bases = ix->line_bases;
     r->last_x = ix->last_x; r->last_y = ix->last_y;
     r->hints = ix->hints;
-    auto fail = [&](const char* what) {
-      set_error("replicate to device %d: %s: %s", dev, what, cudaGetErrorString(cudaGetLastError()));
-      delete r;
-      cudaSetDevice(ix->device);
-      return -1;
-    };
     // direct NVLink / NVSwitch copies need peer access enabled on both ends; "already enabled" is fine
     int can = 0;
     if (cudaDeviceCanAccessPeer(&can, ix->device, dev) == cudaSuccess && can) {
@@ -1068,7 +1076,7 @@ int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
       cudaDeviceEnablePeerAccess(dev, 0);
       cudaGetLastError();
     }
-    if (cudaSetDevice(dev) != cudaSuccess) return fail("cudaSetDevice");
+    if (cudaSetDevice(dev) != cudaSuccess) return abandon(dev, "cudaSetDevice");
     if (cudaDeviceCanAccessPeer(&can, dev, ix->device) == cudaSuccess && can) {
       cudaDeviceEnablePeerAccess(ix->device, 0);
       cudaGetLastError();
@@ -1076,18 +1084,21 @@ int sapling_b200_replicate(sapling_b200_index* ix, uint64_t gpu_mask) {
     auto copy = [&](auto** dst, const auto* src, uint64_t count) -> bool {
       if (!src) return true;
       if (dev_alloc(r, dst, count)) return false;
-      return cudaMemcpyPeer(*dst, dev, src, ix->device, count * sizeof(**dst)) == cudaSuccess;
+      return cudaMemcpyPeerAsync(*dst, dev, src, ix->device, count * sizeof(**dst), 0) == cudaSuccess;
     };
-    if (!copy(&r->d_genome, ix->d_genome, packed_words(ix->n))) return fail("genome");
-    if (!copy(&r->d_lines, ix->d_lines, line_sectors(ix->n) * 8)) return fail("rank lines");
-    if (!copy(&r->d_narrow, ix->d_narrow, B + 1)) return fail("model");
-    if (!copy(&r->d_model, ix->d_model, B + 1)) return fail("wide model");
-    if (!copy(&r->d_isa, ix->d_isa, ix->n)) return fail("inverse suffix array");
-    if (!copy(&r->d_kflag, ix->d_kflag, ix->n)) return fail("k flags");
-    if (dev_alloc(r, &r->d_oob, 1) || cudaMemset(r->d_oob, 0, 8) != cudaSuccess) return fail("counter");
-    if (cudaDeviceSynchronize() != cudaSuccess) return fail("synchronize");
-    ix->replicas.push_back(r);
+    if (!copy(&r->d_genome, ix->d_genome, packed_words(ix->n))) return abandon(dev, "genome");
+    if (!copy(&r->d_lines, ix->d_lines, line_sectors(ix->n) * 8)) return abandon(dev, "rank lines");
+    if (!copy(&r->d_narrow, ix->d_narrow, B + 1)) return abandon(dev, "model");
+    if (!copy(&r->d_model, ix->d_model, B + 1)) return abandon(dev, "wide model");
+    if (!copy(&r->d_isa, ix->d_isa, ix->n)) return abandon(dev, "inverse suffix array");
+    if (!copy(&r->d_kflag, ix->d_kflag, ix->n)) return abandon(dev, "k flags");
+    if (dev_alloc(r, &r->d_oob, 1) || cudaMemsetAsync(r->d_oob, 0, 8, 0) != cudaSuccess) return abandon(dev, "counter");
   }
+  // pass 2: wait for them
+  for (auto* r : fresh) {
+    if (cudaSetDevice(r->device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return abandon(r->device, "copy");
+  }
+  for (auto* r : fresh) ix->replicas.push_back(r);
   cudaSetDevice(ix->device);
   return 0;
 }
