@@ -39,11 +39,12 @@ struct KmerKey {
   uint64_t qlo;      // smallest / largest line_bases-base integer whose first min(k, line_bases) bases are the query's
   uint64_t qhi;
 };
+template <bool kTies>
 __device__ __forceinline__ KmerKey make_key(const IndexView& ix, uint64_t x) {
   KmerKey key;
   const int k = ix.k, b = ix.line_bases;
   key.q = x << (64 - 2 * k);
-  if (k <= b) {
+  if (!kTies) {  // k <= line_bases: pad the k-mer with the smallest / largest bases
     key.qlo = x << (2 * (b - k));
     key.qhi = key.qlo | ((1ull << (2 * (b - k))) - 1ull);
   } else {  // an entry holds fewer bases than the k-mer: equality on them is a tie the genome decides (see classify)
@@ -159,11 +160,22 @@ struct Search {
   // bisecting, extending a run), and a branch per case would keep them apart -- through the NEXT round's classification
   // as well, because the branches only reconverge where the paths that are done rejoin (ncu s3: the second round ran twice
   // per tile with 7 lanes each).
+  // kFresh: the state is the one begin() left (the first sector of a query) -- told to the compiler, which then folds
+  // most of the update away.
+  template <bool kFresh = false>
   __device__ __forceinline__ bool feed(const IndexView& ix, uint32_t pred, const Sector& x, bool is_first, Bounds* out) {
     const uint32_t n32 = (uint32_t)ix.n;
     const int32_t last_s = (int32_t)((n32 - 1u) >> 2);
     const uint32_t last_valid = n32 - 4u * (uint32_t)last_s;
     const uint32_t valid = (int32_t)x.s == last_s ? last_valid : 4u;
+    if (kFresh) {
+      yes = -1;
+      no_s = (uint32_t)(last_s + 1);
+      no_c = no_m = 0;
+      step_log2 = 0;
+      mode = 0;
+      is_first = true;
+    }
     first_c = is_first ? x.c : first_c;
     first_m = is_first ? x.m : first_m;
     const bool has = mode ? (x.m == valid) : (x.c == 4u);
@@ -225,6 +237,58 @@ struct Search {
     t = next_t;
   }
 };
+
+// The common case of phase 1 without the general search: the sector of the predicted rank, and at most ONE neighbour.
+// A third of the queries match at the predicted rank; for most of the others the boundary lb lies in that sector or in
+// the next one to the side the classification points to, and the run of matches ends there too.  Everything else (errors
+// beyond a sector, long runs of equal k-mers) is left to Search.
+//   two_sector_first : 0 = *b is final; 1 = classify sector *neighbour and call two_sector_second
+//   two_sector_second: 0 = *b is final; 2 = not decided by these two sectors
+__device__ __forceinline__ int two_sector_first(const IndexView& ix, const Sector& x0, Bounds* b, uint32_t* neighbour) {
+  const uint32_t n32 = (uint32_t)ix.n;
+  const uint32_t last_s = (n32 - 1u) >> 2;
+  const uint32_t v0 = x0.s == last_s ? n32 - 4u * last_s : 4u;
+  const bool all_small = x0.c == 4u;                     // lb lies further right
+  const bool none_small = x0.c == 0u && x0.s != 0u;      // lb may lie further left
+  const bool is_last = x0.s == last_s;
+  const uint32_t lb = all_small ? n32 : 4u * x0.s + x0.c;  // (all small in the last sector: every rank is smaller)
+  const bool run_ends = x0.c + x0.m < v0 || is_last;
+  b->lb = lb;
+  b->ub = all_small ? n32 : lb + x0.m;
+  *neighbour = none_small ? x0.s - 1u : x0.s + 1u;
+  const bool resolved = all_small ? is_last : (!none_small && run_ends);
+  return resolved ? 0 : 1;
+}
+__device__ __forceinline__ int two_sector_second(const IndexView& ix, const Sector& x0, const Sector& x1, Bounds* b) {
+  const uint32_t n32 = (uint32_t)ix.n;
+  const uint32_t last_s = (n32 - 1u) >> 2;
+  const uint32_t v0 = x0.s == last_s ? n32 - 4u * last_s : 4u;
+  const uint32_t v1 = x1.s == last_s ? n32 - 4u * last_s : 4u;
+  int rc;
+  if (x1.s > x0.s) {           // right neighbour
+    const bool x1_last = x1.s == last_s;
+    if (x0.c == 4u) {          // looking for lb
+      const bool all_small = x1.c == 4u;
+      const uint32_t lb = all_small ? n32 : 4u * x1.s + x1.c;
+      b->lb = lb;
+      b->ub = all_small ? n32 : lb + x1.m;
+      const bool ok = all_small ? x1_last : (x1.c + x1.m < v1 || x1_last);
+      rc = ok ? 0 : 2;
+    } else {                   // lb = 4 s0 + c0 is known, the matches ran to the end of s0: where do they stop?
+      b->ub = 4u * x1.s + x1.m;
+      rc = (x1.m < v1 || x1_last) ? 0 : 2;
+    }
+  } else {                     // left neighbour (s0 has no smaller entry)
+    const bool further_left = x1.c == 0u && x1.s != 0u;
+    const uint32_t lb = 4u * x1.s + x1.c;
+    const bool into_s0 = x1.c + x1.m == 4u;   // the matches (if any) reach the end of s1 and go on in s0
+    b->lb = lb;
+    b->ub = into_s0 ? 4u * x0.s + x0.m : lb + x1.m;
+    const bool ok = !further_left && (!into_s0 || x0.m < v0 || x0.s == last_s);
+    rc = ok ? 0 : 2;
+  }
+  return rc;
+}
 
 // rev[predicted] when it matches the query (:164), from the classification of its own sector
 __device__ __forceinline__ bool direct_match(uint32_t pred, const Sector& x, const uint32_t pos[4], uint32_t* idx) {
@@ -346,10 +410,11 @@ __device__ __forceinline__ long long finish_kmer_pos(const IndexView& ix, uint32
   return (long long)rev_at(ix, r, pol.sa);  // :247
 }
 
-// The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.
+// The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.  (The general search on
+// its own; the kernels try the two-sector shortcut first and come here for what it leaves.)
 template <bool kTies>
 __device__ __forceinline__ long long answer_kmer(const IndexView& ix, uint64_t x, uint32_t pred, const L2Policies& pol) {
-  const KmerKey key = make_key(ix, x);
+  const KmerKey key = make_key<kTies>(ix, x);
   Search se;
   se.begin(ix, pred);
   Bounds b;
@@ -363,6 +428,23 @@ __device__ __forceinline__ long long answer_kmer(const IndexView& ix, uint64_t x
     is_first = false;
   }
   return finish_kmer(ix, pred, b, pol);
+}
+
+// The same answer by the kernels' schedule: sector of the prediction, one neighbour, and only then the general search.
+template <bool kTies>
+__device__ __forceinline__ long long answer_kmer_fast(const IndexView& ix, uint64_t x, uint32_t pred, const L2Policies& pol) {
+  const KmerKey key = make_key<kTies>(ix, x);
+  uint32_t pos[4], idx, neighbour;
+  const Sector s0 = classify_sector<kTies>(ix, key, pred >> 2, pol, pos);
+  if (direct_match(pred, s0, pos, &idx)) return (long long)idx;  // :164
+  Bounds b;
+  int st = two_sector_first(ix, s0, &b, &neighbour);
+  if (st == 1) {
+    const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
+    st = two_sector_second(ix, s0, s1, &b);
+  }
+  if (st == 0) return finish_kmer(ix, pred, b, pol);
+  return answer_kmer<kTies>(ix, x, pred, pol);
 }
 
 }  // namespace sb

@@ -33,7 +33,7 @@ kmer_query_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
     const uint64_t x = __ldcs(kmers + i) & kmask;  // bits above 2k are not part of a k-mer: ignored, never indexed with
     const uint32_t pred = (uint32_t)clamp_prediction(ix, predict_rank(ix, x, pol.model));
-    const long long r = answer_kmer<kTies>(ix, x, pred, pol);
+    const long long r = answer_kmer_fast<kTies>(ix, x, pred, pol);
     __stcs(out + i, (Out)r);
   }
 }
@@ -74,15 +74,15 @@ struct ModelPair<false> {
 // one neighbouring sector; one in eight needs a third sector or more (errors beyond the 95 % bounds, match runs crossing a
 // sector end, absent k-mers far from their prediction).  A warp that loops until its slowest lane is done spends most of
 // its instructions with 2-4 lanes alive (ncu, profiles/s2_*: 13.7 of 32 lanes active per instruction).  So a tile gets
-// exactly TWO classification rounds in place; what is still unresolved is pushed -- its search state is 36 bytes -- onto
-// the warp's own stack in shared memory, and whenever 32 have piled up the warp pops them and runs one more round with
-// every lane busy.  No block-wide barrier: the warps stay independent.
+// exactly TWO classification rounds in place, decided by the two-sector shortcut (kmer.cuh: a handful of compares, no
+// search state); what is still undecided -- one query in eight -- is pushed onto the warp's own stack in shared memory, and
+// whenever 32 have piled up the warp pops them and answers them with the general search, every lane busy at the start.
+// No block-wide barrier: the warps stay independent.
 constexpr int kWarpsPerBlock = kQueryThreads / 32;
-constexpr int kStackCap = 64;  // at most 31 left over + 32 pushed by a tile (or pushed back by a drain)
-struct TailStacks {
+constexpr int kStackCap = 64;  // at most 31 left over + 32 pushed by a tile
+struct TailStacks {            // per warp: the queries the two-sector shortcut left undecided (k-mer word, prediction, index)
   uint32_t x_lo[kWarpsPerBlock][kStackCap], x_hi[kWarpsPerBlock][kStackCap];
-  uint32_t pred[kWarpsPerBlock][kStackCap], idx[kWarpsPerBlock][kStackCap], t[kWarpsPerBlock][kStackCap];
-  uint4 st[kWarpsPerBlock][kStackCap];
+  uint32_t pred[kWarpsPerBlock][kStackCap], idx[kWarpsPerBlock][kStackCap];
 };
 
 // kAhead: what travels one tile ahead with the prediction -- 0 nothing, 1 an L2 prefetch of its sector, 2 the sector itself
@@ -126,8 +126,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     __stcs(out + i, slot_word(sl, r));
   };
   unsigned stacked = 0;  // warp-uniform: entries on this warp's stack
-  // push the lanes with `pending` set; everything a later round needs travels in the record
-  auto push = [&](bool pending, uint64_t xw, uint32_t pred, uint32_t i, const Search& se) {
+  auto push = [&](bool pending, uint64_t xw, uint32_t pred, uint32_t i) {
     const unsigned m = __ballot_sync(0xffffffffu, pending);
     if (pending) {
       const unsigned e = stacked + (unsigned)__popc(m & lt_mask);
@@ -135,38 +134,20 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       stacks.x_hi[warp][e] = (uint32_t)(xw >> 32);
       stacks.pred[warp][e] = pred;
       stacks.idx[warp][e] = i;
-      stacks.t[warp][e] = se.t;
-      stacks.st[warp][e] = se.pack();
     }
     stacked += (unsigned)__popc(m);
     __syncwarp();
   };
-  // pop the top `m` (<= 32) entries: one more classification round with every lane busy
+  // pop the top `m` (<= 32) entries and answer them with the general search
   auto drain = [&](unsigned m) {
     stacked -= m;
-    const bool have = lane < m;
-    const unsigned e = stacked + lane;
-    uint64_t xw = 0;
-    uint32_t pred = 0, i = 0;
-    Search se;
-    se.begin(ix, 0);
-    if (have) {
-      xw = ((uint64_t)stacks.x_hi[warp][e] << 32) | stacks.x_lo[warp][e];
-      pred = stacks.pred[warp][e];
-      i = stacks.idx[warp][e];
-      se.unpack(stacks.st[warp][e], stacks.t[warp][e]);
+    if (lane < m) {
+      const unsigned e = stacked + lane;
+      const uint64_t xw = ((uint64_t)stacks.x_hi[warp][e] << 32) | stacks.x_lo[warp][e];
+      const uint32_t i = stacks.idx[warp][e];
+      store(i, xw, answer_kmer<kTies>(ix, xw & kmask, stacks.pred[warp][e], pol));
     }
-    __syncwarp();  // every record is in registers before any slot is written again
-    bool pending = false;
-    if (have) {
-      const KmerKey key = make_key(ix, xw & kmask);
-      uint32_t pos[4];
-      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
-      Bounds b;
-      if (se.feed(ix, pred, sc, false, &b)) store(i, xw, finish_kmer(ix, pred, b, pol));
-      else pending = true;
-    }
-    push(pending, xw, pred, i, se);
+    __syncwarp();
   };
 
   // Pipeline, in tiles ahead of the one being answered: k-mers 3, model checkpoints 2, prediction 1 -- and with the
@@ -207,41 +188,37 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     const uint32_t i = t0 + lane;
     // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
     const bool active = i < nq32;
-    bool done = false, resolved = false;
+    bool done = false;
+    int st = 2;  // 0: bounds final, 1: wants the neighbour, 2: left to the general search
     long long r = -1;
-    uint32_t pred = 0;
+    uint32_t pred = 0, neighbour = 0;
     KmerKey key;
     key.q = key.qlo = key.qhi = 0;
     Bounds b;
     b.lb = b.ub = 0;
-    Search se;
-    se.begin(ix, 0);
-    uint32_t pos_a[4] = {0, 0, 0, 0}, pos_b[4] = {0, 0, 0, 0};
-    uint32_t sec_a = 0xFFFFFFFFu, sec_b = 0xFFFFFFFFu;
+    Sector s0;
+    s0.s = s0.c = s0.m = 0;
     if (active) {  // round 1: the sector of the predicted rank
-      const uint64_t x = x0 & kmask;
       pred = pred0;
-      key = make_key(ix, x);
-      se.begin(ix, pred);
-      uint32_t idx = 0;
-      sec_a = se.t;
-      const Sector sc = kAhead == 2 ? classify_loaded<kTies>(ix, key, se.t, sec0, pol, pos_a)
-                                    : classify_sector<kTies>(ix, key, se.t, pol, pos_a);
-      done = direct_match(pred, sc, pos_a, &idx);  // :164
+      key = make_key<kTies>(ix, x0 & kmask);
+      uint32_t pos[4], idx = 0;
+      s0 = kAhead == 2 ? classify_loaded<kTies>(ix, key, pred >> 2, sec0, pol, pos)
+                       : classify_sector<kTies>(ix, key, pred >> 2, pol, pos);
+      done = direct_match(pred, s0, pos, &idx);  // :164
       r = (long long)idx;
-      resolved = se.feed(ix, pred, sc, true, &b);
+      st = two_sector_first(ix, s0, &b, &neighbour);
     }
-    if (active && !done && !resolved) {  // round 2: the neighbour the search asks for
-      sec_b = se.t;
-      const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos_b);
-      resolved = se.feed(ix, pred, sc, false, &b);
+    if (active && !done && st == 1) {  // round 2: the neighbour the first one points to
+      uint32_t pos[4];
+      const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
+      st = two_sector_second(ix, s0, s1, &b);
     }
-    if (active && !done && resolved) {  // phase 2 + rev[rank]
-      r = kKeepPos ? finish_kmer_pos(ix, pred, b, pol, sec_a, pos_a, sec_b, pos_b) : finish_kmer(ix, pred, b, pol);
+    if (active && !done && st == 0) {  // phase 2 + rev[rank]
+      r = finish_kmer(ix, pred, b, pol);
       done = true;
     }
     if (active && done) store(i, x0, r);
-    push(active && !done, x0, pred, i, se);
+    push(active && !done, x0, pred, i);
     while (stacked >= 32u) drain(32u);
     x0 = x1;
     x1 = x2;
@@ -311,7 +288,7 @@ seed_kernel(const IndexView ix, const uint32_t* __restrict__ isa, const uint8_t*
       }
       if (valid) {
         const uint32_t pred = (uint32_t)clamp_prediction(ix, predict_rank(ix, x, pol.model));
-        const long long a = answer_kmer<kTies>(ix, x, pred, pol);
+        const long long a = answer_kmer_fast<kTies>(ix, x, pred, pol);
         if (a >= 0 && (uint64_t)a + k <= ix.n &&
             (load_bases_upto(ix.genome, (uint64_t)a, k) >> (64u - 2u * k)) == x) {
           hit = (uint32_t)a;
