@@ -164,6 +164,12 @@ __device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t 
 // ranks in shared memory and re-read the run starts: 9 shared-memory operations per k-mer against 6 here.)
 constexpr int kScatterThreads = kPartChunk / 16;  // 16 k-mers per thread in registers
 constexpr int kScatterPer = kPartChunk / kScatterThreads;
+// Persistent: one block per SM (the staging buffer takes most of its shared memory) walks chunks blockIdx, blockIdx +
+// gridDim, ...  With a block per chunk the phases of a chunk ran one after the other -- load, scan, sort, write out -- and
+// the SM sat idle through every load (ncu r2u: 81 % of the stalls long-scoreboard, 49 % of the copy bandwidth).  Here the
+// k-mers and the offset-table rows of the NEXT chunk are requested as soon as the current chunk has been sorted into shared
+// memory (its k-mer registers are dead by then, so they are simply reused) and arrive while the current chunk is written
+// out.
 template <bool kSlotInKmer>
 __global__ void __launch_bounds__(kScatterThreads)
 part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
@@ -175,63 +181,75 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
   uint32_t* lstart = reinterpret_cast<uint32_t*>(ss + kPartChunk);              // [2048] next free sorted index of the bin
   uint32_t* gdelta = lstart + 2048;                                             // [2048] global position - sorted index
   __shared__ uint32_t wsum[32];
-  const size_t c = blockIdx.x;
-  const size_t base = c * kPartChunk;
-  const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  uint64_t x[kScatterPer];
-#pragma unroll
-  for (int j = 0; j < kScatterPer; j++) {
-    const uint32_t i = threadIdx.x + (uint32_t)j * kScatterThreads;
-    x[j] = i < m ? __ldcs(kmers + base + i) : 0ull;
-    if (kSlotInKmer) x[j] = (x[j] & kSlotKmerMask) | ((uint64_t)i << kSlotShift);
-  }
   constexpr int kBins = 2048 / kScatterThreads;  // bins per thread
-  uint32_t gpos[kBins];
+  uint64_t x[kScatterPer];
+  uint32_t r0[kBins], r1[kBins], bs[kBins];
+  auto request = [&](size_t c) {  // the k-mers of chunk c and this thread's piece of rows c, c + 1 of the offset table
+    const size_t base = c * kPartChunk;
+    const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
 #pragma unroll
-  for (int j = 0; j < kBins; j++) {
-    const uint32_t b = (uint32_t)kBins * threadIdx.x + j;
-    uint32_t len = 0;
-    gpos[j] = 0;
-    if (b < nbins) {
-      const uint32_t* row = off + c * nbins + b;  // rows c and c + 1 of the offset table: coalesced
-      const uint32_t r0 = __ldg(row);
-      len = __ldg(row + nbins) - r0;
-      gpos[j] = __ldg(bin_start + b) + r0;
-    }
-    lstart[b] = len;
-  }
-  __syncthreads();
-  {
-    uint32_t own[kBins];
-    scan_2048<kScatterThreads>(lstart, wsum, own);  // run lengths -> first sorted index of every run
-#pragma unroll
-    for (int j = 0; j < kBins; j++) gdelta[(uint32_t)kBins * threadIdx.x + j] = gpos[j] - own[j];
-  }
-  __syncthreads();
-  // four atomics in flight per thread, then their four stores (more would spill: the 16 k-mers hold 32 registers)
-#pragma unroll
-  for (int h = 0; h < kScatterPer; h += 4) {
-    uint32_t p[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
-      p[j] = i < m ? atomicAdd(&lstart[bin_of(kSlotInKmer ? (x[h + j] & kSlotKmerMask) : x[h + j], pshift, nbins)], 1u) : 0u;
+    for (int j = 0; j < kScatterPer; j++) {
+      const uint32_t i = threadIdx.x + (uint32_t)j * kScatterThreads;
+      x[j] = i < m ? __ldcs(kmers + base + i) : 0ull;
     }
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
-      if (i < m) {
-        sk[p[j]] = x[h + j];
-        if (!kSlotInKmer) ss[p[j]] = (uint16_t)i;
+    for (int j = 0; j < kBins; j++) {
+      const uint32_t b = (uint32_t)kBins * threadIdx.x + j;
+      r0[j] = r1[j] = bs[j] = 0;
+      if (b < nbins) {
+        const uint32_t* row = off + c * nbins + b;  // coalesced
+        r0[j] = __ldg(row);
+        r1[j] = __ldg(row + nbins);
+        bs[j] = __ldg(bin_start + b);
       }
     }
-  }
-  __syncthreads();
-  for (uint32_t i = threadIdx.x; i < m; i += kScatterThreads) {
-    const uint64_t v = sk[i];
-    const uint32_t g = gdelta[bin_of(kSlotInKmer ? (v & kSlotKmerMask) : v, pshift, nbins)] + i;
-    part_kmer[g] = v;
-    if (!kSlotInKmer) part_slot[g] = ss[i];
+  };
+  size_t c = blockIdx.x;
+  if (c < nchunks) request(c);
+  for (; c < nchunks; c += gridDim.x) {
+    const size_t base = c * kPartChunk;
+    const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
+    uint32_t gpos[kBins];
+#pragma unroll
+    for (int j = 0; j < kBins; j++) {
+      gpos[j] = bs[j] + r0[j];
+      lstart[(uint32_t)kBins * threadIdx.x + j] = r1[j] - r0[j];
+    }
+    __syncthreads();
+    {
+      uint32_t own[kBins];
+      scan_2048<kScatterThreads>(lstart, wsum, own);  // run lengths -> first sorted index of every run
+#pragma unroll
+      for (int j = 0; j < kBins; j++) gdelta[(uint32_t)kBins * threadIdx.x + j] = gpos[j] - own[j];
+    }
+    __syncthreads();
+    // four atomics in flight per thread, then their four stores (more would spill: the 16 k-mers hold 32 registers)
+#pragma unroll
+    for (int h = 0; h < kScatterPer; h += 4) {
+      uint32_t p[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
+        p[j] = i < m ? atomicAdd(&lstart[bin_of(x[h + j] & (kSlotInKmer ? kSlotKmerMask : ~0ull), pshift, nbins)], 1u) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
+        if (i < m) {
+          sk[p[j]] = kSlotInKmer ? ((x[h + j] & kSlotKmerMask) | ((uint64_t)i << kSlotShift)) : x[h + j];
+          if (!kSlotInKmer) ss[p[j]] = (uint16_t)i;
+        }
+      }
+    }
+    if (c + gridDim.x < nchunks) request(c + gridDim.x);  // in flight during the write-out below
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < m; i += kScatterThreads) {
+      const uint64_t v = sk[i];
+      const uint32_t g = gdelta[bin_of(kSlotInKmer ? (v & kSlotKmerMask) : v, pshift, nbins)] + i;
+      part_kmer[g] = v;
+      if (!kSlotInKmer) part_slot[g] = ss[i];
+    }
+    __syncthreads();  // the staging buffer and the tables are rewritten by the next chunk
   }
 }
 
@@ -420,11 +438,12 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   // the slot of a query rides in bits 50-63 of its k-mer word when the k-mer leaves room (k <= 25): one store and one
   // load per query instead of two of each
   const bool slot_in_kmer = 2 * ix.k + 14 <= 64;
+  const unsigned sgrid = (unsigned)(nchunks < 148 ? nchunks : 148);  // persistent: one block per SM
   if (slot_in_kmer)
-    part_scatter_staged_kernel<true><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
+    part_scatter_staged_kernel<true><<<sgrid, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
   else
-    part_scatter_staged_kernel<false><<<(unsigned)nchunks, kScatterThreads, kScatterSmem, st>>>(
+    part_scatter_staged_kernel<false><<<sgrid, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
   SB_CUDA_CHECK(cudaGetLastError());
   if (ev) cudaEventRecord(ev[2], st);

@@ -527,9 +527,15 @@ int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers,
   // Measured (gpurun s7, c3, 4 blocks per SM, ms per 250 M queries): nothing ahead 6.70, L2 prefetch of the sector 6.43,
   // the sector itself a tile ahead 6.59; keeping the classified sectors' positions for the final rev[] lookup costs more
   // registers than the load it saves (6.94 / 6.68 / 6.55).  The prefetch variant is the one instantiated.
-  (void)variant;
-#define SB_LAUNCH_N(B, T, N) \
-  kmer_query_ordered_kernel<B, T, N, 1, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
+#define SB_LAUNCH_N(B, T, N)                                                                                             \
+  do {                                                                                                                   \
+    if (variant == 4)                                                                                                    \
+      kmer_query_ordered_kernel<B, T, N, 2, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
+    else if (variant == 0)                                                                                               \
+      kmer_query_ordered_kernel<B, T, N, 0, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
+    else                                                                                                                 \
+      kmer_query_ordered_kernel<B, T, N, 1, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
+  } while (0)
 #define SB_LAUNCH(B)                                       \
   do {                                                     \
     if (ties && narrow) SB_LAUNCH_N(B, true, true);        \
