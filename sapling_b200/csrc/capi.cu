@@ -64,7 +64,6 @@ struct Tuning {
   int line_bases = 0;                 // line_bases=b: leading bases per rank-line entry (tests: forces escapes / ties)
   int chunk_log2 = 0;                 // chunk_log2=l: chunk size of the host-pointer batch path
   int narrow = 1;                     // narrow=0: keep the wide model table
-  int query_variant = -1;             // qv=0..5: what the in-order kernel carries a tile ahead / keeps (query.cu)
   static Tuning from_env() {
     Tuning t;
     const char* e = getenv("SAPLING_B200_TUNE");
@@ -87,7 +86,6 @@ struct Tuning {
         else if (key == "line_bases") t.line_bases = (int)v;
         else if (key == "chunk_log2") t.chunk_log2 = (int)v;
         else if (key == "narrow") t.narrow = (int)v;
-        else if (key == "qv") t.query_variant = (int)v;
       }
       p = q + 1;
     }
@@ -1338,7 +1336,7 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
   }
   if (!ws) return plain();
   ix->launches.fetch_add(8, std::memory_order_relaxed);  // histogram, three column-scan passes, bin scan, scatter, query, un-permute
-  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, ix->tune.occupancy, ix->tune.query_variant, st, ev);
+  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, ix->tune.occupancy, st, ev);
 }
 
 int sapling_b200_profile(sapling_b200_index* ix, int on) {

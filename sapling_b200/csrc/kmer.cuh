@@ -391,25 +391,6 @@ __device__ __forceinline__ long long finish_kmer(const IndexView& ix, uint32_t p
   SB_SIM_ADD(g_sim_final_loads, 1);
   return (long long)rev_at(ix, (uint32_t)rank, pol.sa);  // :247
 }
-// The same with the positions of the (up to) two sectors the lane classified still in registers: the answer rank nearly
-// always lies in one of them, and the dependent rev[] load (and its sector request) is skipped.
-__device__ __forceinline__ long long finish_kmer_pos(const IndexView& ix, uint32_t pred, const Bounds& b, const L2Policies& pol,
-                                                     uint32_t sec_a, const uint32_t pos_a[4], uint32_t sec_b,
-                                                     const uint32_t pos_b[4]) {
-  const long long rank = replay_plquery(ix, pred, b);
-  if (rank < 0) return -1;  // :246
-  const uint32_t r = (uint32_t)rank, rs = r >> 2, j = r & 3u;
-  if (rs == sec_a || rs == sec_b) {
-    const bool use_b = rs == sec_b;
-    const uint32_t p0 = use_b ? pos_b[0] : pos_a[0], p1 = use_b ? pos_b[1] : pos_a[1];
-    const uint32_t p2 = use_b ? pos_b[2] : pos_a[2], p3 = use_b ? pos_b[3] : pos_a[3];
-    const uint32_t lo = (j & 1u) ? p1 : p0, hi = (j & 1u) ? p3 : p2;
-    return (long long)((j & 2u) ? hi : lo);
-  }
-  SB_SIM_ADD(g_sim_final_loads, 1);
-  return (long long)rev_at(ix, r, pol.sa);  // :247
-}
-
 // The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.  (The general search on
 // its own; the kernels try the two-sector shortcut first and come here for what it leaves.)
 template <bool kTies>

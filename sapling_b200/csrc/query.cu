@@ -85,10 +85,7 @@ struct TailStacks {            // per warp: the queries the two-sector shortcut 
   uint32_t pred[kWarpsPerBlock][kStackCap], idx[kWarpsPerBlock][kStackCap];
 };
 
-// kAhead: what travels one tile ahead with the prediction -- 0 nothing, 1 an L2 prefetch of its sector, 2 the sector itself
-// (the first classification then never waits for memory; eight more registers).  kKeepPos: the text positions of the
-// sectors classified in place stay in registers for the final rev[] lookup.
-template <int kMinBlocks, bool kTies, bool kNarrow, int kAhead, bool kKeepPos>
+template <int kMinBlocks, bool kTies, bool kNarrow>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
@@ -150,17 +147,15 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     __syncwarp();
   };
 
-  // Pipeline, in tiles ahead of the one being answered: k-mers 3, model checkpoints 2, prediction 1 -- and with the
-  // prediction its sector (kAhead): the first read of a query is the one that goes to DRAM (the later ones stay in the same
-  // 128-byte line), and it is on its way a whole tile before the lane needs it.
+  // Pipeline, in tiles ahead of the one being answered: k-mers 3, model checkpoints 2, prediction AND ITS SECTOR 1: the first
+  // read of a query is the one that goes to DRAM (the later ones stay in the same 128-byte line), and it is in registers a
+  // whole tile before the lane classifies it.  (Measured, gpurun s9, c3, ms per 250 M queries at 4 blocks per SM: nothing
+  // ahead 6.17, an L2 prefetch of the sector 5.83, the sector itself 5.74.)
   auto predict = [&](uint64_t xw, const ModelPair<kNarrow>& m, bool real, U32x8* sector) -> uint32_t {
     uint64_t p = m.predict(ix, xw & kmask, pol.model);
     if (real) p = clamp_prediction(ix, p);  // counts predictions past the last rank: real queries only
     else if (p >= ix.n) p = ix.n - 1;
-    if (kAhead == 2) *sector = load_sector(ix, (uint32_t)(p >> 2), pol);
-#ifndef SB_HOST_SIM
-    if (kAhead == 1) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(ix.lines + (p >> 2) * 8u));
-#endif
+    *sector = load_sector(ix, (uint32_t)(p >> 2), pol);
     return (uint32_t)p;
   };
   uint32_t t0 = claim(), t1 = claim(), t2 = claim(), t3 = claim();
@@ -169,8 +164,6 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   ModelPair<kNarrow> m1;
   uint32_t pred0;
   U32x8 sec0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) sec0.v[j] = 0;
   {
     ModelPair<kNarrow> m0;
     m0.load(ix, x0 & kmask, pol.model);
@@ -182,8 +175,6 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     ModelPair<kNarrow> m2;
     m2.load(ix, x2 & kmask, pol.model);
     U32x8 sec1;
-#pragma unroll
-    for (int j = 0; j < 8; j++) sec1.v[j] = 0;
     const uint32_t pred1 = predict(x1, m1, t1 + lane < nq32, &sec1);
     const uint32_t i = t0 + lane;
     // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
@@ -202,8 +193,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       pred = pred0;
       key = make_key<kTies>(ix, x0 & kmask);
       uint32_t pos[4], idx = 0;
-      s0 = kAhead == 2 ? classify_loaded<kTies>(ix, key, pred >> 2, sec0, pol, pos)
-                       : classify_sector<kTies>(ix, key, pred >> 2, pol, pos);
+      s0 = classify_loaded<kTies>(ix, key, pred >> 2, sec0, pol, pos);
       done = direct_match(pred, s0, pos, &idx);  // :164
       r = (long long)idx;
       st = two_sector_first(ix, s0, &b, &neighbour);
@@ -225,7 +215,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     x2 = x3;
     m1 = m2;
     pred0 = pred1;
-    if (kAhead == 2) sec0 = sec1;
+    sec0 = sec1;
     t0 = t1;
     t1 = t2;
     t2 = t3;
@@ -482,8 +472,8 @@ const char* kmer_query_kernel_name(bool ordered) { return ordered ? "kmer_query_
 // `occupancy` (Tuning, capi.cu) overrides for A/B runs.
 int kmer_query_blocks_per_sm(bool ordered, int occupancy) {
   if (occupancy == 3 || occupancy == 4 || occupancy == 5 || (occupancy == 6 && !ordered)) return occupancy;
-  // measured (gpurun s5, c3): the in-order kernel at 4 blocks per SM (64 registers, nothing spilled) 6.43 ms per 250 M
-  // queries, at 5 (48 registers, 52 bytes spilled) 7.48, at 6 11.7
+  // measured (gpurun s9, c3): the in-order kernel at 4 blocks per SM (64 registers) 5.74 ms per 250 M queries, at 5 (48
+  // registers, spills) 7.3, at 3 6.8
   return 4;
 }
 
@@ -516,26 +506,15 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 }
 
 // A partitioned batch (partition.cu): d_tiles is the zeroed in-order tile counter, d_slot the slot array or
-// slot_in_kmer_tag(); results are slot words (see slot_word).  variant: kAhead * 2 + kKeepPos (Tuning `qv`), < 0 = default.
+// slot_in_kmer_tag(); results are slot words (see slot_word).
 int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
-                              const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, int variant,
-                              cudaStream_t st) {
+                              const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st) {
   if (nq == 0) return 0;
   const int bps = kmer_query_blocks_per_sm(true, occupancy);
   const int grid = query_grid(nq, bps);
   const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
-  // Measured (gpurun s7, c3, 4 blocks per SM, ms per 250 M queries): nothing ahead 6.70, L2 prefetch of the sector 6.43,
-  // the sector itself a tile ahead 6.59; keeping the classified sectors' positions for the final rev[] lookup costs more
-  // registers than the load it saves (6.94 / 6.68 / 6.55).  The prefetch variant is the one instantiated.
-#define SB_LAUNCH_N(B, T, N)                                                                                             \
-  do {                                                                                                                   \
-    if (variant == 4)                                                                                                    \
-      kmer_query_ordered_kernel<B, T, N, 2, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
-    else if (variant == 0)                                                                                               \
-      kmer_query_ordered_kernel<B, T, N, 0, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
-    else                                                                                                                 \
-      kmer_query_ordered_kernel<B, T, N, 1, false><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles); \
-  } while (0)
+#define SB_LAUNCH_N(B, T, N) \
+  kmer_query_ordered_kernel<B, T, N><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
 #define SB_LAUNCH(B)                                       \
   do {                                                     \
     if (ties && narrow) SB_LAUNCH_N(B, true, true);        \

@@ -7,8 +7,8 @@
  * Same command line (sapling_example.cpp:43-84), same experiments (k-10, k, k+10, k+20, k+30, k+80, or qLen; :91-103), same
  * queries (the reference samples them with unseeded rand(), :115 -- the same sequence here), the same queries.out side
  * file (:120-129) and the same two report lines per experiment ("Piecewise linear time: ..", "Piecewise linear
- * correctness: X out of N", :141,:154).  The unmodified driver also runs on the drop-in header (oracle/Makefile
- * drivers_b200), but it calls plQuery once per query -- a kernel launch and a host round trip each; this one times what the
+ * correctness: X out of N", :141,:154).  The unmodified driver also runs on the drop-in header (INTEGRATION.md section 1;
+ * the drivers_b200 build), but it calls plQuery once per query -- a kernel launch and a host round trip each; this one times what the
  * library is built for: ONE call per experiment,
  *   query length == k : Sapling::queryBatch (k-mers as 64-bit words; sharded over the GPUs of SAPLING_B200_GPUS)
  *   any other length  : Sapling::plQueryBatch (strings; the gallop loops of sapling_api.h:184-196,:229-241 on the GPU)
