@@ -142,6 +142,12 @@ struct Sapling
     if (!check(sapling_b200_query_batch_u32(h.get(), kmers, kmer_bytes, nq, out)))
       for (size_t i = 0; i < nq; i++) out[i] = 0xFFFFFFFFu;
   }
+  /* and the densest one: a little-endian bit stream of kmer_bits (2k .. 64) bits per k-mer in (sapling_b200.h) */
+  void queryBatchBits(const void *kmers, int kmer_bits, size_t nq, uint32_t *out)
+  {
+    if (!check(sapling_b200_query_batch_bits(h.get(), kmers, kmer_bits, nq, out)))
+      for (size_t i = 0; i < nq; i++) out[i] = 0xFFFFFFFFu;
+  }
   vector<long long> queryBatch(const vector<long long> &kmers)
   {
     vector<long long> out(kmers.size());

@@ -154,6 +154,12 @@ int sapling_b200_query_batch(sapling_b200_index *ix, const uint64_t *kmers, size
  * array of sapling_b200_query_batch), out[i] = the position as uint32 (n < 2^32 always), 0xFFFFFFFF for -1. */
 int sapling_b200_query_batch_u32(sapling_b200_index *ix, const void *kmers, int kmer_bytes, size_t nq, uint32_t *out);
 
+/* The densest upload: kmers = a little-endian BIT stream, k-mer i in bits [i * kmer_bits, (i + 1) * kmer_bits) of the
+ * buffer (bit j of the stream = bit j % 8 of byte j / 8), 2k <= kmer_bits <= 64; the buffer holds ceil(nq * kmer_bits / 8)
+ * bytes.  kmer_bits = 2k uploads nothing but the k-mers: 5.25 + 4 bytes per query at k = 21.  (kmer_bits = 8 * kmer_bytes
+ * is sapling_b200_query_batch_u32.) */
+int sapling_b200_query_batch_bits(sapling_b200_index *ix, const void *kmers, int kmer_bits, size_t nq, uint32_t *out);
+
 /* Same on device-resident buffers, enqueued on `stream` (a cudaStream_t; NULL = default stream),
  * no copies, no synchronisation. */
 int sapling_b200_query_batch_dev(sapling_b200_index *ix, const uint64_t *d_kmers, size_t nq,

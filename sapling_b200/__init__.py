@@ -6,7 +6,7 @@ thin ctypes binding the tests and ``bench.py`` use; it mirrors the reference's `
 surface (same member / method names and argument meaning).  There is no CPU fallback.
 """
 from .api import (Sapling, SaplingError, kmerize, kmerize_adjusted, lib, lib_path, gather_bench,  # noqa: F401
-                  gather_bench2)
+                  gather_bench2, pack_kmer_bits)
 
 QUIET = 1
 NO_COMPAT = 2

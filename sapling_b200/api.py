@@ -57,6 +57,7 @@ SYMBOLS = {
     "sapling_b200_query_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     "sapling_b200_query_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "sapling_b200_query_batch_u32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
+    "sapling_b200_query_batch_bits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p]),
     "sapling_b200_query_batch_u32_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "sapling_b200_query_str": (C.c_int64, [C.c_void_p, C.c_char_p, C.c_size_t, C.c_int64, C.c_size_t]),
     "sapling_b200_query_str_batch": (C.c_int, [C.c_void_p, C.c_char_p, _u64p, _u32p, C.c_void_p, _i64p, C.c_size_t, _i64p]),
@@ -350,6 +351,19 @@ class Sapling:
         self._ck(self._L.sapling_b200_query_batch_u32(self._h, ptr_in, kmer_bytes, nq, ptr_out))
         return out
 
+    def queryBatchBits(self, bits, kmer_bits, nq, out=None):
+        """The densest upload of the host path: `bits` (uint8 array, numpy or pinned torch) is a little-endian bit stream
+        with k-mer i in bits [i * kmer_bits, (i + 1) * kmer_bits), 2k <= kmer_bits <= 64 (`pack_kmer_bits` makes one);
+        uint32 positions come back, 0xFFFFFFFF for -1."""
+        ptr_in, count = _host_ptr(bits, 1)
+        assert count * 8 >= nq * kmer_bits
+        if out is None:
+            out = np.empty(nq, dtype=np.uint32)
+        ptr_out, nq2 = _host_ptr(out, 4)
+        assert nq2 >= nq
+        self._ck(self._L.sapling_b200_query_batch_bits(self._h, ptr_in, kmer_bits, nq, ptr_out))
+        return out
+
     def queryBatchU32Device(self, d_kmers_ptr, nq, d_out_ptr, stream=0):
         self._ck(self._L.sapling_b200_query_batch_u32_dev(self._h, d_kmers_ptr, nq, d_out_ptr, stream))
 
@@ -430,6 +444,25 @@ class Sapling:
         a = C.c_uint64(0)
         self._ck(self._L.sapling_b200_count_probes_dev(self._h, d_kmers_ptr, nq, C.byref(a), stream))
         return a.value
+
+
+def pack_kmer_bits(kmers, kmer_bits):
+    """k-mers (integers < 2^kmer_bits) -> the little-endian bit stream `queryBatchBits` uploads: k-mer i in bits
+    [i * kmer_bits, (i + 1) * kmer_bits).  Eight k-mers make kmer_bits whole bytes, so the stream is built in groups of 8."""
+    x = np.ascontiguousarray(kmers, dtype=np.uint64)
+    n = len(x)
+    g = np.zeros(((n + 7) // 8) * 8, dtype=np.uint64)
+    g[:n] = x
+    g = g.reshape(-1, 8)
+    nw = (8 * kmer_bits + 63) // 64
+    W = np.zeros((g.shape[0], nw + 1), dtype=np.uint64)
+    for j in range(8):
+        w, sh = divmod(j * kmer_bits, 64)
+        W[:, w] |= g[:, j] << np.uint64(sh)
+        if sh and sh + kmer_bits > 64:
+            W[:, w + 1] |= g[:, j] >> np.uint64(64 - sh)
+    stream = W.view(np.uint8).reshape(g.shape[0], (nw + 1) * 8)[:, :kmer_bits].reshape(-1)
+    return np.ascontiguousarray(stream[: (n * kmer_bits + 7) // 8])
 
 
 def _host_ptr(a, itemsize):

@@ -38,7 +38,7 @@ int launch_verify(const IndexView& ix, const uint64_t* d_kmers, const long long*
                   unsigned long long* d_counters, cudaStream_t st);
 int launch_probe_count(const IndexView& ix, const uint64_t* d_kmers, size_t nq, unsigned long long* d_total,
                        cudaStream_t st);
-int launch_unpack_kmers(const void* d_packed, int kmer_bytes, size_t nq, uint64_t* d_kmers, cudaStream_t st);
+int launch_unpack_kmers(const void* d_packed, int kmer_bits, size_t nq, uint64_t* d_kmers, cudaStream_t st);
 int run_gather_bench(uint64_t bytes, uint64_t n_loads, int reps, double* gbps);
 int run_gather_bench2(uint64_t bytes, uint64_t n_access, int gran, int chain, int blocks_per_sm, int reps,
                       double* gacc_per_s);
@@ -1396,9 +1396,10 @@ int sapling_b200_query_batch_u32_dev(sapling_b200_index* ix, const uint64_t* d_k
   return run_kmer_batch(ix, ix->view(), d_kmers, nq, nullptr, d_out, static_cast<cudaStream_t>(stream));
 }
 
-// The chunk pipeline of the host-pointer entry points on ONE device.  kmers: nq integers of kmer_bytes (5..8) little-endian
-// bytes each; out: nq answers of out_bytes (8: long long, 4: uint32_t with 0xFFFFFFFF for -1).
-static int host_batch_one(sapling_b200_index* ix, const char* kmers, int kmer_bytes, size_t nq, char* out, int out_bytes) {
+// The chunk pipeline of the host-pointer entry points on ONE device.  kmers: a little-endian bit stream of nq integers of
+// kmer_bits bits each (64: plain uint64; 40 / 48 / 56: whole bytes; 2k: nothing but the k-mer), starting on a byte boundary;
+// out: nq answers of out_bytes (8: long long, 4: uint32_t with 0xFFFFFFFF for -1).
+static int host_batch_one(sapling_b200_index* ix, const char* kmers, int kmer_bits, size_t nq, char* out, int out_bytes) {
   if (nq == 0) return 0;
   std::lock_guard<std::mutex> lock(ix->mu);
   if (cudaSetDevice(ix->device) != cudaSuccess) { set_error("cudaSetDevice(%d) failed", ix->device); return -1; }
@@ -1412,6 +1413,7 @@ static int host_batch_one(sapling_b200_index* ix, const char* kmers, int kmer_by
   const int NS = sapling_b200_index::kSlots;
   const size_t nchunks = (nq + CH - 1) / CH;
   cudaStream_t s_up = ix->streams[0], s_k = ix->streams[1], s_down = ix->streams[2];
+  auto in_bytes = [&](size_t queries) { return (queries * (size_t)kmer_bits + 7) / 8; };  // CH is a multiple of 8 queries
   int rc = 0;
   // chunk c lives in slot c % NS: upload -> kernel -> download, each on its own stream, ordered by events
   for (size_t c = 0; c < nchunks + (size_t)NS && !rc; c++) {
@@ -1427,16 +1429,16 @@ static int host_batch_one(sapling_b200_index* ix, const char* kmers, int kmer_by
     if (c < nchunks) {
       const int s = (int)(c % (size_t)NS);
       const size_t o = c * CH, m = std::min(CH, nq - o);
-      const char* src = kmers + o * kmer_bytes;
+      const char* src = kmers + in_bytes(o);
       if (!pin_in) {
-        memcpy(ix->h_in[s], src, m * kmer_bytes);
+        memcpy(ix->h_in[s], src, in_bytes(m));
         src = static_cast<const char*>(ix->h_in[s]);
       }
-      void* d_up = kmer_bytes == 8 ? (void*)ix->d_in[s] : ix->d_raw[s];
-      if (cudaMemcpyAsync(d_up, src, m * kmer_bytes, cudaMemcpyHostToDevice, s_up) != cudaSuccess) { rc = -1; break; }
+      void* d_up = kmer_bits == 64 ? (void*)ix->d_in[s] : ix->d_raw[s];
+      if (cudaMemcpyAsync(d_up, src, in_bytes(m), cudaMemcpyHostToDevice, s_up) != cudaSuccess) { rc = -1; break; }
       cudaEventRecord(ix->ev_up[s], s_up);
       cudaStreamWaitEvent(s_k, ix->ev_up[s], 0);
-      if (kmer_bytes != 8 && launch_unpack_kmers(ix->d_raw[s], kmer_bytes, m, ix->d_in[s], s_k)) { rc = -1; break; }
+      if (kmer_bits != 64 && launch_unpack_kmers(ix->d_raw[s], kmer_bits, m, ix->d_in[s], s_k)) { rc = -1; break; }
       if (run_kmer_batch(ix, v, ix->d_in[s], m, out_bytes == 8 ? ix->d_out[s] : nullptr,
                          out_bytes == 8 ? nullptr : reinterpret_cast<uint32_t*>(ix->d_out[s]), s_k)) { rc = -2; break; }
       cudaEventRecord(ix->ev_k[s], s_k);
@@ -1455,22 +1457,23 @@ static int host_batch_one(sapling_b200_index* ix, const char* kmers, int kmer_by
   return 0;  // every chunk was retired (event-synchronised) inside the loop
 }
 
-// Host-pointer batch over the handle's GPU and its replicas: contiguous slices, one host thread per device.
-static int host_batch(sapling_b200_index* ix, const void* kmers, int kmer_bytes, size_t nq, void* out, int out_bytes) {
+// Host-pointer batch over the handle's GPU and its replicas: contiguous slices, one host thread per device.  Slices start
+// at multiples of 8 queries, which is a byte boundary of the bit stream for every kmer_bits.
+static int host_batch(sapling_b200_index* ix, const void* kmers, int kmer_bits, size_t nq, void* out, int out_bytes) {
   if (!ix) { set_error("null index"); return -1; }
   if (nq == 0) return 0;
   const char* in = static_cast<const char*>(kmers);
   char* o = static_cast<char*>(out);
   const size_t G = 1 + ix->replicas.size();
-  if (G == 1 || nq < 2 * G * 65536) return host_batch_one(ix, in, kmer_bytes, nq, o, out_bytes);
+  if (G == 1 || nq < 2 * G * 65536) return host_batch_one(ix, in, kmer_bits, nq, o, out_bytes);
   std::vector<int> rcs(G, 0);
   std::vector<std::string> errs(G);
   std::vector<std::thread> th;
   for (size_t g = 0; g < G; g++) {
-    const size_t lo = nq * g / G, hi = nq * (g + 1) / G;
+    const size_t lo = (nq * g / G) & ~(size_t)7, hi = g + 1 == G ? nq : ((nq * (g + 1) / G) & ~(size_t)7);
     sapling_b200_index* dev_ix = g == 0 ? ix : ix->replicas[g - 1];
     th.emplace_back([=, &rcs, &errs]() {
-      rcs[g] = host_batch_one(dev_ix, in + lo * kmer_bytes, kmer_bytes, hi - lo, o + lo * out_bytes, out_bytes);
+      rcs[g] = host_batch_one(dev_ix, in + lo * (size_t)kmer_bits / 8, kmer_bits, hi - lo, o + lo * out_bytes, out_bytes);
       if (rcs[g]) errs[g] = last_error();  // the error text is thread-local
     });
   }
@@ -1482,7 +1485,7 @@ static int host_batch(sapling_b200_index* ix, const void* kmers, int kmer_bytes,
 }
 
 int sapling_b200_query_batch(sapling_b200_index* ix, const uint64_t* kmers, size_t nq, int64_t* out) {
-  return host_batch(ix, kmers, 8, nq, out, 8);
+  return host_batch(ix, kmers, 64, nq, out, 8);
 }
 
 int sapling_b200_query_batch_u32(sapling_b200_index* ix, const void* kmers, int kmer_bytes, size_t nq, uint32_t* out) {
@@ -1490,7 +1493,15 @@ int sapling_b200_query_batch_u32(sapling_b200_index* ix, const void* kmers, int 
     set_error("query_batch_u32: kmer_bytes=%d cannot hold a %d-mer (need ceil(2k/8) .. 8)", kmer_bytes, ix->k);
     return -1;
   }
-  return host_batch(ix, kmers, kmer_bytes, nq, out, 4);
+  return host_batch(ix, kmers, 8 * kmer_bytes, nq, out, 4);
+}
+
+int sapling_b200_query_batch_bits(sapling_b200_index* ix, const void* kmers, int kmer_bits, size_t nq, uint32_t* out) {
+  if (ix && (kmer_bits < 2 * ix->k || kmer_bits > 64)) {
+    set_error("query_batch_bits: kmer_bits=%d cannot hold a %d-mer (need 2k .. 64)", kmer_bits, ix->k);
+    return -1;
+  }
+  return host_batch(ix, kmers, kmer_bits, nq, out, 4);
 }
 
 int sapling_b200_query_str_batch(sapling_b200_index* ix, const char* s, const uint64_t* offsets, const uint32_t* slens,

@@ -33,6 +33,11 @@ static unsigned long long g_sim_sector_loads = 0, g_sim_slow_entries = 0, g_sim_
 #define SB_SIM_ADD(x, v) ((void)0)
 #endif
 
+// A meeting point for the lanes of a warp.  The value passes through an empty asm statement, so the compiler cannot tell
+// which way a lane came from and cannot thread the branches in front of it past it: the paths that lead here join here
+// (BSYNC) and the code behind it runs once for all of them, not once per path.
+#define SB_MEET(v32) asm volatile("" : "+r"(v32))
+
 // What a lane needs to classify sectors for one query.
 struct KmerKey {
   uint64_t q;        // the k bases left-aligned (base 0 in the top two bits)
@@ -260,34 +265,36 @@ __device__ __forceinline__ int two_sector_first(const IndexView& ix, const Secto
   return resolved ? 0 : 1;
 }
 __device__ __forceinline__ int two_sector_second(const IndexView& ix, const Sector& x0, const Sector& x1, Bounds* b) {
+  // Three cases, all computed and then selected (the lanes of a warp are spread over them):
+  //   right neighbour, s0 all smaller: lb and the run of matches are looked for in s1
+  //   right neighbour, lb = 4 s0 + c0 known and the matches ran to the end of s0: where do they stop?
+  //   left neighbour (s0 has no smaller entry): lb is looked for in s1, the matches may go on into s0
   const uint32_t n32 = (uint32_t)ix.n;
   const uint32_t last_s = (n32 - 1u) >> 2;
   const uint32_t v0 = x0.s == last_s ? n32 - 4u * last_s : 4u;
   const uint32_t v1 = x1.s == last_s ? n32 - 4u * last_s : 4u;
-  int rc;
-  if (x1.s > x0.s) {           // right neighbour
-    const bool x1_last = x1.s == last_s;
-    if (x0.c == 4u) {          // looking for lb
-      const bool all_small = x1.c == 4u;
-      const uint32_t lb = all_small ? n32 : 4u * x1.s + x1.c;
-      b->lb = lb;
-      b->ub = all_small ? n32 : lb + x1.m;
-      const bool ok = all_small ? x1_last : (x1.c + x1.m < v1 || x1_last);
-      rc = ok ? 0 : 2;
-    } else {                   // lb = 4 s0 + c0 is known, the matches ran to the end of s0: where do they stop?
-      b->ub = 4u * x1.s + x1.m;
-      rc = (x1.m < v1 || x1_last) ? 0 : 2;
-    }
-  } else {                     // left neighbour (s0 has no smaller entry)
-    const bool further_left = x1.c == 0u && x1.s != 0u;
-    const uint32_t lb = 4u * x1.s + x1.c;
-    const bool into_s0 = x1.c + x1.m == 4u;   // the matches (if any) reach the end of s1 and go on in s0
-    b->lb = lb;
-    b->ub = into_s0 ? 4u * x0.s + x0.m : lb + x1.m;
-    const bool ok = !further_left && (!into_s0 || x0.m < v0 || x0.s == last_s);
-    rc = ok ? 0 : 2;
-  }
-  return rc;
+  const bool right = x1.s > x0.s, want_lb = x0.c == 4u;
+  const bool x1_last = x1.s == last_s;
+  const uint32_t lb1 = 4u * x1.s + x1.c;
+  const bool run_ends = x1.c + x1.m < v1 || x1_last;
+  // right, looking for lb
+  const bool all_small = x1.c == 4u;
+  const uint32_t lb_r = all_small ? n32 : lb1;
+  const uint32_t ub_r = all_small ? n32 : lb1 + x1.m;
+  const bool ok_r = all_small ? x1_last : run_ends;
+  // right, looking for the end of the run (x1.c == 0 whenever x1.m > 0: the entries are sorted)
+  const uint32_t ub_e = 4u * x1.s + x1.m;
+  const bool ok_e = x1.m < v1 || x1_last;
+  // left
+  const bool further_left = x1.c == 0u && x1.s != 0u;
+  const bool into_s0 = x1.c + x1.m == 4u;  // the matches (if any) reach the end of s1 and go on in s0
+  const uint32_t ub_l = into_s0 ? 4u * x0.s + x0.m : lb1 + x1.m;
+  const bool ok_l = !further_left && (!into_s0 || x0.m < v0 || x0.s == last_s);
+  const uint32_t lb_keep = b->lb;
+  b->lb = right ? (want_lb ? lb_r : lb_keep) : lb1;
+  b->ub = right ? (want_lb ? ub_r : ub_e) : ub_l;
+  const bool ok = right ? (want_lb ? ok_r : ok_e) : ok_l;
+  return ok ? 0 : 2;
 }
 
 // rev[predicted] when it matches the query (:164), from the classification of its own sector
@@ -318,34 +325,50 @@ __device__ __forceinline__ int kmer_flog2(uint32_t v) {  // floor(log2 v), v >= 
 #endif
 }
 
-// binarySearch (:133-153) over {lb, ub}; returns the rank it returns, or -1.
-__device__ __forceinline__ long long replay_binary_search(uint32_t lo, uint32_t hi, const Bounds& b) {
-  // A long search whose steps all go right (every mid below lb: the search from rank 0 that the (int)predicted arithmetic
-  // of :209,:225 causes for predicted ranks >= 2^31) is jumped in closed form: after j such steps
-  // lo = hi - ceil(D / 2^j), D = hi - lo.  Those mids are below lb (no match, "too small") as long as ceil(D / 2^j) >
-  // hi - lb, the base case hi == lo + 2 (:136) and the empty-interval exit (:142) need ceil(D / 2^(j-1)) >= 3; both hold
-  // for ceil(D / 2^j) >= G = max(hi - lb + 1, 2), and j = floor(log2(D - 1)) - floor(log2(G - 1)) - 1 guarantees that.
+// Phase 2 in pieces, so that a kernel can run the one loop in it with a warp-uniform trip count (query.cu) and meet all its
+// lanes again before rev[rank] is read; replay_plquery below strings the same pieces together for a single query.
+constexpr uint32_t kNoRank = 0xFFFFFFFFu;  // "-1" (ranks are < n <= 2^32 - 16)
+struct ReplayState {
+  uint32_t rank;    // the rank whose rev[] plQuery returns, or kNoRank; final once !searching()
+  uint32_t lo, hi;  // binarySearch's interval (:133); the reference only ever calls it with lo <= hi, so lo > hi = "over"
+  __device__ __forceinline__ bool searching() const { return lo <= hi; }
+};
+
+// One level of binarySearch (:133-153) over {lb, ub}, written as selects; a no-op once the search is over, so that the
+// lanes of a warp can step together.  hi == lo + 2 returns lo + 1 unverified (:136), which is the mid of that interval:
+// "base case or match at mid" is one outcome, rank = mid.
+__device__ __forceinline__ void replay_search_step(const Bounds& b, ReplayState* rs) {
+  const uint32_t lo = rs->lo, hi = rs->hi;
+  const uint32_t mid = kmer_uhadd(lo, hi);
+  // (bitwise on purpose: no short-circuit branches inside the warp-uniform loop)
+  const bool found = (lo <= hi) & ((hi - lo == 2u) | ((mid >= b.lb) & (mid < b.ub)));  // :136, :141
+  const bool over = found | (lo + 1u >= hi);                                           // :142 (true as well once lo > hi)
+  const bool small = mid < b.lb;                                                    // :143-147 / :148-152
+  rs->rank = found ? mid : rs->rank;
+  rs->lo = over ? 1u : (small ? mid : lo);
+  rs->hi = over ? 0u : (small ? hi : mid);
+}
+
+// A long search whose steps all go right (every mid below lb: the search from rank 0 that the (int)predicted arithmetic
+// of :209,:225 causes for predicted ranks >= 2^31) is jumped in closed form: after j such steps
+// lo = hi - ceil(D / 2^j), D = hi - lo.  Those mids are below lb (no match, "too small") as long as ceil(D / 2^j) >
+// hi - lb, the base case hi == lo + 2 (:136) and the empty-interval exit (:142) need ceil(D / 2^(j-1)) >= 3; both hold
+// for ceil(D / 2^j) >= G = max(hi - lb + 1, 2), and j = floor(log2(D - 1)) - floor(log2(G - 1)) - 1 guarantees that.
+__device__ __forceinline__ void replay_search_jump(const Bounds& b, ReplayState* rs) {
+  const uint32_t lo = rs->lo, hi = rs->hi;
   if (hi > lo && hi - lo > 32u) {
     const uint32_t D = hi - lo;
     const uint32_t T = b.lb > hi ? 0u : hi - b.lb;
     const uint32_t G = T + 1u > 2u ? T + 1u : 2u;
     const int j = kmer_flog2(D - 1u) - kmer_flog2(G - 1u) - 1;
-    if (j >= 1) lo = hi - (((D - 1u) >> j) + 1u);
-  }
-  for (;;) {
-    if (hi - lo == 2u) return (long long)(lo + 1u);               // :136 (unverified)
-    const uint32_t mid = kmer_uhadd(lo, hi);
-    if (mid >= b.lb && mid < b.ub) return (long long)mid;         // :141
-    if (lo + 1u >= hi) return -1;                                 // :142
-    if (mid < b.lb) lo = mid;                                     // :143-147
-    else hi = mid;                                                // :148-152
+    if (j >= 1) rs->lo = hi - (((D - 1u) >> j) + 1u);
   }
 }
 
-// Phase 2: plQuery (:159-248) for s.length() == length == k (no gallop loops) over {lb, ub}: the rank whose rev[] it
-// returns, or -1.  pred < n.  Both sides' windows are computed for every lane and selected (the lanes of a warp go left
-// and right in equal numbers); only binarySearch is a loop.
-__device__ __forceinline__ long long replay_plquery(const IndexView& ix, uint32_t pred, const Bounds& b) {
+// plQuery (:159-248) for s.length() == length == k (no gallop loops) over {lb, ub}, up to the call of binarySearch (:245).
+// pred < n.  Both sides' windows are computed for every lane and selected (the lanes of a warp go left and right in equal
+// numbers).
+__device__ __forceinline__ void replay_windows(const IndexView& ix, uint32_t pred, const Bounds& b, ReplayState* rs) {
   const uint32_t nm1 = (uint32_t)ix.n - 1u;
   auto is_match = [&](uint32_t r) { return r >= b.lb && r < b.ub; };
   // look right (:167-204): hi = min(n-1, predicted + mostOver), then min(n-1, predicted + maxOver + 1)
@@ -369,14 +392,26 @@ __device__ __forceinline__ long long replay_plquery(const IndexView& ix, uint32_
   const uint32_t p2 = right ? hi2 : lo2;   // the second one (:180 / :225)
   // the second bound is probed when the first is still on the same side of the query as the prediction (:175 / :220)
   const bool second = right ? (p1 < b.lb) : !(p1 < b.lb);
-  long long rank = -2;                                        // -2: not decided before binarySearch
-  if (is_match(pred)) rank = (long long)pred;                 // :164
-  else if (is_match(p1)) rank = (long long)p1;                // :174 / :213
-  else if (second && is_match(p2)) rank = (long long)p2;      // :183 / :228
-  if (rank != -2) return rank;
+  const bool m0 = is_match(pred), m1 = is_match(p1), m2 = second && is_match(p2);  // :164, :174 / :213, :183 / :228
   const uint32_t lo = right ? (second ? hi1 : pred) : (second ? lo2 : lo1);
   const uint32_t hi = right ? (second ? hi2 : hi1) : (second ? lo1 : pred);
-  return replay_binary_search(lo, hi, b);  // :245
+  // lo > hi happens in one way only: the (int) wrap of :209 sends lo1 to 0 while :225 does not wrap, for a query smaller
+  // than every suffix.  binarySearch (size_t arithmetic) then probes (lo + hi) / 2 once and gives up (:141-142).
+  const uint32_t mid = kmer_uhadd(lo, hi);
+  const bool m3 = lo > hi && is_match(mid);
+  const bool decided = m0 || m1 || m2 || lo > hi;
+  rs->rank = m0 ? pred : (m1 ? p1 : (m2 ? p2 : (m3 ? mid : kNoRank)));
+  rs->lo = decided ? 1u : lo;
+  rs->hi = decided ? 0u : hi;
+}
+
+// Phase 2 for one query: the rank whose rev[] plQuery returns, or -1.
+__device__ __forceinline__ long long replay_plquery(const IndexView& ix, uint32_t pred, const Bounds& b) {
+  ReplayState rs;
+  replay_windows(ix, pred, b, &rs);
+  replay_search_jump(b, &rs);
+  while (rs.searching()) replay_search_step(b, &rs);  // :245
+  return rs.rank == kNoRank ? -1ll : (long long)rs.rank;
 }
 
 // rev[r] (the reference's suffix array, sapling_api.h:41) read from the rank lines
@@ -386,10 +421,15 @@ __device__ __forceinline__ uint32_t rev_at(const IndexView& ix, uint64_t r, uint
 
 // The answer once the bounds are known: phase 2, then rev[rank] -- in a line this lane has just read.
 __device__ __forceinline__ long long finish_kmer(const IndexView& ix, uint32_t pred, const Bounds& b, const L2Policies& pol) {
-  const long long rank = replay_plquery(ix, pred, b);
-  if (rank < 0) return -1;  // :246
+  ReplayState rs;
+  replay_windows(ix, pred, b, &rs);
+  replay_search_jump(b, &rs);
+  while (rs.searching()) replay_search_step(b, &rs);  // :245
+  uint32_t rank = rs.rank;
+  SB_MEET(rank);  // the lanes leave the loop after different numbers of steps: one read for all of them
+  if (rank == kNoRank) return -1;  // :246
   SB_SIM_ADD(g_sim_final_loads, 1);
-  return (long long)rev_at(ix, (uint32_t)rank, pol.sa);  // :247
+  return (long long)rev_at(ix, rank, pol.sa);  // :247
 }
 // The whole path for one k-mer x whose predicted rank is pred (< n): plQuery's return value.  (The general search on
 // its own; the kernels try the two-sector shortcut first and come here for what it leaves.)
@@ -399,15 +439,20 @@ __device__ __forceinline__ long long answer_kmer(const IndexView& ix, uint64_t x
   Search se;
   se.begin(ix, pred);
   Bounds b;
-  bool is_first = true;
+  b.lb = b.ub = 0;
+  bool is_first = true, direct = false;
+  uint32_t idx = 0;
+  // one way out of the loop: the lanes of a warp leave it after different numbers of sectors and meet again behind it,
+  // before phase 2, instead of each group running phase 2 on its own
   for (;;) {
     uint32_t pos[4];
     const Sector sc = classify_sector<kTies>(ix, key, se.t, pol, pos);
-    uint32_t idx;
-    if (is_first && direct_match(pred, sc, pos, &idx)) return (long long)idx;  // :164: a third of all queries
-    if (se.feed(ix, pred, sc, is_first, &b)) break;
+    direct = is_first && direct_match(pred, sc, pos, &idx);  // :164: a third of all queries
+    if (direct || se.feed(ix, pred, sc, is_first, &b)) break;
     is_first = false;
   }
+  SB_MEET(idx);
+  if (direct) return (long long)idx;
   return finish_kmer(ix, pred, b, pol);
 }
 

@@ -10,6 +10,8 @@
 #include "kmer.cuh"
 #include "query.cuh"
 
+#include <mutex>
+
 namespace sb {
 
 namespace {
@@ -203,9 +205,22 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
       st = two_sector_second(ix, s0, s1, &b);
     }
-    if (active && !done && st == 0) {  // phase 2 + rev[rank]
-      r = finish_kmer(ix, pred, b, pol);
+    // phase 2 (kmer.cuh replay_plquery, in its pieces): the one loop in it runs with a warp-uniform trip count, so all
+    // lanes are together again when rev[rank] is read
+    const bool fin = active && !done && st == 0;
+    ReplayState rs;
+    rs.rank = kNoRank;
+    rs.lo = 1u;  // lo > hi: not searching
+    rs.hi = 0u;
+    if (fin) {
+      replay_windows(ix, pred, b, &rs);
+      replay_search_jump(b, &rs);
+    }
+    while (__any_sync(0xffffffffu, rs.searching())) replay_search_step(b, &rs);  // :245; a no-op for the lanes that are done
+    if (fin) {
       done = true;
+      r = -1;                                                               // :246
+      if (rs.rank != kNoRank) r = (long long)rev_at(ix, rs.rank, pol.sa);  // :247
     }
     if (active && done) store(i, x0, r);
     push(active && !done, x0, pred, i);
@@ -221,6 +236,244 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     t2 = t3;
     t3 = claim();
   }
+  while (stacked) drain(stacked < 32u ? stacked : 32u);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same kernel with its software pipeline in SHARED MEMORY (cp.async rings) instead of registers.
+//
+// Why.  kmer_query_ordered_kernel keeps the loads that are in flight -- the k-mers of three tiles, two pairs of model
+// checkpoints, the sector of the next tile -- in registers and rotates them at the end of an iteration.  ptxas hoists
+// those rotations: the k-mer loaded at the top of an iteration is moved into its next register a few instructions later,
+// and the warp sits on a DRAM round trip it was supposed to sleep through (ncu s10, SASS page: 15.5 % of all stall samples
+// on that one MOV, 5.3 % on the rotation of the sector registers).  An asynchronous copy has no destination register to
+// wait on: every lane copies its own 8 / 16 / 32 bytes into its own slot of a per-warp ring (LDGSTS), one commit per
+// tile, one wait at the top of the next tile, and the 28 registers of in-flight data are free.
+//   ring, per warp: k-mers 4 stages x 256 B, checkpoint pairs 3 stages x 512 B (narrow) or 1 KB (wide), sectors 2 stages x
+//   1 KB, laid out [stage][piece][lane] so that the 8- and 16-byte reads are conflict-free.
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, uint64_t) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, uint64_t) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+               ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <bool kNarrow>
+struct RingModel;
+template <>
+struct RingModel<true> {
+  uint2 e[3][2][32];
+  __device__ __forceinline__ void request(const IndexView& ix, uint64_t x, unsigned stage, unsigned lane, uint64_t pol) {
+    const uint2* p = ix.narrow + (uint32_t)(x >> ix.shift);  // entries b and b + 1 (the table has a pad entry)
+    cp_async8(&e[stage][0][lane], p, pol);
+    cp_async8(&e[stage][1][lane], p + 1, pol);
+  }
+  __device__ __forceinline__ uint64_t predict(const IndexView& ix, uint64_t x, unsigned stage, unsigned lane, uint64_t pol) const {
+    NarrowPair pr;
+    pr.e0 = e[stage][0][lane];
+    pr.e1 = e[stage][1][lane];
+    return narrow_finish(ix, x, pr, pol);
+  }
+};
+template <>
+struct RingModel<false> {
+  longlong2 e[3][2][32];
+  __device__ __forceinline__ void request(const IndexView& ix, uint64_t x, unsigned stage, unsigned lane, uint64_t pol) {
+    const uint64_t b = x >> ix.shift;
+    cp_async16(&e[stage][0][lane], ix.model + b, pol);
+    cp_async16(&e[stage][1][lane], ix.model + b + 1, pol);
+  }
+  __device__ __forceinline__ uint64_t predict(const IndexView&, uint64_t x, unsigned stage, unsigned lane, uint64_t) const {
+    const longlong2 lo = e[stage][0][lane], hi = e[stage][1][lane];
+    return interpolate((long long)x, lo.x, lo.y, hi.x, hi.y);
+  }
+};
+template <bool kNarrow>
+struct WarpRing {
+  uint4 sector[2][2][32];
+  uint64_t kmer[4][32];
+  RingModel<kNarrow> model;
+};
+template <bool kNarrow>
+struct RingBlock {
+  WarpRing<kNarrow> ring[kWarpsPerBlock];
+  TailStacks stacks;
+};
+
+template <int kMinBlocks, bool kTies, bool kNarrow>
+__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
+kmer_query_ring_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+                       const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
+  extern __shared__ __align__(16) unsigned char ring_raw[];
+  RingBlock<kNarrow>& sh = *reinterpret_cast<RingBlock<kNarrow>*>(ring_raw);
+  TailStacks& stacks = sh.stacks;
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  WarpRing<kNarrow>& ring = sh.ring[warp];
+  const unsigned lt_mask = (1u << lane) - 1u;
+  const L2Policies pol = make_policies(ix.hints);
+  uint64_t pol_stream;
+  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+  const uint32_t nq32 = (uint32_t)nq, last = nq32 - 1u;
+  constexpr unsigned kSpan = 4;
+  uint32_t span_next = 0;
+  unsigned span_left = 0;  // warp-uniform
+  auto claim = [&]() -> uint32_t {
+    if (span_left == 0) {
+      unsigned long long a = 0;
+      if (lane == 0) a = atomicAdd(tiles, 32ull * kSpan);
+      a = __shfl_sync(0xffffffffu, a, 0);
+      span_next = a < 0xFFFFFE00ull ? (uint32_t)a : 0xFFFFFE00u;  // past the end either way; keeps t + lane from wrapping
+      span_left = kSpan;
+    }
+    const uint32_t t = span_next;
+    span_next += 32u;
+    span_left--;
+    return t;
+  };
+  const bool in_kmer = slot == slot_in_kmer_tag();
+  const uint64_t kmask = ix.k >= 32 ? ~0ull : ((1ull << (2 * ix.k)) - 1ull);
+  auto store = [&](uint32_t i, uint64_t xw, long long r) {
+    const unsigned long long sl = in_kmer ? (unsigned long long)(xw >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
+    __stcs(out + i, slot_word(sl, r));
+  };
+  unsigned stacked = 0;  // warp-uniform: entries on this warp's stack
+  auto push = [&](bool pending, uint64_t xw, uint32_t pred, uint32_t i) {
+    const unsigned m = __ballot_sync(0xffffffffu, pending);
+    if (pending) {
+      const unsigned e = stacked + (unsigned)__popc(m & lt_mask);
+      stacks.x_lo[warp][e] = (uint32_t)xw;
+      stacks.x_hi[warp][e] = (uint32_t)(xw >> 32);
+      stacks.pred[warp][e] = pred;
+      stacks.idx[warp][e] = i;
+    }
+    stacked += (unsigned)__popc(m);
+    __syncwarp();
+  };
+  auto drain = [&](unsigned m) {
+    stacked -= m;
+    if (lane < m) {
+      const unsigned e = stacked + lane;
+      const uint64_t xw = ((uint64_t)stacks.x_hi[warp][e] << 32) | stacks.x_lo[warp][e];
+      const uint32_t i = stacks.idx[warp][e];
+      store(i, xw, answer_kmer<kTies>(ix, xw & kmask, stacks.pred[warp][e], pol));
+    }
+    __syncwarp();
+  };
+  // the three requests of the pipeline; a tile past the end asks for the last k-mer again (predicted for, never answered)
+  auto request_kmers = [&](uint32_t t, unsigned stage) {
+    const uint32_t i = t + lane;
+    cp_async8(&ring.kmer[stage][lane], kmers + (i < last ? i : last), pol_stream);
+  };
+  auto request_sector = [&](uint32_t pred, unsigned stage) {
+    const uint32_t* p = ix.lines + (uint64_t)(pred >> 2) * 8u;
+    cp_async16(&ring.sector[stage][0][lane], p, pol.sa);
+    cp_async16(&ring.sector[stage][1][lane], p + 4, pol.sa);
+  };
+  auto predict = [&](uint64_t xw, unsigned mstage, bool real) -> uint32_t {
+    uint64_t p = ring.model.predict(ix, xw & kmask, mstage, lane, pol.model);
+    if (real) p = clamp_prediction(ix, p);  // counts predictions past the last rank: real queries only
+    else if (p >= ix.n) p = ix.n - 1;
+    return (uint32_t)p;
+  };
+
+  uint32_t t0 = claim(), t1 = claim(), t2 = claim(), t3 = claim();
+  if (t0 >= nq32) return;
+  // fill: k-mers of three tiles, then the checkpoints of two, then the prediction and the sector of the first
+  request_kmers(t0, 0);
+  request_kmers(t1, 1);
+  request_kmers(t2, 2);
+  cp_async_commit();
+  cp_async_wait_all();
+  ring.model.request(ix, ring.kmer[0][lane] & kmask, 0, lane, pol.model);
+  ring.model.request(ix, ring.kmer[1][lane] & kmask, 1, lane, pol.model);
+  cp_async_commit();
+  cp_async_wait_all();
+  uint32_t pred0 = predict(ring.kmer[0][lane], 0, t0 + lane < nq32);
+  request_sector(pred0, 0);
+  cp_async_commit();
+  unsigned kq = 0;  // ring stage of the current tile's k-mers (mod 4); its sector sits in stage kq & 1
+  unsigned mq = 0;  // ring stage of the current tile's checkpoints (mod 3)
+  while (t0 < nq32) {
+    cp_async_wait_all();  // everything the previous tile asked for has landed (it had a whole tile to do so)
+    // three tiles ahead: k-mers; two: checkpoints; one: prediction and its sector
+    request_kmers(t3, (kq + 3u) & 3u);
+    const unsigned m2 = mq >= 1u ? mq - 1u : 2u, m1 = mq == 2u ? 0u : mq + 1u;  // (mq + 2) % 3, (mq + 1) % 3
+    ring.model.request(ix, ring.kmer[(kq + 2u) & 3u][lane] & kmask, m2, lane, pol.model);
+    const uint32_t pred1 = predict(ring.kmer[(kq + 1u) & 3u][lane], m1, t1 + lane < nq32);
+    request_sector(pred1, (kq + 1u) & 1u);
+    cp_async_commit();
+
+    const uint32_t i = t0 + lane;
+    const bool active = i < nq32;
+    const uint64_t x0 = ring.kmer[kq][lane];
+    bool done = false;
+    int st = 2;  // 0: bounds final, 1: wants the neighbour, 2: left to the general search
+    long long r = -1;
+    uint32_t pred = 0, neighbour = 0;
+    KmerKey key;
+    key.q = key.qlo = key.qhi = 0;
+    Bounds b;
+    b.lb = b.ub = 0;
+    Sector s0;
+    s0.s = s0.c = s0.m = 0;
+    if (active) {  // round 1: the sector of the predicted rank
+      pred = pred0;
+      key = make_key<kTies>(ix, x0 & kmask);
+      U32x8 sec0;
+      {
+        const uint4 a = ring.sector[kq & 1u][0][lane], c = ring.sector[kq & 1u][1][lane];
+        sec0.v[0] = a.x; sec0.v[1] = a.y; sec0.v[2] = a.z; sec0.v[3] = a.w;
+        sec0.v[4] = c.x; sec0.v[5] = c.y; sec0.v[6] = c.z; sec0.v[7] = c.w;
+      }
+      uint32_t pos[4], idx = 0;
+      s0 = classify_loaded<kTies>(ix, key, pred >> 2, sec0, pol, pos);
+      done = direct_match(pred, s0, pos, &idx);  // :164
+      r = (long long)idx;
+      st = two_sector_first(ix, s0, &b, &neighbour);
+    }
+    if (active && !done && st == 1) {  // round 2: the neighbour the first one points to
+      uint32_t pos[4];
+      const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
+      st = two_sector_second(ix, s0, s1, &b);
+    }
+    // phase 2 (kmer.cuh replay_plquery, in its pieces): the one loop in it runs with a warp-uniform trip count, so all
+    // lanes are together again when rev[rank] is read
+    const bool fin = active && !done && st == 0;
+    ReplayState rs;
+    rs.rank = kNoRank;
+    rs.lo = 1u;  // lo > hi: not searching
+    rs.hi = 0u;
+    if (fin) {
+      replay_windows(ix, pred, b, &rs);
+      replay_search_jump(b, &rs);
+    }
+    while (__any_sync(0xffffffffu, rs.searching())) replay_search_step(b, &rs);  // :245; a no-op for the lanes that are done
+    if (fin) {
+      done = true;
+      r = -1;  // :246
+      if (rs.rank != kNoRank) {  // :247 -- from the sector in the ring when the rank lies in it
+        if ((rs.rank >> 2) == (pred >> 2))
+          r = (long long)reinterpret_cast<const uint32_t*>(&ring.sector[kq & 1u][1][lane])[rs.rank & 3u];
+        else
+          r = (long long)rev_at(ix, rs.rank, pol.sa);
+      }
+    }
+    if (active && done) store(i, x0, r);
+    push(active && !done, x0, pred, i);
+    while (stacked >= 32u) drain(32u);
+    pred0 = pred1;
+    kq = (kq + 1u) & 3u;
+    mq = m1;
+    t0 = t1;
+    t1 = t2;
+    t2 = t3;
+    t3 = claim();
+  }
+  cp_async_wait_all();
   while (stacked) drain(stacked < 32u ? stacked : 32u);
 }
 
@@ -308,17 +561,18 @@ __global__ void predict_kernel(const IndexView ix, const uint64_t* __restrict__ 
     out[i] = predict_rank(ix, kmers[i], make_policies(0).model);
 }
 
-// k-mers that arrive as kmer_bytes (< 8) little-endian bytes each (the narrow upload format of the host path) -> one
-// 64-bit word each.  Two aligned 8-byte loads and a funnel shift per k-mer; the buffer is readable 8 bytes past its end.
-__global__ void unpack_kmers_kernel(const uint64_t* __restrict__ raw, int kmer_bytes, size_t nq, uint64_t* __restrict__ out) {
+// k-mers that arrive as a dense little-endian bit stream, kmer_bits (< 64) bits each (the narrow upload formats of the
+// host path: whole bytes, or exactly 2k bits) -> one 64-bit word each.  Two aligned 8-byte loads and a funnel shift per
+// k-mer; the buffer is readable 8 bytes past its end.
+__global__ void unpack_kmers_kernel(const uint64_t* __restrict__ raw, int kmer_bits, size_t nq, uint64_t* __restrict__ out) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const uint64_t mask = (1ull << (8 * kmer_bytes)) - 1ull;
+  const uint64_t mask = (1ull << kmer_bits) - 1ull;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
-    const size_t byte = i * (size_t)kmer_bytes;
-    const unsigned sh = (unsigned)(byte & 7u) * 8u;
-    const uint64_t lo = __ldg(raw + (byte >> 3));
+    const size_t bit = i * (size_t)kmer_bits;
+    const unsigned sh = (unsigned)(bit & 63u);
+    const uint64_t lo = __ldg(raw + (bit >> 6));
     uint64_t v = lo >> sh;
-    if (sh + 8u * (unsigned)kmer_bytes > 64u) v |= __ldg(raw + (byte >> 3) + 1) << (64u - sh);
+    if (sh + (unsigned)kmer_bits > 64u) v |= __ldg(raw + (bit >> 6) + 1) << (64u - sh);
     out[i] = v & mask;
   }
 }
@@ -507,12 +761,56 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 
 // A partitioned batch (partition.cu): d_tiles is the zeroed in-order tile counter, d_slot the slot array or
 // slot_in_kmer_tag(); results are slot words (see slot_word).
+// Opt-in to the dynamic shared memory of the ring kernel: function attributes belong to the device they were set on.
+template <int B, bool T, bool N>
+static int ring_attribute() {
+  static std::mutex mu;
+  static bool done[64] = {};
+  int dev = 0;
+  SB_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev >= 0 && dev < 64 && done[dev]) return 0;
+  SB_CUDA_CHECK(cudaFuncSetAttribute(kmer_query_ring_kernel<B, T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)sizeof(RingBlock<N>)));
+  cudaFuncSetAttribute(kmer_query_ring_kernel<B, T, N>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                       cudaSharedmemCarveoutMaxShared);
+  cudaGetLastError();
+  if (dev >= 0 && dev < 64) done[dev] = true;
+  return 0;
+}
+
 int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
                               const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st) {
   if (nq == 0) return 0;
+  const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
+  if (occupancy >= 10) {  // EXPERIMENT: occ = 10 + blocks per SM selects the ring kernel
+    const int bps = occupancy - 10 == 5 ? 5 : (occupancy - 10 == 3 ? 3 : 4);
+    const int grid = query_grid(nq, bps);
+#define SB_RING_N(B, T, N)                                                                                             \
+  do {                                                                                                                 \
+    if (ring_attribute<B, T, N>()) return -1;                                                                          \
+    kmer_query_ring_kernel<B, T, N><<<grid, kQueryThreads, sizeof(RingBlock<N>), st>>>(ix, d_part_kmers, nq, d_res,   \
+                                                                                        d_slot, d_tiles);             \
+  } while (0)
+#define SB_RING(B)                                       \
+  do {                                                   \
+    if (ties && narrow) SB_RING_N(B, true, true);        \
+    else if (ties) SB_RING_N(B, true, false);            \
+    else if (narrow) SB_RING_N(B, false, true);          \
+    else SB_RING_N(B, false, false);                     \
+  } while (0)
+    switch (bps) {
+      case 3: SB_RING(3); break;
+      case 5: SB_RING(5); break;
+      default: SB_RING(4); break;
+    }
+#undef SB_RING
+#undef SB_RING_N
+    SB_CUDA_CHECK(cudaGetLastError());
+    return 0;
+  }
   const int bps = kmer_query_blocks_per_sm(true, occupancy);
   const int grid = query_grid(nq, bps);
-  const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
 #define SB_LAUNCH_N(B, T, N) \
   kmer_query_ordered_kernel<B, T, N><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
 #define SB_LAUNCH(B)                                       \
@@ -565,10 +863,10 @@ int launch_predict(const IndexView& ix, const uint64_t* d_kmers, size_t nq, uint
   return 0;
 }
 
-int launch_unpack_kmers(const void* d_packed, int kmer_bytes, size_t nq, uint64_t* d_kmers, cudaStream_t st) {
+int launch_unpack_kmers(const void* d_packed, int kmer_bits, size_t nq, uint64_t* d_kmers, cudaStream_t st) {
   if (nq == 0) return 0;
-  if (kmer_bytes < 1 || kmer_bytes > 7) { set_error("unpack_kmers: kmer_bytes=%d out of range", kmer_bytes); return -1; }
-  unpack_kmers_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(static_cast<const uint64_t*>(d_packed), kmer_bytes, nq,
+  if (kmer_bits < 2 || kmer_bits > 63) { set_error("unpack_kmers: kmer_bits=%d out of range", kmer_bits); return -1; }
+  unpack_kmers_kernel<<<query_grid(nq, 8), kQueryThreads, 0, st>>>(static_cast<const uint64_t*>(d_packed), kmer_bits, nq,
                                                                    d_kmers);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;

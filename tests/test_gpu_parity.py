@@ -9,6 +9,7 @@ import pytest
 
 import _fixtures as F
 import _oracle as O
+from sapling_b200.api import pack_kmer_bits
 
 pytestmark = pytest.mark.gpu
 
@@ -403,9 +404,36 @@ def test_partitioned_large_batch(S, oracle_built, name, k, monkeypatch):
         raw = kmers if kb == 8 else np.ascontiguousarray(kmers.view(np.uint8).reshape(-1, 8)[:, :kb]).reshape(-1)
         got32 = ix.queryBatchU32(raw, kmer_bytes=kb, nq=len(kmers))
         assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, k, tune, "packed")
+        got32 = ix.queryBatchBits(pack_kmer_bits(kmers, 2 * k), 2 * k, len(kmers))  # nothing but the k-mers
+        assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, k, tune, "bits")
         ix.close()
     monkeypatch.delenv("SAPLING_B200_TUNE", raising=False)
     port.close()
+
+
+@pytest.mark.parametrize("name,k", [("rand200k", 21), ("gc1991", 16), ("tandem50", 31), ("rand200k", 32), ("gc0110", 11)])
+def test_bit_stream_upload_format(S, oracle_built, name, k):
+    """sapling_b200_query_batch_bits: k-mers as a little-endian bit stream of kmer_bits bits each -- exactly 2k, odd widths,
+    whole bytes, 64 -- give the answers of the uint64 entry point, for ragged counts (streams ending inside a byte) and for
+    batches of several pipeline chunks; widths below 2k are refused."""
+    g = GENOMES[name]
+    ix = S.Sapling.from_memory(g, None, k=k, flags=S.QUIET)
+    kmers = F.query_mix(g, k, 70001, seed=k)
+    exp = ix.queryBatch(kmers)
+    if k <= 31:
+        port = O.Port.from_memory(g, k=k)
+        assert np.array_equal(exp, port.query_batch(kmers, nthreads=4))
+        port.close()
+    for bits in sorted({2 * k, min(2 * k + 1, 64), min(2 * k + 7, 64), 8 * ((2 * k + 7) // 8), 64}):
+        for m in (len(kmers), 1, 7, 8, 9, 4099):
+            got = ix.queryBatchBits(pack_kmer_bits(kmers[:m], bits), bits, m)
+            assert np.array_equal(np.where(got == 0xFFFFFFFF, -1, got.astype(np.int64)), exp[:m]), (name, k, bits, m)
+    big = np.tile(kmers, 20)[: (1 << 20) + 5]
+    got = ix.queryBatchBits(pack_kmer_bits(big, 2 * k), 2 * k, len(big))
+    assert np.array_equal(np.where(got == 0xFFFFFFFF, -1, got.astype(np.int64)), np.tile(exp, 20)[: len(big)])
+    with pytest.raises(S.SaplingError):
+        ix.queryBatchBits(pack_kmer_bits(kmers[:8], 64), 2 * k - 1, 8)
+    ix.close()
 
 
 def test_stray_high_bits_are_ignored(S, oracle_built, monkeypatch):
@@ -458,6 +486,10 @@ def test_replicas_answer_like_the_primary(S, oracle_built):
     assert np.array_equal(ix.queryBatch(kmers), one)
     got32 = ix.queryBatchU32(kmers)
     assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), one)
+    # bit streams are cut between the GPUs at multiples of 8 k-mers (byte boundaries); a ragged count on purpose
+    m = len(kmers) - 13
+    got32 = ix.queryBatchBits(pack_kmer_bits(kmers[:m], 2 * k), 2 * k, m)
+    assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), one[:m])
     ix.close()
 
 
