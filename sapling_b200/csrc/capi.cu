@@ -1265,9 +1265,14 @@ static int partition_bits(const sapling_b200_index* ix, size_t nq) {
   } else {
     const double sa_bytes = (double)line_sectors(ix->n) * 32.0;
     const double model_bytes = (ix->d_narrow ? 8.0 : 16.0) * (double)(1ull << ix->nb);
-    const double slice = 32e6;  // measured (gpurun r2f): c3 10 bits (26 MB slices) 15.0 ms per step, 11 bits 15.9, 9 bits bistable
+    // 32 MB slices, but no more than 512 of them: a (chunk, slice) run of the scatter and un-permute passes then still
+    // averages 32 queries = 256 bytes.  Measured at c3 (gpurun s13 / s14, ms per 250 M queries, passes + kernel Q): 8 bits
+    // (105 MB slices) 2.30 + 5.92, 9 bits (53 MB) 2.59 + 5.66, 10 bits (26 MB) 3.14 + 5.60, 11 bits 4.9 + 5.6; at c2 4 to 8
+    // bits differ by 3 %.
+    const double slice = 32e6;
+    const int auto_max = 9;
     bits = 1;
-    while (bits < kPartMaxBits && (sa_bytes + model_bytes) / (double)(1ull << bits) > slice) bits++;
+    while (bits < auto_max && (sa_bytes + model_bytes) / (double)(1ull << bits) > slice) bits++;
     while (bits > 0 && (nq >> bits) < 4096) bits--;
     if (bits < 3) return 0;
   }

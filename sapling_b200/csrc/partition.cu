@@ -26,7 +26,7 @@ namespace sb {
 namespace {
 
 constexpr int kHistThreads = 512;
-constexpr int kUnpermThreads = 1024;
+constexpr int kUnpermThreads = 512;  // the warp-per-run kernel: two blocks per SM at up to 64 registers, 8 answers in flight per lane
 
 __device__ __forceinline__ uint32_t bin_of(uint64_t x, int pshift, uint32_t nbins) {
   const uint64_t b = x >> pshift;
@@ -265,6 +265,8 @@ __device__ __forceinline__ void store_answer<long long>(long long* p, uint32_t v
 template <>
 __device__ __forceinline__ void store_answer<uint32_t>(uint32_t* p, uint32_t v) { __stcs(p, v); }
 
+// Both kernels below request the answers of a step together, before the first shared-memory store that depends on one: an
+// SM issues in order, so a loop of "load, store what was loaded" waits out one DRAM round trip per answer.
 template <typename Out>
 __global__ void __launch_bounds__(kUnpermThreads, 2)
 part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
@@ -273,29 +275,24 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
   // share an SM and one block's loads overlap the other's stores
   extern __shared__ uint32_t buf32[];
   const size_t c = blockIdx.x;
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  // bounds of this warp's runs, two bins per lane (nbins <= 2048 = 32 warps x 32 lanes x 2)
-  uint32_t lo[2], hi[2];
+  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x / 32u;
+  constexpr uint32_t kWarps = kUnpermThreads / 32;
+  constexpr int kAhead = 8;  // answers in flight per lane
+  // warp w walks the runs of bins w, w + kWarps, ...: 32 consecutive answers per step, kAhead steps requested at once
+  for (uint32_t b = warp; b < nbins; b += kWarps) {
+    const uint32_t* row = off + c * nbins + b;
+    const uint32_t s = __ldg(bin_start + b);
+    const uint32_t a = s + __ldg(row), e = s + __ldg(row + nbins);
+    for (uint32_t p0 = a + lane; p0 < e; p0 += 32u * kAhead) {
+      unsigned long long v[kAhead];
 #pragma unroll
-  for (int j = 0; j < 2; j++) {
-    const uint32_t b = warp + 32u * (lane + 32u * j);
-    if (b < nbins) {
-      const uint32_t* row = off + c * nbins + b;
-      const uint32_t s = bin_start[b];
-      lo[j] = s + row[0];
-      hi[j] = s + row[nbins];
-    } else {
-      lo[j] = hi[j] = 0;
-    }
-  }
-  const uint32_t per_warp = (nbins + 31u - warp) / 32u;  // bins warp, warp+32, ... below nbins
-#pragma unroll 4
-  for (uint32_t t = 0; t < per_warp; t++) {
-    const uint32_t a = __shfl_sync(0xffffffffu, t < 32u ? lo[0] : lo[1], (int)(t & 31u));
-    const uint32_t e = __shfl_sync(0xffffffffu, t < 32u ? hi[0] : hi[1], (int)(t & 31u));
-    for (uint32_t p = a + lane; p < e; p += 32u) {
-      const unsigned long long v = (unsigned long long)__ldcs(res + p);
-      buf32[v >> 48] = (uint32_t)v;  // the low 32 bits of the 48-bit answer: -1 reads back as 0xFFFFFFFF
+      for (int t = 0; t < kAhead; t++) {
+        const uint32_t p = p0 + 32u * (uint32_t)t;
+        v[t] = p < e ? (unsigned long long)__ldcs(res + p) : 0ull;
+      }
+#pragma unroll
+      for (int t = 0; t < kAhead; t++)
+        if (p0 + 32u * (uint32_t)t < e) buf32[v[t] >> 48] = (uint32_t)v[t];  // low 32 bits: -1 reads back as 0xFFFFFFFF
     }
   }
   __syncthreads();
@@ -305,17 +302,20 @@ part_unpermute_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbi
 }
 
 // U': lane GROUPS per run.  Above, a warp walks whole (bin, chunk) runs, which leaves most lanes idle once runs are shorter
-// than a warp (2048 bins: 8 queries per run).  Here kGroup lanes (a power of two near half the mean run length) own a run: they read its bounds once and then
-// kGroup consecutive answers per step -- no scan, no search, and neighbouring lanes still read neighbouring addresses.
-// The bounds of kBatch runs are requested before the first answer is, so the two dependent loads overlap across runs.
+// than a warp (1024 bins: 16 answers per run).  Here kGroup lanes (the power of two at or above the mean run length) own
+// a run; per step a lane takes kBatch runs: their bounds are requested together, then its first answer of every run --
+// kBatch loads in flight -- and only then the stores; what a run has beyond kGroup answers follows in a tail loop.
+// 1024 threads, two blocks per SM (32 registers): measured against 512 threads with 16 loads in flight per lane (48
+// registers, gpurun s14): 1.23 against 1.49 ms at c3 -- the pass lives on resident warps, every run is a new DRAM page.
+constexpr int kGroupThreads = 1024;
 template <int kGroup, typename Out>
-__global__ void __launch_bounds__(kUnpermThreads, 2)
+__global__ void __launch_bounds__(kGroupThreads, 2)
 part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32_t nbins, size_t nchunks,
                             const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
                             Out* __restrict__ out) {
   extern __shared__ uint32_t buf32[];  // [kPartChunk] answers in the caller's order, 32 bits each (see part_unpermute_kernel)
-  constexpr uint32_t kGroups = kUnpermThreads / kGroup;
-  constexpr int kBatch = 4;  // 8 was measured slower (spills at the 32-register cap of two 1024-thread blocks per SM)
+  constexpr uint32_t kGroups = kGroupThreads / kGroup;
+  constexpr int kBatch = 4;
   const size_t c = blockIdx.x;
   const uint32_t g = threadIdx.x / kGroup, l = threadIdx.x % kGroup;
   for (uint32_t b0 = g; b0 < nbins; b0 += kGroups * kBatch) {
@@ -327,22 +327,28 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
       if (b < nbins) {
         const uint32_t* row = off + c * nbins + b;
         const uint32_t s = __ldg(bin_start + b);
-        lo[j] = s + __ldg(row);
+        lo[j] = s + __ldg(row) + l;
         hi[j] = s + __ldg(row + nbins);
       }
     }
+    unsigned long long v[kBatch];
+#pragma unroll
+    for (int j = 0; j < kBatch; j++) v[j] = lo[j] < hi[j] ? (unsigned long long)__ldcs(res + lo[j]) : 0ull;
+#pragma unroll
+    for (int j = 0; j < kBatch; j++)
+      if (lo[j] < hi[j]) buf32[v[j] >> 48] = (uint32_t)v[j];
 #pragma unroll
     for (int j = 0; j < kBatch; j++) {
-      for (uint32_t p = lo[j] + l; p < hi[j]; p += kGroup) {
-        const unsigned long long v = (unsigned long long)__ldcs(res + p);
-        buf32[v >> 48] = (uint32_t)v;
+      for (uint32_t p = lo[j] + kGroup; p < hi[j]; p += kGroup) {  // the rest of a long run
+        const unsigned long long w = (unsigned long long)__ldcs(res + p);
+        buf32[w >> 48] = (uint32_t)w;
       }
     }
   }
   __syncthreads();
   const size_t base = c * kPartChunk;
   const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-  for (uint32_t i = threadIdx.x; i < m; i += kUnpermThreads) store_answer<Out>(out + base + i, buf32[i]);
+  for (uint32_t i = threadIdx.x; i < m; i += kGroupThreads) store_answer<Out>(out + base + i, buf32[i]);
 }
 
 }  // namespace
@@ -374,12 +380,12 @@ static int set_kernel_attributes() {
   SB_SMEM(part_scatter_staged_kernel<true>, kScatterSmem);
   SB_SMEM(part_unpermute_kernel<long long>, kUnpermSmem);
   SB_SMEM(part_unpermute_kernel<uint32_t>, kUnpermSmem);
-  SB_SMEM((part_unpermute_group_kernel<4, long long>), kUnpermSmem);
   SB_SMEM((part_unpermute_group_kernel<8, long long>), kUnpermSmem);
   SB_SMEM((part_unpermute_group_kernel<16, long long>), kUnpermSmem);
-  SB_SMEM((part_unpermute_group_kernel<4, uint32_t>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<32, long long>), kUnpermSmem);
   SB_SMEM((part_unpermute_group_kernel<8, uint32_t>), kUnpermSmem);
   SB_SMEM((part_unpermute_group_kernel<16, uint32_t>), kUnpermSmem);
+  SB_SMEM((part_unpermute_group_kernel<32, uint32_t>), kUnpermSmem);
 #undef SB_SMEM
   cudaGetLastError();
   if (dev >= 0 && dev < 64) done[dev] = true;
@@ -389,17 +395,17 @@ static int set_kernel_attributes() {
 template <typename Out>
 static void launch_unpermute(const long long* res, size_t nq, uint32_t nbins, size_t nchunks, const uint32_t* cnt,
                              const uint32_t* bin_start, Out* out, int pbits, cudaStream_t st) {
-  // lane groups per run, the group about half the mean run length; a whole warp per run from 64 answers per run
+  // lane groups per run, the group at the mean run length; a whole warp per run from 64 answers per run
   const uint32_t mean_run = kPartChunk >> pbits;
   const unsigned g = (unsigned)nchunks;
   if (mean_run >= 64)
     part_unpermute_kernel<Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
   else if (mean_run >= 32)
-    part_unpermute_group_kernel<16, Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+    part_unpermute_group_kernel<32, Out><<<g, kGroupThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
   else if (mean_run >= 16)
-    part_unpermute_group_kernel<8, Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+    part_unpermute_group_kernel<16, Out><<<g, kGroupThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
   else
-    part_unpermute_group_kernel<4, Out><<<g, kUnpermThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
+    part_unpermute_group_kernel<8, Out><<<g, kGroupThreads, kUnpermSmem, st>>>(res, nq, nbins, nchunks, cnt, bin_start, out);
 }
 
 int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,

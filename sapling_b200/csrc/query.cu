@@ -10,8 +10,6 @@
 #include "kmer.cuh"
 #include "query.cuh"
 
-#include <mutex>
-
 namespace sb {
 
 namespace {
@@ -87,11 +85,24 @@ struct TailStacks {            // per warp: the queries the two-sector shortcut 
   uint32_t pred[kWarpsPerBlock][kStackCap], idx[kWarpsPerBlock][kStackCap];
 };
 
+// The k-mer stream goes through shared memory: ptxas hoists the register rotation x2 = x3 to just behind the load of x3, so
+// the warp waits out the DRAM round trip of a k-mer it does not need for another tile (ncu s10, SASS page: 15.5 % of all
+// stall samples on that one MOV).  An asynchronous copy has no destination register to wait on: one coalesced LDGSTS per
+// tile into a 2-stage ring of the warp, read back a tile later (gpurun s13: 5.78 -> 5.60 ms at c3, 1.086 -> 1.041 at c2).
+// The per-lane gathers -- checkpoints, sectors -- stay register loads: as scattered LDGSTS they cost more in the
+// shared-memory pipe than they save (gpurun s12: 8.4 ms).
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <int kMinBlocks, bool kTies, bool kNarrow>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
 kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
   __shared__ TailStacks stacks;
+  __shared__ uint64_t kmer_ring[kWarpsPerBlock][2][32];  // the k-mers of tile t2 (landed) and of t3 (in flight)
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const L2Policies pol = make_policies(ix.hints);
@@ -116,6 +127,11 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   auto kmer_at = [&](uint32_t t) {  // past the end: the last k-mer again (loaded, predicted for, never answered)
     const uint32_t i = t + lane;
     return __ldcs(kmers + (i < last ? i : last));
+  };
+  auto kmer_request = [&](uint32_t t, unsigned stage) {
+    const uint32_t i = t + lane;
+    cp_async8(&kmer_ring[warp][stage][lane], kmers + (i < last ? i : last));
+    cp_async_commit();
   };
   const bool in_kmer = slot == slot_in_kmer_tag();
   // bits above 2k are not part of a k-mer (and bits 50-63 may carry the slot): never indexed with
@@ -152,7 +168,9 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   // Pipeline, in tiles ahead of the one being answered: k-mers 3, model checkpoints 2, prediction AND ITS SECTOR 1: the first
   // read of a query is the one that goes to DRAM (the later ones stay in the same 128-byte line), and it is in registers a
   // whole tile before the lane classifies it.  (Measured, gpurun s9, c3, ms per 250 M queries at 4 blocks per SM: nothing
-  // ahead 6.17, an L2 prefetch of the sector 5.83, the sector itself 5.74.)
+  // ahead 6.17, an L2 prefetch of the sector 5.83, the sector itself 5.74.  The neighbour a second round is most likely to
+  // ask for, prefetched into L1 along with it: 5.81 against 5.60, gpurun s14 -- one more sector request per query costs more
+  // than the shorter wait of the 43 % of lanes that use it.)
   auto predict = [&](uint64_t xw, const ModelPair<kNarrow>& m, bool real, U32x8* sector) -> uint32_t {
     uint64_t p = m.predict(ix, xw & kmask, pol.model);
     if (real) p = clamp_prediction(ix, p);  // counts predictions past the last rank: real queries only
@@ -162,7 +180,9 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   };
   uint32_t t0 = claim(), t1 = claim(), t2 = claim(), t3 = claim();
   if (t0 >= nq32) return;
-  uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1), x2 = kmer_at(t2);
+  uint64_t x0 = kmer_at(t0), x1 = kmer_at(t1), x2 = 0;
+  unsigned kq = 0;  // ring stage of the k-mers of t2
+  kmer_request(t2, kq);
   ModelPair<kNarrow> m1;
   uint32_t pred0;
   U32x8 sec0;
@@ -173,7 +193,10 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     pred0 = predict(x0, m0, t0 + lane < nq32, &sec0);
   }
   while (t0 < nq32) {
-    const uint64_t x3 = kmer_at(t3);
+    cp_async_wait_all();  // the k-mers of t2, asked for a tile ago
+    x2 = kmer_ring[warp][kq][lane];
+    kq ^= 1u;
+    kmer_request(t3, kq);
     ModelPair<kNarrow> m2;
     m2.load(ix, x2 & kmask, pol.model);
     U32x8 sec1;
@@ -227,7 +250,6 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     while (stacked >= 32u) drain(32u);
     x0 = x1;
     x1 = x2;
-    x2 = x3;
     m1 = m2;
     pred0 = pred1;
     sec0 = sec1;
@@ -236,244 +258,6 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     t2 = t3;
     t3 = claim();
   }
-  while (stacked) drain(stacked < 32u ? stacked : 32u);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// The same kernel with its software pipeline in SHARED MEMORY (cp.async rings) instead of registers.
-//
-// Why.  kmer_query_ordered_kernel keeps the loads that are in flight -- the k-mers of three tiles, two pairs of model
-// checkpoints, the sector of the next tile -- in registers and rotates them at the end of an iteration.  ptxas hoists
-// those rotations: the k-mer loaded at the top of an iteration is moved into its next register a few instructions later,
-// and the warp sits on a DRAM round trip it was supposed to sleep through (ncu s10, SASS page: 15.5 % of all stall samples
-// on that one MOV, 5.3 % on the rotation of the sector registers).  An asynchronous copy has no destination register to
-// wait on: every lane copies its own 8 / 16 / 32 bytes into its own slot of a per-warp ring (LDGSTS), one commit per
-// tile, one wait at the top of the next tile, and the 28 registers of in-flight data are free.
-//   ring, per warp: k-mers 4 stages x 256 B, checkpoint pairs 3 stages x 512 B (narrow) or 1 KB (wide), sectors 2 stages x
-//   1 KB, laid out [stage][piece][lane] so that the 8- and 16-byte reads are conflict-free.
-__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, uint64_t) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;"
-               ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, uint64_t) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
-               ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-template <bool kNarrow>
-struct RingModel;
-template <>
-struct RingModel<true> {
-  uint2 e[3][2][32];
-  __device__ __forceinline__ void request(const IndexView& ix, uint64_t x, unsigned stage, unsigned lane, uint64_t pol) {
-    const uint2* p = ix.narrow + (uint32_t)(x >> ix.shift);  // entries b and b + 1 (the table has a pad entry)
-    cp_async8(&e[stage][0][lane], p, pol);
-    cp_async8(&e[stage][1][lane], p + 1, pol);
-  }
-  __device__ __forceinline__ uint64_t predict(const IndexView& ix, uint64_t x, unsigned stage, unsigned lane, uint64_t pol) const {
-    NarrowPair pr;
-    pr.e0 = e[stage][0][lane];
-    pr.e1 = e[stage][1][lane];
-    return narrow_finish(ix, x, pr, pol);
-  }
-};
-template <>
-struct RingModel<false> {
-  longlong2 e[3][2][32];
-  __device__ __forceinline__ void request(const IndexView& ix, uint64_t x, unsigned stage, unsigned lane, uint64_t pol) {
-    const uint64_t b = x >> ix.shift;
-    cp_async16(&e[stage][0][lane], ix.model + b, pol);
-    cp_async16(&e[stage][1][lane], ix.model + b + 1, pol);
-  }
-  __device__ __forceinline__ uint64_t predict(const IndexView&, uint64_t x, unsigned stage, unsigned lane, uint64_t) const {
-    const longlong2 lo = e[stage][0][lane], hi = e[stage][1][lane];
-    return interpolate((long long)x, lo.x, lo.y, hi.x, hi.y);
-  }
-};
-template <bool kNarrow>
-struct WarpRing {
-  uint4 sector[2][2][32];
-  uint64_t kmer[4][32];
-  RingModel<kNarrow> model;
-};
-template <bool kNarrow>
-struct RingBlock {
-  WarpRing<kNarrow> ring[kWarpsPerBlock];
-  TailStacks stacks;
-};
-
-template <int kMinBlocks, bool kTies, bool kNarrow>
-__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
-kmer_query_ring_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
-                       const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
-  extern __shared__ __align__(16) unsigned char ring_raw[];
-  RingBlock<kNarrow>& sh = *reinterpret_cast<RingBlock<kNarrow>*>(ring_raw);
-  TailStacks& stacks = sh.stacks;
-  const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  WarpRing<kNarrow>& ring = sh.ring[warp];
-  const unsigned lt_mask = (1u << lane) - 1u;
-  const L2Policies pol = make_policies(ix.hints);
-  uint64_t pol_stream;
-  asm("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
-  const uint32_t nq32 = (uint32_t)nq, last = nq32 - 1u;
-  constexpr unsigned kSpan = 4;
-  uint32_t span_next = 0;
-  unsigned span_left = 0;  // warp-uniform
-  auto claim = [&]() -> uint32_t {
-    if (span_left == 0) {
-      unsigned long long a = 0;
-      if (lane == 0) a = atomicAdd(tiles, 32ull * kSpan);
-      a = __shfl_sync(0xffffffffu, a, 0);
-      span_next = a < 0xFFFFFE00ull ? (uint32_t)a : 0xFFFFFE00u;  // past the end either way; keeps t + lane from wrapping
-      span_left = kSpan;
-    }
-    const uint32_t t = span_next;
-    span_next += 32u;
-    span_left--;
-    return t;
-  };
-  const bool in_kmer = slot == slot_in_kmer_tag();
-  const uint64_t kmask = ix.k >= 32 ? ~0ull : ((1ull << (2 * ix.k)) - 1ull);
-  auto store = [&](uint32_t i, uint64_t xw, long long r) {
-    const unsigned long long sl = in_kmer ? (unsigned long long)(xw >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
-    __stcs(out + i, slot_word(sl, r));
-  };
-  unsigned stacked = 0;  // warp-uniform: entries on this warp's stack
-  auto push = [&](bool pending, uint64_t xw, uint32_t pred, uint32_t i) {
-    const unsigned m = __ballot_sync(0xffffffffu, pending);
-    if (pending) {
-      const unsigned e = stacked + (unsigned)__popc(m & lt_mask);
-      stacks.x_lo[warp][e] = (uint32_t)xw;
-      stacks.x_hi[warp][e] = (uint32_t)(xw >> 32);
-      stacks.pred[warp][e] = pred;
-      stacks.idx[warp][e] = i;
-    }
-    stacked += (unsigned)__popc(m);
-    __syncwarp();
-  };
-  auto drain = [&](unsigned m) {
-    stacked -= m;
-    if (lane < m) {
-      const unsigned e = stacked + lane;
-      const uint64_t xw = ((uint64_t)stacks.x_hi[warp][e] << 32) | stacks.x_lo[warp][e];
-      const uint32_t i = stacks.idx[warp][e];
-      store(i, xw, answer_kmer<kTies>(ix, xw & kmask, stacks.pred[warp][e], pol));
-    }
-    __syncwarp();
-  };
-  // the three requests of the pipeline; a tile past the end asks for the last k-mer again (predicted for, never answered)
-  auto request_kmers = [&](uint32_t t, unsigned stage) {
-    const uint32_t i = t + lane;
-    cp_async8(&ring.kmer[stage][lane], kmers + (i < last ? i : last), pol_stream);
-  };
-  auto request_sector = [&](uint32_t pred, unsigned stage) {
-    const uint32_t* p = ix.lines + (uint64_t)(pred >> 2) * 8u;
-    cp_async16(&ring.sector[stage][0][lane], p, pol.sa);
-    cp_async16(&ring.sector[stage][1][lane], p + 4, pol.sa);
-  };
-  auto predict = [&](uint64_t xw, unsigned mstage, bool real) -> uint32_t {
-    uint64_t p = ring.model.predict(ix, xw & kmask, mstage, lane, pol.model);
-    if (real) p = clamp_prediction(ix, p);  // counts predictions past the last rank: real queries only
-    else if (p >= ix.n) p = ix.n - 1;
-    return (uint32_t)p;
-  };
-
-  uint32_t t0 = claim(), t1 = claim(), t2 = claim(), t3 = claim();
-  if (t0 >= nq32) return;
-  // fill: k-mers of three tiles, then the checkpoints of two, then the prediction and the sector of the first
-  request_kmers(t0, 0);
-  request_kmers(t1, 1);
-  request_kmers(t2, 2);
-  cp_async_commit();
-  cp_async_wait_all();
-  ring.model.request(ix, ring.kmer[0][lane] & kmask, 0, lane, pol.model);
-  ring.model.request(ix, ring.kmer[1][lane] & kmask, 1, lane, pol.model);
-  cp_async_commit();
-  cp_async_wait_all();
-  uint32_t pred0 = predict(ring.kmer[0][lane], 0, t0 + lane < nq32);
-  request_sector(pred0, 0);
-  cp_async_commit();
-  unsigned kq = 0;  // ring stage of the current tile's k-mers (mod 4); its sector sits in stage kq & 1
-  unsigned mq = 0;  // ring stage of the current tile's checkpoints (mod 3)
-  while (t0 < nq32) {
-    cp_async_wait_all();  // everything the previous tile asked for has landed (it had a whole tile to do so)
-    // three tiles ahead: k-mers; two: checkpoints; one: prediction and its sector
-    request_kmers(t3, (kq + 3u) & 3u);
-    const unsigned m2 = mq >= 1u ? mq - 1u : 2u, m1 = mq == 2u ? 0u : mq + 1u;  // (mq + 2) % 3, (mq + 1) % 3
-    ring.model.request(ix, ring.kmer[(kq + 2u) & 3u][lane] & kmask, m2, lane, pol.model);
-    const uint32_t pred1 = predict(ring.kmer[(kq + 1u) & 3u][lane], m1, t1 + lane < nq32);
-    request_sector(pred1, (kq + 1u) & 1u);
-    cp_async_commit();
-
-    const uint32_t i = t0 + lane;
-    const bool active = i < nq32;
-    const uint64_t x0 = ring.kmer[kq][lane];
-    bool done = false;
-    int st = 2;  // 0: bounds final, 1: wants the neighbour, 2: left to the general search
-    long long r = -1;
-    uint32_t pred = 0, neighbour = 0;
-    KmerKey key;
-    key.q = key.qlo = key.qhi = 0;
-    Bounds b;
-    b.lb = b.ub = 0;
-    Sector s0;
-    s0.s = s0.c = s0.m = 0;
-    if (active) {  // round 1: the sector of the predicted rank
-      pred = pred0;
-      key = make_key<kTies>(ix, x0 & kmask);
-      U32x8 sec0;
-      {
-        const uint4 a = ring.sector[kq & 1u][0][lane], c = ring.sector[kq & 1u][1][lane];
-        sec0.v[0] = a.x; sec0.v[1] = a.y; sec0.v[2] = a.z; sec0.v[3] = a.w;
-        sec0.v[4] = c.x; sec0.v[5] = c.y; sec0.v[6] = c.z; sec0.v[7] = c.w;
-      }
-      uint32_t pos[4], idx = 0;
-      s0 = classify_loaded<kTies>(ix, key, pred >> 2, sec0, pol, pos);
-      done = direct_match(pred, s0, pos, &idx);  // :164
-      r = (long long)idx;
-      st = two_sector_first(ix, s0, &b, &neighbour);
-    }
-    if (active && !done && st == 1) {  // round 2: the neighbour the first one points to
-      uint32_t pos[4];
-      const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
-      st = two_sector_second(ix, s0, s1, &b);
-    }
-    // phase 2 (kmer.cuh replay_plquery, in its pieces): the one loop in it runs with a warp-uniform trip count, so all
-    // lanes are together again when rev[rank] is read
-    const bool fin = active && !done && st == 0;
-    ReplayState rs;
-    rs.rank = kNoRank;
-    rs.lo = 1u;  // lo > hi: not searching
-    rs.hi = 0u;
-    if (fin) {
-      replay_windows(ix, pred, b, &rs);
-      replay_search_jump(b, &rs);
-    }
-    while (__any_sync(0xffffffffu, rs.searching())) replay_search_step(b, &rs);  // :245; a no-op for the lanes that are done
-    if (fin) {
-      done = true;
-      r = -1;  // :246
-      if (rs.rank != kNoRank) {  // :247 -- from the sector in the ring when the rank lies in it
-        if ((rs.rank >> 2) == (pred >> 2))
-          r = (long long)reinterpret_cast<const uint32_t*>(&ring.sector[kq & 1u][1][lane])[rs.rank & 3u];
-        else
-          r = (long long)rev_at(ix, rs.rank, pol.sa);
-      }
-    }
-    if (active && done) store(i, x0, r);
-    push(active && !done, x0, pred, i);
-    while (stacked >= 32u) drain(32u);
-    pred0 = pred1;
-    kq = (kq + 1u) & 3u;
-    mq = m1;
-    t0 = t1;
-    t1 = t2;
-    t2 = t3;
-    t3 = claim();
-  }
-  cp_async_wait_all();
   while (stacked) drain(stacked < 32u ? stacked : 32u);
 }
 
@@ -761,54 +545,10 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
 
 // A partitioned batch (partition.cu): d_tiles is the zeroed in-order tile counter, d_slot the slot array or
 // slot_in_kmer_tag(); results are slot words (see slot_word).
-// Opt-in to the dynamic shared memory of the ring kernel: function attributes belong to the device they were set on.
-template <int B, bool T, bool N>
-static int ring_attribute() {
-  static std::mutex mu;
-  static bool done[64] = {};
-  int dev = 0;
-  SB_CUDA_CHECK(cudaGetDevice(&dev));
-  std::lock_guard<std::mutex> lock(mu);
-  if (dev >= 0 && dev < 64 && done[dev]) return 0;
-  SB_CUDA_CHECK(cudaFuncSetAttribute(kmer_query_ring_kernel<B, T, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)sizeof(RingBlock<N>)));
-  cudaFuncSetAttribute(kmer_query_ring_kernel<B, T, N>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                       cudaSharedmemCarveoutMaxShared);
-  cudaGetLastError();
-  if (dev >= 0 && dev < 64) done[dev] = true;
-  return 0;
-}
-
 int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
                               const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st) {
   if (nq == 0) return 0;
   const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
-  if (occupancy >= 10) {  // EXPERIMENT: occ = 10 + blocks per SM selects the ring kernel
-    const int bps = occupancy - 10 == 5 ? 5 : (occupancy - 10 == 3 ? 3 : 4);
-    const int grid = query_grid(nq, bps);
-#define SB_RING_N(B, T, N)                                                                                             \
-  do {                                                                                                                 \
-    if (ring_attribute<B, T, N>()) return -1;                                                                          \
-    kmer_query_ring_kernel<B, T, N><<<grid, kQueryThreads, sizeof(RingBlock<N>), st>>>(ix, d_part_kmers, nq, d_res,   \
-                                                                                        d_slot, d_tiles);             \
-  } while (0)
-#define SB_RING(B)                                       \
-  do {                                                   \
-    if (ties && narrow) SB_RING_N(B, true, true);        \
-    else if (ties) SB_RING_N(B, true, false);            \
-    else if (narrow) SB_RING_N(B, false, true);          \
-    else SB_RING_N(B, false, false);                     \
-  } while (0)
-    switch (bps) {
-      case 3: SB_RING(3); break;
-      case 5: SB_RING(5); break;
-      default: SB_RING(4); break;
-    }
-#undef SB_RING
-#undef SB_RING_N
-    SB_CUDA_CHECK(cudaGetLastError());
-    return 0;
-  }
   const int bps = kmer_query_blocks_per_sm(true, occupancy);
   const int grid = query_grid(nq, bps);
 #define SB_LAUNCH_N(B, T, N) \
