@@ -64,20 +64,20 @@ struct ModelPair<false> {
 
 // In-order, software-pipelined kernel of the partitioned batch path (partition.cu).  The batch arrives bucketed by the top
 // bits of the k-mer and must be WALKED IN ORDER for that to pay: warps claim tiles of 32 consecutive queries from a global
-// counter (four tiles per atomic), so the ~190 k queries in flight on the GPU always fall into one or two slices of the
+// counter (four tiles per atomic), so the ~150 k queries in flight on the GPU always fall into one or two slices of the
 // index -- the slice of the rank lines and of the model is L2 resident, a DRAM line is filled once per batch.  While a lane
-// answers query t of its warp's tile sequence the k-mers of tile t+2 and the model checkpoints of tile t+1 are already
-// requested, so the two dependent round trips that head every query (k-mer -> checkpoints -> first sector) overlap with
-// the previous tile.  The slot of a query rides in bits 50-63 of its k-mer word (k <= 25) or comes from a side array.
+// answers its query of tile t, the k-mers of tile t+3, the model checkpoints of t+2 and the prediction and sector of t+1
+// are on their way, so the dependent round trips that head every query (k-mer -> checkpoints -> first sector) overlap with
+// the previous tiles.  The slot of a query rides in bits 50-63 of its k-mer word (k <= 25) or comes from a side array.
 //
 // Lane occupancy.  A third of the queries are answered by the sector of their predicted rank, nearly all the others by
-// one neighbouring sector; one in eight needs a third sector or more (errors beyond the 95 % bounds, match runs crossing a
-// sector end, absent k-mers far from their prediction).  A warp that loops until its slowest lane is done spends most of
-// its instructions with 2-4 lanes alive (ncu, profiles/s2_*: 13.7 of 32 lanes active per instruction).  So a tile gets
-// exactly TWO classification rounds in place, decided by the two-sector shortcut (kmer.cuh: a handful of compares, no
-// search state); what is still undecided -- one query in eight -- is pushed onto the warp's own stack in shared memory, and
-// whenever 32 have piled up the warp pops them and answers them with the general search, every lane busy at the start.
-// No block-wide barrier: the warps stay independent.
+// one neighbouring sector; 1 % of present k-mers (more of absent ones) need a third sector or more (errors beyond the 95 %
+// bounds, match runs crossing a sector end, absent k-mers far from their prediction).  A warp that loops until its slowest
+// lane is done spends most of its instructions with 2-4 lanes alive (ncu, gpurun s2: 13.7 of 32 lanes active per
+// instruction).  So a tile gets exactly TWO classification rounds in place, decided by the two-sector shortcut (kmer.cuh:
+// a handful of compares, no search state); what is still undecided is pushed onto the warp's own stack in shared memory,
+// and whenever 32 have piled up the warp pops them and answers them with the general search, every lane busy at the start.
+// No block-wide barrier: the warps stay independent.  (ncu r3e: 26 of 32 lanes active per instruction.)
 constexpr int kWarpsPerBlock = kQueryThreads / 32;
 constexpr int kStackCap = 64;  // at most 31 left over + 32 pushed by a tile
 struct TailStacks {            // per warp: the queries the two-sector shortcut left undecided (k-mer word, prediction, index)
@@ -96,6 +96,10 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_but_last() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
 
 template <int kMinBlocks, bool kTies, bool kNarrow>
 __global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
@@ -103,6 +107,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
   __shared__ TailStacks stacks;
   __shared__ uint64_t kmer_ring[kWarpsPerBlock][2][32];  // the k-mers of tile t2 (landed) and of t3 (in flight)
+  __shared__ uint4 near_ring[kWarpsPerBlock][2][32];  // second-round sectors of the current tile, in two halves
   const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const unsigned lt_mask = (1u << lane) - 1u;
   const L2Policies pol = make_policies(ix.hints);
@@ -193,14 +198,19 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     pred0 = predict(x0, m0, t0 + lane < nq32, &sec0);
   }
   while (t0 < nq32) {
-    cp_async_wait_all();  // the k-mers of t2, asked for a tile ago
-    x2 = kmer_ring[warp][kq][lane];
-    kq ^= 1u;
-    kmer_request(t3, kq);
-    ModelPair<kNarrow> m2;
-    m2.load(ix, x2 & kmask, pol.model);
+    uint32_t pred1 = 0;
     U32x8 sec1;
-    const uint32_t pred1 = predict(x1, m1, t1 + lane < nq32, &sec1);
+    ModelPair<kNarrow> m2;
+    // what the next tiles need: the k-mers of t2 out of the ring and those of t3 asked for, checkpoints for t2, prediction
+    // and sector for t1 -- done BETWEEN the request of a second-round sector and its use (below)
+    auto look_ahead = [&]() {
+      cp_async_wait_but_last();  // the k-mers of t2, asked for a tile ago (the last group is this tile's neighbour sectors)
+      x2 = kmer_ring[warp][kq][lane];
+      kq ^= 1u;
+      kmer_request(t3, kq);
+      m2.load(ix, x2 & kmask, pol.model);
+      pred1 = predict(x1, m1, t1 + lane < nq32, &sec1);
+    };
     const uint32_t i = t0 + lane;
     // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
     const bool active = i < nq32;
@@ -223,10 +233,30 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       r = (long long)idx;
       st = two_sector_first(ix, s0, &b, &neighbour);
     }
-    if (active && !done && st == 1) {  // round 2: the neighbour the first one points to
-      uint32_t pos[4];
-      const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
-      st = two_sector_second(ix, s0, s1, &b);
+    {
+      // round 2, asked for here and used after the look-ahead: the ~100 instructions of the next tiles' prologue (times
+      // the other warps of the scheduler) run while the neighbour sector travels from L2.  Loaded in place it was the one
+      // wait of the loop that nothing overlapped (ncu s13: 25 % of all stall samples on its first use; gpurun s16: 5.65 ->
+      // 5.53 ms at c3, 5.72 -> 5.61 at c4, 1.04 -> 1.05 at c2).  Through shared memory: a register destination would be
+      // live across the whole look-ahead.
+      const bool second = active && !done && st == 1;
+      if (second) {
+        const uint32_t* p = ix.lines + (uint64_t)neighbour * 8u;
+        cp_async16(&near_ring[warp][0][lane], p);
+        cp_async16(&near_ring[warp][1][lane], p + 4);
+      }
+      cp_async_commit();
+      look_ahead();
+      cp_async_wait_but_last();  // the neighbour sectors (the last group is the k-mers of t3)
+      if (second) {
+        U32x8 sec;
+        const uint4 lo4 = near_ring[warp][0][lane], hi4 = near_ring[warp][1][lane];
+        sec.v[0] = lo4.x; sec.v[1] = lo4.y; sec.v[2] = lo4.z; sec.v[3] = lo4.w;
+        sec.v[4] = hi4.x; sec.v[5] = hi4.y; sec.v[6] = hi4.z; sec.v[7] = hi4.w;
+        uint32_t pos[4];
+        const Sector s1 = classify_loaded<kTies>(ix, key, neighbour, sec, pol, pos);
+        st = two_sector_second(ix, s0, s1, &b);
+      }
     }
     // phase 2 (kmer.cuh replay_plquery, in its pieces): the one loop in it runs with a warp-uniform trip count, so all
     // lanes are together again when rev[rank] is read
@@ -245,6 +275,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       r = -1;                                                               // :246
       if (rs.rank != kNoRank) r = (long long)rev_at(ix, rs.rank, pol.sa);  // :247
     }
+    // (stored a tile later instead, so that the read of rev[rank] has a tile to arrive: 9.6 against 5.5 ms, gpurun s17)
     if (active && done) store(i, x0, r);
     push(active && !done, x0, pred, i);
     while (stacked >= 32u) drain(32u);
@@ -258,6 +289,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     t2 = t3;
     t3 = claim();
   }
+  cp_async_wait_all();
   while (stacked) drain(stacked < 32u ? stacked : 32u);
 }
 
@@ -510,8 +542,8 @@ const char* kmer_query_kernel_name(bool ordered) { return ordered ? "kmer_query_
 // `occupancy` (Tuning, capi.cu) overrides for A/B runs.
 int kmer_query_blocks_per_sm(bool ordered, int occupancy) {
   if (occupancy == 3 || occupancy == 4 || occupancy == 5 || (occupancy == 6 && !ordered)) return occupancy;
-  // measured (gpurun s9, c3): the in-order kernel at 4 blocks per SM (64 registers) 5.74 ms per 250 M queries, at 5 (48
-  // registers, spills) 7.3, at 3 6.8
+  // measured (gpurun s16, c3): the in-order kernel at 4 blocks per SM (64 registers, no spills) 5.53 ms per 250 M queries,
+  // at 5 (48 registers, spills) 6.8; at 3 (gpurun s8) 6.8
   return 4;
 }
 
