@@ -202,15 +202,20 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
     U32x8 sec1;
     ModelPair<kNarrow> m2;
     // what the next tiles need: the k-mers of t2 out of the ring and those of t3 asked for, checkpoints for t2, prediction
-    // and sector for t1 -- done BETWEEN the request of a second-round sector and its use (below)
+    // and sector for t1 -- done BETWEEN the request of a second-round sector and its use (below).  Not with ties (k longer
+    // than the lines' prefixes: every match waits for a genome read inside round 1): there the look-ahead goes first, as
+    // its requests then travel during that wait (k = 31, c4: 15.0 ms with the look-ahead first, 18.3 behind round 1).
+    constexpr bool kLate = !kTies;
     auto look_ahead = [&]() {
-      cp_async_wait_but_last();  // the k-mers of t2, asked for a tile ago (the last group is this tile's neighbour sectors)
+      if (kLate) cp_async_wait_but_last();  // the k-mers of t2, asked for a tile ago (the last group: this tile's neighbours)
+      else cp_async_wait_all();
       x2 = kmer_ring[warp][kq][lane];
       kq ^= 1u;
       kmer_request(t3, kq);
       m2.load(ix, x2 & kmask, pol.model);
       pred1 = predict(x1, m1, t1 + lane < nq32, &sec1);
     };
+    if (!kLate) look_ahead();
     const uint32_t i = t0 + lane;
     // Every phase below is its own `if`: the lanes that need it meet there again whatever they did before.
     const bool active = i < nq32;
@@ -233,7 +238,7 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
       r = (long long)idx;
       st = two_sector_first(ix, s0, &b, &neighbour);
     }
-    {
+    if (kLate) {
       // round 2, asked for here and used after the look-ahead: the ~100 instructions of the next tiles' prologue (times
       // the other warps of the scheduler) run while the neighbour sector travels from L2.  Loaded in place it was the one
       // wait of the loop that nothing overlapped (ncu s13: 25 % of all stall samples on its first use; gpurun s16: 5.65 ->
@@ -257,6 +262,10 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
         const Sector s1 = classify_loaded<kTies>(ix, key, neighbour, sec, pol, pos);
         st = two_sector_second(ix, s0, s1, &b);
       }
+    } else if (active && !done && st == 1) {  // round 2 in place
+      uint32_t pos[4];
+      const Sector s1 = classify_sector<kTies>(ix, key, neighbour, pol, pos);
+      st = two_sector_second(ix, s0, s1, &b);
     }
     // phase 2 (kmer.cuh replay_plquery, in its pieces): the one loop in it runs with a warp-uniform trip count, so all
     // lanes are together again when rev[rank] is read
