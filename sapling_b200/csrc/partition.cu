@@ -164,6 +164,11 @@ __device__ __forceinline__ void scan_2048(uint32_t* a, uint32_t* wsum, uint32_t 
 // ranks in shared memory and re-read the run starts: 9 shared-memory operations per k-mer against 6 here.)
 constexpr int kScatterThreads = kPartChunk / 16;  // 16 k-mers per thread in registers
 constexpr int kScatterPer = kPartChunk / kScatterThreads;
+// (Measured and dropped, gpurun s22: the write-out as one bulk copy per run -- cp.async.bulk shared -> global, runs padded in
+// the staging buffer to the parity of their global index so that both sides are 16-byte aligned together -- takes 128 of a
+// thread's ~740 instructions per chunk away and changes nothing: 1.055 against 1.057 ms.  The pass waits for its k-mers
+// (29 % of the stall samples) and at its barriers: one staging buffer per SM means load, sort and write-out of a chunk
+// take turns, and a second buffer does not fit.)
 // Persistent: one block per SM (the staging buffer takes most of its shared memory) walks chunks blockIdx, blockIdx +
 // gridDim, ...  With a block per chunk the phases of a chunk ran one after the other -- load, scan, sort, write out -- and
 // the SM sat idle through every load (ncu r2u: 81 % of the stalls long-scoreboard, 49 % of the copy bandwidth).  Here the
@@ -251,107 +256,6 @@ part_scatter_staged_kernel(const uint64_t* __restrict__ kmers, size_t nq, int ps
     }
     __syncthreads();  // the staging buffer and the tables are rewritten by the next chunk
   }
-}
-
-// B with the write-out done by the copy engine (k <= 25: the slot rides in the k-mer word, one 8-byte array to write).
-// Above, every sorted k-mer costs a shared-memory load, a table look-up and an 8-byte global store issued by its thread
-// -- 128 of the ~250 instructions a thread spends per chunk, and the pass stalls on the load/store queue (ncu r3e:
-// lg_throttle).  Here the thread that owns a bin copies the bin's whole run with ONE bulk copy (cp.async.bulk, shared ->
-// global).  A bulk copy wants 16-byte aligned addresses on both sides and runs start at arbitrary 8-byte offsets, so every
-// run gets one spare slot in the staging buffer and starts at a shared-memory index of the same parity as its global
-// index: then the two sides are misaligned together, the odd first / last element is stored by hand and everything in
-// between goes in one copy.
-constexpr uint32_t kTmaStage = kPartChunk + 2048;  // one spare slot per bin
-__device__ __forceinline__ void bulk_store(void* gmem, const void* smem, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
-               ::"l"(gmem), "r"((uint32_t)__cvta_generic_to_shared(smem)), "r"(bytes) : "memory");
-}
-__global__ void __launch_bounds__(kScatterThreads)
-part_scatter_tma_kernel(const uint64_t* __restrict__ kmers, size_t nq, int pshift, uint32_t nbins, size_t nchunks,
-                        const uint32_t* __restrict__ off, const uint32_t* __restrict__ bin_start,
-                        uint64_t* __restrict__ part_kmer) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* sk = reinterpret_cast<uint64_t*>(smem_raw);              // [kTmaStage] k-mers sorted by bin, runs parity-padded
-  uint32_t* lstart = reinterpret_cast<uint32_t*>(sk + kTmaStage);    // [2048] next free staging index of the bin
-  __shared__ uint32_t wsum[32];
-  constexpr int kBins = 2048 / kScatterThreads;  // bins per thread
-  uint64_t x[kScatterPer];
-  uint32_t r0[kBins], r1[kBins], bs[kBins];
-  auto request = [&](size_t c) {  // the k-mers of chunk c and this thread's piece of rows c, c + 1 of the offset table
-    const size_t base = c * kPartChunk;
-    const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-#pragma unroll
-    for (int j = 0; j < kScatterPer; j++) {
-      const uint32_t i = threadIdx.x + (uint32_t)j * kScatterThreads;
-      x[j] = i < m ? __ldcs(kmers + base + i) : 0ull;
-    }
-#pragma unroll
-    for (int j = 0; j < kBins; j++) {
-      const uint32_t b = (uint32_t)kBins * threadIdx.x + j;
-      r0[j] = r1[j] = bs[j] = 0;
-      if (b < nbins) {
-        const uint32_t* row = off + c * nbins + b;  // coalesced
-        r0[j] = __ldg(row);
-        r1[j] = __ldg(row + nbins);
-        bs[j] = __ldg(bin_start + b);
-      }
-    }
-  };
-  size_t c = blockIdx.x;
-  if (c < nchunks) request(c);
-  for (; c < nchunks; c += gridDim.x) {
-    const size_t base = c * kPartChunk;
-    const uint32_t m = (uint32_t)(nq - base < kPartChunk ? nq - base : kPartChunk);
-    uint32_t gpos[kBins], len[kBins], sbeg[kBins];
-#pragma unroll
-    for (int j = 0; j < kBins; j++) {
-      gpos[j] = bs[j] + r0[j];
-      len[j] = r1[j] - r0[j];
-      lstart[(uint32_t)kBins * threadIdx.x + j] = len[j] + 1u;  // the run and its spare slot
-    }
-    __syncthreads();
-    {
-      uint32_t own[kBins];
-      scan_2048<kScatterThreads>(lstart, wsum, own);
-#pragma unroll
-      for (int j = 0; j < kBins; j++) {
-        sbeg[j] = own[j] + ((gpos[j] ^ own[j]) & 1u);  // same parity as the run's global index
-        lstart[(uint32_t)kBins * threadIdx.x + j] = sbeg[j];
-      }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int h = 0; h < kScatterPer; h += 4) {
-      uint32_t p[4];
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
-        p[j] = i < m ? atomicAdd(&lstart[bin_of(x[h + j] & kSlotKmerMask, pshift, nbins)], 1u) : 0u;
-      }
-#pragma unroll
-      for (int j = 0; j < 4; j++) {
-        const uint32_t i = threadIdx.x + (uint32_t)(h + j) * kScatterThreads;
-        if (i < m) sk[p[j]] = (x[h + j] & kSlotKmerMask) | ((uint64_t)i << kSlotShift);
-      }
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the staged k-mers, for the copy engine
-    if (c + gridDim.x < nchunks) request(c + gridDim.x);         // in flight during the write-out below
-    __syncthreads();
-#pragma unroll
-    for (int j = 0; j < kBins; j++) {
-      if (len[j]) {
-        const uint32_t head = gpos[j] & 1u;
-        if (head) part_kmer[gpos[j]] = sk[sbeg[j]];
-        const uint32_t rest = len[j] - head, mid = rest & ~1u;
-        if (mid) bulk_store(part_kmer + gpos[j] + head, sk + sbeg[j] + head, mid * 8u);
-        if (rest & 1u) part_kmer[gpos[j] + len[j] - 1u] = sk[sbeg[j] + len[j] - 1u];
-      }
-    }
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the staging buffer may be rewritten
-    __syncthreads();
-  }
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 // U: chunk c collects its answers.  Warp w walks bins w, w+32, ...; the run (bin, c) is read coalesced by the lanes.
@@ -455,7 +359,6 @@ part_unpermute_group_kernel(const long long* __restrict__ res, size_t nq, uint32
 }  // namespace
 
 constexpr size_t kScatterSmem = (size_t)kPartChunk * 10 + 2 * 2048 * 4;
-constexpr size_t kScatterTmaSmem = (size_t)kTmaStage * 8 + 2048 * 4;
 constexpr size_t kUnpermSmem = (size_t)kPartChunk * sizeof(uint32_t);
 
 size_t partition_workspace_bytes(size_t nq, int pbits) {
@@ -480,7 +383,6 @@ static int set_kernel_attributes() {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
   SB_SMEM(part_scatter_staged_kernel<false>, kScatterSmem);
   SB_SMEM(part_scatter_staged_kernel<true>, kScatterSmem);
-  SB_SMEM(part_scatter_tma_kernel, kScatterTmaSmem);
   SB_SMEM(part_unpermute_kernel<long long>, kUnpermSmem);
   SB_SMEM(part_unpermute_kernel<uint32_t>, kUnpermSmem);
   SB_SMEM((part_unpermute_group_kernel<8, long long>), kUnpermSmem);
@@ -548,10 +450,7 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
   // load per query instead of two of each
   const bool slot_in_kmer = 2 * ix.k + 14 <= 64;
   const unsigned sgrid = (unsigned)(nchunks < 148 ? nchunks : 148);  // persistent: one block per SM
-  if (slot_in_kmer && occupancy >= 10)  // EXPERIMENT: occ = 10 + blocks per SM selects the bulk-copy write-out
-    part_scatter_tma_kernel<<<sgrid, kScatterThreads, kScatterTmaSmem, st>>>(d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start,
-                                                                            part_kmer);
-  else if (slot_in_kmer)
+  if (slot_in_kmer)
     part_scatter_staged_kernel<true><<<sgrid, kScatterThreads, kScatterSmem, st>>>(
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
   else
@@ -559,8 +458,7 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
   SB_CUDA_CHECK(cudaGetLastError());
   if (ev) cudaEventRecord(ev[2], st);
-  if (launch_kmer_query_ordered(ix, part_kmer, nq, res, slot_in_kmer ? slot_in_kmer_tag() : part_slot, tiles,
-                                occupancy >= 10 ? occupancy - 10 : occupancy, st))
+  if (launch_kmer_query_ordered(ix, part_kmer, nq, res, slot_in_kmer ? slot_in_kmer_tag() : part_slot, tiles, occupancy, st))
     return -1;
   if (ev) cudaEventRecord(ev[3], st);
   if (d_out32) launch_unpermute<uint32_t>(res, nq, nbins, nchunks, cnt, bin_start, d_out32, pbits, st);
