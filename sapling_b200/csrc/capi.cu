@@ -64,6 +64,7 @@ struct Tuning {
   int line_bases = 0;                 // line_bases=b: leading bases per rank-line entry (tests: forces escapes / ties)
   int chunk_log2 = 0;                 // chunk_log2=l: chunk size of the host-pointer batch path
   int narrow = 1;                     // narrow=0: keep the wide model table
+  long long inorder_min = 1 << 15;    // inorder_min=N: smallest unpartitioned batch that takes the pipelined in-order kernel (-1: never)
   static Tuning from_env() {
     Tuning t;
     const char* e = getenv("SAPLING_B200_TUNE");
@@ -86,6 +87,7 @@ struct Tuning {
         else if (key == "line_bases") t.line_bases = (int)v;
         else if (key == "chunk_log2") t.chunk_log2 = (int)v;
         else if (key == "narrow") t.narrow = (int)v;
+        else if (key == "inorder_min") t.inorder_min = v;
       }
       p = q + 1;
     }
@@ -1282,6 +1284,11 @@ static int partition_bits(const sapling_b200_index* ix, size_t nq) {
 }
 
 // One batch of k-mers already on the device -> answers (long long, or uint32_t when d_out32 != nullptr), enqueued on st.
+// An unpartitioned batch takes the in-order kernel (query.cu) when every warp of its grid gets a few tiles to pipeline.
+static bool inorder_batch(const sapling_b200_index* ix, size_t nq) {
+  return ix->tune.inorder_min >= 0 && nq >= (size_t)ix->tune.inorder_min && nq < (1ull << 32);
+}
+
 static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint64_t* d_kmers, size_t nq, long long* d_out,
                           uint32_t* d_out32, cudaStream_t st) {
   if (nq == 0) return 0;
@@ -1305,6 +1312,26 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
       ev = evs;
     }
   }
+  // per-stream scratch: the partition workspace, or just the tile counter of the in-order kernel
+  auto scratch = [&](size_t need) -> void* {
+    std::lock_guard<std::mutex> lock(ix->mu_ws);
+    sapling_b200_index::PartWs& w = ix->part_ws[st];
+    if (w.bytes < need) {
+      if (w.p) { cudaFree(w.p); ix->device_bytes -= w.bytes; }  // cudaFree waits for work that still uses the block
+      w.p = nullptr;
+      w.bytes = 0;
+      if (cudaMalloc(&w.p, need) != cudaSuccess) {
+        cudaGetLastError();
+        w.p = nullptr;  // no room for the scratch: the plain kernel needs none
+      } else {
+        w.bytes = need;
+        ix->device_bytes += need;
+      }
+    }
+    return w.p;
+  };
+  // a batch answered in the caller's order: the pipelined in-order kernel from a few tiles per warp on, else one query
+  // per thread
   auto plain = [&]() -> int {
     ix->launches.fetch_add(1, std::memory_order_relaxed);
     if (ev) {  // unpartitioned call: stages 0, 1 and 3 are empty
@@ -1312,7 +1339,9 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
       cudaEventRecord(ev[1], st);
       cudaEventRecord(ev[2], st);
     }
-    const int rc = launch_kmer_query(v, d_kmers, nq, d_out, d_out32, ix->tune.occupancy, st);
+    void* tiles = inorder_batch(ix, nq) ? scratch(256) : nullptr;
+    const int rc = tiles ? launch_kmer_query_inorder(v, d_kmers, nq, d_out, d_out32, static_cast<unsigned long long*>(tiles), st)
+                         : launch_kmer_query(v, d_kmers, nq, d_out, d_out32, ix->tune.occupancy, st);
     if (ev) {
       cudaEventRecord(ev[3], st);
       cudaEventRecord(ev[4], st);
@@ -1320,28 +1349,10 @@ static int run_kmer_batch(sapling_b200_index* ix, const IndexView& v, const uint
     return rc;
   };
   if (bits == 0) return plain();
-  void* ws = nullptr;
-  {
-    std::lock_guard<std::mutex> lock(ix->mu_ws);
-    sapling_b200_index::PartWs& w = ix->part_ws[st];
-    const size_t need = partition_workspace_bytes(nq, bits);
-    if (w.bytes < need) {
-      if (w.p) { cudaFree(w.p); ix->device_bytes -= w.bytes; }  // cudaFree waits for work that still uses the block
-      w.p = nullptr;
-      w.bytes = 0;
-      if (cudaMalloc(&w.p, need) != cudaSuccess) {
-        cudaGetLastError();
-        w.p = nullptr;  // no room for the scratch: answer in the caller's order instead
-      } else {
-        w.bytes = need;
-        ix->device_bytes += need;
-      }
-    }
-    ws = w.p;
-  }
+  void* ws = scratch(partition_workspace_bytes(nq, bits));
   if (!ws) return plain();
   ix->launches.fetch_add(8, std::memory_order_relaxed);  // histogram, three column-scan passes, bin scan, scatter, query, un-permute
-  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, ix->tune.occupancy, st, ev);
+  return launch_partitioned_query(v, d_kmers, nq, d_out, d_out32, ws, bits, st, ev);
 }
 
 int sapling_b200_profile(sapling_b200_index* ix, int on) {
@@ -1378,7 +1389,7 @@ int sapling_b200_query_partition_bits(const sapling_b200_index* ix, size_t nq) {
 
 const char* sapling_b200_query_kernel_for(const sapling_b200_index* ix, size_t nq, int* blocks_per_sm) {
   if (!ix) return "";
-  const bool ordered = partition_bits(ix, nq) != 0;
+  const bool ordered = partition_bits(ix, nq) != 0 || inorder_batch(ix, nq);
   if (blocks_per_sm) *blocks_per_sm = kmer_query_blocks_per_sm(ordered, ix->tune.occupancy);
   return kmer_query_kernel_name(ordered);
 }

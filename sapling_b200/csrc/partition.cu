@@ -414,7 +414,7 @@ static void launch_unpermute(const long long* res, size_t nq, uint32_t nbins, si
 }
 
 int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
-                             void* ws, int pbits, int occupancy, cudaStream_t st, cudaEvent_t* ev) {
+                             void* ws, int pbits, cudaStream_t st, cudaEvent_t* ev) {
   if (nq == 0) return 0;
   if (pbits < 1 || pbits > kPartMaxBits || pbits > 2 * ix.k || nq >= (1ull << 32)) {
     set_error("launch_partitioned_query: pbits=%d nq=%zu out of range", pbits, nq);
@@ -458,7 +458,7 @@ int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_
         d_kmers, nq, pshift, nbins, nchunks, cnt, bin_start, part_kmer, part_slot);
   SB_CUDA_CHECK(cudaGetLastError());
   if (ev) cudaEventRecord(ev[2], st);
-  if (launch_kmer_query_ordered(ix, part_kmer, nq, res, slot_in_kmer ? slot_in_kmer_tag() : part_slot, tiles, occupancy, st))
+  if (launch_kmer_query_ordered(ix, part_kmer, nq, res, slot_in_kmer ? slot_in_kmer_tag() : part_slot, tiles, st))
     return -1;
   if (ev) cudaEventRecord(ev[3], st);
   if (d_out32) launch_unpermute<uint32_t>(res, nq, nbins, nchunks, cnt, bin_start, d_out32, pbits, st);

@@ -21,14 +21,17 @@ size_t partition_workspace_bytes(size_t nq, int pbits);
 // ev != nullptr: five events recorded on st around the stages (before the histogram, after the scans, after the scatter,
 // after the query kernel, after the un-permute) -- sapling_b200_stage_ms.
 int launch_partitioned_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
-                             void* ws, int pbits, int occupancy, cudaStream_t st, cudaEvent_t* ev = nullptr);
+                             void* ws, int pbits, cudaStream_t st, cudaEvent_t* ev = nullptr);
 
 // query.cu
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
                       int occupancy, cudaStream_t st);
 // d_tiles: a zeroed device counter the kernel claims its in-order tiles from; d_slot: slot array or slot_in_kmer_tag()
 int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
-                              const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st);
+                              const uint16_t* d_slot, unsigned long long* d_tiles, cudaStream_t st);
+// the same kernel over a batch in the caller's order, answers written directly (d_tiles: 8 bytes of device scratch)
+int launch_kmer_query_inorder(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
+                              unsigned long long* d_tiles, cudaStream_t st);
 const char* kmer_query_kernel_name(bool ordered);
 int kmer_query_blocks_per_sm(bool ordered, int occupancy);
 

@@ -101,9 +101,16 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
 
-template <int kMinBlocks, bool kTies, bool kNarrow>
-__global__ void __launch_bounds__(kQueryThreads, kMinBlocks)
-kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, long long* __restrict__ out,
+// kOut: what a finished query writes.  kOutSlotWord: a partitioned batch -- slot word at the query's partitioned index
+// (slot_word above; the un-permute pass restores the caller's order).  kOutInt64 / kOutU32: a batch in the caller's order
+// answered by the same pipeline (an index small enough to stay in L2 needs no partitioning, but the dependent reads of a
+// query want the look-ahead just the same: 5 M queries at 10 Mbp take 0.36 ms through kmer_query_kernel) -- the answer
+// itself at the query's index, -1 or 0xFFFFFFFF for "not found".
+enum { kOutSlotWord = 0, kOutInt64 = 1, kOutU32 = 2 };
+constexpr int kOrderedBlocks = 4;  // resident blocks per SM: 64 registers, no spills (3: 6.8 ms, 5: spills, 6.8 ms at c3)
+template <bool kTies, bool kNarrow, int kOut>
+__global__ void __launch_bounds__(kQueryThreads, kOrderedBlocks)
+kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers, size_t nq, void* __restrict__ out_raw,
                           const uint16_t* __restrict__ slot, unsigned long long* __restrict__ tiles) {
   __shared__ TailStacks stacks;
   __shared__ uint64_t kmer_ring[kWarpsPerBlock][2][32];  // the k-mers of tile t2 (landed) and of t3 (in flight)
@@ -142,8 +149,14 @@ kmer_query_ordered_kernel(const IndexView ix, const uint64_t* __restrict__ kmers
   // bits above 2k are not part of a k-mer (and bits 50-63 may carry the slot): never indexed with
   const uint64_t kmask = ix.k >= 32 ? ~0ull : ((1ull << (2 * ix.k)) - 1ull);
   auto store = [&](uint32_t i, uint64_t xw, long long r) {
-    const unsigned long long sl = in_kmer ? (unsigned long long)(xw >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
-    __stcs(out + i, slot_word(sl, r));
+    if (kOut == kOutInt64) {
+      __stcs(static_cast<long long*>(out_raw) + i, r);
+    } else if (kOut == kOutU32) {
+      __stcs(static_cast<uint32_t*>(out_raw) + i, (uint32_t)r);
+    } else {
+      const unsigned long long sl = in_kmer ? (unsigned long long)(xw >> kSlotShift) : (unsigned long long)__ldcs(slot + i);
+      __stcs(static_cast<long long*>(out_raw) + i, slot_word(sl, r));
+    }
   };
   unsigned stacked = 0;  // warp-uniform: entries on this warp's stack
   auto push = [&](bool pending, uint64_t xw, uint32_t pred, uint32_t i) {
@@ -550,13 +563,11 @@ const char* kmer_query_kernel_name(bool ordered) { return ordered ? "kmer_query_
 // Resident blocks per SM the kernels are compiled for (register cap = 65536 / (256 * blocks)).  Measured defaults;
 // `occupancy` (Tuning, capi.cu) overrides for A/B runs.
 int kmer_query_blocks_per_sm(bool ordered, int occupancy) {
-  if (occupancy == 3 || occupancy == 4 || occupancy == 5 || (occupancy == 6 && !ordered)) return occupancy;
-  // measured (gpurun s16, c3): the in-order kernel at 4 blocks per SM (64 registers, no spills) 5.53 ms per 250 M queries,
-  // at 5 (48 registers, spills) 6.8; at 3 (gpurun s8) 6.8
+  if (ordered) return kOrderedBlocks;
+  if (occupancy >= 3 && occupancy <= 6) return occupancy;
   return 4;
 }
 
-// A batch in the caller's order.  d_out32 != nullptr: 32-bit answers (0xFFFFFFFF = -1) instead of long long.
 int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
                       int occupancy, cudaStream_t st) {
   if (nq == 0) return 0;
@@ -584,30 +595,33 @@ int launch_kmer_query(const IndexView& ix, const uint64_t* d_kmers, size_t nq, l
   return 0;
 }
 
-// A partitioned batch (partition.cu): d_tiles is the zeroed in-order tile counter, d_slot the slot array or
-// slot_in_kmer_tag(); results are slot words (see slot_word).
-int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
-                              const uint16_t* d_slot, unsigned long long* d_tiles, int occupancy, cudaStream_t st) {
-  if (nq == 0) return 0;
+// The in-order kernel.  d_tiles is its zeroed tile counter.  Partitioned batch (partition.cu): d_slot is the slot array or
+// slot_in_kmer_tag(), the results are slot words in d_res.  Batch in the caller's order (d_slot == nullptr): answers go to
+// d_out (long long) or d_out32 (uint32_t), whichever is given.
+template <int kOut>
+static void launch_ordered(const IndexView& ix, const uint64_t* d_kmers, size_t nq, void* d_out, const uint16_t* d_slot,
+                           unsigned long long* d_tiles, cudaStream_t st) {
   const bool ties = has_ties(ix), narrow = ix.narrow != nullptr;
-  const int bps = kmer_query_blocks_per_sm(true, occupancy);
-  const int grid = query_grid(nq, bps);
-#define SB_LAUNCH_N(B, T, N) \
-  kmer_query_ordered_kernel<B, T, N><<<grid, kQueryThreads, 0, st>>>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles)
-#define SB_LAUNCH(B)                                       \
-  do {                                                     \
-    if (ties && narrow) SB_LAUNCH_N(B, true, true);        \
-    else if (ties) SB_LAUNCH_N(B, true, false);            \
-    else if (narrow) SB_LAUNCH_N(B, false, true);          \
-    else SB_LAUNCH_N(B, false, false);                     \
-  } while (0)
-  switch (bps) {
-    case 3: SB_LAUNCH(3); break;
-    case 5: SB_LAUNCH(5); break;
-    default: SB_LAUNCH(4); break;
-  }
-#undef SB_LAUNCH
-#undef SB_LAUNCH_N
+  const int grid = query_grid(nq, kOrderedBlocks);
+  if (ties && narrow) kmer_query_ordered_kernel<true, true, kOut><<<grid, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);
+  else if (ties) kmer_query_ordered_kernel<true, false, kOut><<<grid, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);
+  else if (narrow) kmer_query_ordered_kernel<false, true, kOut><<<grid, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);
+  else kmer_query_ordered_kernel<false, false, kOut><<<grid, kQueryThreads, 0, st>>>(ix, d_kmers, nq, d_out, d_slot, d_tiles);
+}
+int launch_kmer_query_ordered(const IndexView& ix, const uint64_t* d_part_kmers, size_t nq, long long* d_res,
+                              const uint16_t* d_slot, unsigned long long* d_tiles, cudaStream_t st) {
+  if (nq == 0) return 0;
+  launch_ordered<kOutSlotWord>(ix, d_part_kmers, nq, d_res, d_slot, d_tiles, st);
+  SB_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int launch_kmer_query_inorder(const IndexView& ix, const uint64_t* d_kmers, size_t nq, long long* d_out, uint32_t* d_out32,
+                              unsigned long long* d_tiles, cudaStream_t st) {
+  if (nq == 0) return 0;
+  if (nq >= (1ull << 32)) { set_error("launch_kmer_query_inorder: nq=%zu out of range", nq); return -1; }
+  SB_CUDA_CHECK(cudaMemsetAsync(d_tiles, 0, sizeof(unsigned long long), st));
+  if (d_out32) launch_ordered<kOutU32>(ix, d_kmers, nq, d_out32, nullptr, d_tiles, st);
+  else launch_ordered<kOutInt64>(ix, d_kmers, nq, d_out, nullptr, d_tiles, st);
   SB_CUDA_CHECK(cudaGetLastError());
   return 0;
 }

@@ -193,7 +193,8 @@ def test_layout_and_hint_variants_agree(S, oracle_built, monkeypatch):
         kmers = F.query_mix(g, k, 8000, seed=11)
         exp = port.query_batch(kmers, nthreads=4)
         for narrow, hints, occ in ((0, 0, 0), (1, 0, 3), (1, 15, 4), (0, 15, 5), (1, 5, 6), (1, 27, 0)):
-            monkeypatch.setenv("SAPLING_B200_TUNE", f"narrow={narrow},hints={hints},occ={occ}")
+            # (inorder_min=1: the pipelined in-order kernel on this small unpartitioned batch, in half the combinations)
+            monkeypatch.setenv("SAPLING_B200_TUNE", f"narrow={narrow},hints={hints},occ={occ},inorder_min={1 if occ in (0, 3, 5) else -1}")
             ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
             assert np.array_equal(ix.queryBatch(kmers), exp), (name, narrow, hints, occ)
             got32 = ix.queryBatchU32(kmers)
@@ -319,11 +320,12 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
             got32 = ix.queryBatchU32(kmers)
             assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, k, bits, "u32")
             ix.close()
-        monkeypatch.setenv("SAPLING_B200_TUNE", "part=0")
-        ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
-        assert ix.partition_bits(len(kmers)) == 0 and ix.query_kernel(len(kmers))[0] == "kmer_query_kernel"
-        assert np.array_equal(ix.queryBatch(kmers), exp)
-        ix.close()
+        for tune, kernel in (("part=0", "kmer_query_ordered_kernel"), ("part=0,inorder_min=-1", "kmer_query_kernel")):
+            monkeypatch.setenv("SAPLING_B200_TUNE", tune)
+            ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+            assert ix.partition_bits(len(kmers)) == 0 and ix.query_kernel(len(kmers))[0] == kernel
+            assert np.array_equal(ix.queryBatch(kmers), exp), (name, k, tune)
+            ix.close()
         port.close()
     monkeypatch.delenv("SAPLING_B200_TUNE")
 
@@ -436,6 +438,36 @@ def test_bit_stream_upload_format(S, oracle_built, name, k):
     ix.close()
 
 
+@pytest.mark.parametrize("name,k,nb", [("rand200k", 21, -1), ("gc1991", 16, 10), ("tandem50", 31, 8), ("repeat_tailA", 21, -1),
+                                       ("polyC", 11, 4), ("gc0110", 31, -1)])
+def test_inorder_kernel_on_unpartitioned_batches(S, oracle_built, name, k, nb, monkeypatch):
+    """A batch that is not partitioned (index small enough for L2, or partitioning switched off) goes through the same
+    pipelined in-order kernel, in the caller's order, writing the answers directly: every batch size around the tile and
+    claim granularity (32 queries per tile, 128 per claim), int64 and uint32 answers, against the oracle and against the
+    one-query-per-thread kernel."""
+    g = GENOMES[name]
+    if len(g) < 4 * k:
+        pytest.skip("genome shorter than 4k")
+    port = O.Port.from_memory(g, nb=nb, k=k)
+    kmers = F.query_mix(g, k, 40000, seed=5)[:33333]
+    exp = port.query_batch(kmers, nthreads=4)
+    monkeypatch.setenv("SAPLING_B200_TUNE", "part=0,inorder_min=1")
+    ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+    for m in (1, 2, 31, 32, 33, 127, 128, 129, 1000, 4097, len(kmers)):
+        assert ix.query_kernel(m)[0] == "kmer_query_ordered_kernel"
+        assert np.array_equal(ix.queryBatch(kmers[:m]), exp[:m]), (name, k, m)
+        got32 = ix.queryBatchU32(kmers[:m])
+        assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp[:m]), (name, k, m, "u32")
+    ix.close()
+    monkeypatch.setenv("SAPLING_B200_TUNE", "part=0,inorder_min=-1")
+    ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
+    assert ix.query_kernel(len(kmers))[0] == "kmer_query_kernel"
+    assert np.array_equal(ix.queryBatch(kmers), exp)
+    ix.close()
+    monkeypatch.delenv("SAPLING_B200_TUNE")
+    port.close()
+
+
 def test_stray_high_bits_are_ignored(S, oracle_built, monkeypatch):
     """Bits above 2k are not part of a k-mer: a word that carries them (a sign-extended or wider hash) is answered like the
     masked k-mer on every path, never used to index the model (which would read out of bounds)."""
@@ -445,7 +477,7 @@ def test_stray_high_bits_are_ignored(S, oracle_built, monkeypatch):
     kmers = F.query_mix(g, k, 50000, seed=2)
     exp = port.query_batch(kmers, nthreads=4)
     dirty = kmers | (np.uint64(0xABCDE) << np.uint64(42)) | (np.uint64(1) << np.uint64(63))
-    for tune in ("part=0", "part_min=1,part_bits=5,chunk_log2=22"):
+    for tune in ("part=0", "part=0,inorder_min=-1", "part_min=1,part_bits=5,chunk_log2=22"):
         monkeypatch.setenv("SAPLING_B200_TUNE", tune)
         ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
         assert np.array_equal(ix.queryBatch(dirty), exp), tune
