@@ -362,3 +362,20 @@ def test_seed_batch_port_matches_reference_methods(oracle_built, tmp_path):
                 assert np.array_equal(x[defined], y[defined]), (name, k, num_seeds)
         ref.close()
         port.close()
+
+
+@pytest.mark.parametrize("bits", [22, 32, 42, 43, 50, 62, 64])
+def test_pack_kmer_bits_is_a_little_endian_bit_stream(bits):
+    """sapling_b200.api.pack_kmer_bits (the host-side packer of the densest upload format, include/sapling_b200.h
+    sapling_b200_query_batch_bits): k-mer i occupies bits [i * bits, (i + 1) * bits) of the byte stream read as one
+    little-endian integer; ragged counts end inside a byte."""
+    from sapling_b200.api import pack_kmer_bits
+    rng = np.random.default_rng(bits)
+    for n in (1, 7, 8, 9, 1003):
+        x = rng.integers(0, 1 << min(bits, 63), size=n, dtype=np.uint64)
+        if bits == 64:
+            x |= rng.integers(0, 2, size=n, dtype=np.uint64) << np.uint64(63)
+        s = pack_kmer_bits(x, bits)
+        assert s.dtype == np.uint8 and len(s) == (n * bits + 7) // 8
+        big = int.from_bytes(bytes(s), "little")
+        assert all(((big >> (i * bits)) & ((1 << bits) - 1)) == int(x[i]) for i in range(n))
