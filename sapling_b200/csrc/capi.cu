@@ -59,7 +59,7 @@ struct Tuning {
   int partition = 1;                  // part=0: never partition a batch
   size_t partition_min = (size_t)1 << 22;  // part_min=N: smallest batch that is partitioned
   int partition_bits = -1;            // part_bits=B: force the slice count (2^B)
-  int occupancy = 0;                  // occ=3..6: resident blocks per SM of the query kernels (0 = their defaults)
+  int occupancy = 0;                  // occ=3..6: resident blocks per SM of kmer_query_kernel (0 = its default; the in-order kernel has one build)
   int hints = -1;                     // hints=<HINT_* bits>
   int line_bases = 0;                 // line_bases=b: leading bases per rank-line entry (tests: forces escapes / ties)
   int chunk_log2 = 0;                 // chunk_log2=l: chunk size of the host-pointer batch path
