@@ -270,6 +270,11 @@ __device__ __forceinline__ void store_answer<long long>(long long* p, uint32_t v
 template <>
 __device__ __forceinline__ void store_answer<uint32_t>(uint32_t* p, uint32_t v) { __stcs(p, v); }
 
+// (Measured and dropped, gpurun s27: the whole gather of a chunk as cp.async copies into a 128 KB staging buffer -- every
+// answer of the chunk in flight at once, permuted inside shared memory afterwards, one persistent block per SM -- 1.038
+// against 1.031 ms at c3; likewise 512 threads with 16 answers in flight per lane, gpurun s14: slower.  With the scatter's
+// bulk-copy write-out (partition.cu above) that makes three designs of these two passes at the same 3.9 TB/s: what binds
+// them is the memory side of 256-byte runs in 512 streams, not how the SM issues them.)
 // Both kernels below request the answers of a step together, before the first shared-memory store that depends on one: an
 // SM issues in order, so a loop of "load, store what was loaded" waits out one DRAM round trip per answer.
 template <typename Out>
