@@ -389,7 +389,10 @@ def cpu_baseline_and_parity(ix, d_batch, args, sample, stream, log):
     cpu = {"value": sample / t, "unit": "queries/s", "cores": threads, "kind": kind,
            "sample": f"first {sample} queries of batch 0, OpenMP over the unmodified Sapling::plQuery (struct filled from "
                      f"the GPU-built parts), string construction untimed as in sapling_example.cpp:113-140"}
-    parity = {"checked": int(sample), "mismatches_vs_" + kind: int((ref_ans != gpu_ans).sum()),
+    # (a predicted rank >= n is undefined in the reference -- rev[] read out of bounds, SURVEY H9 -- and not run by the harness)
+    defined = ref_ans != getattr(O, "REF_UNDEFINED", None) if kind == "reference" else np.ones(sample, dtype=bool)
+    parity = {"checked": int(defined.sum()), "mismatches_vs_" + kind: int(((ref_ans != gpu_ans) & defined).sum()),
+              "undefined_in_reference": int((~defined).sum()),
               "minus1_answers": int((ref_ans == -1).sum()), "ranks_ge_2^31_branch": bool(n >= (1 << 31)),
               "five": list(ix.five), "nb": ix.buckets}
     if n <= 100_000_000 and kind == "reference":

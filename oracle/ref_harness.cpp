@@ -120,8 +120,18 @@ long long ref_kmerize_adjusted(void *h, int length, const char *s) {
 }
 size_t ref_predict(void *h, long long x) { return ((Sapling *)h)->queryPiecewiseLinear(x); }
 
+/* A predicted rank >= n makes plQuery read rev[] out of bounds (sapling_api.h:162) and go on with whatever it
+   finds there -- undefined, and now and then a segfault.  The harness does not run the reference into it: such a query is
+   answered REF_UNDEFINED (LLONG_MIN) here, -2 in ref_seed_batch, and the callers leave it out of their comparisons
+   (the product clamps the prediction to n - 1 and counts the event). */
+static const long long REF_UNDEFINED = (long long)(1ull << 63);
+static inline bool ref_prediction_out_of_range(Sapling *s, long long kmer) {
+  return s->queryPiecewiseLinear(kmer) >= s->n;
+}
+
 /* plQuery(string s, long kmer, size_t length)  sapling_api.h:159 */
 long long ref_query_str(void *h, const char *s, size_t slen, long long kmer, size_t length) {
+  if (ref_prediction_out_of_range((Sapling *)h, kmer)) return REF_UNDEFINED;
   return ((Sapling *)h)->plQuery(std::string(s, slen), (long)kmer, length);
 }
 
@@ -134,11 +144,14 @@ double ref_query_batch(void *h, const uint64_t *kmers, size_t nq, long long *out
   std::vector<std::string> queries(nq);
   if (nthreads < 1) nthreads = 1;
 #pragma omp parallel for num_threads(nthreads) schedule(static)
-  for (size_t i = 0; i < nq; i++) queries[i] = unpack(kmers[i], k);
+  for (size_t i = 0; i < nq; i++) {
+    queries[i] = unpack(kmers[i], k);
+    out[i] = ref_prediction_out_of_range(s, (long long)kmers[i]) ? REF_UNDEFINED : 0; /* checked outside the timed loop */
+  }
   auto t0 = std::chrono::steady_clock::now();
 #pragma omp parallel for num_threads(nthreads) schedule(static)
   for (size_t i = 0; i < nq; i++)
-    out[i] = s->plQuery(queries[i].substr(0, (size_t)k), (long)kmers[i], queries[i].length());
+    if (out[i] != REF_UNDEFINED) out[i] = s->plQuery(queries[i].substr(0, (size_t)k), (long)kmers[i], queries[i].length());
   auto t1 = std::chrono::steady_clock::now();
   return std::chrono::duration<double>(t1 - t0).count();
 }
@@ -152,7 +165,8 @@ size_t ref_count_hits_right(void *h, size_t sa_pos, size_t maxHits) {
 
 /* The seed lookups of align.cpp seed_extend (:267-300) for a block of reads, written against the reference's own
    methods.  Output slot ((r*2+strand)*num_seeds + i): ref_pos = verified hit position or -1 (plQuery returned -1, or
-   the k bases at the returned position differ from the seed, :280-285); for hits sa_pos/left/right as pushed at
+   the k bases at the returned position differ from the seed, :280-285; -2: undefined in the reference, predicted rank
+   >= n); for hits sa_pos/left/right as pushed at
    :287-297.  The reference reads `sapling->sa[ref_pos]` (:287), a member that is declared (sapling_api.h:38) but never
    filled, so the shipped align crashes there; the intended array is the inverse suffix array lsa.inv (the one
    countHitsLeft/Right index by rank), which is what is used here.  Reads shorter than k are skipped (the reference
@@ -189,6 +203,10 @@ void ref_seed_batch(void *h, const char *reads, const uint64_t *off, size_t n_re
         else if (i > 0) cur_pos = last / (num_seeds - 1) * i;
         std::string query = seq.substr(cur_pos, sapling->k);
         long long val = sapling->kmerize(query);
+        if (ref_prediction_out_of_range(sapling, val)) { /* undefined in the reference (see REF_UNDEFINED) */
+          ref_pos_out[(r * 2 + (size_t)iter) * num_seeds + i] = -2;
+          continue;
+        }
         long long ref_pos_signed = sapling->plQuery(query, val, sapling->k);
         if (ref_pos_signed == -1) continue;
         size_t ref_pos = (size_t)ref_pos_signed;

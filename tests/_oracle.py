@@ -14,6 +14,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PORT_SO = os.path.join(ROOT, "oracle", "_build", "liboracle.so")
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libsapling_ref.so")
+REF_UNDEFINED = -(1 << 63)  # oracle/ref_harness.cpp: the reference's answer is undefined (predicted rank >= n)
 
 u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
 i64p = np.ctypeslib.ndpointer(dtype=np.int64, flags="C_CONTIGUOUS")
@@ -365,6 +366,8 @@ class Ref:
         return int(self.L.ref_query_str(self.h, s, slen, int(kmer), length))
 
     def query_batch(self, kmers, nthreads=1, timed=False):
+        """plQuery per k-mer.  A k-mer whose predicted rank is >= n (undefined in the reference: it reads rev[] out of
+        bounds) is not run; its answer is REF_UNDEFINED."""
         kmers = np.ascontiguousarray(kmers, dtype=np.uint64)
         out = np.empty(len(kmers), dtype=np.int64)
         t = self.L.ref_query_batch(self.h, kmers, len(kmers), out, nthreads)

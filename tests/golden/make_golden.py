@@ -85,7 +85,8 @@ SEED_CASES = [("rand20k", 16), ("gc1991", 16), ("tandem50", 16), ("ssw100k_slice
 def main_seeds():
     """seeds.<genome>.k<k>.npz: the align.cpp:259-300 seed loop driven through the unmodified reference's own methods
     (oracle/ref_harness.cpp ref_seed_batch) on simulated reads; `defined` masks the slots on which the reference itself
-    reads out of bounds (countHitsLeft on the last rank)."""
+    reads out of bounds (countHitsLeft on the last rank; a seed whose predicted rank is >= n, which the harness does not run:
+    ref_pos == -2)."""
     G = genomes()
     with tempfile.TemporaryDirectory(dir="/dev/shm") as tmp:
         for name, k in SEED_CASES:
@@ -96,7 +97,7 @@ def main_seeds():
             reads, _ = O.simulate_reads(g, 150, min(150, len(g) // 4))
             reads += [b"ACGT", g[100:100 + k], g[7:7 + k + 1], b"N" * 60, g[5:155].lower(), g[-150:], g[:150]]
             rp, sp, lf, rt = ref.seed_batch(reads, 7, 32)
-            defined = ~((rp >= 0) & (sp == len(g) - 1))
+            defined = ~((rp >= 0) & (sp == len(g) - 1)) & (rp != -2)
             out = os.path.join(HERE, f"seeds.{name}.k{k}.npz")
             np.savez_compressed(out, genome=np.frombuffer(g, dtype=np.uint8), k=k, num_seeds=7, max_hits=32,
                                 reads=np.frombuffer(b"".join(reads), dtype=np.uint8),

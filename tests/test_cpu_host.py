@@ -358,6 +358,7 @@ def test_seed_batch_port_matches_reference_methods(oracle_built, tmp_path):
             # countHitsLeft on the LAST rank reads lcp[n-1], one past the reference's n-1 entries (sapling_api.h:287):
             # undefined there; port and GPU define that flag as 0.  Excluded from the comparison, everything else equal.
             defined = ~((a[0] >= 0) & (a[1] == len(g) - 1))
+            defined &= a[0] != -2  # predicted rank >= n: the reference reads rev[] out of bounds (not run)
             for x, y in zip(a, b):
                 assert np.array_equal(x[defined], y[defined]), (name, k, num_seeds)
         ref.close()
