@@ -64,7 +64,10 @@ struct Tuning {
   int line_bases = 0;                 // line_bases=b: leading bases per rank-line entry (tests: forces escapes / ties)
   int chunk_log2 = 0;                 // chunk_log2=l: chunk size of the host-pointer batch path
   int narrow = 1;                     // narrow=0: keep the wide model table
-  long long inorder_min = 1 << 15;    // inorder_min=N: smallest unpartitioned batch that takes the pipelined in-order kernel (-1: never)
+  // inorder_min=N: smallest unpartitioned batch that takes the pipelined in-order kernel (-1: never).  Measured on a 10 Mbp
+  // index (tools/inorder_crossover.py, us per batch, in-order / one query per thread): 2^15 27 / 15, 2^18 45 / 31,
+  // 2^19 47 / 46, 2^20 76 / 87, 2^22 203 / 303.
+  long long inorder_min = 1 << 19;
   static Tuning from_env() {
     Tuning t;
     const char* e = getenv("SAPLING_B200_TUNE");

@@ -320,7 +320,7 @@ def test_partitioned_batch(S, oracle_built, name, monkeypatch):
             got32 = ix.queryBatchU32(kmers)
             assert np.array_equal(np.where(got32 == 0xFFFFFFFF, -1, got32.astype(np.int64)), exp), (name, k, bits, "u32")
             ix.close()
-        for tune, kernel in (("part=0", "kmer_query_ordered_kernel"), ("part=0,inorder_min=-1", "kmer_query_kernel")):
+        for tune, kernel in (("part=0,inorder_min=1", "kmer_query_ordered_kernel"), ("part=0", "kmer_query_kernel")):
             monkeypatch.setenv("SAPLING_B200_TUNE", tune)
             ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
             assert ix.partition_bits(len(kmers)) == 0 and ix.query_kernel(len(kmers))[0] == kernel
@@ -477,7 +477,7 @@ def test_stray_high_bits_are_ignored(S, oracle_built, monkeypatch):
     kmers = F.query_mix(g, k, 50000, seed=2)
     exp = port.query_batch(kmers, nthreads=4)
     dirty = kmers | (np.uint64(0xABCDE) << np.uint64(42)) | (np.uint64(1) << np.uint64(63))
-    for tune in ("part=0", "part=0,inorder_min=-1", "part_min=1,part_bits=5,chunk_log2=22"):
+    for tune in ("part=0", "part=0,inorder_min=1", "part_min=1,part_bits=5,chunk_log2=22"):
         monkeypatch.setenv("SAPLING_B200_TUNE", tune)
         ix = S.Sapling.from_model(g, port.sa, k, port.nb, port.xlist, port.ylist, port.five)
         assert np.array_equal(ix.queryBatch(dirty), exp), tune

@@ -26,7 +26,7 @@ def main():
         a = S.Sapling.from_memory(g, None, k=k, flags=S.QUIET)
         exp = a.queryBatch(kmers)
         a.close()
-        for tune in ("part=0", "part_min=1,part_bits=3,chunk_log2=22", "part_min=1,part_bits=9,chunk_log2=22",
+        for tune in ("part=0,inorder_min=1", "part_min=1,part_bits=3,chunk_log2=22", "part_min=1,part_bits=9,chunk_log2=22",
                      "part_min=1,part_bits=11,chunk_log2=16"):
             os.environ["SAPLING_B200_TUNE"] = tune
             b = S.Sapling.from_memory(g, None, k=k, flags=S.QUIET)
