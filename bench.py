@@ -12,6 +12,8 @@ carry 1-2 substitutions, k and nb selectable) and `small` stay selectable.
 One "step" = one pass of the query hot path over one batch.
   value   : device-resident throughput (queries already in HBM), CUDA events on the launching stream
   e2e     : the same batch through the host C ABI from pinned host memory, H2D and D2H copies inside the timed region
+            (sapling_b200_query_batch_bits: 2k bits per k-mer up, uint32 positions down; the whole-byte and the
+            int64 entry points are timed beside it: e2e.byte_api, e2e.int64_api)
   roofline: the WHOLE STEP against the measured HBM copy bandwidth (MEASURED_PEAKS.json): the least DRAM traffic the
             step's launches can do (their streams + every index line some query touches, once) / the step time;
             `kernel` holds the dominant kernel on its own, `reference_bytes` the SURVEY 8d figure 16 + 32 (2 + P) with
